@@ -1,0 +1,119 @@
+/* maskunet_b200 -- C ABI of the B200-native Mask Attention hot path.
+ *
+ * One shared library (libmaskunet_b200.so, built for sm_100a only).  Plain C
+ * symbols, raw device pointers and sizes, no torch types.  This is the
+ * drop-in boundary described in SURVEY.md section 8(b): the reference has no
+ * FFI of its own (it is pure PyTorch), so each entry point cites the reference
+ * lines whose arithmetic it replaces.  All line numbers are into
+ * /root/reference/code/ade20k/ade_semantic.py unless noted.
+ *
+ * Conventions
+ *   - Caller owns every buffer (inputs, outputs, workspace); the library never
+ *     allocates, frees or retains device memory.  Inputs are never modified.
+ *   - All tensors contiguous in the documented layout, 16-byte aligned.
+ *   - Work is enqueued on `stream`; no device synchronisation inside.
+ *   - Return 0 on success, a negative mu_status for argument errors, a positive
+ *     cudaError_t for launch failures.  mu_last_error() gives a thread-local message.
+ *   - dtype codes: MU_F32 computes every contraction in fp32 on CUDA cores
+ *     (validation mode, tolerance 1e-4 vs the reference); MU_BF16 stores
+ *     activations as bf16 and runs the attention contractions on tcgen05 tensor
+ *     cores with fp32 accumulation (tolerance 2e-2).  Parameters, statistics
+ *     (lse, mean, rstd, delta) and parameter gradients are always fp32.
+ *   - B batch, C channels (= head dim, single head), N = H*W tokens,
+ *     NKP = N rounded up to a multiple of 128 (row pitch of compacted K/V).
+ */
+#ifndef MASKUNET_B200_H_
+#define MASKUNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mu_stream_t; /* == cudaStream_t */
+
+enum mu_dtype { MU_F32 = 0, MU_BF16 = 1 };
+
+enum mu_status {
+  MU_OK = 0,
+  MU_ERR_BAD_SHAPE = -1,
+  MU_ERR_BAD_DTYPE = -2,
+  MU_ERR_MISALIGNED = -3,
+  MU_ERR_ARCH = -4,
+  MU_ERR_NULL = -5,
+  MU_ERR_WORKSPACE = -6,
+  MU_ERR_DRIVER = -7
+};
+
+int mu_version(void);
+const char* mu_last_error(void);
+/* 1 when the current device is compute capability 10.x; tcgen05 entry points refuse to run otherwise. */
+int mu_device_supported(void);
+
+/* K2. Mask binarisation (:179-180  `binary_mask > 0.5` -> 0 / -inf bias, per key).
+ *   bits      int64 [B, N]   the torch.randint(0, 2, ...) draw of :178 (stays a torch call)
+ *   keep_bits uint32 [B, ceil(N/32)]  bit n%32 of word n/32 set  <=>  key n kept (bias 0.0)
+ *   n_keep    int32 [B]      number of kept keys
+ *   keep_idx  int32 [B, N]   compacted position -> token index (entries >= n_keep are -1)
+ *   keep_rank int32 [B, N]   token index -> compacted position, -1 when the key is masked
+ * Bit-exact: keep <=> (bits > 0.5). */
+int mu_mask_binarize(const int64_t* bits, int32_t B, int32_t N, uint32_t* keep_bits, int32_t* n_keep,
+                     int32_t* keep_idx, int32_t* keep_rank, mu_stream_t stream);
+
+/* K1. Q/K/V projections (:168-172).  Tokens are x[b, :, n] (the permute of :168 is never materialised).
+ *   x      T   [B, C, N]      w_qkv f32 [3C, C] = cat(query.weight, key.weight, value.weight)
+ *   b_qkv  f32 [3C]
+ *   q      T   [B, N, C]      kc, vc  T [B, NKP, C]: rows of kept keys only, in token order
+ *                             (row keep_rank[b, n]); rows [n_keep, roundup(n_keep, 128)) are zero-filled. */
+int mu_qkv_project(const void* x, const float* w_qkv, const float* b_qkv, const int32_t* keep_rank,
+                   const int32_t* n_keep, void* q, void* kc, void* vc, int32_t B, int32_t C, int32_t N, int32_t NKP,
+                   int32_t dtype, mu_stream_t stream);
+
+/* K3. Masked attention forward (:174-186): O = softmax(Q Kc^T / sqrt(C)) Vc over the kept keys only, which
+ * equals the reference's softmax(QK^T/sqrt(C) + mask) V exactly (masked keys contribute exp(-inf) = 0).
+ *   o   T   [B, N, C]      lse f32 [B, N] = log sum_j exp(s_ij / sqrt(C))
+ * MU_BF16: tcgen05/TMEM tiles fed by TMA, online softmax; MU_F32: CUDA-core fp32. */
+int mu_attn_fwd(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse, int32_t B,
+                int32_t N, int32_t NKP, int32_t C, int32_t dtype, mu_stream_t stream);
+
+/* Diagnostic twins of mu_attn_fwd / mu_attn_bwd that always run the CUDA-core kernels, for either dtype.
+ * Used by the GPU tests to cross-check the tensor-core kernels on-device at sizes the CPU oracle cannot reach. */
+int mu_attn_fwd_cudacore(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse,
+                         int32_t B, int32_t N, int32_t NKP, int32_t C, int32_t dtype, mu_stream_t stream);
+int mu_attn_bwd_cudacore(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
+                         const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int32_t B, int32_t N,
+                         int32_t NKP, int32_t C, int32_t dtype, mu_stream_t stream);
+
+/* K3 epilogue. Residual + LayerNorm over channels (:187-188), output in the [B, N, C] layout that the
+ * module returns re-viewed as [B, C, H, W] (:190).
+ *   y T [B, N, C] = LN_C(o + x^T) * gamma + beta;  mean, rstd f32 [B, N] saved for backward. */
+int mu_residual_ln_fwd(const void* o, const void* x, const float* gamma, const float* beta, float eps, void* y,
+                       float* mean, float* rstd, int32_t B, int32_t C, int32_t N, int32_t dtype, mu_stream_t stream);
+
+/* K4. Backward of the residual + LayerNorm (autograd of :187-188, implicit at :400).
+ *   dy T [B, N, C];  dz T [B, N, C] = dL/d(o + x^T)  (this is both dO and the residual branch of dX^T)
+ *   delta f32 [B, N] = sum_c dz * o    (softmax-backward row term)
+ *   dgamma, dbeta f32 [C]: ACCUMULATED with atomics, caller zero-fills. */
+int mu_residual_ln_bwd(const void* dy, const void* o, const void* x, const float* mean, const float* rstd,
+                       const float* gamma, void* dz, float* delta, float* dgamma, float* dbeta, int32_t B, int32_t C,
+                       int32_t N, int32_t dtype, mu_stream_t stream);
+
+/* K5. Masked attention backward (autograd of :174-186).  Recomputes P from q, kc, lse.
+ *   dq T [B, N, C];  dkc, dvc T [B, NKP, C] (rows >= n_keep untouched). */
+int mu_attn_bwd(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
+                const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int32_t B, int32_t N,
+                int32_t NKP, int32_t C, int32_t dtype, mu_stream_t stream);
+
+/* K6. Backward of the projections and the residual branch (autograd of :168-172, :187).
+ *   dx     T   [B, C, N]  = (dz + dq Wq + scatter(dkc) Wk + scatter(dvc) Wv)^T
+ *   dw_qkv f32 [3C, C], db_qkv f32 [3C]: ACCUMULATED with atomics, caller zero-fills. */
+int mu_qkv_project_bwd(const void* x, const void* dz, const void* dq, const void* dkc, const void* dvc,
+                       const int32_t* keep_rank, const float* w_qkv, void* dx, float* dw_qkv, float* db_qkv,
+                       int32_t B, int32_t C, int32_t N, int32_t NKP, int32_t dtype, mu_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MASKUNET_B200_H_ */

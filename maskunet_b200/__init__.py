@@ -1,0 +1,16 @@
+"""maskunet_b200 -- B200-native Mask Attention Module and the U-Net blocks around it.
+
+Importing this package loads libmaskunet_b200.so (hand-written sm_100a CUDA behind a C ABI,
+include/maskunet_b200.h).  There is no CPU or eager-PyTorch fallback for the attention path: a missing
+library raises ImportError, a CPU tensor raises RuntimeError.
+"""
+from . import _lib
+
+_lib.load()  # fail loudly, now, if the CUDA library is absent
+
+from . import ops  # noqa: E402  (registers the maskunet:: operators)
+from .modules import (ConvBlock, DownSample, InstanceUNet, Mask2FormerAttention, UNet,  # noqa: E402
+                      UpSample)
+
+__all__ = ["Mask2FormerAttention", "ConvBlock", "DownSample", "UpSample", "UNet", "InstanceUNet", "ops"]
+__version__ = "0.1.0"

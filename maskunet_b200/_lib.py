@@ -1,0 +1,61 @@
+"""ctypes binding of libmaskunet_b200.so (the C ABI declared in include/maskunet_b200.h).
+
+There is no fallback: if the library is missing the import fails loudly, and a
+CPU tensor reaching an op raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int32, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmaskunet_b200.so")
+
+MU_F32, MU_BF16 = 0, 1
+
+_P, _I, _F = c_void_p, c_int32, c_float
+
+# name -> argtypes, mirrors include/maskunet_b200.h one to one
+SIGNATURES = {
+    "mu_mask_binarize": [_P, _I, _I, _P, _P, _P, _P, _P],
+    "mu_qkv_project": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mu_attn_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mu_attn_fwd_cudacore": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mu_residual_ln_fwd": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mu_residual_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mu_attn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mu_attn_bwd_cudacore": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mu_qkv_project_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found. maskunet_b200 has no CPU or PyTorch fallback: build the CUDA library with "
+            "`python -m maskunet_b200.build` (needs nvcc, cross-compiles for sm_100a without a GPU).")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.mu_version.restype = c_int32
+    lib.mu_version.argtypes = []
+    lib.mu_last_error.restype = ctypes.c_char_p
+    lib.mu_last_error.argtypes = []
+    lib.mu_device_supported.restype = c_int32
+    lib.mu_device_supported.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int32
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().mu_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (status {rc}): {msg}")

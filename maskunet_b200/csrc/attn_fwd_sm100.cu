@@ -1,0 +1,305 @@
+// K3: masked attention forward on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM).
+// Replaces /root/reference/code/ade20k/ade_semantic.py:174-186: scores = QK^T / sqrt(C) + mask,
+// softmax, PV.  The per-key 0/-inf bias is realised by attending only to the compacted kept keys
+// (kc / vc rows [0, n_keep[b])), so no N x N tensor and no in-loop mask exist; only the tail of the last
+// key tile is masked.
+//
+// One CTA = one 128-query tile of one sample.  Warp roles:
+//   warp 0   TMA producer: Q once, then K_j / V_j tiles through a ring of shared-memory slots
+//   warp 1   allocates TMEM, single thread issues tcgen05.mma:  S_j = Q K_j^T,   O += P_j V_j
+//   warp 2-5 softmax: thread <-> query row (TMEM lane); online max / exp2 / row sum in fp32,
+//            P_j written to shared memory as bf16 in the UMMA K-major 128B-swizzled layout,
+//            O rescaled in TMEM when the running max moves, final O / l and LSE written out.
+// Shared-memory operand tiles are [rows][64 bf16] blocks as TMA SWIZZLE_128B writes them
+// (see sm100_ptx.cuh for the descriptor conventions).
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+#include "tma_host.cuh"
+
+namespace mu {
+
+constexpr int kBM = 128;                 // queries per CTA
+constexpr int kFwdThreads = 192;         // 6 warps
+constexpr float kLog2eF = 1.4426950408889634f;
+
+template <int D, int BN, int SBUFS, int SLOTS>
+struct FwdCfg {
+  static constexpr int kDBlocks = D / 64;                   // 64-column (128-byte) blocks per row
+  static constexpr int kQBytes = kBM * D * 2;
+  static constexpr int kKVBytes = BN * D * 2;               // one K or V tile = one ring slot
+  static constexpr int kPBytes = kBM * BN * 2;
+  static constexpr int kTmemS = 0;
+  static constexpr int kTmemO = SBUFS * BN;
+  static constexpr int kTmemUsed = SBUFS * BN + D;
+  static constexpr int kTmemCols = kTmemUsed <= 256 ? 256 : 512;
+  static constexpr int kBarBytes = 8 * (1 + 2 * SLOTS + 2 * SBUFS + 2) + 8;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kQBytes + SLOTS * kKVBytes + kPBytes + 256;
+  static_assert(kBarBytes <= 256, "barrier block too small");
+  static_assert(kTmemUsed <= 512, "TMEM overflow");
+};
+
+template <int D, int BN, int SBUFS, int SLOTS, int MINB>
+__global__ void __launch_bounds__(kFwdThreads, MINB)
+attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                      const __grid_constant__ CUtensorMap tmap_v, const int32_t* __restrict__ n_keep,
+                      __nv_bfloat16* __restrict__ o, float* __restrict__ lse, int N, float scale_log2) {
+  using Cfg = FwdCfg<D, BN, SBUFS, SLOTS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + Cfg::kQBytes;
+  uint8_t* sP = sKV + SLOTS * Cfg::kKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* kv_full = bars + 1;             // SLOTS
+  uint64_t* kv_empty = kv_full + SLOTS;     // SLOTS
+  uint64_t* s_full = kv_empty + SLOTS;      // SBUFS
+  uint64_t* s_free = s_full + SBUFS;        // SBUFS
+  uint64_t* p_full = s_free + SBUFS;        // 1
+  uint64_t* o_done = p_full + 1;            // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int b = blockIdx.y, q0 = blockIdx.x * kBM;
+  const int nk = n_keep[b];
+  const int T = (nk + BN - 1) / BN;  // key tiles
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < SLOTS; ++i) {
+      mbar_init(kv_full + i, 1);
+      mbar_init(kv_empty + i, 1);
+    }
+    for (int i = 0; i < SBUFS; ++i) {
+      mbar_init(s_full + i, 1);
+      mbar_init(s_free + i, 128);
+    }
+    mbar_init(p_full, 128);
+    mbar_init(o_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane_id() == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane_id() == 0 && T > 0) {
+      mbar_expect_tx(q_full, Cfg::kQBytes);
+      for (int blk = 0; blk < Cfg::kDBlocks; ++blk) tma_load_3d(sQ + blk * (kBM * 128), &tmap_q, q_full, blk * 64, q0, b);
+      for (int t = 0; t < 2 * T; ++t) {  // t = 2j: K_j, t = 2j+1: V_j
+        const int slot = t % SLOTS, use = t / SLOTS;
+        if (use > 0) mbar_wait(kv_empty + slot, (use - 1) & 1);
+        mbar_expect_tx(kv_full + slot, Cfg::kKVBytes);
+        const CUtensorMap* tm = (t & 1) ? &tmap_v : &tmap_k;
+        uint8_t* dst = sKV + slot * Cfg::kKVBytes;
+        for (int blk = 0; blk < Cfg::kDBlocks; ++blk)
+          tma_load_3d(dst + blk * (BN * 128), tm, kv_full + slot, blk * 64, (t >> 1) * BN, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane_id() == 0 && T > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kBM, BN, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(kBM, D, 0, 1);
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), kv_addr = smem_u32(sKV);
+      auto issue_s = [&](int j) {
+        const int t = 2 * j, slot = t % SLOTS, buf = j % SBUFS;
+        mbar_wait(kv_full + slot, (t / SLOTS) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = kv_addr + slot * Cfg::kKVBytes;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t da = make_smem_desc(q_addr + (kk >> 2) * (kBM * 128) + (kk & 3) * 32, 0, 1024);
+          const uint64_t db = make_smem_desc(k_addr + (kk >> 2) * (BN * 128) + (kk & 3) * 32, 0, 1024);
+          umma_ss(tmem_base + Cfg::kTmemS + buf * BN, da, db, idesc_s, kk > 0);
+        }
+        umma_commit(kv_empty + slot);
+        umma_commit(s_full + buf);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) {
+          const int use = (j + 1) / SBUFS;
+          if (use > 0) mbar_wait(s_free + (j + 1) % SBUFS, (use - 1) & 1);
+          issue_s(j + 1);
+        }
+        const int t = 2 * j + 1, slot = t % SLOTS;
+        mbar_wait(kv_full + slot, (t / SLOTS) & 1);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t v_addr = kv_addr + slot * Cfg::kKVBytes;
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          const uint64_t da = make_smem_desc(p_addr + (kk >> 2) * (kBM * 128) + (kk & 3) * 32, 0, 1024);
+          const uint64_t db = make_smem_desc(v_addr + kk * 2048, BN * 128, 1024);
+          umma_ss(tmem_base + Cfg::kTmemO, da, db, idesc_o, (j > 0) || (kk > 0));
+        }
+        umma_commit(kv_empty + slot);
+        umma_commit(o_done);
+      }
+    }
+  } else {
+    // ===================================================== softmax / correction / epilogue
+    const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
+    const int r = quad * 32 + (int)lane_id();       // query row within the tile
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const bool row_ok = q0 + r < N;
+    __nv_bfloat16* orow = o + ((size_t)b * N + q0 + r) * D;
+    if (T == 0) {  // every key masked: the reference yields NaN (softmax over all -inf)
+      if (row_ok) {
+        for (int c = 0; c < D; ++c) orow[c] = __float2bfloat16_rn(__int_as_float(0x7fc00000));
+        lse[(size_t)b * N + q0 + r] = -INFINITY;
+      }
+    } else {
+      float m = -INFINITY, l = 0.f;
+      uint32_t v[32];
+      for (int j = 0; j < T; ++j) {
+        const int buf = j % SBUFS;
+        const uint32_t s_addr = lane_base + Cfg::kTmemS + buf * BN;
+        const int limit = nk - j * BN;  // valid key columns in this tile (>= 1)
+        mbar_wait(s_full + buf, (j / SBUFS) & 1);
+        tc_fence_after();
+        // ---- pass 1: row max
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          tmem_ld32(s_addr + c * 32, v);
+          tmem_wait_ld();
+          if (limit >= BN) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < limit) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+        }
+        const float m_new = fmaxf(m, mx);
+        const float alpha = fast_exp2((m - m_new) * scale_log2);
+        // ---- rescale O once the previous PV has landed
+        if (j > 0) {
+          mbar_wait(o_done, (j - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, m_new > m)) {
+#pragma unroll
+            for (int c = 0; c < D / 32; ++c) {
+              tmem_ld32(lane_base + Cfg::kTmemO + c * 32, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st32(lane_base + Cfg::kTmemO + c * 32, v);
+            }
+            tmem_wait_st();
+          }
+        }
+        // ---- pass 2: p = exp2((s - m) * scale * log2e), bf16 P tile into shared memory
+        const float mb = m_new * scale_log2;
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          tmem_ld32(s_addr + c * 32, v);
+          tmem_wait_ld();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), scale_log2, -mb));
+            float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, -mb));
+            if (limit < BN) {
+              if (c * 32 + 2 * i >= limit) p0 = 0.f;
+              if (c * 32 + 2 * i + 1 >= limit) p1 = 0.f;
+            }
+            sum += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+          // columns [c*32, c*32+32) = 16-byte chunks (c&1)*4 .. +3 of 64-column block c>>1
+          uint8_t* prow = sP + (c >> 1) * (kBM * 128) + r * 128;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const int chunk = ((c & 1) * 4 + ch) ^ (r & 7);
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(s_free + buf);
+        fence_proxy_async_smem();
+        mbar_arrive(p_full);
+        l = l * alpha + sum;
+        m = m_new;
+      }
+      // ---- epilogue: O / l, LSE
+      mbar_wait(o_done, (T - 1) & 1);
+      tc_fence_after();
+      const float inv = 1.f / l;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        tmem_ld32(lane_base + Cfg::kTmemO + c * 32, v);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(v[8 * g + 0]) * inv, __uint_as_float(v[8 * g + 1]) * inv);
+            w.y = pack_bf16(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv);
+            w.z = pack_bf16(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv);
+            w.w = pack_bf16(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = w;
+          }
+        }
+      }
+      if (row_ok) lse[(size_t)b * N + q0 + r] = (m * scale_log2 + log2f(l)) / kLog2eF;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+template <int D, int BN, int SBUFS, int SLOTS, int MINB>
+static int run(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse, int B, int N,
+               int NKP, cudaStream_t s) {
+  using Cfg = FwdCfg<D, BN, SBUFS, SLOTS>;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tq, q, D, N, B, kBM))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tk, kc, D, NKP, B, BN))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tv, vc, D, NKP, B, BN))) return rc;
+  auto kern = attn_fwd_sm100_kernel<D, BN, SBUFS, SLOTS, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (e != cudaSuccess) {
+    set_error("attn_fwd_sm100: cudaFuncSetAttribute(%d bytes): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+    return (int)e;
+  }
+  dim3 grid((N + kBM - 1) / kBM, B);
+  const float scale_log2 = kLog2eF / sqrtf((float)D);
+  kern<<<grid, kFwdThreads, Cfg::kSmemBytes, s>>>(tq, tk, tv, n_keep, (__nv_bfloat16*)o, lse, N, scale_log2);
+  return check_launch("attn_fwd_sm100");
+}
+
+int launch_attn_fwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse,
+                          int B, int N, int NKP, int C, cudaStream_t s) {
+  switch (C) {
+    case 64:  // 2 CTAs / SM: TMEM 256 cols each, 96 KB of tiles each
+      return run<64, 128, 1, 3, 2>(q, kc, vc, n_keep, o, lse, B, N, NKP, s);
+    case 128:
+      return run<128, 128, 2, 4, 1>(q, kc, vc, n_keep, o, lse, B, N, NKP, s);
+    case 256:
+      return run<256, 64, 2, 4, 1>(q, kc, vc, n_keep, o, lse, B, N, NKP, s);
+    default:
+      set_error("attn_fwd_sm100: channels must be 64, 128 or 256 (got %d)", C);
+      return MU_ERR_BAD_SHAPE;
+  }
+}
+
+}  // namespace mu

@@ -1,0 +1,160 @@
+// extern "C" boundary: argument validation, dtype / architecture dispatch, error text.
+// See include/maskunet_b200.h for the contract of every entry point.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace mu {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+static int device_cc_major() {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return -1;
+  return major;
+}
+
+static int check_common(const char* fn, int B, int C, int N, int dtype) {
+  MU_REQUIRE(B > 0 && N > 0, MU_ERR_BAD_SHAPE, "%s: B and N must be positive (B=%d N=%d)", fn, B, N);
+  MU_REQUIRE(C == 64 || C == 128 || C == 256, MU_ERR_BAD_SHAPE, "%s: channels must be 64, 128 or 256 (got %d)", fn, C);
+  MU_REQUIRE(dtype == MU_F32 || dtype == MU_BF16, MU_ERR_BAD_DTYPE, "%s: unknown dtype code %d", fn, dtype);
+  return 0;
+}
+static int check_nkp(const char* fn, int N, int NKP) {
+  MU_REQUIRE(NKP % 128 == 0 && NKP >= N, MU_ERR_BAD_SHAPE, "%s: NKP must be a multiple of 128 and >= N (N=%d NKP=%d)",
+             fn, N, NKP);
+  return 0;
+}
+#define MU_PTRS(fn, ...)                                                                        \
+  do {                                                                                          \
+    const void* ptrs_[] = {__VA_ARGS__};                                                        \
+    for (size_t i_ = 0; i_ < sizeof(ptrs_) / sizeof(ptrs_[0]); ++i_) {                          \
+      MU_REQUIRE(ptrs_[i_] != nullptr, MU_ERR_NULL, "%s: null pointer (argument %zu)", fn, i_); \
+      MU_REQUIRE(aligned16(ptrs_[i_]), MU_ERR_MISALIGNED, "%s: pointer %zu not 16-byte aligned", fn, i_); \
+    }                                                                                           \
+  } while (0)
+
+}  // namespace mu
+
+using namespace mu;
+
+extern "C" {
+
+int mu_version(void) { return 100; }  // 0.1.0
+
+const char* mu_last_error(void) { return g_err; }
+
+int mu_device_supported(void) { return device_cc_major() == 10 ? 1 : 0; }
+
+int mu_mask_binarize(const int64_t* bits, int32_t B, int32_t N, uint32_t* keep_bits, int32_t* n_keep,
+                     int32_t* keep_idx, int32_t* keep_rank, mu_stream_t stream) {
+  MU_REQUIRE(B > 0 && N > 0, MU_ERR_BAD_SHAPE, "mu_mask_binarize: B and N must be positive (B=%d N=%d)", B, N);
+  MU_PTRS("mu_mask_binarize", bits, keep_bits, n_keep, keep_idx, keep_rank);
+  return launch_mask_binarize(bits, B, N, keep_bits, n_keep, keep_idx, keep_rank, (cudaStream_t)stream);
+}
+
+int mu_qkv_project(const void* x, const float* w_qkv, const float* b_qkv, const int32_t* keep_rank,
+                   const int32_t* n_keep, void* q, void* kc, void* vc, int32_t B, int32_t C, int32_t N, int32_t NKP,
+                   int32_t dtype, mu_stream_t stream) {
+  int rc;
+  if ((rc = check_common("mu_qkv_project", B, C, N, dtype))) return rc;
+  if ((rc = check_nkp("mu_qkv_project", N, NKP))) return rc;
+  MU_PTRS("mu_qkv_project", x, w_qkv, b_qkv, keep_rank, n_keep, q, kc, vc);
+  return launch_qkv_project(x, w_qkv, b_qkv, keep_rank, n_keep, q, kc, vc, B, C, N, NKP, dtype, (cudaStream_t)stream);
+}
+
+int mu_attn_fwd_cudacore(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse,
+                         int32_t B, int32_t N, int32_t NKP, int32_t C, int32_t dtype, mu_stream_t stream) {
+  int rc;
+  if ((rc = check_common("mu_attn_fwd", B, C, N, dtype))) return rc;
+  if ((rc = check_nkp("mu_attn_fwd", N, NKP))) return rc;
+  MU_PTRS("mu_attn_fwd", q, kc, vc, n_keep, o, lse);
+  return launch_attn_fwd_simt(q, kc, vc, n_keep, o, lse, B, N, NKP, C, dtype, (cudaStream_t)stream);
+}
+
+int mu_attn_fwd(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse, int32_t B,
+                int32_t N, int32_t NKP, int32_t C, int32_t dtype, mu_stream_t stream) {
+  if (dtype != MU_BF16) return mu_attn_fwd_cudacore(q, kc, vc, n_keep, o, lse, B, N, NKP, C, dtype, stream);
+  int rc;
+  if ((rc = check_common("mu_attn_fwd", B, C, N, dtype))) return rc;
+  if ((rc = check_nkp("mu_attn_fwd", N, NKP))) return rc;
+  MU_PTRS("mu_attn_fwd", q, kc, vc, n_keep, o, lse);
+  MU_REQUIRE(device_cc_major() == 10, MU_ERR_ARCH,
+             "mu_attn_fwd: the bf16 path is tcgen05-only and needs an sm_100 device (found cc major %d)",
+             device_cc_major());
+  return launch_attn_fwd_sm100(q, kc, vc, n_keep, o, lse, B, N, NKP, C, (cudaStream_t)stream);
+}
+
+int mu_residual_ln_fwd(const void* o, const void* x, const float* gamma, const float* beta, float eps, void* y,
+                       float* mean, float* rstd, int32_t B, int32_t C, int32_t N, int32_t dtype, mu_stream_t stream) {
+  int rc;
+  if ((rc = check_common("mu_residual_ln_fwd", B, C, N, dtype))) return rc;
+  MU_PTRS("mu_residual_ln_fwd", o, x, gamma, beta, y, mean, rstd);
+  return launch_residual_ln_fwd(o, x, gamma, beta, eps, y, mean, rstd, B, C, N, dtype, (cudaStream_t)stream);
+}
+
+int mu_residual_ln_bwd(const void* dy, const void* o, const void* x, const float* mean, const float* rstd,
+                       const float* gamma, void* dz, float* delta, float* dgamma, float* dbeta, int32_t B, int32_t C,
+                       int32_t N, int32_t dtype, mu_stream_t stream) {
+  int rc;
+  if ((rc = check_common("mu_residual_ln_bwd", B, C, N, dtype))) return rc;
+  MU_PTRS("mu_residual_ln_bwd", dy, o, x, mean, rstd, gamma, dz, delta, dgamma, dbeta);
+  return launch_residual_ln_bwd(dy, o, x, mean, rstd, gamma, dz, delta, dgamma, dbeta, B, C, N, dtype,
+                                (cudaStream_t)stream);
+}
+
+int mu_attn_bwd_cudacore(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
+                         const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int32_t B, int32_t N,
+                         int32_t NKP, int32_t C, int32_t dtype, mu_stream_t stream) {
+  int rc;
+  if ((rc = check_common("mu_attn_bwd", B, C, N, dtype))) return rc;
+  if ((rc = check_nkp("mu_attn_bwd", N, NKP))) return rc;
+  MU_PTRS("mu_attn_bwd", q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc);
+  return launch_attn_bwd_simt(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, B, N, NKP, C, dtype,
+                              (cudaStream_t)stream);
+}
+
+int mu_attn_bwd(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
+                const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int32_t B, int32_t N,
+                int32_t NKP, int32_t C, int32_t dtype, mu_stream_t stream) {
+  if (dtype != MU_BF16)
+    return mu_attn_bwd_cudacore(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, B, N, NKP, C, dtype, stream);
+  int rc;
+  if ((rc = check_common("mu_attn_bwd", B, C, N, dtype))) return rc;
+  if ((rc = check_nkp("mu_attn_bwd", N, NKP))) return rc;
+  MU_PTRS("mu_attn_bwd", q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc);
+  MU_REQUIRE(device_cc_major() == 10, MU_ERR_ARCH,
+             "mu_attn_bwd: the bf16 path is tcgen05-only and needs an sm_100 device (found cc major %d)",
+             device_cc_major());
+  return launch_attn_bwd_sm100(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, B, N, NKP, C, (cudaStream_t)stream);
+}
+
+int mu_qkv_project_bwd(const void* x, const void* dz, const void* dq, const void* dkc, const void* dvc,
+                       const int32_t* keep_rank, const float* w_qkv, void* dx, float* dw_qkv, float* db_qkv,
+                       int32_t B, int32_t C, int32_t N, int32_t NKP, int32_t dtype, mu_stream_t stream) {
+  int rc;
+  if ((rc = check_common("mu_qkv_project_bwd", B, C, N, dtype))) return rc;
+  if ((rc = check_nkp("mu_qkv_project_bwd", N, NKP))) return rc;
+  MU_PTRS("mu_qkv_project_bwd", x, dz, dq, dkc, dvc, keep_rank, w_qkv, dx, dw_qkv, db_qkv);
+  return launch_qkv_project_bwd(x, dz, dq, dkc, dvc, keep_rank, w_qkv, dx, dw_qkv, db_qkv, B, C, N, NKP, dtype,
+                                (cudaStream_t)stream);
+}
+
+}  // extern "C"

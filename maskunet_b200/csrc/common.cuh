@@ -1,0 +1,72 @@
+// Shared host/device helpers for the maskunet_b200 library.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/maskunet_b200.h"
+
+namespace mu {
+
+// thread-local error text behind mu_last_error()
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);  // returns 0 or the positive cudaError_t of the last launch
+
+#define MU_REQUIRE(cond, code, ...)  \
+  do {                               \
+    if (!(cond)) {                   \
+      ::mu::set_error(__VA_ARGS__);  \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---- element load/store with conversion (T = float or __nv_bfloat16) ----
+template <typename T> __device__ __forceinline__ float ld_f(const T* p);
+template <> __device__ __forceinline__ float ld_f<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld_f<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void st_f(T* p, float v);
+template <> __device__ __forceinline__ void st_f<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_f<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- launchers implemented in the .cu files (dtype-dispatched inside) ----
+int launch_mask_binarize(const int64_t* bits, int B, int N, uint32_t* keep_bits, int32_t* n_keep, int32_t* keep_idx,
+                         int32_t* keep_rank, cudaStream_t s);
+int launch_qkv_project(const void* x, const float* w, const float* b, const int32_t* rank, const int32_t* n_keep,
+                       void* q, void* kc, void* vc, int B, int C, int N, int NKP, int dtype, cudaStream_t s);
+int launch_attn_fwd_simt(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse,
+                         int B, int N, int NKP, int C, int dtype, cudaStream_t s);
+int launch_attn_bwd_simt(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
+                         const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int B, int N, int NKP,
+                         int C, int dtype, cudaStream_t s);
+int launch_residual_ln_fwd(const void* o, const void* x, const float* gamma, const float* beta, float eps, void* y,
+                           float* mean, float* rstd, int B, int C, int N, int dtype, cudaStream_t s);
+int launch_residual_ln_bwd(const void* dy, const void* o, const void* x, const float* mean, const float* rstd,
+                           const float* gamma, void* dz, float* delta, float* dgamma, float* dbeta, int B, int C, int N,
+                           int dtype, cudaStream_t s);
+int launch_qkv_project_bwd(const void* x, const void* dz, const void* dq, const void* dkc, const void* dvc,
+                           const int32_t* rank, const float* w, void* dx, float* dw, float* db, int B, int C, int N,
+                           int NKP, int dtype, cudaStream_t s);
+// tcgen05 path (bf16 only)
+int launch_attn_fwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse,
+                          int B, int N, int NKP, int C, cudaStream_t s);
+int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
+                          const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int B, int N, int NKP,
+                          int C, cudaStream_t s);
+
+}  // namespace mu

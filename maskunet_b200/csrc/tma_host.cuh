@@ -1,0 +1,50 @@
+// Host-side TMA descriptor construction without linking libcuda: the driver entry point is fetched
+// through the runtime (cudaGetDriverEntryPoint), so the library loads on machines with no driver and
+// only fails -- loudly -- when a tcgen05 entry point is actually called.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace mu {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+    set_error("cuTensorMapEncodeTiled unavailable (cudaGetDriverEntryPoint: %s)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// bf16 tensor [batch][rows][cols] (cols contiguous); box = [1][box_rows][64 cols], 128-byte swizzle.
+// Out-of-bounds rows are zero-filled on load and dropped on store.
+inline int make_tmap_bf16_3d(CUtensorMap* map, const void* base, int cols, int rows, int batch, int box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return MU_ERR_DRIVER;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)cols * 2 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (cols %d rows %d batch %d box_rows %d)", (int)r, cols, rows,
+              batch, box_rows);
+    return MU_ERR_DRIVER;
+  }
+  return 0;
+}
+
+}  // namespace mu

@@ -1,0 +1,229 @@
+"""Drop-in nn.Modules for the reference's model block.
+
+Same class names, constructor and forward signatures, attribute names and
+state_dict keys as /root/reference/code/ade20k/ade_semantic.py:152-314 (and the
+three-output variant /root/reference/code/cityscapes/city_instance.py:216-276),
+so a script can replace its inline classes with
+
+    from maskunet_b200 import Mask2FormerAttention, ConvBlock, DownSample, UpSample, UNet
+
+and a reference checkpoint loads unchanged.  The Mask Attention Module runs on
+the hand-written sm_100a kernels behind ``maskunet::mask_attention``; it needs
+CUDA tensors and has no CPU path.  Extra switches are keyword-only and default
+to the reference's behaviour.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+class Mask2FormerAttention(nn.Module):
+    """Single-head masked self-attention over H*W tokens + residual + LayerNorm.
+
+    Reference: ade_semantic.py:152-190.  Semantics kept exactly:
+      * tokens are x[b, :, n]; Q/K/V = Linear with bias; scores / sqrt(C)
+      * mask: per sample, per KEY, shared by all queries, drawn once by the same
+        ``torch.randint(0, 2, (B, H, W), device=x.device)`` call and cached in ``self.mask`` as the
+        expanded [B, N, N] 0/-inf view; regenerated only when None or N changes; not in state_dict
+      * output is the [B, N, C] result re-viewed (not permuted back) as [B, C, H, W]
+
+    Keyword-only extras: ``mask_mode='cached'|'resample'`` ('resample' draws a new mask every forward,
+    which is what the reference does under multi-GPU nn.DataParallel);
+    ``compute_dtype`` (None = follow the input: float32 -> fp32 validation kernels, bfloat16 -> tcgen05).
+    """
+
+    def __init__(self, channels: int, size: int, *, mask_mode: str = "cached",
+                 compute_dtype: Optional[torch.dtype] = None):
+        super().__init__()
+        if mask_mode not in ("cached", "resample"):
+            raise ValueError("mask_mode must be 'cached' or 'resample'")
+        self.channels = channels
+        self.size = size
+        self.query = nn.Linear(channels, channels)
+        self.key = nn.Linear(channels, channels)
+        self.value = nn.Linear(channels, channels)
+        self.mask = None
+        self.norm = nn.LayerNorm([channels])
+        self.mask_mode = mask_mode
+        self.compute_dtype = compute_dtype
+        self._compaction = None  # (mask object it was derived from, keep_bits, n_keep, keep_idx, keep_rank)
+
+    # -- mask handling ---------------------------------------------------------------------------
+    def _draw_mask(self, batch: int, height: int, width: int, device) -> None:
+        bits = torch.randint(0, 2, (batch, height, width), device=device)          # :178, same RNG use
+        flat = bits.view(batch, -1)
+        comp = ops.mask_binarize(flat)                                               # :179-180 on device
+        zero = torch.tensor(0.0, device=device)
+        ninf = torch.tensor(-float("inf"), device=device)
+        bias = torch.where(comp[3] >= 0, zero, ninf)                                 # keep_rank >= 0 <=> kept
+        self.mask = bias.unsqueeze(1).expand(-1, height * width, -1)                 # :181, stride (N, 0, 1)
+        self._compaction = (self.mask,) + tuple(comp)
+
+    def _compaction_for(self, mask: torch.Tensor):
+        """keep_bits / n_keep / keep_idx / keep_rank for the current ``self.mask`` (which tests may inject)."""
+        if self._compaction is None or self._compaction[0] is not mask:
+            keep = (mask[:, 0, :] == 0).to(torch.int64).contiguous()
+            self._compaction = (mask,) + tuple(ops.mask_binarize(keep))
+        return self._compaction[1:]
+
+    # -- forward -----------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        batch, channels, height, width = x.size()
+        if channels != self.channels:
+            raise ValueError("Input channel size does not match initialized channel size.")
+        if not x.is_cuda:
+            raise RuntimeError("maskunet_b200.Mask2FormerAttention runs on CUDA (sm_100a) only; "
+                               "there is no CPU fallback")
+        n_tok = height * width
+        if self.mask_mode == "resample" or self.mask is None or self.mask.size(-1) != n_tok:
+            self._draw_mask(batch, height, width, x.device)
+        if self.mask.size(0) != batch:
+            raise RuntimeError(f"The size of tensor a ({batch}) must match the size of tensor b "
+                               f"({self.mask.size(0)}) at non-singleton dimension 0 (cached mask batch)")
+        _, n_keep, _, keep_rank = self._compaction_for(self.mask)
+
+        dtype = self.compute_dtype or x.dtype
+        if dtype not in (torch.float32, torch.bfloat16):
+            dtype = torch.float32
+        tokens = x.contiguous().view(batch, channels, n_tok).to(dtype)
+        w_qkv = torch.cat([self.query.weight, self.key.weight, self.value.weight], dim=0).float()
+        b_qkv = torch.cat([self.query.bias, self.key.bias, self.value.bias], dim=0).float()
+        y = ops.mask_attention(tokens, w_qkv, b_qkv, self.norm.weight.float(), self.norm.bias.float(),
+                               keep_rank, n_keep, self.norm.eps)[0]
+        return y.view(batch, channels, height, width)                               # :190
+
+
+class ConvBlock(nn.Module):
+    """conv3x3 -> BN -> GELU(erf) -> conv3x3 -> BN, optionally gelu(x + block(x)).  ade_semantic.py:192-210."""
+
+    def __init__(self, in_channels, out_channels, mid_channels=None, residual=False):
+        super().__init__()
+        self.residual = residual
+        mid = mid_channels if mid_channels else out_channels
+        layers = [nn.Conv2d(in_channels, mid, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(mid), nn.GELU(),
+                  nn.Conv2d(mid, out_channels, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(out_channels)]
+        self.conv_block = nn.Sequential(*layers)
+
+    def forward(self, x):
+        h = self.conv_block(x)
+        return F.gelu(x + h) if self.residual else h
+
+
+def _dead_embedding(emb_dim, out_channels):
+    # constructed by the reference (ade_semantic.py:222-225, 243-246) but never called; kept so that
+    # parameter init consumes the same RNG stream and state_dict keys match
+    return nn.Sequential(nn.SiLU(), nn.Linear(emb_dim, out_channels))
+
+
+class DownSample(nn.Module):
+    """MaxPool2d(2) -> ConvBlock(res) -> ConvBlock -> BN.  ade_semantic.py:212-229."""
+
+    def __init__(self, in_channels, out_channels, emb_dim=256):
+        super().__init__()
+        self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), ConvBlock(in_channels, in_channels, residual=True),
+                                          ConvBlock(in_channels, out_channels), nn.BatchNorm2d(out_channels))
+        self.emb_layer = _dead_embedding(emb_dim, out_channels)
+
+    def forward(self, x):
+        return self.maxpool_conv(x)
+
+
+class UpSample(nn.Module):
+    """bilinear x2 (align_corners) -> cat([skip, x]) -> ConvBlock(res) -> ConvBlock(mid=in/2) -> BN.
+    ade_semantic.py:231-256."""
+
+    def __init__(self, in_channels, out_channels, emb_dim=256):
+        super().__init__()
+        self.upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+        self.out_channels = out_channels
+        self.conv = nn.Sequential(ConvBlock(in_channels, in_channels, residual=True),
+                                  ConvBlock(in_channels, out_channels, in_channels // 2),
+                                  nn.BatchNorm2d(out_channels))
+        self.emb_layer = _dead_embedding(emb_dim, out_channels)
+
+    def forward(self, x, skip_x):
+        up = self.upsample(x)
+        return self.conv(torch.cat([skip_x, up.to(skip_x.dtype)], dim=1))
+
+
+class UNet(nn.Module):
+    """3-level U-Net with six Mask Attention sites.  ade_semantic.py:258-314.
+
+    ``embed_dim`` selects the Cityscapes-instance variant (city_instance.py:216-276): two extra heads and a
+    (semantic, boundary, embeddings) tuple output.  Keyword-only extras: ``compute_dtype=torch.bfloat16``
+    runs activations in bf16 (fp32 master parameters, fp32 statistics) -- BASELINE.json configs 2-4;
+    ``mask_mode`` is forwarded to the attention modules.
+    """
+
+    def __init__(self, c_in=3, c_out=3, embed_dim: Optional[int] = None, *,
+                 compute_dtype: torch.dtype = torch.float32, mask_mode: str = "cached"):
+        super().__init__()
+        akw = dict(mask_mode=mask_mode)
+        self.initial_conv = ConvBlock(c_in, 64)
+        self.downsample1 = DownSample(64, 128)
+        self.self_attention1 = Mask2FormerAttention(128, 128, **akw)
+        self.downsample2 = DownSample(128, 256)
+        self.self_attention2 = Mask2FormerAttention(256, 256, **akw)
+        self.downsample3 = DownSample(256, 256)
+        self.self_attention3 = Mask2FormerAttention(256, 256, **akw)
+        self.bottom1 = ConvBlock(256, 512)
+        self.bottom2 = ConvBlock(512, 512)
+        self.bottom3 = ConvBlock(512, 256)
+        self.dropout = nn.Dropout(0.3)
+        self.upsample1 = UpSample(512, 128)
+        self.self_attention4 = Mask2FormerAttention(128, 128, **akw)
+        self.upsample2 = UpSample(256, 64)
+        self.self_attention5 = Mask2FormerAttention(64, 64, **akw)
+        self.upsample3 = UpSample(128, 64)
+        self.self_attention6 = Mask2FormerAttention(64, 64, **akw)
+        self.norm = nn.LayerNorm([64, 128, 128])
+        self.final_layer = nn.Sequential(nn.Conv2d(64, c_out, kernel_size=1), nn.BatchNorm2d(c_out), nn.ReLU())
+        self.instance_variant = embed_dim is not None
+        if self.instance_variant:  # construction order as city_instance.py:242-252
+            self.boundary_head = nn.Sequential(nn.Conv2d(c_out, 32, kernel_size=3, padding=1), nn.BatchNorm2d(32),
+                                               nn.ReLU(), nn.Conv2d(32, 1, kernel_size=1))
+            self.embedding_head = nn.Sequential(nn.Conv2d(64, embed_dim, kernel_size=1),
+                                                nn.BatchNorm2d(embed_dim), nn.ReLU())
+        self.compute_dtype = compute_dtype
+
+    def attention_sites(self):
+        return [getattr(self, f"self_attention{i}") for i in range(1, 7)]
+
+    def _trunk(self, x):
+        x1 = self.initial_conv(x)
+        x2 = self.self_attention1(self.downsample1(x1))
+        x3 = self.self_attention2(self.downsample2(x2))
+        x4 = self.self_attention3(self.downsample3(x3))
+        x4 = self.bottom3(self.bottom2(self.bottom1(x4)))
+        h = self.self_attention4(self.dropout(self.upsample1(x4, x3)))
+        h = self.self_attention5(self.dropout(self.upsample2(h, x2)))
+        h = self.self_attention6(self.upsample3(h, x1))
+        return self.norm(h)
+
+    def _heads(self, h):
+        if not self.instance_variant:
+            return self.final_layer(h)
+        embeddings = self.embedding_head(h)          # city_instance.py:273-276 order
+        semantic = self.final_layer(h)
+        boundary = self.boundary_head(semantic)
+        return semantic, boundary, embeddings
+
+    def forward(self, x):
+        if self.compute_dtype == torch.bfloat16:
+            with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+                return self._heads(self._trunk(x.to(torch.bfloat16)))
+        return self._heads(self._trunk(x))
+
+
+class InstanceUNet(UNet):
+    """The Cityscapes-instance model (city_instance.py:216-276): ``UNet(c_in, c_out, embed_dim=16)`` with
+    boundary and embedding heads and a 3-tuple output.  Import as ``InstanceUNet as UNet`` in that script."""
+
+    def __init__(self, c_in=3, c_out=3, embed_dim=16, **kw):
+        super().__init__(c_in, c_out, embed_dim, **kw)

@@ -1,0 +1,271 @@
+"""torch.library operators (namespace ``maskunet::``) over the C ABI.
+
+Each op allocates its outputs with the PyTorch caching allocator, passes raw
+device pointers and the current CUDA stream to libmaskunet_b200.so and converts
+a non-zero status into RuntimeError(mu_last_error()).  CUDA tensors only.
+
+Layouts (B batch, C channels, N = H*W tokens, NKP = roundup(N, 128)):
+  x   [B, C, N]   NCHW activations flattened (token-contiguous)
+  q, o, y, dz     [B, N, C]
+  kc, vc          [B, NKP, C]  K / V rows of the kept keys only
+  w_qkv [3C, C], b_qkv [3C]    cat(query, key, value) parameters, fp32
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import MU_BF16, MU_F32, check
+
+_L = _lib.load()
+
+
+def _p(t: Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t: Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _code(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return MU_F32
+    if t.dtype == torch.bfloat16:
+        return MU_BF16
+    raise TypeError(f"maskunet ops take float32 or bfloat16 activations, got {t.dtype}")
+
+
+def _cuda(*ts: Tensor) -> None:
+    for t in ts:
+        if not t.is_cuda:
+            raise RuntimeError("maskunet ops run on CUDA tensors only (there is no CPU fallback)")
+        if not t.is_contiguous():
+            raise RuntimeError("maskunet ops need contiguous tensors")
+
+
+def nkp_of(n: int) -> int:
+    return (n + 127) // 128 * 128
+
+
+# ------------------------------------------------------------------ K2
+@torch.library.custom_op("maskunet::mask_binarize", mutates_args=(), device_types="cuda")
+def mask_binarize(bits: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """bits int64 [B, N] -> keep_bits int32 [B, ceil(N/32)], n_keep int32 [B], keep_idx, keep_rank int32 [B, N]."""
+    _cuda(bits)
+    assert bits.dtype == torch.int64 and bits.dim() == 2
+    B, N = bits.shape
+    dev = bits.device
+    keep_bits = torch.empty((B, (N + 31) // 32), dtype=torch.int32, device=dev)
+    n_keep = torch.empty((B,), dtype=torch.int32, device=dev)
+    keep_idx = torch.empty((B, N), dtype=torch.int32, device=dev)
+    keep_rank = torch.empty((B, N), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_L.mu_mask_binarize(_p(bits), B, N, _p(keep_bits), _p(n_keep), _p(keep_idx), _p(keep_rank),
+                                  _stream(bits)), "mu_mask_binarize")
+    return keep_bits, n_keep, keep_idx, keep_rank
+
+
+@mask_binarize.register_fake
+def _(bits):
+    B, N = bits.shape
+    i32 = dict(dtype=torch.int32, device=bits.device)
+    return (torch.empty((B, (N + 31) // 32), **i32), torch.empty((B,), **i32),
+            torch.empty((B, N), **i32), torch.empty((B, N), **i32))
+
+
+# ------------------------------------------------------------------ kernel-level ops
+@torch.library.custom_op("maskunet::qkv_project", mutates_args=(), device_types="cuda")
+def qkv_project(x: Tensor, w_qkv: Tensor, b_qkv: Tensor, keep_rank: Tensor, n_keep: Tensor
+                ) -> Tuple[Tensor, Tensor, Tensor]:
+    _cuda(x, w_qkv, b_qkv, keep_rank, n_keep)
+    B, C, N = x.shape
+    NKP = nkp_of(N)
+    q = torch.empty((B, N, C), dtype=x.dtype, device=x.device)
+    kc = torch.empty((B, NKP, C), dtype=x.dtype, device=x.device)
+    vc = torch.empty((B, NKP, C), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_L.mu_qkv_project(_p(x), _p(w_qkv), _p(b_qkv), _p(keep_rank), _p(n_keep), _p(q), _p(kc), _p(vc),
+                                B, C, N, NKP, _code(x), _stream(x)), "mu_qkv_project")
+    return q, kc, vc
+
+
+@qkv_project.register_fake
+def _(x, w_qkv, b_qkv, keep_rank, n_keep):
+    B, C, N = x.shape
+    return x.new_empty((B, N, C)), x.new_empty((B, nkp_of(N), C)), x.new_empty((B, nkp_of(N), C))
+
+
+def _attn_fwd_impl(fn, name, q, kc, vc, n_keep):
+    _cuda(q, kc, vc, n_keep)
+    B, N, C = q.shape
+    NKP = kc.shape[1]
+    o = torch.empty_like(q)
+    lse = torch.empty((B, N), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        check(fn(_p(q), _p(kc), _p(vc), _p(n_keep), _p(o), _p(lse), B, N, NKP, C, _code(q), _stream(q)), name)
+    return o, lse
+
+
+@torch.library.custom_op("maskunet::attn_fwd", mutates_args=(), device_types="cuda")
+def attn_fwd(q: Tensor, kc: Tensor, vc: Tensor, n_keep: Tensor) -> Tuple[Tensor, Tensor]:
+    """O = softmax(Q Kc^T / sqrt(C)) Vc over kept keys; bf16 -> tcgen05 kernel, fp32 -> CUDA cores."""
+    return _attn_fwd_impl(_L.mu_attn_fwd, "mu_attn_fwd", q, kc, vc, n_keep)
+
+
+@attn_fwd.register_fake
+def _(q, kc, vc, n_keep):
+    return torch.empty_like(q), q.new_empty(q.shape[:2], dtype=torch.float32)
+
+
+def attn_fwd_cudacore(q, kc, vc, n_keep):
+    """Diagnostic: the CUDA-core kernel for either dtype (cross-check of the tcgen05 kernel)."""
+    return _attn_fwd_impl(_L.mu_attn_fwd_cudacore, "mu_attn_fwd_cudacore", q, kc, vc, n_keep)
+
+
+def _attn_bwd_impl(fn, name, q, kc, vc, n_keep, d_o, lse, delta):
+    _cuda(q, kc, vc, n_keep, d_o, lse, delta)
+    B, N, C = q.shape
+    NKP = kc.shape[1]
+    dq = torch.empty_like(q)
+    dkc = torch.zeros_like(kc)
+    dvc = torch.zeros_like(vc)
+    with torch.cuda.device(q.device):
+        check(fn(_p(q), _p(kc), _p(vc), _p(n_keep), _p(d_o), _p(lse), _p(delta), _p(dq), _p(dkc), _p(dvc),
+                 B, N, NKP, C, _code(q), _stream(q)), name)
+    return dq, dkc, dvc
+
+
+@torch.library.custom_op("maskunet::attn_bwd", mutates_args=(), device_types="cuda")
+def attn_bwd(q: Tensor, kc: Tensor, vc: Tensor, n_keep: Tensor, d_o: Tensor, lse: Tensor, delta: Tensor
+             ) -> Tuple[Tensor, Tensor, Tensor]:
+    return _attn_bwd_impl(_L.mu_attn_bwd, "mu_attn_bwd", q, kc, vc, n_keep, d_o, lse, delta)
+
+
+@attn_bwd.register_fake
+def _(q, kc, vc, n_keep, d_o, lse, delta):
+    return torch.empty_like(q), torch.empty_like(kc), torch.empty_like(vc)
+
+
+def attn_bwd_cudacore(q, kc, vc, n_keep, d_o, lse, delta):
+    return _attn_bwd_impl(_L.mu_attn_bwd_cudacore, "mu_attn_bwd_cudacore", q, kc, vc, n_keep, d_o, lse, delta)
+
+
+@torch.library.custom_op("maskunet::residual_ln_fwd", mutates_args=(), device_types="cuda")
+def residual_ln_fwd(o: Tensor, x: Tensor, gamma: Tensor, beta: Tensor, eps: float) -> Tuple[Tensor, Tensor, Tensor]:
+    _cuda(o, x, gamma, beta)
+    B, N, C = o.shape
+    y = torch.empty_like(o)
+    mean = torch.empty((B, N), dtype=torch.float32, device=o.device)
+    rstd = torch.empty((B, N), dtype=torch.float32, device=o.device)
+    with torch.cuda.device(o.device):
+        check(_L.mu_residual_ln_fwd(_p(o), _p(x), _p(gamma), _p(beta), eps, _p(y), _p(mean), _p(rstd),
+                                    B, C, N, _code(o), _stream(o)), "mu_residual_ln_fwd")
+    return y, mean, rstd
+
+
+@residual_ln_fwd.register_fake
+def _(o, x, gamma, beta, eps):
+    s = o.new_empty(o.shape[:2], dtype=torch.float32)
+    return torch.empty_like(o), s, torch.empty_like(s)
+
+
+@torch.library.custom_op("maskunet::residual_ln_bwd", mutates_args=(), device_types="cuda")
+def residual_ln_bwd(dy: Tensor, o: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor
+                    ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    _cuda(dy, o, x, mean, rstd, gamma)
+    B, N, C = o.shape
+    dz = torch.empty_like(o)
+    delta = torch.empty((B, N), dtype=torch.float32, device=o.device)
+    dgamma = torch.zeros((C,), dtype=torch.float32, device=o.device)
+    dbeta = torch.zeros((C,), dtype=torch.float32, device=o.device)
+    with torch.cuda.device(o.device):
+        check(_L.mu_residual_ln_bwd(_p(dy), _p(o), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dz), _p(delta),
+                                    _p(dgamma), _p(dbeta), B, C, N, _code(o), _stream(o)), "mu_residual_ln_bwd")
+    return dz, delta, dgamma, dbeta
+
+
+@residual_ln_bwd.register_fake
+def _(dy, o, x, mean, rstd, gamma):
+    C = o.shape[-1]
+    return (torch.empty_like(o), o.new_empty(o.shape[:2], dtype=torch.float32),
+            o.new_empty((C,), dtype=torch.float32), o.new_empty((C,), dtype=torch.float32))
+
+
+@torch.library.custom_op("maskunet::qkv_project_bwd", mutates_args=(), device_types="cuda")
+def qkv_project_bwd(x: Tensor, dz: Tensor, dq: Tensor, dkc: Tensor, dvc: Tensor, keep_rank: Tensor, w_qkv: Tensor
+                    ) -> Tuple[Tensor, Tensor, Tensor]:
+    _cuda(x, dz, dq, dkc, dvc, keep_rank, w_qkv)
+    B, C, N = x.shape
+    NKP = dkc.shape[1]
+    dx = torch.empty_like(x)
+    dw = torch.zeros((3 * C, C), dtype=torch.float32, device=x.device)
+    db = torch.zeros((3 * C,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_L.mu_qkv_project_bwd(_p(x), _p(dz), _p(dq), _p(dkc), _p(dvc), _p(keep_rank), _p(w_qkv), _p(dx),
+                                    _p(dw), _p(db), B, C, N, NKP, _code(x), _stream(x)), "mu_qkv_project_bwd")
+    return dx, dw, db
+
+
+@qkv_project_bwd.register_fake
+def _(x, dz, dq, dkc, dvc, keep_rank, w_qkv):
+    C = x.shape[1]
+    return torch.empty_like(x), x.new_empty((3 * C, C), dtype=torch.float32), x.new_empty((3 * C,), dtype=torch.float32)
+
+
+# ------------------------------------------------------------------ the module-level op (A3-A9 of SURVEY.md 8(a))
+@torch.library.custom_op("maskunet::mask_attention", mutates_args=(), device_types="cuda")
+def mask_attention(x: Tensor, w_qkv: Tensor, b_qkv: Tensor, gamma: Tensor, beta: Tensor, keep_rank: Tensor,
+                   n_keep: Tensor, eps: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """y [B, N, C] = LN_C(softmax(QK^T/sqrt(C) + mask) V + x^T); also returns what backward needs."""
+    q, kc, vc = qkv_project(x, w_qkv, b_qkv, keep_rank, n_keep)
+    o, lse = attn_fwd(q, kc, vc, n_keep)
+    y, mean, rstd = residual_ln_fwd(o, x, gamma, beta, eps)
+    return y, q, kc, vc, o, lse, mean, rstd
+
+
+@mask_attention.register_fake
+def _(x, w_qkv, b_qkv, gamma, beta, keep_rank, n_keep, eps):
+    B, C, N = x.shape
+    f32 = dict(dtype=torch.float32)
+    return (x.new_empty((B, N, C)), x.new_empty((B, N, C)), x.new_empty((B, nkp_of(N), C)),
+            x.new_empty((B, nkp_of(N), C)), x.new_empty((B, N, C)), x.new_empty((B, N), **f32),
+            x.new_empty((B, N), **f32), x.new_empty((B, N), **f32))
+
+
+@torch.library.custom_op("maskunet::mask_attention_bwd", mutates_args=(), device_types="cuda")
+def mask_attention_bwd(dy: Tensor, x: Tensor, w_qkv: Tensor, gamma: Tensor, keep_rank: Tensor, n_keep: Tensor,
+                       q: Tensor, kc: Tensor, vc: Tensor, o: Tensor, lse: Tensor, mean: Tensor, rstd: Tensor
+                       ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    dz, delta, dgamma, dbeta = residual_ln_bwd(dy, o, x, mean, rstd, gamma)
+    dq, dkc, dvc = attn_bwd(q, kc, vc, n_keep, dz, lse, delta)
+    dx, dw, db = qkv_project_bwd(x, dz, dq, dkc, dvc, keep_rank, w_qkv)
+    return dx, dw, db, dgamma, dbeta
+
+
+@mask_attention_bwd.register_fake
+def _(dy, x, w_qkv, gamma, keep_rank, n_keep, q, kc, vc, o, lse, mean, rstd):
+    C = x.shape[1]
+    f32 = dict(dtype=torch.float32)
+    return (torch.empty_like(x), x.new_empty((3 * C, C), **f32), x.new_empty((3 * C,), **f32),
+            x.new_empty((C,), **f32), x.new_empty((C,), **f32))
+
+
+def _ma_setup(ctx, inputs, output):
+    x, w_qkv, b_qkv, gamma, beta, keep_rank, n_keep, eps = inputs
+    y, q, kc, vc, o, lse, mean, rstd = output
+    ctx.save_for_backward(x, w_qkv, gamma, keep_rank, n_keep, q, kc, vc, o, lse, mean, rstd)
+
+
+def _ma_backward(ctx, dy, *unused):
+    x, w_qkv, gamma, keep_rank, n_keep, q, kc, vc, o, lse, mean, rstd = ctx.saved_tensors
+    dx, dw, db, dgamma, dbeta = mask_attention_bwd(dy.contiguous(), x, w_qkv, gamma, keep_rank, n_keep,
+                                                   q, kc, vc, o, lse, mean, rstd)
+    return dx, dw, db, dgamma, dbeta, None, None, None
+
+
+mask_attention.register_autograd(_ma_backward, setup_context=_ma_setup)

@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory FROM THE REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It AST-loads the reference's classes (oracle/ref_loader.py), runs them on
+seeded inputs and stores inputs + outputs.  The reference tree does not travel
+to the GPU box, these files do.  Seeds and recipes follow SURVEY.md 8(c).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle.ref_loader import load_reference_classes  # noqa: E402
+from oracle import unet_oracle as uo  # noqa: E402
+
+ATTN_CASES = [  # name, B, C, H, W
+    ("attn_b2_c64_8x8", 2, 64, 8, 8),
+    ("attn_b2_c128_16x16", 2, 128, 16, 16),
+    ("attn_b1_c256_16x16", 1, 256, 16, 16),
+    ("attn_b3_c64_16x8", 3, 64, 16, 8),       # ragged: H != W, N = 128 = exactly one tile
+    ("attn_b2_c64_20x20", 2, 64, 20, 20),     # N = 400: not a multiple of the 128-row tile
+]
+
+
+def np32(t):
+    return t.detach().cpu().numpy().astype(np.float32)
+
+
+def make_attention(ref):
+    for name, B, C, H, W in ATTN_CASES:
+        torch.manual_seed(1234)
+        m = ref.Mask2FormerAttention(C, C)
+        x = torch.randn(B, C, H, W, requires_grad=True)
+        y = m(x)                                   # draws the mask (ade_semantic.py:178)
+        keep = (m.mask[:, 0, :] == 0)
+        # KAT scalars as recorded in SURVEY.md 8(c): loss = y.square().sum()
+        (gx_sq,) = torch.autograd.grad(y.square().sum(), x, retain_graph=True)
+        m.zero_grad()
+        y.square().sum().backward(retain_graph=True)
+        dwq_sq = m.query.weight.grad.abs().sum().item()
+        m.zero_grad()
+        x.grad = None
+        # well-conditioned gradient check: loss = <y, dy> with a fixed random dy
+        gen = torch.Generator().manual_seed(4321)
+        dy = torch.randn(y.shape, generator=gen)
+        (y * dy).sum().backward()
+        out = dict(x=np32(x), y=np32(y), dy=np32(dy), dx=np32(x.grad),
+                   keep=keep.numpy().astype(np.uint8),
+                   kat=np.array([y.abs().sum().item(), gx_sq.abs().sum().item(), dwq_sq], dtype=np.float64))
+        for k, p in m.named_parameters():
+            out[f"param.{k}"] = np32(p)
+            out[f"grad.{k}"] = np32(p.grad)
+        np.savez(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "keep", keep.sum(1).tolist(), "y.abs.sum", out["kat"][0])
+
+
+def param_digest(sd):
+    return {k: float(v.double().abs().sum()) for k, v in sd.items() if v.dtype.is_floating_point}
+
+
+def make_unet(script, variant, c_out, fname, batch=2):
+    ref = load_reference_classes(script)
+    torch.manual_seed(1234)
+    model = ref.UNet(3, c_out)
+    digest = param_digest(model.state_dict())
+    model.eval()
+    x = torch.rand(batch, 3, 128, 128)
+    with torch.no_grad():
+        outs = model(x)
+    outs = outs if isinstance(outs, tuple) else (outs,)
+    keeps = {n: (getattr(model, n).mask[:, 0, :] == 0) for n, _, _ in uo.ATTN_SITES}
+    gen = torch.Generator().manual_seed(99)
+    store = {"x_seed_note": np.array([1234], dtype=np.int64)}
+    for i, o in enumerate(outs):
+        flat = o.reshape(-1)
+        idx = torch.randint(0, flat.numel(), (8192,), generator=gen)
+        store[f"out{i}.shape"] = np.array(o.shape, dtype=np.int64)
+        store[f"out{i}.sample_idx"] = idx.numpy()
+        store[f"out{i}.sample"] = np32(flat[idx])
+        store[f"out{i}.stats"] = np.array([o.double().sum().item(), o.abs().max().item(),
+                                          (o == 0).double().mean().item()], dtype=np.float64)
+    store["argmax"] = outs[0].argmax(dim=1).numpy().astype(np.uint8)
+    top2 = outs[0].topk(2, dim=1).values
+    store["argmax_margin"] = np32(top2[:, 0] - top2[:, 1]).astype(np.float16)
+    for n, k in keeps.items():
+        store[f"keep.{n}"] = np.packbits(k.numpy().astype(np.uint8), axis=1)
+
+    # one train-mode step with dropout disabled: loss + per-parameter grad norms
+    model.train()
+    model.dropout.p = 0.0
+    labels = torch.randint(0, c_out, (batch, 128, 128), generator=torch.Generator().manual_seed(1))
+    outs_t = model(x)
+    sem = outs_t[0] if isinstance(outs_t, tuple) else outs_t
+    loss = torch.nn.functional.cross_entropy(sem, labels)
+    loss.backward()
+    names, norms = [], []
+    for k, p in model.named_parameters():
+        names.append(k)
+        norms.append(float(p.grad.double().norm()) if p.grad is not None else -1.0)
+    store["train.loss"] = np.array([loss.item()], dtype=np.float64)
+    store["train.grad_norms"] = np.array(norms, dtype=np.float64)
+    store["train.logits_stats"] = np.array([sem.double().sum().item(), sem.abs().max().item()], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, fname + ".npz"), **store)
+    with open(os.path.join(HERE, fname + ".json"), "w") as fh:
+        json.dump({"script": script, "variant": variant, "c_out": c_out, "seed": 1234, "batch": batch,
+                   "torch": torch.__version__, "param_digest": digest, "grad_names": names}, fh, indent=0)
+    print(fname, "out0 stats", store["out0.stats"], "loss", loss.item())
+
+
+def main():
+    ref = load_reference_classes("ade_semantic")
+    make_attention(ref)
+    make_unet("ade_semantic", "semantic", 150, "unet_semantic")
+    make_unet("city_instance", "instance", 19, "unet_instance")
+
+
+if __name__ == "__main__":
+    main()

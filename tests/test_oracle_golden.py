@@ -1,0 +1,92 @@
+"""CPU: the oracle restatement against golden vectors produced by the reference's own classes."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ATTN_CASES, GOLDEN, load_attn_golden, rel_err
+from oracle import mask_attention_oracle as mao
+from oracle import unet_oracle as uo
+
+
+@pytest.mark.parametrize("name", ATTN_CASES)
+def test_attention_forward_backward_matches_reference_golden(name):
+    g = load_attn_golden(name)
+    x = g["x"]
+    B, C, H, W = x.shape
+    out = mao.attention_forward(x, g["params"], g["keep"])
+    y = mao.module_output(out["y"], C, H, W)
+    assert rel_err(y, g["y"]) < 2e-6
+    grads = mao.attention_backward(out, g["dy"].view(B, H * W, C))
+    assert rel_err(grads["x"].view_as(x), g["dx"]) < 5e-6
+    scale = max(float(v.abs().max()) for v in g["grads"].values())
+    for k, ref in g["grads"].items():
+        if k == "key.bias":  # analytically zero (softmax is shift invariant): absolute check
+            assert float((grads[k] - ref).abs().max()) < 1e-5 * scale
+        else:
+            assert rel_err(grads[k], ref) < 5e-6, k
+
+
+def test_kat_scalars_from_survey():
+    # B2 C64 8x8 -> keep [25, 30], y.abs().sum() = 6566.9102
+    g = load_attn_golden("attn_b2_c64_8x8")
+    assert g["keep"].sum(1).tolist() == [25, 30]
+    assert abs(float(g["kat"][0]) - 6566.9102) < 1e-2
+    g = load_attn_golden("attn_b1_c256_16x16")
+    assert g["keep"].sum(1).tolist() == [123]
+    assert abs(float(g["kat"][0]) - 52385.5781) < 1e-1
+
+
+def test_binarize_is_bits_gt_half():
+    bits = torch.tensor([[0, 1, 1, 0, 2, -1]])
+    keep = mao.binarize_mask(bits)
+    assert keep.tolist() == [[False, True, True, False, True, False]]
+    bias = mao.additive_bias(keep)
+    assert bias[0, 0] == float("-inf") and bias[0, 1] == 0
+    m = mao.expand_bias(bias, 6)
+    assert m.shape == (1, 6, 6) and m.stride() == (6, 0, 1)
+
+
+def test_mask_draw_consumes_rng_like_reference():
+    torch.manual_seed(7)
+    a = mao.draw_mask_bits(2, 4, 4)
+    torch.manual_seed(7)
+    b = torch.randint(0, 2, (2, 4, 4))
+    assert torch.equal(a, b)
+
+
+def _unet_golden(fname):
+    with open(os.path.join(GOLDEN, fname + ".json")) as fh:
+        meta = json.load(fh)
+    z = np.load(os.path.join(GOLDEN, fname + ".npz"))
+    return meta, z
+
+
+@pytest.mark.parametrize("fname,variant", [("unet_semantic", "semantic"), ("unet_instance", "instance")])
+def test_unet_oracle_matches_reference_golden(fname, variant):
+    meta, z = _unet_golden(fname)
+    torch.manual_seed(meta["seed"])
+    sd = uo.init_state(3, meta["c_out"], variant)
+    digest = {k: float(v.double().abs().sum()) for k, v in sd.items() if v.dtype.is_floating_point}
+    if any(abs(digest[k] - v) > 1e-6 * max(1.0, abs(v)) for k, v in meta["param_digest"].items()):
+        pytest.skip("torch RNG stream differs from the one that generated the golden (other torch build)")
+    x = torch.rand(meta["batch"], 3, 128, 128)
+    keeps = {}
+    for n, _, side in uo.ATTN_SITES:
+        packed = torch.from_numpy(z[f"keep.{n}"])
+        keeps[n] = torch.from_numpy(np.unpackbits(packed.numpy(), axis=1)[:, : side * side]).bool()
+    with torch.no_grad():
+        outs = uo.unet_forward(sd, x, keeps, variant=variant)
+    outs = outs if isinstance(outs, tuple) else (outs,)
+    for i, o in enumerate(outs):
+        idx = torch.from_numpy(z[f"out{i}.sample_idx"])
+        ref = torch.from_numpy(z[f"out{i}.sample"])
+        got = o.reshape(-1)[idx]
+        assert float((got - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max())), i
+    am = outs[0].argmax(1).numpy().astype(np.uint8)
+    margin = z["argmax_margin"].astype(np.float32)
+    safe = margin > 1e-3
+    assert (am[safe] == z["argmax"][safe]).all()
+    assert (am == z["argmax"]).mean() > 0.999

@@ -1,0 +1,63 @@
+"""CPU, build container only: the oracle against the reference's classes loaded live from /root/reference."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import mask_attention_oracle as mao
+from oracle import unet_oracle as uo
+from oracle.ref_loader import load_reference_classes, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 8, 8), (1, 128, 12, 20), (2, 256, 8, 8)])
+def test_attention_module_live(B, C, H, W):
+    ref = load_reference_classes("ade_semantic")
+    torch.manual_seed(5)
+    m = ref.Mask2FormerAttention(C, C)
+    x = torch.randn(B, C, H, W, requires_grad=True)
+    torch.manual_seed(11)
+    y = m(x)
+    torch.manual_seed(11)
+    keep = mao.binarize_mask(mao.draw_mask_bits(B, H, W))          # same RNG stream -> identical bits
+    assert torch.equal(keep, mao.keep_from_module_mask(m.mask))
+    dy = torch.randn_like(y)
+    (y * dy).sum().backward()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    out = mao.attention_forward(x.detach(), sd, keep)
+    assert rel_err(mao.module_output(out["y"], C, H, W), y) < 2e-6
+    g = mao.attention_backward(out, dy.view(B, H * W, C))
+    assert rel_err(g["x"].view_as(x), x.grad) < 5e-6
+    for k, p in m.named_parameters():
+        if k != "key.bias":
+            assert rel_err(g[k], p.grad) < 5e-6, k
+
+
+def test_mask_cache_semantics_of_reference():
+    """Appendix A.3: cached after first forward, no RNG afterwards, different batch later errors."""
+    ref = load_reference_classes("ade_semantic")
+    m = ref.Mask2FormerAttention(64, 64)
+    m(torch.randn(2, 64, 4, 4))
+    first = m.mask
+    state = torch.get_rng_state()
+    x2 = torch.randn(2, 64, 4, 4)
+    after_input = torch.get_rng_state()
+    m(x2)
+    assert m.mask is first                                   # cached, not redrawn
+    assert torch.equal(torch.get_rng_state(), after_input)   # second forward consumes no RNG
+    assert not torch.equal(state, after_input)
+    with pytest.raises(RuntimeError):
+        m(torch.randn(3, 64, 4, 4))
+
+
+@pytest.mark.parametrize("script,variant,c_out", [("ade_semantic", "semantic", 150), ("coco_panoptic", "semantic", 133),
+                                                  ("city_instance", "instance", 19)])
+def test_unet_init_and_keys_identical(script, variant, c_out):
+    ref = load_reference_classes(script)
+    torch.manual_seed(3)
+    model = ref.UNet(3, c_out)
+    torch.manual_seed(3)
+    sd = uo.init_state(3, c_out, variant)
+    rsd = model.state_dict()
+    assert list(rsd.keys()) == list(sd.keys())
+    assert all(torch.equal(rsd[k], sd[k]) for k in sd)
