@@ -1,0 +1,200 @@
+"""GPU parity tests of the Mask Attention hot path, through the C ABI (torch.library ops -> ctypes -> .so).
+
+Tolerances are the ones BASELINE.json's north_star states: fp32 rel-err <= 1e-4, bf16 <= 2e-2 on outputs
+and gradients (norm-wise relative error), binary masks bit-exact.
+"""
+import pytest
+import torch
+
+from conftest import ATTN_CASES, load_attn_golden, rel_err
+from oracle import mask_attention_oracle as mao
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _module_from_golden(g, dtype):
+    from maskunet_b200 import Mask2FormerAttention
+    B, C, H, W = g["x"].shape
+    m = Mask2FormerAttention(C, C).to(_dev())
+    m.load_state_dict(g["params"])
+    bias = mao.additive_bias(g["keep"]).to(_dev())
+    m.mask = mao.expand_bias(bias, H * W)          # inject the reference's mask, as tests may
+    return m
+
+
+# ------------------------------------------------------------------ K2
+@pytest.mark.parametrize("B,N", [(3, 400), (2, 16384), (5, 37), (1, 1), (4, 1024), (2, 4099)])
+def test_mask_binarize_bit_exact(B, N):
+    from maskunet_b200 import ops
+    gen = torch.Generator().manual_seed(B * 100003 + N)
+    bits = torch.randint(0, 2, (B, N), generator=gen)
+    keep = mao.binarize_mask(bits)                                  # oracle
+    keep_bits, n_keep, keep_idx, keep_rank = [t.cpu() for t in ops.mask_binarize(bits.to(_dev()))]
+    assert n_keep.tolist() == keep.sum(1).tolist()
+    assert torch.equal(keep_rank >= 0, keep)
+    for b in range(B):
+        idx = keep[b].nonzero().flatten().to(torch.int32)
+        assert torch.equal(keep_idx[b, : len(idx)], idx)
+        assert (keep_idx[b, len(idx):] == -1).all()
+        assert torch.equal(keep_rank[b][keep[b]], torch.arange(len(idx), dtype=torch.int32))
+        words = keep_bits[b].to(torch.int64) & 0xFFFFFFFF
+        unpacked = ((words.unsqueeze(1) >> torch.arange(32)) & 1).flatten()[:N].bool()
+        assert torch.equal(unpacked, keep[b])
+
+
+def test_mask_binarize_edge_all_and_none():
+    from maskunet_b200 import ops
+    for val in (0, 1):
+        bits = torch.full((2, 300), val, dtype=torch.int64, device=_dev())
+        _, n_keep, _, keep_rank = ops.mask_binarize(bits)
+        assert n_keep.tolist() == [300 * val] * 2
+        assert bool((keep_rank >= 0).all()) == bool(val)
+
+
+def test_module_mask_bits_match_oracle_same_rng_stream():
+    from maskunet_b200 import Mask2FormerAttention
+    m = Mask2FormerAttention(64, 64).to(_dev())
+    x = torch.randn(3, 64, 12, 12, device=_dev())
+    torch.manual_seed(2024)
+    m(x)
+    torch.manual_seed(2024)
+    keep = mao.binarize_mask(mao.draw_mask_bits(3, 12, 12, device=_dev()))   # the reference's call, same device
+    assert m.mask.shape == (3, 144, 144) and m.mask.stride() == (144, 0, 1)
+    assert torch.equal(m.mask[:, 0, :] == 0, keep)
+    assert torch.equal(m.mask[:, 5, :], mao.additive_bias(keep))
+    # cached: second forward keeps the object and consumes no RNG
+    first, state = m.mask, torch.cuda.get_rng_state()
+    m(x)
+    assert m.mask is first and torch.equal(torch.cuda.get_rng_state(), state)
+    with pytest.raises(RuntimeError):
+        m(torch.randn(2, 64, 12, 12, device=_dev()))
+
+
+# ------------------------------------------------------------------ kernel level
+@pytest.mark.parametrize("name", ATTN_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["float32", "bfloat16"])
+def test_kernels_stagewise_vs_oracle(name, dtype):
+    from maskunet_b200 import ops
+    g = load_attn_golden(name)
+    x = g["x"]
+    B, C, H, W = x.shape
+    N = H * W
+    tol = TOL[dtype]
+    ref = mao.attention_forward(x, g["params"], g["keep"])
+    dev = _dev()
+    _, n_keep, keep_idx, keep_rank = ops.mask_binarize(g["keep"].to(torch.int64).to(dev))
+    w = torch.cat([g["params"][f"{k}.weight"] for k in ("query", "key", "value")]).to(dev)
+    bqkv = torch.cat([g["params"][f"{k}.bias"] for k in ("query", "key", "value")]).to(dev)
+    xt = x.view(B, C, N).to(dev, dtype)
+    q, kc, vc = ops.qkv_project(xt, w, bqkv, keep_rank, n_keep)
+    assert rel_err(q, ref["q"]) < tol
+    for b in range(B):
+        nk = int(n_keep[b])
+        idx = keep_idx[b, :nk].long().cpu()
+        assert rel_err(kc[b, :nk], ref["k"][b, idx]) < tol
+        assert rel_err(vc[b, :nk], ref["v"][b, idx]) < tol
+        pad_end = min(kc.shape[1], (nk + 127) // 128 * 128)
+        assert (kc[b, nk:pad_end] == 0).all() and (vc[b, nk:pad_end] == 0).all()
+    o, lse = ops.attn_fwd(q, kc, vc, n_keep)
+    assert rel_err(o, ref["o"]) < tol
+    assert rel_err(lse, ref["lse"]) < tol
+    gamma, beta = g["params"]["norm.weight"].to(dev), g["params"]["norm.bias"].to(dev)
+    y, mean, rstd = ops.residual_ln_fwd(o, xt, gamma, beta, 1e-5)
+    assert rel_err(y, ref["y"]) < tol
+    assert rel_err(rstd, ref["rstd"].squeeze(-1)) < tol
+
+
+@pytest.mark.parametrize("C,N,B", [(64, 4096, 2), (64, 16384, 1), (128, 4096, 1), (256, 1024, 2), (128, 1000, 2),
+                                   (64, 300, 3)])
+def test_tcgen05_forward_matches_cudacore_kernel(C, N, B):
+    """bf16 tensor-core kernel vs the fp32-math CUDA-core kernel on identical bf16 inputs (sizes beyond the CPU oracle)."""
+    from maskunet_b200 import ops
+    dev = _dev()
+    gen = torch.Generator(device=dev).manual_seed(C + N)
+    NKP = ops.nkp_of(N)
+    q = torch.randn(B, N, C, device=dev, generator=gen).bfloat16()
+    kc = torch.randn(B, NKP, C, device=dev, generator=gen).bfloat16()
+    vc = torch.randn(B, NKP, C, device=dev, generator=gen).bfloat16()
+    n_keep = torch.tensor([max(1, (N * (b + 1)) // (B + 1) + 3 * b) for b in range(B)], dtype=torch.int32, device=dev)
+    for b in range(B):
+        kc[b, int(n_keep[b]):] = 0
+        vc[b, int(n_keep[b]):] = 0
+    o_ref, lse_ref = ops.attn_fwd_cudacore(q, kc, vc, n_keep)
+    o, lse = ops.attn_fwd(q, kc, vc, n_keep)
+    assert rel_err(o, o_ref) < 1e-2
+    assert float((lse - lse_ref).abs().max()) < 2e-2
+
+
+def test_attention_sdpa_oracle_small():
+    """attn_fwd against the kernel-level oracle (explicit softmax) including a fully kept and a 1-key sample."""
+    from maskunet_b200 import ops
+    dev = _dev()
+    B, N, C = 3, 200, 64
+    gen = torch.Generator().manual_seed(0)
+    qf, kf, vf = (torch.randn(B, N, C, generator=gen) for _ in range(3))
+    keep = torch.rand(B, N, generator=gen) > 0.5
+    keep[1] = True
+    keep[2] = False
+    keep[2, 17] = True
+    o_ref, lse_ref = mao.sdpa_reference(qf, kf, vf, keep, C)
+    for dtype in (torch.float32, torch.bfloat16):
+        NKP = ops.nkp_of(N)
+        kc = torch.zeros(B, NKP, C, dtype=dtype, device=dev)
+        vc = torch.zeros(B, NKP, C, dtype=dtype, device=dev)
+        for b in range(B):
+            idx = keep[b].nonzero().flatten()
+            kc[b, : len(idx)] = kf[b, idx].to(dev, dtype)
+            vc[b, : len(idx)] = vf[b, idx].to(dev, dtype)
+        n_keep = keep.sum(1).to(torch.int32).to(dev)
+        o, lse = ops.attn_fwd(qf.to(dev, dtype), kc, vc, n_keep)
+        assert rel_err(o, o_ref) < TOL[dtype]
+        assert rel_err(lse, lse_ref) < TOL[dtype]
+
+
+# ------------------------------------------------------------------ module level (forward + backward)
+@pytest.mark.parametrize("name", ATTN_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["float32", "bfloat16"])
+def test_module_matches_reference_golden(name, dtype):
+    g = load_attn_golden(name)
+    tol = TOL[dtype]
+    m = _module_from_golden(g, dtype)
+    x = g["x"].to(_dev(), dtype).requires_grad_(True)
+    y = m(x)
+    assert y.shape == g["y"].shape and y.dtype == dtype
+    assert rel_err(y, g["y"]) < tol
+    (y.float() * g["dy"].to(_dev())).sum().backward()
+    assert rel_err(x.grad, g["dx"]) < tol
+    scale = max(float(v.abs().max()) for v in g["grads"].values())
+    for k, p in m.named_parameters():
+        ref = g["grads"][k]
+        if k == "key.bias":   # analytically zero; absolute check against the gradient scale
+            assert float((p.grad.cpu() - ref).abs().max()) < tol * scale
+        else:
+            assert rel_err(p.grad, ref) < tol, k
+
+
+def test_module_output_is_view_not_permute():
+    """ade_semantic.py:190 returns the [B, N, C] buffer re-viewed as [B, C, H, W] (no transpose back)."""
+    g = load_attn_golden("attn_b2_c64_8x8")
+    m = _module_from_golden(g, torch.float32)
+    x = g["x"].to(_dev())
+    y = m(x)
+    ref = mao.attention_forward(g["x"], g["params"], g["keep"])["y"]          # [B, N, C]
+    assert rel_err(y.reshape(2, 64, 64), ref.reshape(2, 64, 64)) < 1e-4
+    assert rel_err(y, ref.permute(0, 2, 1).reshape(2, 64, 8, 8)) > 0.5
+
+
+def test_resample_mode_draws_new_mask_each_forward():
+    from maskunet_b200 import Mask2FormerAttention
+    m = Mask2FormerAttention(64, 64, mask_mode="resample").to(_dev())
+    x = torch.randn(2, 64, 16, 16, device=_dev())
+    m(x)
+    a = m.mask[:, 0, :].clone()
+    m(x)
+    assert not torch.equal(a, m.mask[:, 0, :])
