@@ -23,6 +23,34 @@ from ._lib import MU_BF16, MU_F32, check
 
 _L = _lib.load()
 
+# ---- instrumentation used by bench.py (not by the product path) ---------------------------------
+LAUNCHES = {"count": 0}          # kernels of OURS launched so far (each C-ABI call adds what it enqueues)
+KERNEL_TIMING = {"enabled": False, "events": {}}   # name -> [(start_event, end_event, meta), ...]
+
+
+def _count(n: int) -> None:
+    LAUNCHES["count"] += n
+
+
+class _timed:
+    """Bracket one C-ABI call with CUDA events on the launching stream when timing is enabled."""
+
+    def __init__(self, name, meta=None):
+        self.name, self.meta = name, meta
+
+    def __enter__(self):
+        if KERNEL_TIMING["enabled"]:
+            self.t0 = torch.cuda.Event(enable_timing=True)
+            self.t1 = torch.cuda.Event(enable_timing=True)
+            self.t0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if KERNEL_TIMING["enabled"]:
+            self.t1.record()
+            KERNEL_TIMING["events"].setdefault(self.name, []).append((self.t0, self.t1, self.meta))
+        return False
+
 
 def _p(t: Tensor) -> ctypes.c_void_p:
     return ctypes.c_void_p(t.data_ptr())
@@ -65,6 +93,7 @@ def mask_binarize(bits: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     keep_idx = torch.empty((B, N), dtype=torch.int32, device=dev)
     keep_rank = torch.empty((B, N), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
+        _count(1)
         check(_L.mu_mask_binarize(_p(bits), B, N, _p(keep_bits), _p(n_keep), _p(keep_idx), _p(keep_rank),
                                   _stream(bits)), "mu_mask_binarize")
     return keep_bits, n_keep, keep_idx, keep_rank
@@ -89,6 +118,7 @@ def qkv_project(x: Tensor, w_qkv: Tensor, b_qkv: Tensor, keep_rank: Tensor, n_ke
     kc = torch.empty((B, NKP, C), dtype=x.dtype, device=x.device)
     vc = torch.empty((B, NKP, C), dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
+        _count(2)
         check(_L.mu_qkv_project(_p(x), _p(w_qkv), _p(b_qkv), _p(keep_rank), _p(n_keep), _p(q), _p(kc), _p(vc),
                                 B, C, N, NKP, _code(x), _stream(x)), "mu_qkv_project")
     return q, kc, vc
@@ -106,7 +136,8 @@ def _attn_fwd_impl(fn, name, q, kc, vc, n_keep):
     NKP = kc.shape[1]
     o = torch.empty_like(q)
     lse = torch.empty((B, N), dtype=torch.float32, device=q.device)
-    with torch.cuda.device(q.device):
+    with torch.cuda.device(q.device), _timed(name, (B, N, C)):
+        _count(1)
         check(fn(_p(q), _p(kc), _p(vc), _p(n_keep), _p(o), _p(lse), B, N, NKP, C, _code(q), _stream(q)), name)
     return o, lse
 
@@ -134,7 +165,8 @@ def _attn_bwd_impl(fn, name, q, kc, vc, n_keep, d_o, lse, delta):
     dq = torch.empty_like(q)
     dkc = torch.zeros_like(kc)
     dvc = torch.zeros_like(vc)
-    with torch.cuda.device(q.device):
+    with torch.cuda.device(q.device), _timed(name, (B, N, C)):
+        _count(2)
         check(fn(_p(q), _p(kc), _p(vc), _p(n_keep), _p(d_o), _p(lse), _p(delta), _p(dq), _p(dkc), _p(dvc),
                  B, N, NKP, C, _code(q), _stream(q)), name)
     return dq, dkc, dvc
@@ -163,6 +195,7 @@ def residual_ln_fwd(o: Tensor, x: Tensor, gamma: Tensor, beta: Tensor, eps: floa
     mean = torch.empty((B, N), dtype=torch.float32, device=o.device)
     rstd = torch.empty((B, N), dtype=torch.float32, device=o.device)
     with torch.cuda.device(o.device):
+        _count(1)
         check(_L.mu_residual_ln_fwd(_p(o), _p(x), _p(gamma), _p(beta), eps, _p(y), _p(mean), _p(rstd),
                                     B, C, N, _code(o), _stream(o)), "mu_residual_ln_fwd")
     return y, mean, rstd
@@ -184,6 +217,7 @@ def residual_ln_bwd(dy: Tensor, o: Tensor, x: Tensor, mean: Tensor, rstd: Tensor
     dgamma = torch.zeros((C,), dtype=torch.float32, device=o.device)
     dbeta = torch.zeros((C,), dtype=torch.float32, device=o.device)
     with torch.cuda.device(o.device):
+        _count(1)
         check(_L.mu_residual_ln_bwd(_p(dy), _p(o), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dz), _p(delta),
                                     _p(dgamma), _p(dbeta), B, C, N, _code(o), _stream(o)), "mu_residual_ln_bwd")
     return dz, delta, dgamma, dbeta
@@ -206,6 +240,7 @@ def qkv_project_bwd(x: Tensor, dz: Tensor, dq: Tensor, dkc: Tensor, dvc: Tensor,
     dw = torch.zeros((3 * C, C), dtype=torch.float32, device=x.device)
     db = torch.zeros((3 * C,), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
+        _count(2)
         check(_L.mu_qkv_project_bwd(_p(x), _p(dz), _p(dq), _p(dkc), _p(dvc), _p(keep_rank), _p(w_qkv), _p(dx),
                                     _p(dw), _p(db), B, C, N, NKP, _code(x), _stream(x)), "mu_qkv_project_bwd")
     return dx, dw, db

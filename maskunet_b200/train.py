@@ -1,0 +1,47 @@
+"""The reference's timed loop body as a reusable step.
+
+/root/reference/code/ade20k/ade_semantic.py:394-401:
+    inputs, labels = inputs.to(device), labels.to(device)
+    optimizer.zero_grad(); outputs = model(inputs); loss = criterion(outputs, labels)
+    loss.backward(); optimizer.step()
+with ``criterion = nn.CrossEntropyLoss()`` and ``optim.AdamW(lr=5e-5, weight_decay=1e-1)`` (:377-379).
+Under data parallelism the gradient all-reduce (ddp.GradReducer) sits between backward and the optimiser.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from .ddp import GradReducer
+
+
+class Trainer:
+    def __init__(self, model: torch.nn.Module, lr: float = 5e-5, weight_decay: float = 1e-1,
+                 ignore_index: int = -100, data_parallel: bool = False, bucket_bytes: int = 25 * 1024 * 1024):
+        self.model = model
+        self.device = next(model.parameters()).device
+        self.ignore_index = ignore_index
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.optimizer = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, fused=self.device.type == "cuda")
+        self.reducer: Optional[GradReducer] = None
+        if data_parallel:
+            self.reducer = GradReducer(params, bucket_bytes=bucket_bytes)
+            self.reducer.broadcast_parameters(model)
+
+    def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """One training step; ``images``/``labels`` may live in (pinned) host memory.  Returns the loss (device)."""
+        if images.device != self.device:
+            images = images.to(self.device, non_blocking=True)
+        if labels.device != self.device:
+            labels = labels.to(self.device, non_blocking=True)
+        self.optimizer.zero_grad(set_to_none=True)
+        out = self.model(images)
+        logits = out[0] if isinstance(out, tuple) else out
+        loss = F.cross_entropy(logits.float(), labels, ignore_index=self.ignore_index)
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        self.optimizer.step()
+        return loss.detach()

@@ -1,0 +1,99 @@
+"""GPU parity of the full U-Net (attention on our kernels) against goldens produced by the reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import mask_attention_oracle as mao
+from oracle import unet_oracle as uo
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+# fp32 parity means fp32: no TF32 in the stock torch convolutions / matmuls around our kernels
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _load(fname):
+    with open(os.path.join(GOLDEN, fname + ".json")) as fh:
+        meta = json.load(fh)
+    return meta, np.load(os.path.join(GOLDEN, fname + ".npz"))
+
+
+def _build(cls, meta, z, **kw):
+    torch.manual_seed(meta["seed"])
+    net = cls(3, meta["c_out"], **kw)
+    digest = {k: float(v.double().abs().sum()) for k, v in net.state_dict().items() if v.dtype.is_floating_point}
+    if any(abs(digest[k] - v) > 1e-6 * max(1.0, abs(v)) for k, v in meta["param_digest"].items()):
+        pytest.skip("torch RNG stream differs from the golden's")
+    x = torch.rand(meta["batch"], 3, 128, 128)
+    net = net.to(DEV)
+    for n, _, side in uo.ATTN_SITES:   # inject the reference's masks
+        keep = torch.from_numpy(np.unpackbits(z[f"keep.{n}"], axis=1)[:, : side * side]).bool()
+        getattr(net, n).mask = mao.expand_bias(mao.additive_bias(keep).to(DEV), side * side)
+    return net, x
+
+
+@pytest.mark.parametrize("fname,variant", [("unet_semantic", "semantic"), ("unet_instance", "instance")])
+def test_unet_eval_fp32_matches_reference(fname, variant):
+    import maskunet_b200
+    meta, z = _load(fname)
+    cls = maskunet_b200.UNet if variant == "semantic" else maskunet_b200.InstanceUNet
+    net, x = _build(cls, meta, z)
+    net.eval()
+    with torch.no_grad():
+        outs = net(x.to(DEV))
+    outs = outs if isinstance(outs, tuple) else (outs,)
+    for i, o in enumerate(outs):
+        assert tuple(o.shape) == tuple(z[f"out{i}.shape"])
+        got = o.reshape(-1)[torch.from_numpy(z[f"out{i}.sample_idx"]).to(DEV)].cpu()
+        ref = torch.from_numpy(z[f"out{i}.sample"])
+        err = float((got - ref).norm() / ref.norm())
+        assert err < 1e-4, (i, err)
+    am = outs[0].argmax(1).cpu().numpy().astype(np.uint8)
+    safe = z["argmax_margin"].astype(np.float32) > 1e-3
+    assert (am[safe] == z["argmax"][safe]).all()           # argmax maps identical away from numerical ties
+    assert (am == z["argmax"]).mean() > 0.9995
+
+
+def test_unet_train_step_fp32_grad_norms_match_reference():
+    import maskunet_b200
+    meta, z = _load("unet_semantic")
+    net, x = _build(maskunet_b200.UNet, meta, z)
+    net.train()
+    net.dropout.p = 0.0
+    labels = torch.randint(0, meta["c_out"], (meta["batch"], 128, 128), generator=torch.Generator().manual_seed(1))
+    out = net(x.to(DEV))
+    loss = torch.nn.functional.cross_entropy(out, labels.to(DEV))
+    loss.backward()
+    assert abs(float(loss) - float(z["train.loss"][0])) < 1e-4 * float(z["train.loss"][0])
+    ref = z["train.grad_norms"]
+    for (name, p), r in zip(net.named_parameters(), ref):
+        if r < 0:
+            assert p.grad is None, name                    # dead emb_layer parameters
+            continue
+        g = float(p.grad.double().norm())
+        if name.endswith(("key.bias",)) or r < 1e-7:
+            continue                                       # analytically zero gradients
+        assert abs(g - r) < 2e-3 * r + 1e-7, (name, g, r)
+
+
+def test_unet_bf16_logits_within_tolerance():
+    import maskunet_b200
+    meta, z = _load("unet_semantic")
+    net, x = _build(maskunet_b200.UNet, meta, z, compute_dtype=torch.bfloat16)
+    net.eval()
+    with torch.no_grad():
+        out = net(x.to(DEV)).float()
+    got = out.reshape(-1)[torch.from_numpy(z["out0.sample_idx"]).to(DEV)].cpu()
+    ref = torch.from_numpy(z["out0.sample"])
+    err = float((got - ref).norm() / ref.norm())
+    assert err < 2e-2, err
+    am = out.argmax(1).cpu().numpy().astype(np.uint8)
+    safe = z["argmax_margin"].astype(np.float32) > 0.1
+    mismatch = float((am != z["argmax"]).mean())
+    print(f"bf16: logits rel-err {err:.3e}, raw argmax mismatch fraction {mismatch:.4f}")
+    assert (am[safe] == z["argmax"][safe]).mean() > 0.995
