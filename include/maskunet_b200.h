@@ -101,10 +101,14 @@ int mu_residual_ln_bwd(const void* dy, const void* o, const void* x, const float
                        int32_t N, int32_t dtype, mu_stream_t stream);
 
 /* K5. Masked attention backward (autograd of :174-186).  Recomputes P from q, kc, lse.
- *   dq T [B, N, C];  dkc, dvc T [B, NKP, C] (rows >= n_keep untouched). */
+ *   dq T [B, N, C];  dkc, dvc T [B, NKP, C] (rows >= n_keep untouched).
+ *   workspace: mu_attn_bwd_workspace_bytes(...) bytes of scratch (the fp32 dQ accumulator that key tiles add
+ *   into with red.global.add); 0 bytes / NULL allowed for MU_F32. */
+size_t mu_attn_bwd_workspace_bytes(int32_t B, int32_t N, int32_t C, int32_t dtype);
 int mu_attn_bwd(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-                const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int32_t B, int32_t N,
-                int32_t NKP, int32_t C, int32_t dtype, mu_stream_t stream);
+                const float* lse, const float* delta, void* dq, void* dkc, void* dvc, void* workspace,
+                size_t workspace_bytes, int32_t B, int32_t N, int32_t NKP, int32_t C, int32_t dtype,
+                mu_stream_t stream);
 
 /* K6. Backward of the projections and the residual branch (autograd of :168-172, :187).
  *   dx     T   [B, C, N]  = (dz + dq Wq + scatter(dkc) Wk + scatter(dvc) Wv)^T

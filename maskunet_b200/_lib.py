@@ -24,7 +24,7 @@ SIGNATURES = {
     "mu_attn_fwd_cudacore": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "mu_residual_ln_fwd": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _P],
     "mu_residual_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "mu_attn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mu_attn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _I, _I, _I, _I, _I, _P],
     "mu_attn_bwd_cudacore": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "mu_qkv_project_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
 }
@@ -39,7 +39,7 @@ def load() -> ctypes.CDLL:
     if not os.path.isfile(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} not found. maskunet_b200 has no CPU or PyTorch fallback: build the CUDA library with "
-            "`python -m maskunet_b200.build` (needs nvcc, cross-compiles for sm_100a without a GPU).")
+            "`python maskunet_b200/build.py` (needs nvcc, cross-compiles for sm_100a without a GPU).")
     lib = ctypes.CDLL(LIB_PATH)
     lib.mu_version.restype = c_int32
     lib.mu_version.argtypes = []
@@ -47,6 +47,8 @@ def load() -> ctypes.CDLL:
     lib.mu_last_error.argtypes = []
     lib.mu_device_supported.restype = c_int32
     lib.mu_device_supported.argtypes = []
+    lib.mu_attn_bwd_workspace_bytes.restype = ctypes.c_size_t
+    lib.mu_attn_bwd_workspace_bytes.argtypes = [_I, _I, _I, _I]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int32

@@ -1,6 +1,6 @@
 """Build libmaskunet_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m maskunet_b200.build [--force]
+    python maskunet_b200/build.py [--force] [-v]
 
 The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 """

@@ -1,13 +1,413 @@
-// K5: masked attention backward for the bf16 path.
-// PLACEHOLDER until the tcgen05 kernel lands: forwards to the CUDA-core kernels (bf16 I/O, fp32 math).
+// K5: masked attention backward on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM).
+// Autograd of /root/reference/code/ade20k/ade_semantic.py:174-186 (implicit at :400).  P is recomputed from
+// Q, Kc and the saved LSE, so no N x N tensor is ever stored (the reference keeps P, 1 GiB per image at N=16384).
+//
+// One CTA owns one 128-key tile j of one sample (compacted kept keys) and walks over all query tiles i:
+//   MMA1  S^T  = K_j  Q_i^T            [128 keys x BM queries]   TMEM
+//   MMA2  dP^T = V_j  dO_i^T           [128 x BM]                TMEM
+//   threads (row = key): P^T = exp2(S^T c - lse), dS^T = P^T (dP^T - delta)  -> bf16 tiles in shared memory
+//   MMA3  dV_j += P^T  dO_i            [128 x DH]  TMEM, accumulates over i
+//   MMA4  dK_j += dS^T Q_i             [128 x DH]  TMEM, accumulates over i
+//   MMA5  dQ_i  = dS K_j  (D = 64: [BM queries x 64];  D >= 128: transposed, [128 channels x BM queries])
+//         read back by a second warpgroup and added into an fp32 dQ accumulator with red.global.add
+// D = 256 splits the accumulator width over blockIdx.z (DH = 128 channels each) because dK + dV alone
+// would need 512 TMEM columns.  The 1/sqrt(C) factor of dS is applied when dK / dQ leave the chip.
 #include "common.cuh"
+#include "sm100_ptx.cuh"
+#include "tma_host.cuh"
 
 namespace mu {
 
+constexpr int kBK = 128;            // keys per CTA
+constexpr int kBwdThreads = 384;    // warps 0-3: TMA, MMA, 2 idle; 4-7: softmax; 8-11: dQ reduction
+constexpr float kLog2eB = 1.4426950408889634f;
+
+template <int D, int BM, int DH, int STAGES>
+struct BwdCfg {
+  static constexpr bool kDQT = (D >= 128);               // dQ tile computed transposed
+  static constexpr int kKBytes = kBK * D * 2;            // K_j or V_j
+  static constexpr int kQBytes = BM * D * 2;             // Q_i or dO_i
+  static constexpr int kPBytes = kBK * BM * 2;           // P^T or dS^T
+  static constexpr int kTmS = 0, kTmDP = BM, kTmDV = 2 * BM, kTmDK = 2 * BM + DH, kTmDQ = 2 * BM + 2 * DH;
+  static constexpr int kDQCols = kDQT ? BM : DH;
+  static constexpr int kTmemUsed = kTmDQ + kDQCols;
+  static_assert(kTmemUsed <= 512, "TMEM overflow");
+  static constexpr int kStatBytes = 2 * 2 * BM * 4;       // lse2, delta, double-buffered over tiles
+  static constexpr int kSmemBytes = 1024 + 2 * kKBytes + 2 * STAGES * kQBytes + 2 * kPBytes + kStatBytes + 256;
+  static_assert(kSmemBytes <= 232448, "shared memory overflow");
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int D, int BM, int DH, int STAGES>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+                      const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                      const int32_t* __restrict__ n_keep, const float* __restrict__ lse,
+                      const float* __restrict__ delta, float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dkc,
+                      __nv_bfloat16* __restrict__ dvc, int N, int NKP, float scale) {
+  using Cfg = BwdCfg<D, BM, DH, STAGES>;
+  constexpr bool DQT = Cfg::kDQT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + Cfg::kKBytes;
+  uint8_t* sQ = sV + Cfg::kKBytes;                       // STAGES x Q_i
+  uint8_t* sDO = sQ + STAGES * Cfg::kQBytes;             // STAGES x dO_i
+  uint8_t* sP = sDO + STAGES * Cfg::kQBytes;
+  uint8_t* sDS = sP + Cfg::kPBytes;
+  float* sLse = reinterpret_cast<float*>(sDS + Cfg::kPBytes);   // [2][BM], already * log2e
+  float* sDelta = sLse + 2 * BM;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * BM);
+  uint64_t* kv_full = bars;                 // 1
+  uint64_t* qdo_full = bars + 1;            // STAGES
+  uint64_t* qdo_empty = qdo_full + STAGES;  // STAGES
+  uint64_t* s_full = qdo_empty + STAGES;    // 1
+  uint64_t* pds_full = s_full + 1;          // 1 (128 arrivals)
+  uint64_t* pds_free = pds_full + 1;        // 1
+  uint64_t* dq_full = pds_free + 1;         // 1
+  uint64_t* dq_free = dq_full + 1;          // 1 (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_free + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int b = blockIdx.y, k0 = blockIdx.x * kBK, half = blockIdx.z;
+  const int nk = n_keep[b];
+  if (k0 >= nk) return;                      // whole CTA: nothing kept in this tile
+  const int T = (N + BM - 1) / BM;           // query tiles
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(qdo_full + i, 1);
+      mbar_init(qdo_empty + i, 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(pds_free, 1);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_free, 128);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<512>(tmem_slot);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane_id() == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane_id() == 0) {
+      mbar_expect_tx(kv_full, 2 * Cfg::kKBytes);
+      for (int blk = 0; blk < D / 64; ++blk) {
+        tma_load_3d(sK + blk * (kBK * 128), &tmap_k, kv_full, blk * 64, k0, b);
+        tma_load_3d(sV + blk * (kBK * 128), &tmap_v, kv_full, blk * 64, k0, b);
+      }
+      for (int i = 0; i < T; ++i) {
+        const int st = i % STAGES, use = i / STAGES;
+        if (use > 0) mbar_wait(qdo_empty + st, (use - 1) & 1);
+        mbar_expect_tx(qdo_full + st, 2 * Cfg::kQBytes);
+        for (int blk = 0; blk < D / 64; ++blk) {
+          tma_load_3d(sQ + st * Cfg::kQBytes + blk * (BM * 128), &tmap_q, qdo_full + st, blk * 64, i * BM, b);
+          tma_load_3d(sDO + st * Cfg::kQBytes + blk * (BM * 128), &tmap_do, qdo_full + st, blk * 64, i * BM, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane_id() == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kBK, BM, 0, 0);     // S^T, dP^T
+      constexpr uint32_t idesc_acc = make_idesc_bf16(kBK, DH, 0, 1);   // dV, dK: A K-major, B MN-major
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, DQT ? BM : DH, 1, 1);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
+      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+      auto issue_s_dp = [&](int i) {
+        const int st = i % STAGES;
+        mbar_wait(qdo_full + st, (i / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t qa = q_addr + st * Cfg::kQBytes, da = do_addr + st * Cfg::kQBytes;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t offa = (kk >> 2) * (kBK * 128) + (kk & 3) * 32, offb = (kk >> 2) * (BM * 128) + (kk & 3) * 32;
+          umma_ss(tmem_base + Cfg::kTmS, make_smem_desc(k_addr + offa, 0, 1024), make_smem_desc(qa + offb, 0, 1024),
+                  idesc_s, kk > 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t offa = (kk >> 2) * (kBK * 128) + (kk & 3) * 32, offb = (kk >> 2) * (BM * 128) + (kk & 3) * 32;
+          umma_ss(tmem_base + Cfg::kTmDP, make_smem_desc(v_addr + offa, 0, 1024), make_smem_desc(da + offb, 0, 1024),
+                  idesc_s, kk > 0);
+        }
+        umma_commit(s_full);
+      };
+      auto issue_acc = [&](int i) {
+        const int st = i % STAGES;
+        const uint32_t qa = q_addr + st * Cfg::kQBytes + half * 2 * (BM * 128);
+        const uint32_t da = do_addr + st * Cfg::kQBytes + half * 2 * (BM * 128);
+#pragma unroll
+        for (int kk = 0; kk < BM / 16; ++kk) {   // dV += P^T dO_i
+          const uint64_t a = make_smem_desc(p_addr + (kk >> 2) * (kBK * 128) + (kk & 3) * 32, 0, 1024);
+          const uint64_t bd = make_smem_desc(da + kk * 2048, BM * 128, 1024);
+          umma_ss(tmem_base + Cfg::kTmDV, a, bd, idesc_acc, (i > 0) || (kk > 0));
+        }
+#pragma unroll
+        for (int kk = 0; kk < BM / 16; ++kk) {   // dK += dS^T Q_i
+          const uint64_t a = make_smem_desc(ds_addr + (kk >> 2) * (kBK * 128) + (kk & 3) * 32, 0, 1024);
+          const uint64_t bd = make_smem_desc(qa + kk * 2048, BM * 128, 1024);
+          umma_ss(tmem_base + Cfg::kTmDK, a, bd, idesc_acc, (i > 0) || (kk > 0));
+        }
+        if (i > 0) {
+          mbar_wait(dq_free, (i - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int kk = 0; kk < kBK / 16; ++kk) {  // dQ tile: contraction over the 128 keys of this CTA
+          uint64_t a, bd;
+          if (DQT) {  // dQ^T [channels x queries] = K_j^T (MN-major A) . dS (MN-major B)
+            a = make_smem_desc(k_addr + half * 2 * (kBK * 128) + kk * 2048, kBK * 128, 1024);
+            bd = make_smem_desc(ds_addr + kk * 2048, kBK * 128, 1024);
+          } else {    // dQ [queries x channels] = dS (MN-major A over queries) . K_j (MN-major B)
+            a = make_smem_desc(ds_addr + kk * 2048, kBK * 128, 1024);
+            bd = make_smem_desc(k_addr + kk * 2048, kBK * 128, 1024);
+          }
+          umma_ss(tmem_base + Cfg::kTmDQ, a, bd, idesc_dq, kk > 0);
+        }
+        umma_commit(qdo_empty + st);
+        umma_commit(pds_free);
+        umma_commit(dq_full);
+      };
+      mbar_wait(kv_full, 0);
+      issue_s_dp(0);
+      for (int i = 0; i < T; ++i) {
+        mbar_wait(pds_full, i & 1);          // P^T / dS^T of tile i in smem, S^T / dP^T TMEM drained
+        tc_fence_after();
+        if (STAGES >= 2) {
+          if (i + 1 < T) issue_s_dp(i + 1);
+          issue_acc(i);
+        } else {
+          issue_acc(i);
+          if (i + 1 < T) issue_s_dp(i + 1);
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================================== softmax-backward warps: thread <-> key row
+    const int quad = warp & 3;
+    const int r = quad * 32 + (int)lane_id();
+    const int t = threadIdx.x - 128;                     // 0..127 within this warpgroup
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const bool key_ok = k0 + r < nk;
+    const float scale_log2 = scale * kLog2eB;
+    const float* lse_b = lse + (size_t)b * N;
+    const float* delta_b = delta + (size_t)b * N;
+    auto fetch = [&](int i, float& l2, float& dl) {
+      const int qi = i * BM + t;
+      const bool ok = (t < BM) && (qi < N);
+      l2 = ok ? lse_b[qi] * kLog2eB : INFINITY;          // +inf -> p = 0 for rows past N
+      dl = ok ? delta_b[qi] : 0.f;
+    };
+    float nl2, ndl;
+    fetch(0, nl2, ndl);
+    uint32_t s[32], dp[32];
+    for (int i = 0; i < T; ++i) {
+      float* my_lse = sLse + (i & 1) * BM;
+      float* my_delta = sDelta + (i & 1) * BM;
+      if (t < BM) {
+        my_lse[t] = nl2;
+        my_delta[t] = ndl;
+      }
+      if (i + 1 < T) fetch(i + 1, nl2, ndl);
+      named_bar_sync(1, 128);
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      if (i > 0) mbar_wait(pds_free, (i - 1) & 1);       // previous tile's MMAs no longer read sP / sDS
+#pragma unroll
+      for (int c = 0; c < BM / 32; ++c) {
+        tmem_ld32(lane_base + Cfg::kTmS + c * 32, s);
+        tmem_ld32(lane_base + Cfg::kTmDP + c * 32, dp);
+        tmem_wait_ld();
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float2 l2 = *reinterpret_cast<const float2*>(my_lse + c * 32 + 2 * e);
+          const float2 dl = *reinterpret_cast<const float2*>(my_delta + c * 32 + 2 * e);
+          float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * e]), scale_log2, -l2.x));
+          float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * e + 1]), scale_log2, -l2.y));
+          if (!key_ok) p0 = p1 = 0.f;
+          const float d0 = p0 * (__uint_as_float(dp[2 * e]) - dl.x);
+          const float d1 = p1 * (__uint_as_float(dp[2 * e + 1]) - dl.y);
+          pk[e] = pack_bf16(p0, p1);
+          dk[e] = pack_bf16(d0, d1);
+        }
+        uint8_t* prow = sP + (c >> 1) * (kBK * 128) + r * 128;
+        uint8_t* drow = sDS + (c >> 1) * (kBK * 128) + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int chunk = ((c & 1) * 4 + ch) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+          *reinterpret_cast<uint4*>(drow + chunk * 16) = make_uint4(dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(pds_full);
+    }
+    // ---- epilogue: dV_j, dK_j out of TMEM (rows of kept keys only)
+    mbar_wait(pds_free, (T - 1) & 1);
+    tc_fence_after();
+    const size_t row_off = ((size_t)b * NKP + k0 + r) * D + half * DH;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      __nv_bfloat16* dst = (which == 0 ? dvc : dkc) + row_off;
+      const float mul = which == 0 ? 1.f : scale;
+      const int col0 = which == 0 ? Cfg::kTmDV : Cfg::kTmDK;
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c) {
+        tmem_ld32(lane_base + col0 + c * 32, s);
+        tmem_wait_ld();
+        if (key_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(s[8 * g + 0]) * mul, __uint_as_float(s[8 * g + 1]) * mul);
+            w.y = pack_bf16(__uint_as_float(s[8 * g + 2]) * mul, __uint_as_float(s[8 * g + 3]) * mul);
+            w.z = pack_bf16(__uint_as_float(s[8 * g + 4]) * mul, __uint_as_float(s[8 * g + 5]) * mul);
+            w.w = pack_bf16(__uint_as_float(s[8 * g + 6]) * mul, __uint_as_float(s[8 * g + 7]) * mul);
+            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = w;
+          }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================================================== dQ reduction warps
+    const int quad = warp & 3;
+    const int r = quad * 32 + (int)lane_id();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint32_t v[32];
+    for (int i = 0; i < T; ++i) {
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+      if (DQT) {
+        // lanes = channel (half * 128 + r), columns = queries of tile i: coalesced scalar reductions
+        float* base = dq_acc + ((size_t)b * N + (size_t)i * BM) * D + half * DH + r;
+#pragma unroll
+        for (int c = 0; c < BM / 32; ++c) {
+          tmem_ld32(lane_base + Cfg::kTmDQ + c * 32, v);
+          tmem_wait_ld();
+          if (c == BM / 32 - 1) {
+            tc_fence_before();
+            mbar_arrive(dq_free);
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (i * BM + c * 32 + e < N) atomicAdd(base + (size_t)(c * 32 + e) * D, __uint_as_float(v[e]) * scale);
+        }
+      } else {
+        // lanes = query row, columns = channels
+        const bool ok = i * BM + r < N;
+        float* base = dq_acc + ((size_t)b * N + (size_t)i * BM + r) * D;
+#pragma unroll
+        for (int c = 0; c < DH / 32; ++c) {
+          tmem_ld32(lane_base + Cfg::kTmDQ + c * 32, v);
+          tmem_wait_ld();
+          if (c == DH / 32 - 1) {
+            tc_fence_before();
+            mbar_arrive(dq_free);
+          }
+          if (ok) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              red_add_v4(base + c * 32 + 4 * e, __uint_as_float(v[4 * e]) * scale, __uint_as_float(v[4 * e + 1]) * scale,
+                         __uint_as_float(v[4 * e + 2]) * scale, __uint_as_float(v[4 * e + 3]) * scale);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// fp32 accumulator -> bf16 dq
+__global__ void dq_convert_kernel(const float4* __restrict__ acc, uint2* __restrict__ out, size_t n4) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 a = acc[i];
+    uint2 o;
+    o.x = pack_bf16(a.x, a.y);
+    o.y = pack_bf16(a.z, a.w);
+    out[i] = o;
+  }
+}
+
+template <int D, int BM, int DH, int STAGES>
+static int run(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
+               const float* lse, const float* delta, void* dq, void* dkc, void* dvc, float* dq_acc, int B, int N,
+               int NKP, cudaStream_t s) {
+  using Cfg = BwdCfg<D, BM, DH, STAGES>;
+  CUtensorMap tq, tdo, tk, tv;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tq, q, D, N, B, BM))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tdo, d_o, D, N, B, BM))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tk, kc, D, NKP, B, kBK))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tv, vc, D, NKP, B, kBK))) return rc;
+  auto kern = attn_bwd_sm100_kernel<D, BM, DH, STAGES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (e != cudaSuccess) {
+    set_error("attn_bwd_sm100: cudaFuncSetAttribute(%d bytes): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+    return (int)e;
+  }
+  const size_t n = (size_t)B * N * D;
+  cudaMemsetAsync(dq_acc, 0, n * sizeof(float), s);
+  dim3 grid(NKP / kBK, B, D / DH);
+  const float scale = 1.f / sqrtf((float)D);
+  kern<<<grid, kBwdThreads, Cfg::kSmemBytes, s>>>(tq, tdo, tk, tv, n_keep, lse, delta, dq_acc, (__nv_bfloat16*)dkc,
+                                                  (__nv_bfloat16*)dvc, N, NKP, scale);
+  if ((rc = check_launch("attn_bwd_sm100"))) return rc;
+  const size_t n4 = n / 4;
+  const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  dq_convert_kernel<<<blocks, 256, 0, s>>>((const float4*)dq_acc, (uint2*)dq, n4);
+  return check_launch("dq_convert");
+}
+
+size_t attn_bwd_sm100_workspace(int B, int N, int C) { return (size_t)B * N * C * sizeof(float); }
+
 int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-                          const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int B, int N, int NKP,
-                          int C, cudaStream_t s) {
-  return launch_attn_bwd_simt(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, B, N, NKP, C, MU_BF16, s);
+                          const float* lse, const float* delta, void* dq, void* dkc, void* dvc, void* workspace,
+                          size_t workspace_bytes, int B, int N, int NKP, int C, cudaStream_t s) {
+  MU_REQUIRE(workspace != nullptr && workspace_bytes >= attn_bwd_sm100_workspace(B, N, C), MU_ERR_WORKSPACE,
+             "mu_attn_bwd: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+             attn_bwd_sm100_workspace(B, N, C));
+  float* acc = (float*)workspace;
+  switch (C) {
+    case 64:
+      return run<64, 128, 64, 2>(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+    case 128:
+      return run<128, 64, 128, 2>(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+    case 256:
+      return run<256, 64, 128, 1>(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+    default:
+      set_error("attn_bwd_sm100: channels must be 64, 128 or 256 (got %d)", C);
+      return MU_ERR_BAD_SHAPE;
+  }
 }
 
 }  // namespace mu

@@ -131,9 +131,14 @@ int mu_attn_bwd_cudacore(const void* q, const void* kc, const void* vc, const in
                               (cudaStream_t)stream);
 }
 
+size_t mu_attn_bwd_workspace_bytes(int32_t B, int32_t N, int32_t C, int32_t dtype) {
+  return dtype == MU_BF16 ? attn_bwd_sm100_workspace(B, N, C) : 0;
+}
+
 int mu_attn_bwd(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-                const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int32_t B, int32_t N,
-                int32_t NKP, int32_t C, int32_t dtype, mu_stream_t stream) {
+                const float* lse, const float* delta, void* dq, void* dkc, void* dvc, void* workspace,
+                size_t workspace_bytes, int32_t B, int32_t N, int32_t NKP, int32_t C, int32_t dtype,
+                mu_stream_t stream) {
   if (dtype != MU_BF16)
     return mu_attn_bwd_cudacore(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, B, N, NKP, C, dtype, stream);
   int rc;
@@ -143,7 +148,8 @@ int mu_attn_bwd(const void* q, const void* kc, const void* vc, const int32_t* n_
   MU_REQUIRE(device_cc_major() == 10, MU_ERR_ARCH,
              "mu_attn_bwd: the bf16 path is tcgen05-only and needs an sm_100 device (found cc major %d)",
              device_cc_major());
-  return launch_attn_bwd_sm100(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, B, N, NKP, C, (cudaStream_t)stream);
+  return launch_attn_bwd_sm100(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, workspace, workspace_bytes, B, N, NKP,
+                               C, (cudaStream_t)stream);
 }
 
 int mu_qkv_project_bwd(const void* x, const void* dz, const void* dq, const void* dkc, const void* dvc,

@@ -66,7 +66,8 @@ int launch_qkv_project_bwd(const void* x, const void* dz, const void* dq, const 
 int launch_attn_fwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse,
                           int B, int N, int NKP, int C, cudaStream_t s);
 int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-                          const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int B, int N, int NKP,
-                          int C, cudaStream_t s);
+                          const float* lse, const float* delta, void* dq, void* dkc, void* dvc, void* workspace,
+                          size_t workspace_bytes, int B, int N, int NKP, int C, cudaStream_t s);
+size_t attn_bwd_sm100_workspace(int B, int N, int C);
 
 }  // namespace mu

@@ -158,24 +158,34 @@ def attn_fwd_cudacore(q, kc, vc, n_keep):
     return _attn_fwd_impl(_L.mu_attn_fwd_cudacore, "mu_attn_fwd_cudacore", q, kc, vc, n_keep)
 
 
-def _attn_bwd_impl(fn, name, q, kc, vc, n_keep, d_o, lse, delta):
+def _attn_bwd_impl(tensor_core, q, kc, vc, n_keep, d_o, lse, delta):
     _cuda(q, kc, vc, n_keep, d_o, lse, delta)
     B, N, C = q.shape
     NKP = kc.shape[1]
     dq = torch.empty_like(q)
     dkc = torch.zeros_like(kc)
     dvc = torch.zeros_like(vc)
-    with torch.cuda.device(q.device), _timed(name, (B, N, C)):
-        _count(2)
-        check(fn(_p(q), _p(kc), _p(vc), _p(n_keep), _p(d_o), _p(lse), _p(delta), _p(dq), _p(dkc), _p(dvc),
-                 B, N, NKP, C, _code(q), _stream(q)), name)
+    name = "mu_attn_bwd" if tensor_core else "mu_attn_bwd_cudacore"
+    with torch.cuda.device(q.device):
+        if tensor_core:
+            ws_bytes = int(_L.mu_attn_bwd_workspace_bytes(B, N, C, _code(q)))
+            ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=q.device)
+            with _timed(name, (B, N, C)):
+                _count(3 if ws_bytes else 2)
+                check(_L.mu_attn_bwd(_p(q), _p(kc), _p(vc), _p(n_keep), _p(d_o), _p(lse), _p(delta), _p(dq), _p(dkc),
+                                     _p(dvc), _p(ws), ws_bytes, B, N, NKP, C, _code(q), _stream(q)), name)
+        else:
+            with _timed(name, (B, N, C)):
+                _count(2)
+                check(_L.mu_attn_bwd_cudacore(_p(q), _p(kc), _p(vc), _p(n_keep), _p(d_o), _p(lse), _p(delta), _p(dq),
+                                              _p(dkc), _p(dvc), B, N, NKP, C, _code(q), _stream(q)), name)
     return dq, dkc, dvc
 
 
 @torch.library.custom_op("maskunet::attn_bwd", mutates_args=(), device_types="cuda")
 def attn_bwd(q: Tensor, kc: Tensor, vc: Tensor, n_keep: Tensor, d_o: Tensor, lse: Tensor, delta: Tensor
              ) -> Tuple[Tensor, Tensor, Tensor]:
-    return _attn_bwd_impl(_L.mu_attn_bwd, "mu_attn_bwd", q, kc, vc, n_keep, d_o, lse, delta)
+    return _attn_bwd_impl(True, q, kc, vc, n_keep, d_o, lse, delta)
 
 
 @attn_bwd.register_fake
@@ -184,7 +194,7 @@ def _(q, kc, vc, n_keep, d_o, lse, delta):
 
 
 def attn_bwd_cudacore(q, kc, vc, n_keep, d_o, lse, delta):
-    return _attn_bwd_impl(_L.mu_attn_bwd_cudacore, "mu_attn_bwd_cudacore", q, kc, vc, n_keep, d_o, lse, delta)
+    return _attn_bwd_impl(False, q, kc, vc, n_keep, d_o, lse, delta)
 
 
 @torch.library.custom_op("maskunet::residual_ln_fwd", mutates_args=(), device_types="cuda")

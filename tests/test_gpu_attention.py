@@ -131,6 +131,32 @@ def test_tcgen05_forward_matches_cudacore_kernel(C, N, B):
     assert float((lse - lse_ref).abs().max()) < 2e-2
 
 
+@pytest.mark.parametrize("C,N,B", [(64, 1024, 2), (64, 4096, 1), (128, 1024, 2), (256, 512, 2), (64, 300, 3),
+                                   (128, 200, 2), (256, 130, 1)])
+def test_tcgen05_backward_matches_cudacore_kernel(C, N, B):
+    """bf16 tensor-core backward vs the fp32-math CUDA-core backward on identical bf16 inputs."""
+    from maskunet_b200 import ops
+    dev = _dev()
+    gen = torch.Generator(device=dev).manual_seed(7 * C + N)
+    NKP = ops.nkp_of(N)
+    q = (0.5 * torch.randn(B, N, C, device=dev, generator=gen)).bfloat16()
+    kc = torch.randn(B, NKP, C, device=dev, generator=gen).bfloat16()
+    vc = torch.randn(B, NKP, C, device=dev, generator=gen).bfloat16()
+    d_o = torch.randn(B, N, C, device=dev, generator=gen).bfloat16()
+    n_keep = torch.tensor([max(1, (N * (b + 1)) // (B + 1) + 3 * b) for b in range(B)], dtype=torch.int32, device=dev)
+    for b in range(B):
+        kc[b, int(n_keep[b]):] = 0
+        vc[b, int(n_keep[b]):] = 0
+    o, lse = ops.attn_fwd_cudacore(q, kc, vc, n_keep)
+    delta = (d_o.float() * o.float()).sum(-1).contiguous()
+    ref = ops.attn_bwd_cudacore(q, kc, vc, n_keep, d_o, lse, delta)
+    got = ops.attn_bwd(q, kc, vc, n_keep, d_o, lse, delta)
+    for name, g, r in zip(("dq", "dkc", "dvc"), got, ref):
+        for b in range(B):
+            nk = int(n_keep[b]) if name != "dq" else N
+            assert rel_err(g[b, :nk], r[b, :nk]) < 2e-2, (name, b)
+
+
 def test_attention_sdpa_oracle_small():
     """attn_fwd against the kernel-level oracle (explicit softmax) including a fully kept and a 1-key sample."""
     from maskunet_b200 import ops
