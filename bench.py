@@ -165,7 +165,10 @@ def run_ours(args):
 
     B, c_out = args.batch_per_gpu, 150
     torch.manual_seed(42)                                   # identical weights on every rank
-    model = maskunet_b200.UNet(3, c_out, compute_dtype=torch.bfloat16).to(dev)
+    cl = os.environ.get("MASKUNET_CHANNELS_LAST", "0") == "1"
+    model = maskunet_b200.UNet(3, c_out, compute_dtype=torch.bfloat16, channels_last=cl).to(dev)
+    if cl:
+        model = model.to(memory_format=torch.channels_last)
     trainer = Trainer(model, lr=5e-5, weight_decay=1e-1, data_parallel=world > 1)
     torch.manual_seed(42 + rank)                            # masks / dropout differ per rank
     img_host = torch.rand(B, 3, 128, 128, generator=torch.Generator().manual_seed(rank)).pin_memory()

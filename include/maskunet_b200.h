@@ -36,6 +36,11 @@ typedef struct CUstream_st* mu_stream_t; /* == cudaStream_t */
 
 enum mu_dtype { MU_F32 = 0, MU_BF16 = 1 };
 
+/* Layout of the module input x (and of dx): channel-major = NCHW as the reference holds it ([B, C, N]);
+ * token-major = channels-last / NHWC ([B, N, C]), which is the reference's permuted token view (:168) in memory.
+ * The CUDA-core kernels take channel-major x; the tcgen05 projection kernels take token-major bf16 x. */
+enum mu_layout { MU_X_CHANNEL_MAJOR = 0, MU_X_TOKEN_MAJOR = 1 };
+
 enum mu_status {
   MU_OK = 0,
   MU_ERR_BAD_SHAPE = -1,
@@ -63,13 +68,14 @@ int mu_mask_binarize(const int64_t* bits, int32_t B, int32_t N, uint32_t* keep_b
                      int32_t* keep_idx, int32_t* keep_rank, mu_stream_t stream);
 
 /* K1. Q/K/V projections (:168-172).  Tokens are x[b, :, n] (the permute of :168 is never materialised).
- *   x      T   [B, C, N]      w_qkv f32 [3C, C] = cat(query.weight, key.weight, value.weight)
- *   b_qkv  f32 [3C]
+ *   x      T   [B, C, N] (MU_X_CHANNEL_MAJOR, CUDA cores) or [B, N, C] (MU_X_TOKEN_MAJOR, MU_BF16 only, tcgen05)
+ *   w_qkv  f32 [3C, C] = cat(query.weight, key.weight, value.weight);  b_qkv f32 [3C]
+ *   w_qkv_lp   bf16 copy of w_qkv, required by the token-major path (the tensor-core operand), else may be NULL
  *   q      T   [B, N, C]      kc, vc  T [B, NKP, C]: rows of kept keys only, in token order
  *                             (row keep_rank[b, n]); rows [n_keep, roundup(n_keep, 128)) are zero-filled. */
-int mu_qkv_project(const void* x, const float* w_qkv, const float* b_qkv, const int32_t* keep_rank,
-                   const int32_t* n_keep, void* q, void* kc, void* vc, int32_t B, int32_t C, int32_t N, int32_t NKP,
-                   int32_t dtype, mu_stream_t stream);
+int mu_qkv_project(const void* x, const float* w_qkv, const void* w_qkv_lp, const float* b_qkv,
+                   const int32_t* keep_rank, const int32_t* n_keep, void* q, void* kc, void* vc, int32_t B, int32_t C,
+                   int32_t N, int32_t NKP, int32_t dtype, int32_t x_layout, mu_stream_t stream);
 
 /* K3. Masked attention forward (:174-186): O = softmax(Q Kc^T / sqrt(C)) Vc over the kept keys only, which
  * equals the reference's softmax(QK^T/sqrt(C) + mask) V exactly (masked keys contribute exp(-inf) = 0).
@@ -82,15 +88,17 @@ int mu_attn_fwd(const void* q, const void* kc, const void* vc, const int32_t* n_
  * Used by the GPU tests to cross-check the tensor-core kernels on-device at sizes the CPU oracle cannot reach. */
 int mu_attn_fwd_cudacore(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse,
                          int32_t B, int32_t N, int32_t NKP, int32_t C, int32_t dtype, mu_stream_t stream);
-int mu_attn_bwd_cudacore(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-                         const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int32_t B, int32_t N,
-                         int32_t NKP, int32_t C, int32_t dtype, mu_stream_t stream);
+int mu_attn_bwd_cudacore(const void* q, const void* kc, const void* vc, const int32_t* n_keep,
+                         const int32_t* keep_idx, const void* d_o, const float* lse, const float* delta, void* dq,
+                         void* dk, void* dv, int32_t B, int32_t N, int32_t NKP, int32_t C, int32_t dtype,
+                         mu_stream_t stream);
 
 /* K3 epilogue. Residual + LayerNorm over channels (:187-188), output in the [B, N, C] layout that the
  * module returns re-viewed as [B, C, H, W] (:190).
  *   y T [B, N, C] = LN_C(o + x^T) * gamma + beta;  mean, rstd f32 [B, N] saved for backward. */
 int mu_residual_ln_fwd(const void* o, const void* x, const float* gamma, const float* beta, float eps, void* y,
-                       float* mean, float* rstd, int32_t B, int32_t C, int32_t N, int32_t dtype, mu_stream_t stream);
+                       float* mean, float* rstd, int32_t B, int32_t C, int32_t N, int32_t dtype, int32_t x_layout,
+                       mu_stream_t stream);
 
 /* K4. Backward of the residual + LayerNorm (autograd of :187-188, implicit at :400).
  *   dy T [B, N, C];  dz T [B, N, C] = dL/d(o + x^T)  (this is both dO and the residual branch of dX^T)
@@ -98,24 +106,31 @@ int mu_residual_ln_fwd(const void* o, const void* x, const float* gamma, const f
  *   dgamma, dbeta f32 [C]: ACCUMULATED with atomics, caller zero-fills. */
 int mu_residual_ln_bwd(const void* dy, const void* o, const void* x, const float* mean, const float* rstd,
                        const float* gamma, void* dz, float* delta, float* dgamma, float* dbeta, int32_t B, int32_t C,
-                       int32_t N, int32_t dtype, mu_stream_t stream);
+                       int32_t N, int32_t dtype, int32_t x_layout, mu_stream_t stream);
 
 /* K5. Masked attention backward (autograd of :174-186).  Recomputes P from q, kc, lse.
- *   dq T [B, N, C];  dkc, dvc T [B, NKP, C] (rows >= n_keep untouched).
+ *   dq, dk, dv T [B, N, C], all in TOKEN space: the gradient of compacted key row r is scattered back to
+ *   token keep_idx[b, r]; rows of masked keys are zero (the entry point clears dk / dv itself).
  *   workspace: mu_attn_bwd_workspace_bytes(...) bytes of scratch (the fp32 dQ accumulator that key tiles add
  *   into with red.global.add); 0 bytes / NULL allowed for MU_F32. */
 size_t mu_attn_bwd_workspace_bytes(int32_t B, int32_t N, int32_t C, int32_t dtype);
-int mu_attn_bwd(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-                const float* lse, const float* delta, void* dq, void* dkc, void* dvc, void* workspace,
+int mu_attn_bwd(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const int32_t* keep_idx,
+                const void* d_o, const float* lse, const float* delta, void* dq, void* dk, void* dv, void* workspace,
                 size_t workspace_bytes, int32_t B, int32_t N, int32_t NKP, int32_t C, int32_t dtype,
                 mu_stream_t stream);
 
 /* K6. Backward of the projections and the residual branch (autograd of :168-172, :187).
- *   dx     T   [B, C, N]  = (dz + dq Wq + scatter(dkc) Wk + scatter(dvc) Wv)^T
+ *   dq, dk, dv T [B, N, C] as produced by mu_attn_bwd (token space).
+ *   dx     T   in the layout of x:  channel-major [B, C, N] = (dz + dq Wq + dk Wk + dv Wv)^T, token-major [B, N, C]
  *   dw_qkv f32 [3C, C], db_qkv f32 [3C]: ACCUMULATED with atomics, caller zero-fills. */
-int mu_qkv_project_bwd(const void* x, const void* dz, const void* dq, const void* dkc, const void* dvc,
-                       const int32_t* keep_rank, const float* w_qkv, void* dx, float* dw_qkv, float* db_qkv,
-                       int32_t B, int32_t C, int32_t N, int32_t NKP, int32_t dtype, mu_stream_t stream);
+int mu_qkv_project_bwd(const void* x, const void* dz, const void* dq, const void* dk, const void* dv,
+                       const float* w_qkv, const void* w_qkv_lp, void* dx, float* dw_qkv, float* db_qkv, int32_t B,
+                       int32_t C, int32_t N, int32_t dtype, int32_t x_layout, mu_stream_t stream);
+
+/* Batched 2-D transpose in[batch][rows][cols] -> out[batch][cols][rows] (elem_bytes 2 or 4): the NCHW <-> NHWC bridge
+ * between the module's re-viewed output (:190) and channels-last convolutions. */
+int mu_transpose(const void* in, void* out, int32_t batch, int32_t rows, int32_t cols, int32_t elem_bytes,
+                 mu_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -19,14 +19,15 @@ _P, _I, _F = c_void_p, c_int32, c_float
 # name -> argtypes, mirrors include/maskunet_b200.h one to one
 SIGNATURES = {
     "mu_mask_binarize": [_P, _I, _I, _P, _P, _P, _P, _P],
-    "mu_qkv_project": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mu_qkv_project": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "mu_attn_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "mu_attn_fwd_cudacore": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "mu_residual_ln_fwd": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _P],
-    "mu_residual_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "mu_attn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _I, _I, _I, _I, _I, _P],
-    "mu_attn_bwd_cudacore": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mu_residual_ln_fwd": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mu_residual_ln_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mu_attn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _I, _I, _I, _I, _I, _P],
+    "mu_attn_bwd_cudacore": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "mu_qkv_project_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mu_transpose": [_P, _P, _I, _I, _I, _I, _P],
 }
 
 _lib = None

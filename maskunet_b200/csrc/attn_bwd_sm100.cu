@@ -48,9 +48,9 @@ template <int D, int BM, int DH, int STAGES>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                       const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
-                      const int32_t* __restrict__ n_keep, const float* __restrict__ lse,
-                      const float* __restrict__ delta, float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dkc,
-                      __nv_bfloat16* __restrict__ dvc, int N, int NKP, float scale) {
+                      const int32_t* __restrict__ n_keep, const int32_t* __restrict__ keep_idx,
+                      const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
+                      __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int N, int NKP, float scale) {
   using Cfg = BwdCfg<D, BM, DH, STAGES>;
   constexpr bool DQT = Cfg::kDQT;
   extern __shared__ uint8_t smem_raw[];
@@ -268,10 +268,12 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     // ---- epilogue: dV_j, dK_j out of TMEM (rows of kept keys only)
     mbar_wait(pds_free, (T - 1) & 1);
     tc_fence_after();
-    const size_t row_off = ((size_t)b * NKP + k0 + r) * D + half * DH;
+    // dense token-space outputs: key row r of this tile goes back to token keep_idx[k0 + r]
+    const int tok = key_ok ? keep_idx[(size_t)b * N + k0 + r] : 0;
+    const size_t row_off = ((size_t)b * N + tok) * D + half * DH;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* dst = (which == 0 ? dvc : dkc) + row_off;
+      __nv_bfloat16* dst = (which == 0 ? dv : dk) + row_off;
       const float mul = which == 0 ? 1.f : scale;
       const int col0 = which == 0 ? Cfg::kTmDV : Cfg::kTmDK;
 #pragma unroll
@@ -359,9 +361,9 @@ __global__ void dq_convert_kernel(const float4* __restrict__ acc, uint2* __restr
 }
 
 template <int D, int BM, int DH, int STAGES>
-static int run(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-               const float* lse, const float* delta, void* dq, void* dkc, void* dvc, float* dq_acc, int B, int N,
-               int NKP, cudaStream_t s) {
+static int run(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const int32_t* keep_idx,
+               const void* d_o, const float* lse, const float* delta, void* dq, void* dkc, void* dvc, float* dq_acc,
+               int B, int N, int NKP, cudaStream_t s) {
   using Cfg = BwdCfg<D, BM, DH, STAGES>;
   CUtensorMap tq, tdo, tk, tv;
   int rc;
@@ -377,9 +379,11 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
   }
   const size_t n = (size_t)B * N * D;
   cudaMemsetAsync(dq_acc, 0, n * sizeof(float), s);
+  cudaMemsetAsync(dkc, 0, n * 2, s);   // rows of masked keys stay zero
+  cudaMemsetAsync(dvc, 0, n * 2, s);
   dim3 grid(NKP / kBK, B, D / DH);
   const float scale = 1.f / sqrtf((float)D);
-  kern<<<grid, kBwdThreads, Cfg::kSmemBytes, s>>>(tq, tdo, tk, tv, n_keep, lse, delta, dq_acc, (__nv_bfloat16*)dkc,
+  kern<<<grid, kBwdThreads, Cfg::kSmemBytes, s>>>(tq, tdo, tk, tv, n_keep, keep_idx, lse, delta, dq_acc, (__nv_bfloat16*)dkc,
                                                   (__nv_bfloat16*)dvc, N, NKP, scale);
   if ((rc = check_launch("attn_bwd_sm100"))) return rc;
   const size_t n4 = n / 4;
@@ -390,20 +394,21 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
 
 size_t attn_bwd_sm100_workspace(int B, int N, int C) { return (size_t)B * N * C * sizeof(float); }
 
-int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-                          const float* lse, const float* delta, void* dq, void* dkc, void* dvc, void* workspace,
-                          size_t workspace_bytes, int B, int N, int NKP, int C, cudaStream_t s) {
+int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep,
+                          const int32_t* keep_idx, const void* d_o, const float* lse, const float* delta, void* dq,
+                          void* dkc, void* dvc, void* workspace, size_t workspace_bytes, int B, int N, int NKP, int C,
+                          cudaStream_t s) {
   MU_REQUIRE(workspace != nullptr && workspace_bytes >= attn_bwd_sm100_workspace(B, N, C), MU_ERR_WORKSPACE,
              "mu_attn_bwd: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
              attn_bwd_sm100_workspace(B, N, C));
   float* acc = (float*)workspace;
   switch (C) {
     case 64:
-      return run<64, 128, 64, 2>(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+      return run<64, 128, 64, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
     case 128:
-      return run<128, 64, 128, 2>(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+      return run<128, 64, 128, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
     case 256:
-      return run<256, 64, 128, 1>(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+      return run<256, 64, 128, 1>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
     default:
       set_error("attn_bwd_sm100: channels must be 64, 128 or 256 (got %d)", C);
       return MU_ERR_BAD_SHAPE;

@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(kThreadsA) attn_bwd_dq_simt_kernel(
 template <typename T, int D>
 __global__ void __launch_bounds__(kThreadsA) attn_bwd_dkv_simt_kernel(
     const T* __restrict__ q, const T* __restrict__ kc, const T* __restrict__ vc, const int32_t* __restrict__ n_keep,
-    const T* __restrict__ d_o, const float* __restrict__ lse, const float* __restrict__ delta, T* __restrict__ dkc,
-    T* __restrict__ dvc, int N, int NKP, float scale) {
+    const T* __restrict__ d_o, const float* __restrict__ lse, const float* __restrict__ delta,
+    const int32_t* __restrict__ keep_idx, T* __restrict__ dk, T* __restrict__ dv, int N, int NKP, float scale) {
   constexpr int KT = 32, LD = D + 1;
   extern __shared__ float sm[];
   float* Ks = sm;
@@ -245,12 +245,12 @@ __global__ void __launch_bounds__(kThreadsA) attn_bwd_dkv_simt_kernel(
       }
     }
   }
-  if (k0 + row < nk) {
-    const size_t off = ((size_t)b * NKP + k0 + row) * D;
+  if (k0 + row < nk) {  // scatter the key row back to its token position (dense [B, N, D] outputs)
+    const size_t off = ((size_t)b * N + keep_idx[(size_t)b * N + k0 + row]) * D;
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) {
-      st_f(dkc + off + sub + 8 * i, accK[i]);
-      st_f(dvc + off + sub + 8 * i, accV[i]);
+      st_f(dk + off + sub + 8 * i, accK[i]);
+      st_f(dv + off + sub + 8 * i, accV[i]);
     }
   }
 }
@@ -270,9 +270,11 @@ static int run_fwd(const void* q, const void* kc, const void* vc, const int32_t*
 }
 
 template <typename T, int D>
-static int run_bwd(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-                   const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int B, int N, int NKP,
-                   cudaStream_t s) {
+static int run_bwd(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const int32_t* keep_idx,
+                   const void* d_o, const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int B, int N,
+                   int NKP, cudaStream_t s) {
+  cudaMemsetAsync(dkc, 0, (size_t)B * N * D * sizeof(T), s);
+  cudaMemsetAsync(dvc, 0, (size_t)B * N * D * sizeof(T), s);
   const float scale = 1.f / sqrtf((float)D);
   {
     const size_t smem = sizeof(float) * (4 * 32 * (D + 1) + 32 * 33);
@@ -288,7 +290,7 @@ static int run_bwd(const void* q, const void* kc, const void* vc, const int32_t*
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((N + 31) / 32, B);
     kern<<<grid, kThreadsA, smem, s>>>((const T*)q, (const T*)kc, (const T*)vc, n_keep, (const T*)d_o, lse, delta,
-                                       (T*)dkc, (T*)dvc, N, NKP, scale);
+                                       keep_idx, (T*)dkc, (T*)dvc, N, NKP, scale);
   }
   return check_launch("attn_bwd_simt");
 }
@@ -307,13 +309,13 @@ int launch_attn_fwd_simt(const void* q, const void* kc, const void* vc, const in
   MU_DISPATCH_D(C, (run_fwd<__nv_bfloat16, D>(q, kc, vc, n_keep, o, lse, B, N, NKP, s)))
 }
 
-int launch_attn_bwd_simt(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-                         const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int B, int N, int NKP,
-                         int C, int dtype, cudaStream_t s) {
+int launch_attn_bwd_simt(const void* q, const void* kc, const void* vc, const int32_t* n_keep,
+                         const int32_t* keep_idx, const void* d_o, const float* lse, const float* delta, void* dq,
+                         void* dk, void* dv, int B, int N, int NKP, int C, int dtype, cudaStream_t s) {
   if (dtype == MU_F32) {
-    MU_DISPATCH_D(C, (run_bwd<float, D>(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, B, N, NKP, s)))
+    MU_DISPATCH_D(C, (run_bwd<float, D>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dk, dv, B, N, NKP, s)))
   }
-  MU_DISPATCH_D(C, (run_bwd<__nv_bfloat16, D>(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, B, N, NKP, s)))
+  MU_DISPATCH_D(C, (run_bwd<__nv_bfloat16, D>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dk, dv, B, N, NKP, s)))
 }
 
 }  // namespace mu

@@ -70,14 +70,22 @@ int mu_mask_binarize(const int64_t* bits, int32_t B, int32_t N, uint32_t* keep_b
   return launch_mask_binarize(bits, B, N, keep_bits, n_keep, keep_idx, keep_rank, (cudaStream_t)stream);
 }
 
-int mu_qkv_project(const void* x, const float* w_qkv, const float* b_qkv, const int32_t* keep_rank,
-                   const int32_t* n_keep, void* q, void* kc, void* vc, int32_t B, int32_t C, int32_t N, int32_t NKP,
-                   int32_t dtype, mu_stream_t stream) {
+int mu_qkv_project(const void* x, const float* w_qkv, const void* w_qkv_lp, const float* b_qkv,
+                   const int32_t* keep_rank, const int32_t* n_keep, void* q, void* kc, void* vc, int32_t B, int32_t C,
+                   int32_t N, int32_t NKP, int32_t dtype, int32_t x_layout, mu_stream_t stream) {
   int rc;
   if ((rc = check_common("mu_qkv_project", B, C, N, dtype))) return rc;
   if ((rc = check_nkp("mu_qkv_project", N, NKP))) return rc;
   MU_PTRS("mu_qkv_project", x, w_qkv, b_qkv, keep_rank, n_keep, q, kc, vc);
-  return launch_qkv_project(x, w_qkv, b_qkv, keep_rank, n_keep, q, kc, vc, B, C, N, NKP, dtype, (cudaStream_t)stream);
+  if (x_layout == MU_X_CHANNEL_MAJOR)
+    return launch_qkv_project(x, w_qkv, b_qkv, keep_rank, n_keep, q, kc, vc, B, C, N, NKP, dtype, (cudaStream_t)stream);
+  MU_REQUIRE(x_layout == MU_X_TOKEN_MAJOR && dtype == MU_BF16, MU_ERR_BAD_DTYPE,
+             "mu_qkv_project: token-major x is supported for MU_BF16 only (tcgen05 path)");
+  MU_PTRS("mu_qkv_project", w_qkv_lp);
+  MU_REQUIRE(device_cc_major() == 10, MU_ERR_ARCH, "mu_qkv_project: tcgen05 path needs an sm_100 device");
+  if ((rc = launch_qkv_project_sm100(x, w_qkv_lp, b_qkv, keep_rank, q, kc, vc, B, C, N, NKP, (cudaStream_t)stream)))
+    return rc;
+  return launch_zero_pad_rows(n_keep, kc, vc, B, C, NKP, dtype, (cudaStream_t)stream);
 }
 
 int mu_attn_fwd_cudacore(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse,
@@ -103,31 +111,34 @@ int mu_attn_fwd(const void* q, const void* kc, const void* vc, const int32_t* n_
 }
 
 int mu_residual_ln_fwd(const void* o, const void* x, const float* gamma, const float* beta, float eps, void* y,
-                       float* mean, float* rstd, int32_t B, int32_t C, int32_t N, int32_t dtype, mu_stream_t stream) {
+                       float* mean, float* rstd, int32_t B, int32_t C, int32_t N, int32_t dtype, int32_t x_layout,
+                       mu_stream_t stream) {
   int rc;
   if ((rc = check_common("mu_residual_ln_fwd", B, C, N, dtype))) return rc;
   MU_PTRS("mu_residual_ln_fwd", o, x, gamma, beta, y, mean, rstd);
-  return launch_residual_ln_fwd(o, x, gamma, beta, eps, y, mean, rstd, B, C, N, dtype, (cudaStream_t)stream);
+  return launch_residual_ln_fwd(o, x, gamma, beta, eps, y, mean, rstd, B, C, N, dtype, x_layout == MU_X_TOKEN_MAJOR,
+                                (cudaStream_t)stream);
 }
 
 int mu_residual_ln_bwd(const void* dy, const void* o, const void* x, const float* mean, const float* rstd,
                        const float* gamma, void* dz, float* delta, float* dgamma, float* dbeta, int32_t B, int32_t C,
-                       int32_t N, int32_t dtype, mu_stream_t stream) {
+                       int32_t N, int32_t dtype, int32_t x_layout, mu_stream_t stream) {
   int rc;
   if ((rc = check_common("mu_residual_ln_bwd", B, C, N, dtype))) return rc;
   MU_PTRS("mu_residual_ln_bwd", dy, o, x, mean, rstd, gamma, dz, delta, dgamma, dbeta);
   return launch_residual_ln_bwd(dy, o, x, mean, rstd, gamma, dz, delta, dgamma, dbeta, B, C, N, dtype,
-                                (cudaStream_t)stream);
+                                x_layout == MU_X_TOKEN_MAJOR, (cudaStream_t)stream);
 }
 
-int mu_attn_bwd_cudacore(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-                         const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int32_t B, int32_t N,
-                         int32_t NKP, int32_t C, int32_t dtype, mu_stream_t stream) {
+int mu_attn_bwd_cudacore(const void* q, const void* kc, const void* vc, const int32_t* n_keep,
+                         const int32_t* keep_idx, const void* d_o, const float* lse, const float* delta, void* dq,
+                         void* dk, void* dv, int32_t B, int32_t N, int32_t NKP, int32_t C, int32_t dtype,
+                         mu_stream_t stream) {
   int rc;
   if ((rc = check_common("mu_attn_bwd", B, C, N, dtype))) return rc;
   if ((rc = check_nkp("mu_attn_bwd", N, NKP))) return rc;
-  MU_PTRS("mu_attn_bwd", q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc);
-  return launch_attn_bwd_simt(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, B, N, NKP, C, dtype,
+  MU_PTRS("mu_attn_bwd", q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dk, dv);
+  return launch_attn_bwd_simt(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dk, dv, B, N, NKP, C, dtype,
                               (cudaStream_t)stream);
 }
 
@@ -135,32 +146,45 @@ size_t mu_attn_bwd_workspace_bytes(int32_t B, int32_t N, int32_t C, int32_t dtyp
   return dtype == MU_BF16 ? attn_bwd_sm100_workspace(B, N, C) : 0;
 }
 
-int mu_attn_bwd(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-                const float* lse, const float* delta, void* dq, void* dkc, void* dvc, void* workspace,
+int mu_attn_bwd(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const int32_t* keep_idx,
+                const void* d_o, const float* lse, const float* delta, void* dq, void* dkc, void* dvc, void* workspace,
                 size_t workspace_bytes, int32_t B, int32_t N, int32_t NKP, int32_t C, int32_t dtype,
                 mu_stream_t stream) {
   if (dtype != MU_BF16)
-    return mu_attn_bwd_cudacore(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, B, N, NKP, C, dtype, stream);
+    return mu_attn_bwd_cudacore(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, B, N, NKP, C, dtype,
+                                stream);
   int rc;
   if ((rc = check_common("mu_attn_bwd", B, C, N, dtype))) return rc;
   if ((rc = check_nkp("mu_attn_bwd", N, NKP))) return rc;
-  MU_PTRS("mu_attn_bwd", q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc);
+  MU_PTRS("mu_attn_bwd", q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc);
   MU_REQUIRE(device_cc_major() == 10, MU_ERR_ARCH,
              "mu_attn_bwd: the bf16 path is tcgen05-only and needs an sm_100 device (found cc major %d)",
              device_cc_major());
-  return launch_attn_bwd_sm100(q, kc, vc, n_keep, d_o, lse, delta, dq, dkc, dvc, workspace, workspace_bytes, B, N, NKP,
-                               C, (cudaStream_t)stream);
+  return launch_attn_bwd_sm100(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, workspace, workspace_bytes,
+                               B, N, NKP, C, (cudaStream_t)stream);
 }
 
-int mu_qkv_project_bwd(const void* x, const void* dz, const void* dq, const void* dkc, const void* dvc,
-                       const int32_t* keep_rank, const float* w_qkv, void* dx, float* dw_qkv, float* db_qkv,
-                       int32_t B, int32_t C, int32_t N, int32_t NKP, int32_t dtype, mu_stream_t stream) {
+int mu_qkv_project_bwd(const void* x, const void* dz, const void* dq, const void* dk, const void* dv,
+                       const float* w_qkv, const void* w_qkv_lp, void* dx, float* dw_qkv, float* db_qkv, int32_t B,
+                       int32_t C, int32_t N, int32_t dtype, int32_t x_layout, mu_stream_t stream) {
   int rc;
   if ((rc = check_common("mu_qkv_project_bwd", B, C, N, dtype))) return rc;
-  if ((rc = check_nkp("mu_qkv_project_bwd", N, NKP))) return rc;
-  MU_PTRS("mu_qkv_project_bwd", x, dz, dq, dkc, dvc, keep_rank, w_qkv, dx, dw_qkv, db_qkv);
-  return launch_qkv_project_bwd(x, dz, dq, dkc, dvc, keep_rank, w_qkv, dx, dw_qkv, db_qkv, B, C, N, NKP, dtype,
-                                (cudaStream_t)stream);
+  MU_PTRS("mu_qkv_project_bwd", x, dz, dq, dk, dv, w_qkv, dx, dw_qkv, db_qkv);
+  if (x_layout == MU_X_CHANNEL_MAJOR)
+    return launch_qkv_project_bwd(x, dz, dq, dk, dv, nullptr, w_qkv, dx, dw_qkv, db_qkv, B, C, N, 0, dtype,
+                                  (cudaStream_t)stream);
+  MU_REQUIRE(x_layout == MU_X_TOKEN_MAJOR && dtype == MU_BF16, MU_ERR_BAD_DTYPE,
+             "mu_qkv_project_bwd: token-major x is supported for MU_BF16 only (tcgen05 path)");
+  MU_PTRS("mu_qkv_project_bwd", w_qkv_lp);
+  MU_REQUIRE(device_cc_major() == 10, MU_ERR_ARCH, "mu_qkv_project_bwd: tcgen05 path needs an sm_100 device");
+  return launch_qkv_project_bwd_sm100(x, dz, dq, dk, dv, w_qkv_lp, dx, dw_qkv, db_qkv, B, C, N, (cudaStream_t)stream);
+}
+
+int mu_transpose(const void* in, void* out, int32_t batch, int32_t rows, int32_t cols, int32_t elem_bytes,
+                 mu_stream_t stream) {
+  MU_REQUIRE(batch > 0 && rows > 0 && cols > 0, MU_ERR_BAD_SHAPE, "mu_transpose: bad shape");
+  MU_PTRS("mu_transpose", in, out);
+  return launch_transpose(in, out, batch, rows, cols, elem_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -51,23 +51,31 @@ int launch_qkv_project(const void* x, const float* w, const float* b, const int3
                        void* q, void* kc, void* vc, int B, int C, int N, int NKP, int dtype, cudaStream_t s);
 int launch_attn_fwd_simt(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse,
                          int B, int N, int NKP, int C, int dtype, cudaStream_t s);
-int launch_attn_bwd_simt(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-                         const float* lse, const float* delta, void* dq, void* dkc, void* dvc, int B, int N, int NKP,
-                         int C, int dtype, cudaStream_t s);
+int launch_attn_bwd_simt(const void* q, const void* kc, const void* vc, const int32_t* n_keep,
+                         const int32_t* keep_idx, const void* d_o, const float* lse, const float* delta, void* dq,
+                         void* dk, void* dv, int B, int N, int NKP, int C, int dtype, cudaStream_t s);
 int launch_residual_ln_fwd(const void* o, const void* x, const float* gamma, const float* beta, float eps, void* y,
-                           float* mean, float* rstd, int B, int C, int N, int dtype, cudaStream_t s);
+                           float* mean, float* rstd, int B, int C, int N, int dtype, int tok, cudaStream_t s);
 int launch_residual_ln_bwd(const void* dy, const void* o, const void* x, const float* mean, const float* rstd,
                            const float* gamma, void* dz, float* delta, float* dgamma, float* dbeta, int B, int C, int N,
-                           int dtype, cudaStream_t s);
+                           int dtype, int tok, cudaStream_t s);
 int launch_qkv_project_bwd(const void* x, const void* dz, const void* dq, const void* dkc, const void* dvc,
                            const int32_t* rank, const float* w, void* dx, float* dw, float* db, int B, int C, int N,
                            int NKP, int dtype, cudaStream_t s);
 // tcgen05 path (bf16 only)
 int launch_attn_fwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse,
                           int B, int N, int NKP, int C, cudaStream_t s);
-int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const void* d_o,
-                          const float* lse, const float* delta, void* dq, void* dkc, void* dvc, void* workspace,
-                          size_t workspace_bytes, int B, int N, int NKP, int C, cudaStream_t s);
+int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep,
+                          const int32_t* keep_idx, const void* d_o, const float* lse, const float* delta, void* dq,
+                          void* dk, void* dv, void* workspace, size_t workspace_bytes, int B, int N, int NKP, int C,
+                          cudaStream_t s);
 size_t attn_bwd_sm100_workspace(int B, int N, int C);
+int launch_qkv_project_sm100(const void* xt, const void* w_bf16, const float* bias, const int32_t* rank, void* q,
+                             void* kc, void* vc, int B, int C, int N, int NKP, cudaStream_t s);
+int launch_qkv_project_bwd_sm100(const void* xt, const void* dz, const void* dq, const void* dk, const void* dv,
+                                 const void* w_bf16, void* dxt, float* dw, float* db, int B, int C, int N,
+                                 cudaStream_t s);
+int launch_zero_pad_rows(const int32_t* n_keep, void* kc, void* vc, int B, int C, int NKP, int dtype, cudaStream_t s);
+int launch_transpose(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t s);
 
 }  // namespace mu

@@ -100,6 +100,12 @@ static int run_fwd(const void* x, const float* w, const float* b, const int32_t*
   return check_launch("qkv_project");
 }
 
+int launch_zero_pad_rows(const int32_t* n_keep, void* kc, void* vc, int B, int C, int NKP, int dtype, cudaStream_t s) {
+  if (dtype == MU_F32) zero_pad_rows_kernel<float><<<B, 256, 0, s>>>(n_keep, (float*)kc, (float*)vc, C, NKP);
+  else zero_pad_rows_kernel<__nv_bfloat16><<<B, 256, 0, s>>>(n_keep, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, C, NKP);
+  return check_launch("zero_pad_rows");
+}
+
 int launch_qkv_project(const void* x, const float* w, const float* b, const int32_t* rank, const int32_t* n_keep,
                        void* q, void* kc, void* vc, int B, int C, int N, int NKP, int dtype, cudaStream_t s) {
   if (dtype == MU_F32) return run_fwd<float>(x, w, b, rank, n_keep, q, kc, vc, B, C, N, NKP, s);
@@ -107,15 +113,15 @@ int launch_qkv_project(const void* x, const float* w, const float* b, const int3
 }
 
 // ------------------------------------------------------------------ backward: dx
-// A[t, o] for o in [0, 3C): dq | gathered dkc | gathered dvc   (zero where the key was masked)
+// A[t, o] for o in [0, 3C): dq | dk | dv, all in token space (dk / dv rows of masked keys are zero)
 template <typename T>
-__device__ __forceinline__ float load_dqkv(const T* dq, const T* dkc, const T* dvc, const int32_t* rank, int b, int n,
+__device__ __forceinline__ float load_dqkv(const T* dq, const T* dk, const T* dv, const int32_t* rank, int b, int n,
                                            int o, int C, int N, int NKP) {
-  if (o < C) return ld_f(dq + ((size_t)b * N + n) * C + o);
-  const int r = rank[(size_t)b * N + n];
-  if (r < 0) return 0.f;
-  if (o < 2 * C) return ld_f(dkc + ((size_t)b * NKP + r) * C + (o - C));
-  return ld_f(dvc + ((size_t)b * NKP + r) * C + (o - 2 * C));
+  // dq, dk, dv are all dense [B, N, C]; rows of masked keys are zero in dk / dv
+  const size_t row = ((size_t)b * N + n) * C;
+  if (o < C) return ld_f(dq + row + o);
+  if (o < 2 * C) return ld_f(dk + row + (o - C));
+  return ld_f(dv + row + (o - 2 * C));
 }
 
 // dx[b, i, n] = dz[b, n, i] + sum_o A[(b,n), o] * W[o, i]       grid (ceil(N/64), C/64, B)

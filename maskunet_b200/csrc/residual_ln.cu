@@ -21,7 +21,8 @@ __device__ __forceinline__ void load_x_tile(float* xs /*[C][33]*/, const T* xb, 
   }
 }
 
-template <typename T>
+// TOK = true: x is token-major [B, N, C] (NHWC activations), no transposed staging needed
+template <typename T, bool TOK>
 __global__ void __launch_bounds__(kLnThreads) residual_ln_fwd_kernel(const T* __restrict__ o, const T* __restrict__ x,
                                                                      const float* __restrict__ gamma,
                                                                      const float* __restrict__ beta, float eps,
@@ -30,20 +31,23 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_fwd_kernel(const T* __
   extern __shared__ float xs[];
   const int b = blockIdx.y, n0 = blockIdx.x * kLnTokens;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  load_x_tile(xs, x + (size_t)b * C * N, C, N, n0);
-  __syncthreads();
+  if (!TOK) {
+    load_x_tile(xs, x + (size_t)b * C * N, C, N, n0);
+    __syncthreads();
+  }
   const int per = C / 32;
   for (int t = warp; t < kLnTokens; t += kLnThreads / 32) {
     const int n = n0 + t;
     if (n >= N) break;
     const T* orow = o + ((size_t)b * N + n) * C;
+    const T* xrow = x + ((size_t)b * N + n) * C;
     float z[kMaxCPerLane];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxCPerLane; ++i) {
       if (i < per) {
         const int c = lane + 32 * i;
-        z[i] = ld_f(orow + c) + xs[c * 33 + t];
+        z[i] = ld_f(orow + c) + (TOK ? ld_f(xrow + c) : xs[c * 33 + t]);
         s += z[i];
       }
     }
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_fwd_kernel(const T* __
   }
 }
 
-template <typename T>
+template <typename T, bool TOK>
 __global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_kernel(
     const T* __restrict__ dy, const T* __restrict__ o, const T* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dz, float* __restrict__ delta,
@@ -78,8 +82,10 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_kernel(
   extern __shared__ float xs[];  // [C][33] x tile, then reused for the dgamma/dbeta block reduction
   const int b = blockIdx.y, n0 = blockIdx.x * kLnTokens;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  load_x_tile(xs, x + (size_t)b * C * N, C, N, n0);
-  __syncthreads();
+  if (!TOK) {
+    load_x_tile(xs, x + (size_t)b * C * N, C, N, n0);
+    __syncthreads();
+  }
   const int per = C / 32;
   float dg[kMaxCPerLane] = {}, dbt[kMaxCPerLane] = {};
   for (int t = warp; t < kLnTokens; t += kLnThreads / 32) {
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_kernel(
       if (i < per) {
         const int c = lane + 32 * i;
         ov[i] = ld_f(o + row + c);
-        zh[i] = (ov[i] + xs[c * 33 + t] - mu_) * rs;
+        zh[i] = (ov[i] + (TOK ? ld_f(x + row + c) : xs[c * 33 + t]) - mu_) * rs;
         const float d = ld_f(dy + row + c);
         g[i] = d * gamma[c];
         dg[i] += d * zh[i];
@@ -144,32 +150,40 @@ static size_t ln_smem(int C) { return sizeof(float) * (size_t)C * 33; }  // >= 1
 
 template <typename T>
 static int run_fwd(const void* o, const void* x, const float* gamma, const float* beta, float eps, void* y,
-                   float* mean, float* rstd, int B, int C, int N, cudaStream_t s) {
+                   float* mean, float* rstd, int B, int C, int N, int tok, cudaStream_t s) {
   dim3 grid((N + kLnTokens - 1) / kLnTokens, B);
-  residual_ln_fwd_kernel<T><<<grid, kLnThreads, ln_smem(C), s>>>((const T*)o, (const T*)x, gamma, beta, eps, (T*)y,
-                                                                mean, rstd, C, N);
+  if (tok)
+    residual_ln_fwd_kernel<T, true><<<grid, kLnThreads, ln_smem(C), s>>>((const T*)o, (const T*)x, gamma, beta, eps,
+                                                                        (T*)y, mean, rstd, C, N);
+  else
+    residual_ln_fwd_kernel<T, false><<<grid, kLnThreads, ln_smem(C), s>>>((const T*)o, (const T*)x, gamma, beta, eps,
+                                                                         (T*)y, mean, rstd, C, N);
   return check_launch("residual_ln_fwd");
 }
 template <typename T>
 static int run_bwd(const void* dy, const void* o, const void* x, const float* mean, const float* rstd,
                    const float* gamma, void* dz, float* delta, float* dgamma, float* dbeta, int B, int C, int N,
-                   cudaStream_t s) {
+                   int tok, cudaStream_t s) {
   dim3 grid((N + kLnTokens - 1) / kLnTokens, B);
-  residual_ln_bwd_kernel<T><<<grid, kLnThreads, ln_smem(C), s>>>((const T*)dy, (const T*)o, (const T*)x, mean, rstd,
-                                                                gamma, (T*)dz, delta, dgamma, dbeta, C, N);
+  if (tok)
+    residual_ln_bwd_kernel<T, true><<<grid, kLnThreads, ln_smem(C), s>>>(
+        (const T*)dy, (const T*)o, (const T*)x, mean, rstd, gamma, (T*)dz, delta, dgamma, dbeta, C, N);
+  else
+    residual_ln_bwd_kernel<T, false><<<grid, kLnThreads, ln_smem(C), s>>>(
+        (const T*)dy, (const T*)o, (const T*)x, mean, rstd, gamma, (T*)dz, delta, dgamma, dbeta, C, N);
   return check_launch("residual_ln_bwd");
 }
 
 int launch_residual_ln_fwd(const void* o, const void* x, const float* gamma, const float* beta, float eps, void* y,
-                           float* mean, float* rstd, int B, int C, int N, int dtype, cudaStream_t s) {
-  if (dtype == MU_F32) return run_fwd<float>(o, x, gamma, beta, eps, y, mean, rstd, B, C, N, s);
-  return run_fwd<__nv_bfloat16>(o, x, gamma, beta, eps, y, mean, rstd, B, C, N, s);
+                           float* mean, float* rstd, int B, int C, int N, int dtype, int tok, cudaStream_t s) {
+  if (dtype == MU_F32) return run_fwd<float>(o, x, gamma, beta, eps, y, mean, rstd, B, C, N, tok, s);
+  return run_fwd<__nv_bfloat16>(o, x, gamma, beta, eps, y, mean, rstd, B, C, N, tok, s);
 }
 int launch_residual_ln_bwd(const void* dy, const void* o, const void* x, const float* mean, const float* rstd,
                            const float* gamma, void* dz, float* delta, float* dgamma, float* dbeta, int B, int C, int N,
-                           int dtype, cudaStream_t s) {
-  if (dtype == MU_F32) return run_bwd<float>(dy, o, x, mean, rstd, gamma, dz, delta, dgamma, dbeta, B, C, N, s);
-  return run_bwd<__nv_bfloat16>(dy, o, x, mean, rstd, gamma, dz, delta, dgamma, dbeta, B, C, N, s);
+                           int dtype, int tok, cudaStream_t s) {
+  if (dtype == MU_F32) return run_bwd<float>(dy, o, x, mean, rstd, gamma, dz, delta, dgamma, dbeta, B, C, N, tok, s);
+  return run_bwd<__nv_bfloat16>(dy, o, x, mean, rstd, gamma, dz, delta, dgamma, dbeta, B, C, N, tok, s);
 }
 
 }  // namespace mu

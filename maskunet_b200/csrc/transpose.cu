@@ -1,0 +1,43 @@
+// Batched 2-D transpose [batch][rows][cols] -> [batch][cols][rows] through a shared-memory tile.
+// This is the NCHW <-> NHWC bridge around the Mask Attention Module: the reference returns the [B, N, C]
+// result re-viewed as NCHW (/root/reference/code/ade20k/ade_semantic.py:190), while cuDNN's tensor-core
+// convolutions want channels-last; PyTorch's generic strided copy is uncoalesced on one side.
+// HBM-bound: one read + one write of the tensor, 64x64 tiles, both sides coalesced.
+#include "common.cuh"
+
+namespace mu {
+
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int rows,
+                                                        int cols) {
+  __shared__ T tile[64][64 + (4 / sizeof(T) > 0 ? 4 / sizeof(T) : 1)];
+  const size_t base = (size_t)blockIdx.z * rows * cols;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = r0 + ty + 4 * i, c = c0 + tx;
+    if (r < rows && c < cols) tile[ty + 4 * i][tx] = in[base + (size_t)r * cols + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = c0 + ty + 4 * i, r = r0 + tx;
+    if (r < rows && c < cols) out[base + (size_t)c * rows + r] = tile[tx][ty + 4 * i];
+  }
+}
+
+int launch_transpose(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t s) {
+  dim3 grid((cols + 63) / 64, (rows + 63) / 64, batch);
+  if (elem_bytes == 2)
+    transpose_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)in, (uint16_t*)out, rows, cols);
+  else if (elem_bytes == 4)
+    transpose_kernel<uint32_t><<<grid, 256, 0, s>>>((const uint32_t*)in, (uint32_t*)out, rows, cols);
+  else {
+    set_error("transpose: element size must be 2 or 4 bytes (got %d)", elem_bytes);
+    return MU_ERR_BAD_DTYPE;
+  }
+  return check_launch("transpose");
+}
+
+}  // namespace mu

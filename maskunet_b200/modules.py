@@ -86,16 +86,32 @@ class Mask2FormerAttention(nn.Module):
         if self.mask.size(0) != batch:
             raise RuntimeError(f"The size of tensor a ({batch}) must match the size of tensor b "
                                f"({self.mask.size(0)}) at non-singleton dimension 0 (cached mask batch)")
-        _, n_keep, _, keep_rank = self._compaction_for(self.mask)
+        _, n_keep, keep_idx, keep_rank = self._compaction_for(self.mask)
 
         dtype = self.compute_dtype or x.dtype
         if dtype not in (torch.float32, torch.bfloat16):
             dtype = torch.float32
-        tokens = x.contiguous().view(batch, channels, n_tok).to(dtype)
+        channels_last_in = x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
+        if dtype == torch.bfloat16:
+            # tensor-core path: token-major [B, N, C] activations.  Channels-last memory IS that layout (the
+            # reference's permuted view of :168); NCHW input goes through the coalesced transpose kernel.
+            token_major = True
+            if channels_last_in:
+                tokens = x.permute(0, 2, 3, 1).reshape(batch, n_tok, channels).to(dtype)
+            else:
+                tokens = ops.transpose(x.contiguous().view(batch, channels, n_tok).to(dtype))
+        else:
+            token_major = False
+            tokens = x.contiguous().view(batch, channels, n_tok).to(dtype)
         w_qkv = torch.cat([self.query.weight, self.key.weight, self.value.weight], dim=0).float()
         b_qkv = torch.cat([self.query.bias, self.key.bias, self.value.bias], dim=0).float()
         y = ops.mask_attention(tokens, w_qkv, b_qkv, self.norm.weight.float(), self.norm.bias.float(),
-                               keep_rank, n_keep, self.norm.eps)[0]
+                               keep_rank, keep_idx, n_keep, self.norm.eps, token_major)[0]
+        if channels_last_in:
+            # same logical result as :190 (the [B, N, C] buffer re-viewed as [B, C, H, W]), stored channels-last
+            # so the next convolution needs no layout conversion
+            y = ops.transpose(y.view(batch, channels, n_tok))
+            return y.view(batch, height, width, channels).permute(0, 3, 1, 2)
         return y.view(batch, channels, height, width)                               # :190
 
 
@@ -162,9 +178,11 @@ class UNet(nn.Module):
     """
 
     def __init__(self, c_in=3, c_out=3, embed_dim: Optional[int] = None, *,
-                 compute_dtype: torch.dtype = torch.float32, mask_mode: str = "cached"):
+                 compute_dtype: torch.dtype = torch.float32, mask_mode: str = "cached",
+                 channels_last: bool = False):
         super().__init__()
         akw = dict(mask_mode=mask_mode)
+        self.channels_last = channels_last
         self.initial_conv = ConvBlock(c_in, 64)
         self.downsample1 = DownSample(64, 128)
         self.self_attention1 = Mask2FormerAttention(128, 128, **akw)
@@ -215,6 +233,8 @@ class UNet(nn.Module):
         return semantic, boundary, embeddings
 
     def forward(self, x):
+        if self.channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
         if self.compute_dtype == torch.bfloat16:
             with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
                 return self._heads(self._trunk(x.to(torch.bfloat16)))

@@ -5,10 +5,11 @@ device pointers and the current CUDA stream to libmaskunet_b200.so and converts
 a non-zero status into RuntimeError(mu_last_error()).  CUDA tensors only.
 
 Layouts (B batch, C channels, N = H*W tokens, NKP = roundup(N, 128)):
-  x   [B, C, N]   NCHW activations flattened (token-contiguous)
-  q, o, y, dz     [B, N, C]
-  kc, vc          [B, NKP, C]  K / V rows of the kept keys only
-  w_qkv [3C, C], b_qkv [3C]    cat(query, key, value) parameters, fp32
+  x   [B, C, N]   channel-major (NCHW flattened)            -> CUDA-core projection / LN kernels
+      [B, N, C]   token-major (channels-last, bf16 only)    -> tcgen05 projection kernels
+  q, o, y, dz, dq, dk, dv   [B, N, C]
+  kc, vc                    [B, NKP, C]  K / V rows of the kept keys only
+  w_qkv [3C, C], b_qkv [3C]              cat(query, key, value) parameters, fp32
 """
 from __future__ import annotations
 
@@ -80,6 +81,13 @@ def nkp_of(n: int) -> int:
     return (n + 127) // 128 * 128
 
 
+def _bnc(x: Tensor, token_major: bool):
+    """(B, C, N) of an activation in either layout."""
+    if token_major:
+        return x.shape[0], x.shape[2], x.shape[1]
+    return x.shape[0], x.shape[1], x.shape[2]
+
+
 # ------------------------------------------------------------------ K2
 @torch.library.custom_op("maskunet::mask_binarize", mutates_args=(), device_types="cuda")
 def mask_binarize(bits: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
@@ -107,29 +115,31 @@ def _(bits):
             torch.empty((B, N), **i32), torch.empty((B, N), **i32))
 
 
-# ------------------------------------------------------------------ kernel-level ops
+# ------------------------------------------------------------------ K1
 @torch.library.custom_op("maskunet::qkv_project", mutates_args=(), device_types="cuda")
-def qkv_project(x: Tensor, w_qkv: Tensor, b_qkv: Tensor, keep_rank: Tensor, n_keep: Tensor
+def qkv_project(x: Tensor, w_qkv: Tensor, b_qkv: Tensor, keep_rank: Tensor, n_keep: Tensor, token_major: bool
                 ) -> Tuple[Tensor, Tensor, Tensor]:
     _cuda(x, w_qkv, b_qkv, keep_rank, n_keep)
-    B, C, N = x.shape
+    B, C, N = _bnc(x, token_major)
     NKP = nkp_of(N)
     q = torch.empty((B, N, C), dtype=x.dtype, device=x.device)
     kc = torch.empty((B, NKP, C), dtype=x.dtype, device=x.device)
     vc = torch.empty((B, NKP, C), dtype=x.dtype, device=x.device)
+    w_lp = w_qkv.to(torch.bfloat16) if token_major else w_qkv
     with torch.cuda.device(x.device):
         _count(2)
-        check(_L.mu_qkv_project(_p(x), _p(w_qkv), _p(b_qkv), _p(keep_rank), _p(n_keep), _p(q), _p(kc), _p(vc),
-                                B, C, N, NKP, _code(x), _stream(x)), "mu_qkv_project")
+        check(_L.mu_qkv_project(_p(x), _p(w_qkv), _p(w_lp), _p(b_qkv), _p(keep_rank), _p(n_keep), _p(q), _p(kc),
+                                _p(vc), B, C, N, NKP, _code(x), int(token_major), _stream(x)), "mu_qkv_project")
     return q, kc, vc
 
 
 @qkv_project.register_fake
-def _(x, w_qkv, b_qkv, keep_rank, n_keep):
-    B, C, N = x.shape
+def _(x, w_qkv, b_qkv, keep_rank, n_keep, token_major):
+    B, C, N = _bnc(x, token_major)
     return x.new_empty((B, N, C)), x.new_empty((B, nkp_of(N), C)), x.new_empty((B, nkp_of(N), C))
 
 
+# ------------------------------------------------------------------ K3
 def _attn_fwd_impl(fn, name, q, kc, vc, n_keep):
     _cuda(q, kc, vc, n_keep)
     B, N, C = q.shape
@@ -158,13 +168,14 @@ def attn_fwd_cudacore(q, kc, vc, n_keep):
     return _attn_fwd_impl(_L.mu_attn_fwd_cudacore, "mu_attn_fwd_cudacore", q, kc, vc, n_keep)
 
 
-def _attn_bwd_impl(tensor_core, q, kc, vc, n_keep, d_o, lse, delta):
-    _cuda(q, kc, vc, n_keep, d_o, lse, delta)
+# ------------------------------------------------------------------ K5
+def _attn_bwd_impl(tensor_core, q, kc, vc, n_keep, keep_idx, d_o, lse, delta):
+    _cuda(q, kc, vc, n_keep, keep_idx, d_o, lse, delta)
     B, N, C = q.shape
     NKP = kc.shape[1]
     dq = torch.empty_like(q)
-    dkc = torch.zeros_like(kc)
-    dvc = torch.zeros_like(vc)
+    dk = torch.empty_like(q)     # token space; the entry point clears dk / dv before scattering rows
+    dv = torch.empty_like(q)
     name = "mu_attn_bwd" if tensor_core else "mu_attn_bwd_cudacore"
     with torch.cuda.device(q.device):
         if tensor_core:
@@ -172,33 +183,38 @@ def _attn_bwd_impl(tensor_core, q, kc, vc, n_keep, d_o, lse, delta):
             ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=q.device)
             with _timed(name, (B, N, C)):
                 _count(3 if ws_bytes else 2)
-                check(_L.mu_attn_bwd(_p(q), _p(kc), _p(vc), _p(n_keep), _p(d_o), _p(lse), _p(delta), _p(dq), _p(dkc),
-                                     _p(dvc), _p(ws), ws_bytes, B, N, NKP, C, _code(q), _stream(q)), name)
+                check(_L.mu_attn_bwd(_p(q), _p(kc), _p(vc), _p(n_keep), _p(keep_idx), _p(d_o), _p(lse), _p(delta),
+                                     _p(dq), _p(dk), _p(dv), _p(ws), ws_bytes, B, N, NKP, C, _code(q), _stream(q)),
+                      name)
         else:
             with _timed(name, (B, N, C)):
                 _count(2)
-                check(_L.mu_attn_bwd_cudacore(_p(q), _p(kc), _p(vc), _p(n_keep), _p(d_o), _p(lse), _p(delta), _p(dq),
-                                              _p(dkc), _p(dvc), B, N, NKP, C, _code(q), _stream(q)), name)
-    return dq, dkc, dvc
+                check(_L.mu_attn_bwd_cudacore(_p(q), _p(kc), _p(vc), _p(n_keep), _p(keep_idx), _p(d_o), _p(lse),
+                                              _p(delta), _p(dq), _p(dk), _p(dv), B, N, NKP, C, _code(q), _stream(q)),
+                      name)
+    return dq, dk, dv
 
 
 @torch.library.custom_op("maskunet::attn_bwd", mutates_args=(), device_types="cuda")
-def attn_bwd(q: Tensor, kc: Tensor, vc: Tensor, n_keep: Tensor, d_o: Tensor, lse: Tensor, delta: Tensor
-             ) -> Tuple[Tensor, Tensor, Tensor]:
-    return _attn_bwd_impl(True, q, kc, vc, n_keep, d_o, lse, delta)
+def attn_bwd(q: Tensor, kc: Tensor, vc: Tensor, n_keep: Tensor, keep_idx: Tensor, d_o: Tensor, lse: Tensor,
+             delta: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """dq, dk, dv, all [B, N, C] in token space (rows of masked keys are zero)."""
+    return _attn_bwd_impl(True, q, kc, vc, n_keep, keep_idx, d_o, lse, delta)
 
 
 @attn_bwd.register_fake
-def _(q, kc, vc, n_keep, d_o, lse, delta):
-    return torch.empty_like(q), torch.empty_like(kc), torch.empty_like(vc)
+def _(q, kc, vc, n_keep, keep_idx, d_o, lse, delta):
+    return torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
 
 
-def attn_bwd_cudacore(q, kc, vc, n_keep, d_o, lse, delta):
-    return _attn_bwd_impl(False, q, kc, vc, n_keep, d_o, lse, delta)
+def attn_bwd_cudacore(q, kc, vc, n_keep, keep_idx, d_o, lse, delta):
+    return _attn_bwd_impl(False, q, kc, vc, n_keep, keep_idx, d_o, lse, delta)
 
 
+# ------------------------------------------------------------------ K3 epilogue / K4
 @torch.library.custom_op("maskunet::residual_ln_fwd", mutates_args=(), device_types="cuda")
-def residual_ln_fwd(o: Tensor, x: Tensor, gamma: Tensor, beta: Tensor, eps: float) -> Tuple[Tensor, Tensor, Tensor]:
+def residual_ln_fwd(o: Tensor, x: Tensor, gamma: Tensor, beta: Tensor, eps: float, token_major: bool
+                    ) -> Tuple[Tensor, Tensor, Tensor]:
     _cuda(o, x, gamma, beta)
     B, N, C = o.shape
     y = torch.empty_like(o)
@@ -207,18 +223,18 @@ def residual_ln_fwd(o: Tensor, x: Tensor, gamma: Tensor, beta: Tensor, eps: floa
     with torch.cuda.device(o.device):
         _count(1)
         check(_L.mu_residual_ln_fwd(_p(o), _p(x), _p(gamma), _p(beta), eps, _p(y), _p(mean), _p(rstd),
-                                    B, C, N, _code(o), _stream(o)), "mu_residual_ln_fwd")
+                                    B, C, N, _code(o), int(token_major), _stream(o)), "mu_residual_ln_fwd")
     return y, mean, rstd
 
 
 @residual_ln_fwd.register_fake
-def _(o, x, gamma, beta, eps):
+def _(o, x, gamma, beta, eps, token_major):
     s = o.new_empty(o.shape[:2], dtype=torch.float32)
     return torch.empty_like(o), s, torch.empty_like(s)
 
 
 @torch.library.custom_op("maskunet::residual_ln_bwd", mutates_args=(), device_types="cuda")
-def residual_ln_bwd(dy: Tensor, o: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor
+def residual_ln_bwd(dy: Tensor, o: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, token_major: bool
                     ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     _cuda(dy, o, x, mean, rstd, gamma)
     B, N, C = o.shape
@@ -229,53 +245,77 @@ def residual_ln_bwd(dy: Tensor, o: Tensor, x: Tensor, mean: Tensor, rstd: Tensor
     with torch.cuda.device(o.device):
         _count(1)
         check(_L.mu_residual_ln_bwd(_p(dy), _p(o), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dz), _p(delta),
-                                    _p(dgamma), _p(dbeta), B, C, N, _code(o), _stream(o)), "mu_residual_ln_bwd")
+                                    _p(dgamma), _p(dbeta), B, C, N, _code(o), int(token_major), _stream(o)),
+              "mu_residual_ln_bwd")
     return dz, delta, dgamma, dbeta
 
 
 @residual_ln_bwd.register_fake
-def _(dy, o, x, mean, rstd, gamma):
+def _(dy, o, x, mean, rstd, gamma, token_major):
     C = o.shape[-1]
     return (torch.empty_like(o), o.new_empty(o.shape[:2], dtype=torch.float32),
             o.new_empty((C,), dtype=torch.float32), o.new_empty((C,), dtype=torch.float32))
 
 
+# ------------------------------------------------------------------ K6
 @torch.library.custom_op("maskunet::qkv_project_bwd", mutates_args=(), device_types="cuda")
-def qkv_project_bwd(x: Tensor, dz: Tensor, dq: Tensor, dkc: Tensor, dvc: Tensor, keep_rank: Tensor, w_qkv: Tensor
+def qkv_project_bwd(x: Tensor, dz: Tensor, dq: Tensor, dk: Tensor, dv: Tensor, w_qkv: Tensor, token_major: bool
                     ) -> Tuple[Tensor, Tensor, Tensor]:
-    _cuda(x, dz, dq, dkc, dvc, keep_rank, w_qkv)
-    B, C, N = x.shape
-    NKP = dkc.shape[1]
+    _cuda(x, dz, dq, dk, dv, w_qkv)
+    B, C, N = _bnc(x, token_major)
     dx = torch.empty_like(x)
     dw = torch.zeros((3 * C, C), dtype=torch.float32, device=x.device)
     db = torch.zeros((3 * C,), dtype=torch.float32, device=x.device)
+    w_lp = w_qkv.to(torch.bfloat16) if token_major else w_qkv
     with torch.cuda.device(x.device):
-        _count(2)
-        check(_L.mu_qkv_project_bwd(_p(x), _p(dz), _p(dq), _p(dkc), _p(dvc), _p(keep_rank), _p(w_qkv), _p(dx),
-                                    _p(dw), _p(db), B, C, N, NKP, _code(x), _stream(x)), "mu_qkv_project_bwd")
+        _count(3 if token_major else 2)
+        check(_L.mu_qkv_project_bwd(_p(x), _p(dz), _p(dq), _p(dk), _p(dv), _p(w_qkv), _p(w_lp), _p(dx), _p(dw),
+                                    _p(db), B, C, N, _code(x), int(token_major), _stream(x)), "mu_qkv_project_bwd")
     return dx, dw, db
 
 
 @qkv_project_bwd.register_fake
-def _(x, dz, dq, dkc, dvc, keep_rank, w_qkv):
-    C = x.shape[1]
+def _(x, dz, dq, dk, dv, w_qkv, token_major):
+    C = w_qkv.shape[1]
     return torch.empty_like(x), x.new_empty((3 * C, C), dtype=torch.float32), x.new_empty((3 * C,), dtype=torch.float32)
+
+
+# ------------------------------------------------------------------ layout bridge
+@torch.library.custom_op("maskunet::transpose", mutates_args=(), device_types="cuda")
+def transpose(x: Tensor) -> Tensor:
+    """[batch, rows, cols] -> [batch, cols, rows] (2- or 4-byte elements), coalesced on both sides."""
+    _cuda(x)
+    Bt, R, Cc = x.shape
+    out = torch.empty((Bt, Cc, R), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        _count(1)
+        check(_L.mu_transpose(_p(x), _p(out), Bt, R, Cc, x.element_size(), _stream(x)), "mu_transpose")
+    return out
+
+
+@transpose.register_fake
+def _(x):
+    return x.new_empty((x.shape[0], x.shape[2], x.shape[1]))
+
+
+transpose.register_autograd(lambda ctx, g: transpose(g.contiguous()))
 
 
 # ------------------------------------------------------------------ the module-level op (A3-A9 of SURVEY.md 8(a))
 @torch.library.custom_op("maskunet::mask_attention", mutates_args=(), device_types="cuda")
 def mask_attention(x: Tensor, w_qkv: Tensor, b_qkv: Tensor, gamma: Tensor, beta: Tensor, keep_rank: Tensor,
-                   n_keep: Tensor, eps: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """y [B, N, C] = LN_C(softmax(QK^T/sqrt(C) + mask) V + x^T); also returns what backward needs."""
-    q, kc, vc = qkv_project(x, w_qkv, b_qkv, keep_rank, n_keep)
+                   keep_idx: Tensor, n_keep: Tensor, eps: float, token_major: bool
+                   ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """y [B, N, C] = LN_C(softmax(QK^T/sqrt(C) + mask) V + tokens); also returns what backward needs."""
+    q, kc, vc = qkv_project(x, w_qkv, b_qkv, keep_rank, n_keep, token_major)
     o, lse = attn_fwd(q, kc, vc, n_keep)
-    y, mean, rstd = residual_ln_fwd(o, x, gamma, beta, eps)
+    y, mean, rstd = residual_ln_fwd(o, x, gamma, beta, eps, token_major)
     return y, q, kc, vc, o, lse, mean, rstd
 
 
 @mask_attention.register_fake
-def _(x, w_qkv, b_qkv, gamma, beta, keep_rank, n_keep, eps):
-    B, C, N = x.shape
+def _(x, w_qkv, b_qkv, gamma, beta, keep_rank, keep_idx, n_keep, eps, token_major):
+    B, C, N = _bnc(x, token_major)
     f32 = dict(dtype=torch.float32)
     return (x.new_empty((B, N, C)), x.new_empty((B, N, C)), x.new_empty((B, nkp_of(N), C)),
             x.new_empty((B, nkp_of(N), C)), x.new_empty((B, N, C)), x.new_empty((B, N), **f32),
@@ -283,34 +323,35 @@ def _(x, w_qkv, b_qkv, gamma, beta, keep_rank, n_keep, eps):
 
 
 @torch.library.custom_op("maskunet::mask_attention_bwd", mutates_args=(), device_types="cuda")
-def mask_attention_bwd(dy: Tensor, x: Tensor, w_qkv: Tensor, gamma: Tensor, keep_rank: Tensor, n_keep: Tensor,
-                       q: Tensor, kc: Tensor, vc: Tensor, o: Tensor, lse: Tensor, mean: Tensor, rstd: Tensor
-                       ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
-    dz, delta, dgamma, dbeta = residual_ln_bwd(dy, o, x, mean, rstd, gamma)
-    dq, dkc, dvc = attn_bwd(q, kc, vc, n_keep, dz, lse, delta)
-    dx, dw, db = qkv_project_bwd(x, dz, dq, dkc, dvc, keep_rank, w_qkv)
+def mask_attention_bwd(dy: Tensor, x: Tensor, w_qkv: Tensor, gamma: Tensor, keep_idx: Tensor, n_keep: Tensor,
+                       q: Tensor, kc: Tensor, vc: Tensor, o: Tensor, lse: Tensor, mean: Tensor, rstd: Tensor,
+                       token_major: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    dz, delta, dgamma, dbeta = residual_ln_bwd(dy, o, x, mean, rstd, gamma, token_major)
+    dq, dk, dv = attn_bwd(q, kc, vc, n_keep, keep_idx, dz, lse, delta)
+    dx, dw, db = qkv_project_bwd(x, dz, dq, dk, dv, w_qkv, token_major)
     return dx, dw, db, dgamma, dbeta
 
 
 @mask_attention_bwd.register_fake
-def _(dy, x, w_qkv, gamma, keep_rank, n_keep, q, kc, vc, o, lse, mean, rstd):
-    C = x.shape[1]
+def _(dy, x, w_qkv, gamma, keep_idx, n_keep, q, kc, vc, o, lse, mean, rstd, token_major):
+    C = w_qkv.shape[1]
     f32 = dict(dtype=torch.float32)
     return (torch.empty_like(x), x.new_empty((3 * C, C), **f32), x.new_empty((3 * C,), **f32),
             x.new_empty((C,), **f32), x.new_empty((C,), **f32))
 
 
 def _ma_setup(ctx, inputs, output):
-    x, w_qkv, b_qkv, gamma, beta, keep_rank, n_keep, eps = inputs
+    x, w_qkv, b_qkv, gamma, beta, keep_rank, keep_idx, n_keep, eps, token_major = inputs
     y, q, kc, vc, o, lse, mean, rstd = output
-    ctx.save_for_backward(x, w_qkv, gamma, keep_rank, n_keep, q, kc, vc, o, lse, mean, rstd)
+    ctx.token_major = token_major
+    ctx.save_for_backward(x, w_qkv, gamma, keep_idx, n_keep, q, kc, vc, o, lse, mean, rstd)
 
 
 def _ma_backward(ctx, dy, *unused):
-    x, w_qkv, gamma, keep_rank, n_keep, q, kc, vc, o, lse, mean, rstd = ctx.saved_tensors
-    dx, dw, db, dgamma, dbeta = mask_attention_bwd(dy.contiguous(), x, w_qkv, gamma, keep_rank, n_keep,
-                                                   q, kc, vc, o, lse, mean, rstd)
-    return dx, dw, db, dgamma, dbeta, None, None, None
+    x, w_qkv, gamma, keep_idx, n_keep, q, kc, vc, o, lse, mean, rstd = ctx.saved_tensors
+    dx, dw, db, dgamma, dbeta = mask_attention_bwd(dy.contiguous(), x, w_qkv, gamma, keep_idx, n_keep,
+                                                   q, kc, vc, o, lse, mean, rstd, ctx.token_major)
+    return dx, dw, db, dgamma, dbeta, None, None, None, None, None
 
 
 mask_attention.register_autograd(_ma_backward, setup_context=_ma_setup)

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 def test_ops_are_registered_and_refuse_cpu_tensors():
     import maskunet_b200  # noqa: F401
     for name in ("mask_binarize", "attn_fwd", "attn_bwd", "mask_attention", "mask_attention_bwd", "qkv_project",
-                 "residual_ln_fwd", "residual_ln_bwd", "qkv_project_bwd"):
+                 "residual_ln_fwd", "residual_ln_bwd", "qkv_project_bwd", "transpose"):
         assert hasattr(torch.ops.maskunet, name)
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.maskunet.mask_binarize(torch.zeros(1, 8, dtype=torch.int64))
@@ -35,13 +35,13 @@ def test_fake_tensor_shapes():
     import maskunet_b200  # noqa: F401
     from torch._subclasses.fake_tensor import FakeTensorMode
     with FakeTensorMode():
-        x = torch.empty(2, 64, 400, device="cuda", dtype=torch.bfloat16)
+        x = torch.empty(2, 400, 64, device="cuda", dtype=torch.bfloat16)   # token-major
         w = torch.empty(192, 64, device="cuda")
         b = torch.empty(192, device="cuda")
         g = torch.empty(64, device="cuda")
         rank = torch.empty(2, 400, dtype=torch.int32, device="cuda")
         nk = torch.empty(2, dtype=torch.int32, device="cuda")
-        outs = torch.ops.maskunet.mask_attention(x, w, b, g, g, rank, nk, 1e-5)
+        outs = torch.ops.maskunet.mask_attention(x, w, b, g, g, rank, rank, nk, 1e-5, True)
         assert outs[0].shape == (2, 400, 64) and outs[2].shape == (2, 512, 64) and outs[5].dtype == torch.float32
 
 

@@ -73,6 +73,7 @@ def main():
     ap.add_argument("--bwd", action="store_true")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--site", type=int, default=None, help="run only this entry of the site list (for ncu)")
     args = ap.parse_args()
     peak = 1601.0
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -80,6 +81,8 @@ def main():
         peak = json.load(open(pk))["bf16_tflops"]
     recs = []
     sites = [(16384, 64), (4096, 64), (4096, 128), (1024, 128), (1024, 256), (256, 256)]
+    if args.site is not None:
+        sites = [sites[args.site]]
     for N, C in sites:
         B = args.batch if N >= 4096 else args.batch * 8
         recs.append(run(B, N, C, args.bwd, peak))
