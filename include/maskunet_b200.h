@@ -132,6 +132,24 @@ int mu_qkv_project_bwd(const void* x, const void* dz, const void* dq, const void
 int mu_transpose(const void* in, void* out, int32_t batch, int32_t rows, int32_t cols, int32_t elem_bytes,
                  mu_stream_t stream);
 
+/* K8. Training-mode BatchNorm2d fused with activation and residual on channels-last activations
+ * (ConvBlock :198-210, trailing BN :219 / :240, head BN + ReLU :283-287).  x, r, y are [M = B*H*W, C] rows (NHWC).
+ *   y = act(gamma * (x - mean) * rstd + beta [+ r]),  act: 0 none, 1 GELU (erf), 2 ReLU;  r may be NULL
+ *   mean, rstd, a = gamma*rstd, b = beta - mean*a: f32 [C] outputs (saved for backward)
+ *   running_mean / running_var (f32 [C], may be NULL) updated in place with `momentum`, unbiased variance
+ *   sums: f32 [2C] scratch.  Any C with C / vec <= 256 where vec = 8 (C % 8 == 0), 2 (C even) or 1. */
+int mu_bn_act_fwd(const void* x, const void* r, const float* gamma, const float* beta, float* running_mean,
+                  float* running_var, float momentum, float eps, void* y, float* mean, float* rstd, float* a,
+                  float* b, float* sums, int64_t M, int32_t C, int32_t act, int32_t dtype, mu_stream_t stream);
+/* Inference-mode / precomputed-affine variant: y = act(a * x + b [+ r]). */
+int mu_bn_act_apply(const void* x, const void* r, const float* a, const float* b, void* y, int64_t M, int32_t C,
+                    int32_t act, int32_t dtype, mu_stream_t stream);
+/* Backward of mu_bn_act_fwd.  sums f32 [2C] receives (dbeta, dgamma) = (sum dz, sum dz * xhat);
+ * dx [M, C]; dr [M, C] = dz when r was given (else NULL). */
+int mu_bn_act_bwd(const void* dy, const void* x, const void* r, const float* a, const float* b, const float* mean,
+                  const float* rstd, float* sums, void* dx, void* dr, int64_t M, int32_t C, int32_t act,
+                  int32_t dtype, mu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,367 @@
+// K8: training-mode BatchNorm2d fused with its activation and residual, channels-last activations.
+// Replaces the nn.BatchNorm2d -> nn.GELU / F.gelu(x + .) / nn.ReLU chains of the reference's DoubleConv blocks,
+// /root/reference/code/ade20k/ade_semantic.py:198-210 (ConvBlock), :219, :240 (trailing BN of Down/UpSample) and
+// :283-287 (head BN + ReLU), and their autograd.  Activations are [M = B*H*W rows][C channels] (NHWC memory).
+//
+//   forward   stats   : per-channel sum / sum of squares              (1 read of x)
+//             finalize: mean, rstd, running-stat update, a = gamma*rstd, b = beta - mean*a     ([C] work)
+//             apply   : y = act(a*x + b [+ r])                         (1 read of x [+ r], 1 write)
+//   backward  reduce  : dz = dy*act'(z);  S1 = sum dz, S2 = sum dz*xhat (reads dy, x [, r])
+//             apply   : dx = gamma*rstd*(dz - S1/M - xhat*S2/M), dr = dz   (reads dy, x [, r]; writes dx [, dr])
+// All HBM-bound: thread <-> fixed channel group (16-byte vectors when C % 8 == 0), rows strided over the grid,
+// per-thread fp32 partial sums, shared-memory reduction across row lanes, one atomicAdd per channel per CTA.
+#include "common.cuh"
+
+namespace mu {
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+constexpr int kBnThreads = 256;
+
+__device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.f + erff(z * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float z) {
+  const float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
+  return cdf + z * pdf;
+}
+template <int ACT> __device__ __forceinline__ float act_f(float z) {
+  if (ACT == ACT_GELU) return gelu_f(z);
+  if (ACT == ACT_RELU) return fmaxf(z, 0.f);
+  return z;
+}
+template <int ACT> __device__ __forceinline__ float act_grad_f(float z) {
+  if (ACT == ACT_GELU) return gelu_grad_f(z);
+  if (ACT == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+// ---- VEC-wide loads / stores with conversion -------------------------------------------------------
+template <typename T, int VEC> struct Vec;
+template <> struct Vec<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] = __uint_as_float(w[e] << 16);
+      v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(v[0], v[1]); u.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[2], v[3]); u.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[4], v[5]); u.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[6], v[7]); u.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <> struct Vec<float, 8> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <typename T> struct Vec<T, 2> {
+  static __device__ __forceinline__ void load(const T* p, float (&v)[2]) { v[0] = ld_f(p); v[1] = ld_f(p + 1); }
+  static __device__ __forceinline__ void store(T* p, const float (&v)[2]) { st_f(p, v[0]); st_f(p + 1, v[1]); }
+};
+template <typename T> struct Vec<T, 1> {
+  static __device__ __forceinline__ void load(const T* p, float (&v)[1]) { v[0] = ld_f(p); }
+  static __device__ __forceinline__ void store(T* p, const float (&v)[1]) { st_f(p, v[0]); }
+};
+
+// thread -> (channel group g, row lane rl); rows handled: rl + RL*(blockIdx.x + k*gridDim.x)
+struct RowMap {
+  int g, rl, G, RL;
+  bool active;
+  __device__ RowMap(int C, int VEC) {
+    G = C / VEC;
+    RL = kBnThreads / G;
+    g = threadIdx.x % G;
+    rl = threadIdx.x / G;
+    active = rl < RL;
+  }
+};
+
+// block reduction of per-thread [VEC] partials over row lanes, then one atomicAdd per channel
+template <int VEC>
+__device__ __forceinline__ void block_reduce_add(float* red /*[kBnThreads*VEC]*/, const float (&a)[VEC], const RowMap& m,
+                                                 float* out, int C) {
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) red[threadIdx.x * VEC + e] = m.active ? a[e] : 0.f;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kBnThreads) {
+    const int g = c / VEC, e = c - g * VEC;
+    float s = 0.f;
+    for (int rl = 0; rl < m.RL; ++rl) s += red[(rl * m.G + g) * VEC + e];
+    atomicAdd(out + c, s);
+  }
+}
+
+// ------------------------------------------------------------------ forward: statistics
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restrict__ x, float* __restrict__ sums, long M,
+                                                              int C) {
+  __shared__ float red[kBnThreads * VEC];
+  const RowMap m(C, VEC);
+  float s1[VEC], s2[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) s1[e] = s2[e] = 0.f;
+  if (m.active) {
+    for (long r = (long)blockIdx.x * m.RL + m.rl; r < M; r += (long)gridDim.x * m.RL) {
+      float v[VEC];
+      Vec<T, VEC>::load(x + r * C + m.g * VEC, v);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        s1[e] += v[e];
+        s2[e] = fmaf(v[e], v[e], s2[e]);
+      }
+    }
+  }
+  block_reduce_add<VEC>(red, s1, m, sums, C);
+  block_reduce_add<VEC>(red, s2, m, sums + C, C);
+}
+
+// ------------------------------------------------------------------ forward: finalize ([C] work, one CTA)
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long M, int C, float momentum, float eps,
+                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ a,
+                                   float* __restrict__ b) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    const double mu_ = (double)sums[c] / (double)M;
+    double var = (double)sums[C + c] / (double)M - mu_ * mu_;
+    if (var < 0.0) var = 0.0;
+    const float rs = (float)(1.0 / sqrt(var + (double)eps));
+    mean[c] = (float)mu_;
+    rstd[c] = rs;
+    const float ac = gamma[c] * rs;
+    a[c] = ac;
+    b[c] = beta[c] - (float)mu_ * ac;
+    if (running_mean != nullptr) {   // nn.BatchNorm2d: running = (1 - m) * running + m * batch (unbiased variance)
+      const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu_;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ forward: apply
+template <typename T, int VEC, int ACT, bool RES>
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ r,
+                                                              const float* __restrict__ a, const float* __restrict__ b,
+                                                              T* __restrict__ y, long M, int C) {
+  const RowMap m(C, VEC);
+  if (!m.active) return;
+  float av[VEC], bv[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    av[e] = a[m.g * VEC + e];
+    bv[e] = b[m.g * VEC + e];
+  }
+  for (long row = (long)blockIdx.x * m.RL + m.rl; row < M; row += (long)gridDim.x * m.RL) {
+    const long off = row * C + m.g * VEC;
+    float v[VEC], rv[VEC];
+    Vec<T, VEC>::load(x + off, v);
+    if (RES) Vec<T, VEC>::load(r + off, rv);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float z = fmaf(av[e], v[e], bv[e]);
+      if (RES) z += rv[e];
+      v[e] = act_f<ACT>(z);
+    }
+    Vec<T, VEC>::store(y + off, v);
+  }
+}
+
+// ------------------------------------------------------------------ backward: reduce
+template <typename T, int VEC, int ACT, bool RES>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
+    const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ a,
+    const float* __restrict__ b, const float* __restrict__ mean, const float* __restrict__ rstd,
+    float* __restrict__ sums, long M, int C) {
+  __shared__ float red[kBnThreads * VEC];
+  const RowMap m(C, VEC);
+  float s1[VEC], s2[VEC], av[VEC], bv[VEC], mv[VEC], rsv[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    s1[e] = s2[e] = 0.f;
+    const int c = m.active ? m.g * VEC + e : 0;
+    av[e] = a[c]; bv[e] = b[c]; mv[e] = mean[c]; rsv[e] = rstd[c];
+  }
+  if (m.active) {
+    for (long row = (long)blockIdx.x * m.RL + m.rl; row < M; row += (long)gridDim.x * m.RL) {
+      const long off = row * C + m.g * VEC;
+      float g[VEC], v[VEC], rv[VEC];
+      Vec<T, VEC>::load(dy + off, g);
+      Vec<T, VEC>::load(x + off, v);
+      if (RES) Vec<T, VEC>::load(r + off, rv);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        float dz = g[e];
+        if (ACT != ACT_NONE) {
+          float z = fmaf(av[e], v[e], bv[e]);
+          if (RES) z += rv[e];
+          dz *= act_grad_f<ACT>(z);
+        }
+        s1[e] += dz;
+        s2[e] = fmaf(dz, (v[e] - mv[e]) * rsv[e], s2[e]);
+      }
+    }
+  }
+  block_reduce_add<VEC>(red, s1, m, sums, C);
+  block_reduce_add<VEC>(red, s2, m, sums + C, C);
+}
+
+// ------------------------------------------------------------------ backward: apply
+template <typename T, int VEC, int ACT, bool RES>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
+    const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ a,
+    const float* __restrict__ b, const float* __restrict__ mean, const float* __restrict__ rstd,
+    const float* __restrict__ sums, T* __restrict__ dx, T* __restrict__ dr, long M, int C) {
+  const RowMap m(C, VEC);
+  if (!m.active) return;
+  float av[VEC], bv[VEC], mv[VEC], rsv[VEC], c1[VEC], c2[VEC];
+  const float invM = 1.f / (float)M;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    const int c = m.g * VEC + e;
+    av[e] = a[c]; bv[e] = b[c]; mv[e] = mean[c]; rsv[e] = rstd[c];
+    c1[e] = sums[c] * invM;
+    c2[e] = sums[C + c] * invM;
+  }
+  for (long row = (long)blockIdx.x * m.RL + m.rl; row < M; row += (long)gridDim.x * m.RL) {
+    const long off = row * C + m.g * VEC;
+    float g[VEC], v[VEC], rv[VEC], o[VEC];
+    Vec<T, VEC>::load(dy + off, g);
+    Vec<T, VEC>::load(x + off, v);
+    if (RES) Vec<T, VEC>::load(r + off, rv);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float dz = g[e];
+      if (ACT != ACT_NONE) {
+        float z = fmaf(av[e], v[e], bv[e]);
+        if (RES) z += rv[e];
+        dz *= act_grad_f<ACT>(z);
+      }
+      g[e] = dz;
+      const float xhat = (v[e] - mv[e]) * rsv[e];
+      o[e] = av[e] * (dz - c1[e] - xhat * c2[e]);     // a = gamma * rstd
+    }
+    Vec<T, VEC>::store(dx + off, o);
+    if (RES) Vec<T, VEC>::store(dr + off, g);
+  }
+}
+
+// ------------------------------------------------------------------ dispatch
+static int pick_vec(int C) { return (C % 8 == 0) ? 8 : (C % 2 == 0 ? 2 : 1); }
+static int pick_grid(long M, int C, int VEC) {
+  const int RL = kBnThreads / (C / VEC);
+  long blocks = (M + RL - 1) / RL;
+  const long cap = 148L * 8;
+  return (int)(blocks < cap ? blocks : cap);
+}
+static bool bn_shape_ok(long M, int C) {
+  if (M <= 0 || C <= 0) return false;
+  return C / pick_vec(C) <= kBnThreads;
+}
+
+#define MU_BN_VEC(VECV, BODY)                          \
+  switch (VECV) {                                      \
+    case 8: { constexpr int VEC = 8; BODY; } break;    \
+    case 2: { constexpr int VEC = 2; BODY; } break;    \
+    default: { constexpr int VEC = 1; BODY; } break;   \
+  }
+#define MU_BN_ACT(ACTV, RESV, BODY)                                                           \
+  if (RESV) {                                                                                 \
+    constexpr bool RES = true;                                                                \
+    switch (ACTV) {                                                                           \
+      case ACT_GELU: { constexpr int ACT = ACT_GELU; BODY; } break;                           \
+      case ACT_RELU: { constexpr int ACT = ACT_RELU; BODY; } break;                           \
+      default: { constexpr int ACT = ACT_NONE; BODY; } break;                                 \
+    }                                                                                         \
+  } else {                                                                                    \
+    constexpr bool RES = false;                                                               \
+    switch (ACTV) {                                                                           \
+      case ACT_GELU: { constexpr int ACT = ACT_GELU; BODY; } break;                           \
+      case ACT_RELU: { constexpr int ACT = ACT_RELU; BODY; } break;                           \
+      default: { constexpr int ACT = ACT_NONE; BODY; } break;                                 \
+    }                                                                                         \
+  }
+
+template <typename T>
+static int bn_stats_t(const void* x, float* sums, long M, int C, cudaStream_t s) {
+  const int vec = pick_vec(C), grid = pick_grid(M, C, vec);
+  MU_BN_VEC(vec, (bn_stats_kernel<T, VEC><<<grid, kBnThreads, 0, s>>>((const T*)x, sums, M, C)));
+  return check_launch("bn_stats");
+}
+template <typename T>
+static int bn_apply_t(const void* x, const void* r, const float* a, const float* b, void* y, long M, int C, int act,
+                      cudaStream_t s) {
+  const int vec = pick_vec(C), grid = pick_grid(M, C, vec);
+  const bool res = r != nullptr;
+  MU_BN_VEC(vec, MU_BN_ACT(act, res, (bn_apply_kernel<T, VEC, ACT, RES><<<grid, kBnThreads, 0, s>>>(
+                                         (const T*)x, (const T*)r, a, b, (T*)y, M, C))));
+  return check_launch("bn_apply");
+}
+template <typename T>
+static int bn_bwd_t(const void* dy, const void* x, const void* r, const float* a, const float* b, const float* mean,
+                    const float* rstd, float* sums, void* dx, void* dr, long M, int C, int act, cudaStream_t s) {
+  const int vec = pick_vec(C), grid = pick_grid(M, C, vec);
+  const bool res = r != nullptr;
+  MU_BN_VEC(vec, MU_BN_ACT(act, res, (bn_bwd_reduce_kernel<T, VEC, ACT, RES><<<grid, kBnThreads, 0, s>>>(
+                                         (const T*)dy, (const T*)x, (const T*)r, a, b, mean, rstd, sums, M, C))));
+  int rc = check_launch("bn_bwd_reduce");
+  if (rc) return rc;
+  MU_BN_VEC(vec, MU_BN_ACT(act, res, (bn_bwd_apply_kernel<T, VEC, ACT, RES><<<grid, kBnThreads, 0, s>>>(
+                                         (const T*)dy, (const T*)x, (const T*)r, a, b, mean, rstd, sums, (T*)dx,
+                                         (T*)dr, M, C))));
+  return check_launch("bn_bwd_apply");
+}
+
+int launch_bn_forward(const void* x, const void* r, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, float momentum, float eps, void* y, float* mean, float* rstd, float* a,
+                      float* b, float* sums, long M, int C, int act, int dtype, cudaStream_t s) {
+  if (!bn_shape_ok(M, C)) {
+    set_error("bn_forward: unsupported shape M=%ld C=%d", M, C);
+    return MU_ERR_BAD_SHAPE;
+  }
+  cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), s);
+  int rc = dtype == MU_F32 ? bn_stats_t<float>(x, sums, M, C, s) : bn_stats_t<__nv_bfloat16>(x, sums, M, C, s);
+  if (rc) return rc;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, gamma, beta, running_mean, running_var, M, C, momentum, eps,
+                                                    mean, rstd, a, b);
+  if ((rc = check_launch("bn_finalize"))) return rc;
+  return dtype == MU_F32 ? bn_apply_t<float>(x, r, a, b, y, M, C, act, s)
+                         : bn_apply_t<__nv_bfloat16>(x, r, a, b, y, M, C, act, s);
+}
+
+int launch_bn_apply(const void* x, const void* r, const float* a, const float* b, void* y, long M, int C, int act,
+                    int dtype, cudaStream_t s) {
+  if (!bn_shape_ok(M, C)) {
+    set_error("bn_apply: unsupported shape M=%ld C=%d", M, C);
+    return MU_ERR_BAD_SHAPE;
+  }
+  return dtype == MU_F32 ? bn_apply_t<float>(x, r, a, b, y, M, C, act, s)
+                         : bn_apply_t<__nv_bfloat16>(x, r, a, b, y, M, C, act, s);
+}
+
+int launch_bn_backward(const void* dy, const void* x, const void* r, const float* a, const float* b, const float* mean,
+                       const float* rstd, float* sums, void* dx, void* dr, long M, int C, int act, int dtype,
+                       cudaStream_t s) {
+  if (!bn_shape_ok(M, C)) {
+    set_error("bn_backward: unsupported shape M=%ld C=%d", M, C);
+    return MU_ERR_BAD_SHAPE;
+  }
+  cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), s);
+  return dtype == MU_F32 ? bn_bwd_t<float>(dy, x, r, a, b, mean, rstd, sums, dx, dr, M, C, act, s)
+                         : bn_bwd_t<__nv_bfloat16>(dy, x, r, a, b, mean, rstd, sums, dx, dr, M, C, act, s);
+}
+
+}  // namespace mu

@@ -187,4 +187,29 @@ int mu_transpose(const void* in, void* out, int32_t batch, int32_t rows, int32_t
   return launch_transpose(in, out, batch, rows, cols, elem_bytes, (cudaStream_t)stream);
 }
 
+int mu_bn_act_fwd(const void* x, const void* r, const float* gamma, const float* beta, float* running_mean,
+                  float* running_var, float momentum, float eps, void* y, float* mean, float* rstd, float* a,
+                  float* b, float* sums, int64_t M, int32_t C, int32_t act, int32_t dtype, mu_stream_t stream) {
+  MU_REQUIRE(dtype == MU_F32 || dtype == MU_BF16, MU_ERR_BAD_DTYPE, "mu_bn_act_fwd: unknown dtype code %d", dtype);
+  MU_PTRS("mu_bn_act_fwd", x, gamma, beta, y, mean, rstd, a, b, sums);
+  return launch_bn_forward(x, r, gamma, beta, running_mean, running_var, momentum, eps, y, mean, rstd, a, b, sums,
+                           (long)M, C, act, dtype, (cudaStream_t)stream);
+}
+
+int mu_bn_act_apply(const void* x, const void* r, const float* a, const float* b, void* y, int64_t M, int32_t C,
+                    int32_t act, int32_t dtype, mu_stream_t stream) {
+  MU_REQUIRE(dtype == MU_F32 || dtype == MU_BF16, MU_ERR_BAD_DTYPE, "mu_bn_act_apply: unknown dtype code %d", dtype);
+  MU_PTRS("mu_bn_act_apply", x, a, b, y);
+  return launch_bn_apply(x, r, a, b, y, (long)M, C, act, dtype, (cudaStream_t)stream);
+}
+
+int mu_bn_act_bwd(const void* dy, const void* x, const void* r, const float* a, const float* b, const float* mean,
+                  const float* rstd, float* sums, void* dx, void* dr, int64_t M, int32_t C, int32_t act,
+                  int32_t dtype, mu_stream_t stream) {
+  MU_REQUIRE(dtype == MU_F32 || dtype == MU_BF16, MU_ERR_BAD_DTYPE, "mu_bn_act_bwd: unknown dtype code %d", dtype);
+  MU_PTRS("mu_bn_act_bwd", dy, x, a, b, mean, rstd, sums, dx);
+  MU_REQUIRE((r == nullptr) == (dr == nullptr), MU_ERR_NULL, "mu_bn_act_bwd: r and dr must both be given or both NULL");
+  return launch_bn_backward(dy, x, r, a, b, mean, rstd, sums, dx, dr, (long)M, C, act, dtype, (cudaStream_t)stream);
+}
+
 }  // extern "C"

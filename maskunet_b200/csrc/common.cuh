@@ -76,6 +76,14 @@ int launch_qkv_project_bwd_sm100(const void* xt, const void* dz, const void* dq,
                                  const void* w_bf16, void* dxt, float* dw, float* db, int B, int C, int N,
                                  cudaStream_t s);
 int launch_zero_pad_rows(const int32_t* n_keep, void* kc, void* vc, int B, int C, int NKP, int dtype, cudaStream_t s);
+int launch_bn_forward(const void* x, const void* r, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, float momentum, float eps, void* y, float* mean, float* rstd, float* a,
+                      float* b, float* sums, long M, int C, int act, int dtype, cudaStream_t s);
+int launch_bn_apply(const void* x, const void* r, const float* a, const float* b, void* y, long M, int C, int act,
+                    int dtype, cudaStream_t s);
+int launch_bn_backward(const void* dy, const void* x, const void* r, const float* a, const float* b, const float* mean,
+                       const float* rstd, float* sums, void* dx, void* dr, long M, int C, int act, int dtype,
+                       cudaStream_t s);
 int launch_transpose(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t s);
 
 }  // namespace mu

@@ -115,6 +115,47 @@ class Mask2FormerAttention(nn.Module):
         return y.view(batch, channels, height, width)                               # :190
 
 
+def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Optional[torch.Tensor] = None):
+    """act(BatchNorm2d(x) [+ residual]) -- the BN / GELU / ReLU / residual chains of ade_semantic.py:198-210,
+    :219, :240 and :283-287.
+
+    Channels-last CUDA activations (the bf16 production layout) run on our fused sm_100a kernels
+    (csrc/bn_act.cu: one statistics pass, one apply pass; backward one reduce + one apply pass).  Any other
+    layout (the NCHW fp32 validation configuration) is evaluated with the stock torch CUDA ops in the
+    reference's own order.
+    """
+    fused = (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16)
+             and x.is_contiguous(memory_format=torch.channels_last) and bn.affine
+             and (bn.training or not torch.is_grad_enabled()))
+    if not fused:
+        y = bn(x)
+        if residual is not None:
+            y = residual + y
+        if act == ops.ACT_GELU:
+            return F.gelu(y)
+        if act == ops.ACT_RELU:
+            return F.relu(y)
+        return y
+    if residual is not None:
+        residual = residual.to(x.dtype).contiguous(memory_format=torch.channels_last)
+    gamma, beta = bn.weight.float(), bn.bias.float()
+    if bn.training:
+        y, mean, rstd, _, _ = ops.bn_act_fwd(x, residual, gamma, beta, bn.eps, act)
+        if bn.track_running_stats:
+            with torch.no_grad():
+                count = x.shape[0] * x.shape[2] * x.shape[3]
+                var = (1.0 / (rstd * rstd) - bn.eps).clamp_min_(0.0) * (count / max(count - 1, 1))
+                momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
+                bn.running_mean.lerp_(mean, momentum)
+                bn.running_var.lerp_(var, momentum)
+                bn.num_batches_tracked += 1
+        return y
+    with torch.no_grad():
+        a = gamma * torch.rsqrt(bn.running_var.float() + bn.eps)
+        b = beta - bn.running_mean.float() * a
+        return ops.bn_act_apply(x, residual, a, b, act)
+
+
 class ConvBlock(nn.Module):
     """conv3x3 -> BN -> GELU(erf) -> conv3x3 -> BN, optionally gelu(x + block(x)).  ade_semantic.py:192-210."""
 
@@ -127,8 +168,12 @@ class ConvBlock(nn.Module):
         self.conv_block = nn.Sequential(*layers)
 
     def forward(self, x):
-        h = self.conv_block(x)
-        return F.gelu(x + h) if self.residual else h
+        conv1, bn1, _, conv2, bn2 = self.conv_block
+        h = fused_bn_act(conv1(x), bn1, ops.ACT_GELU)
+        h = conv2(h)
+        if self.residual:
+            return fused_bn_act(h, bn2, ops.ACT_GELU, residual=x)
+        return fused_bn_act(h, bn2, ops.ACT_NONE)
 
 
 def _dead_embedding(emb_dim, out_channels):
@@ -147,7 +192,8 @@ class DownSample(nn.Module):
         self.emb_layer = _dead_embedding(emb_dim, out_channels)
 
     def forward(self, x):
-        return self.maxpool_conv(x)
+        pool, block1, block2, bn = self.maxpool_conv
+        return fused_bn_act(block2(block1(pool(x))), bn, ops.ACT_NONE)
 
 
 class UpSample(nn.Module):
@@ -165,7 +211,9 @@ class UpSample(nn.Module):
 
     def forward(self, x, skip_x):
         up = self.upsample(x)
-        return self.conv(torch.cat([skip_x, up.to(skip_x.dtype)], dim=1))
+        block1, block2, bn = self.conv
+        h = torch.cat([skip_x, up.to(skip_x.dtype)], dim=1)
+        return fused_bn_act(block2(block1(h)), bn, ops.ACT_NONE)
 
 
 class UNet(nn.Module):
@@ -224,12 +272,16 @@ class UNet(nn.Module):
         h = self.self_attention6(self.upsample3(h, x1))
         return self.norm(h)
 
+    @staticmethod
+    def _conv_bn_relu(seq, h):
+        return fused_bn_act(seq[0](h), seq[1], ops.ACT_RELU)
+
     def _heads(self, h):
         if not self.instance_variant:
-            return self.final_layer(h)
-        embeddings = self.embedding_head(h)          # city_instance.py:273-276 order
-        semantic = self.final_layer(h)
-        boundary = self.boundary_head(semantic)
+            return self._conv_bn_relu(self.final_layer, h)
+        embeddings = self._conv_bn_relu(self.embedding_head, h)          # city_instance.py:273-276 order
+        semantic = self._conv_bn_relu(self.final_layer, h)
+        boundary = self.boundary_head[3](self._conv_bn_relu(self.boundary_head, semantic))
         return semantic, boundary, embeddings
 
     def forward(self, x):

@@ -301,6 +301,114 @@ def _(x):
 transpose.register_autograd(lambda ctx, g: transpose(g.contiguous()))
 
 
+# ------------------------------------------------------------------ K8: fused BatchNorm + activation (+ residual)
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+
+def _rows(x: Tensor):
+    """x is a 4-D channels-last tensor: its memory is [M = B*H*W, C] rows."""
+    if not (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)):
+        raise RuntimeError("maskunet bn_act ops take 4-D channels-last tensors")
+    return x.shape[0] * x.shape[2] * x.shape[3], x.shape[1]
+
+
+def _optp(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+@torch.library.custom_op("maskunet::bn_act_fwd", mutates_args=(), device_types="cuda")
+def bn_act_fwd(x: Tensor, residual: Tensor | None, gamma: Tensor, beta: Tensor, eps: float, act: int
+               ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Training-mode BN over (B, H, W) + activation (+ residual).  Returns y, mean, rstd, a, b.
+    (Functional: the caller folds mean / rstd into the module's running statistics.)"""
+    M, C = _rows(x)
+    if residual is not None:
+        _rows(residual)
+    y = torch.empty_like(x)
+    f32 = dict(dtype=torch.float32, device=x.device)
+    mean, rstd, a, b = (torch.empty((C,), **f32) for _ in range(4))
+    sums = torch.empty((2 * C,), **f32)
+    with torch.cuda.device(x.device):
+        _count(3)
+        check(_L.mu_bn_act_fwd(_p(x), _optp(residual), _p(gamma), _p(beta), _optp(None), _optp(None),
+                               0.0, eps, _p(y), _p(mean), _p(rstd), _p(a), _p(b), _p(sums), M, C, act, _code(x),
+                               _stream(x)), "mu_bn_act_fwd")
+    return y, mean, rstd, a, b
+
+
+@bn_act_fwd.register_fake
+def _(x, residual, gamma, beta, eps, act):
+    C = x.shape[1]
+    v = lambda: x.new_empty((C,), dtype=torch.float32)
+    return torch.empty_like(x), v(), v(), v(), v()
+
+
+@torch.library.custom_op("maskunet::bn_act_apply", mutates_args=(), device_types="cuda")
+def bn_act_apply(x: Tensor, residual: Tensor | None, a: Tensor, b: Tensor, act: int) -> Tensor:
+    """y = act(a * x + b [+ residual]) with per-channel a, b (inference-mode BN folded to an affine)."""
+    M, C = _rows(x)
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _count(1)
+        check(_L.mu_bn_act_apply(_p(x), _optp(residual), _p(a), _p(b), _p(y), M, C, act, _code(x), _stream(x)),
+              "mu_bn_act_apply")
+    return y
+
+
+@bn_act_apply.register_fake
+def _(x, residual, a, b, act):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("maskunet::bn_act_bwd", mutates_args=(), device_types="cuda")
+def bn_act_bwd(dy: Tensor, x: Tensor, residual: Tensor | None, a: Tensor, b: Tensor, mean: Tensor, rstd: Tensor,
+               act: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Returns dx, dresidual (empty tensor when there was no residual), dgamma, dbeta."""
+    M, C = _rows(x)
+    _rows(dy)
+    dx = torch.empty_like(x)
+    dr = torch.empty_like(x) if residual is not None else None
+    sums = torch.empty((2 * C,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _count(2)
+        check(_L.mu_bn_act_bwd(_p(dy), _p(x), _optp(residual), _p(a), _p(b), _p(mean), _p(rstd), _p(sums), _p(dx),
+                               _optp(dr), M, C, act, _code(x), _stream(x)), "mu_bn_act_bwd")
+    if dr is None:
+        dr = x.new_empty((0,))
+    return dx, dr, sums[C:].clone(), sums[:C].clone()
+
+
+@bn_act_bwd.register_fake
+def _(dy, x, residual, a, b, mean, rstd, act):
+    C = x.shape[1]
+    dr = torch.empty_like(x) if residual is not None else x.new_empty((0,))
+    return torch.empty_like(x), dr, x.new_empty((C,), dtype=torch.float32), x.new_empty((C,), dtype=torch.float32)
+
+
+def _bn_setup(ctx, inputs, output):
+    x, residual, gamma, beta, eps, act = inputs
+    y, mean, rstd, a, b = output
+    ctx.act = act
+    ctx.has_res = residual is not None
+    if residual is not None:
+        ctx.save_for_backward(x, residual, a, b, mean, rstd)
+    else:
+        ctx.save_for_backward(x, a, b, mean, rstd)
+
+
+def _bn_backward(ctx, dy, *unused):
+    if ctx.has_res:
+        x, residual, a, b, mean, rstd = ctx.saved_tensors
+    else:
+        (x, a, b, mean, rstd), residual = ctx.saved_tensors, None
+    dy = dy.contiguous(memory_format=torch.channels_last)
+    dx, dr, dgamma, dbeta = bn_act_bwd(dy, x, residual, a, b, mean, rstd, ctx.act)
+    return dx, (dr if ctx.has_res else None), dgamma, dbeta, None, None
+
+
+bn_act_fwd.register_autograd(_bn_backward, setup_context=_bn_setup)
+
+
 # ------------------------------------------------------------------ the module-level op (A3-A9 of SURVEY.md 8(a))
 @torch.library.custom_op("maskunet::mask_attention", mutates_args=(), device_types="cuda")
 def mask_attention(x: Tensor, w_qkv: Tensor, b_qkv: Tensor, gamma: Tensor, beta: Tensor, keep_rank: Tensor,
