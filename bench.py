@@ -165,7 +165,7 @@ def run_ours(args):
 
     B, c_out = args.batch_per_gpu, 150
     torch.manual_seed(42)                                   # identical weights on every rank
-    cl = os.environ.get("MASKUNET_CHANNELS_LAST", "0") == "1"
+    cl = os.environ.get("MASKUNET_CHANNELS_LAST", "1") == "1"   # NHWC activations: the production layout
     model = maskunet_b200.UNet(3, c_out, compute_dtype=torch.bfloat16, channels_last=cl).to(dev)
     if cl:
         model = model.to(memory_format=torch.channels_last)
@@ -251,7 +251,8 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": gb, "c_out": c_out,
                    "parallelism": f"dp{world}", "optimizer": "AdamW(lr=5e-5, wd=1e-1)",
                    "l2": "per-step working set (tens of GB of activations) exceeds the 126 MB L2; no flush needed",
-                   "precision": "bf16 activations, fp32 master parameters / statistics / accumulation"},
+                   "precision": "bf16 activations, fp32 master parameters / statistics / accumulation",
+                   "layout": "channels_last" if cl else "nchw"},
         "clocks": clocks,
         "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e, "last_loss": losses[-1] if losses else None},

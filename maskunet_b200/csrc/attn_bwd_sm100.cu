@@ -19,10 +19,10 @@
 namespace mu {
 
 constexpr int kBK = 128;            // keys per CTA
-constexpr int kBwdThreads = 384;    // warps 0-3: TMA, MMA, 2 idle; 4-7: softmax; 8-11: dQ reduction
+constexpr int kBwdThreads = 512;    // warps 0-3: TMA, MMA, 2 idle; 4-11: softmax (2 warpgroups); 12-15: dQ reduction
 constexpr float kLog2eB = 1.4426950408889634f;
 
-template <int D, int BM, int DH, int STAGES>
+template <int D, int BM, int DH, int STAGES, int PB>
 struct BwdCfg {
   static constexpr bool kDQT = (D >= 128);               // dQ tile computed transposed
   static constexpr int kKBytes = kBK * D * 2;            // K_j or V_j
@@ -33,7 +33,9 @@ struct BwdCfg {
   static constexpr int kTmemUsed = kTmDQ + kDQCols;
   static_assert(kTmemUsed <= 512, "TMEM overflow");
   static constexpr int kStatBytes = 2 * 2 * BM * 4;       // lse2, delta, double-buffered over tiles
-  static constexpr int kSmemBytes = 1024 + 2 * kKBytes + 2 * STAGES * kQBytes + 2 * kPBytes + kStatBytes + 256;
+  // PB = 2 double-buffers the P^T / dS^T tiles so that the exp / dS work of query tile i+1 overlaps the
+  // dV / dK / dQ MMAs of tile i.  Dynamic shared memory is declared __align__(1024), no alignment slack.
+  static constexpr int kSmemBytes = 2 * kKBytes + 2 * STAGES * kQBytes + 2 * PB * kPBytes + kStatBytes + 256;
   static_assert(kSmemBytes <= 232448, "shared memory overflow");
 };
 
@@ -44,33 +46,36 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int D, int BM, int DH, int STAGES>
+template <int D, int BM, int DH, int STAGES, int PB>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                       const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                       const int32_t* __restrict__ n_keep, const int32_t* __restrict__ keep_idx,
                       const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
                       __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int N, int NKP, float scale) {
-  using Cfg = BwdCfg<D, BM, DH, STAGES>;
+  using Cfg = BwdCfg<D, BM, DH, STAGES, PB>;
   constexpr bool DQT = Cfg::kDQT;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {   // the 128B-swizzled tiles need a 1024-byte aligned base
+    if (threadIdx.x == 0) printf("attn_bwd_sm100: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* sK = smem;
   uint8_t* sV = sK + Cfg::kKBytes;
   uint8_t* sQ = sV + Cfg::kKBytes;                       // STAGES x Q_i
   uint8_t* sDO = sQ + STAGES * Cfg::kQBytes;             // STAGES x dO_i
-  uint8_t* sP = sDO + STAGES * Cfg::kQBytes;
-  uint8_t* sDS = sP + Cfg::kPBytes;
-  float* sLse = reinterpret_cast<float*>(sDS + Cfg::kPBytes);   // [2][BM], already * log2e
+  uint8_t* sP = sDO + STAGES * Cfg::kQBytes;              // PB x P^T
+  uint8_t* sDS = sP + PB * Cfg::kPBytes;                  // PB x dS^T
+  float* sLse = reinterpret_cast<float*>(sDS + PB * Cfg::kPBytes);   // [2][BM], already * log2e
   float* sDelta = sLse + 2 * BM;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * BM);
   uint64_t* kv_full = bars;                 // 1
   uint64_t* qdo_full = bars + 1;            // STAGES
   uint64_t* qdo_empty = qdo_full + STAGES;  // STAGES
   uint64_t* s_full = qdo_empty + STAGES;    // 1
-  uint64_t* pds_full = s_full + 1;          // 1 (128 arrivals)
-  uint64_t* pds_free = pds_full + 1;        // 1
-  uint64_t* dq_full = pds_free + 1;         // 1
+  uint64_t* pds_full = s_full + 1;          // 1 (256 arrivals)
+  uint64_t* pds_free = pds_full + 1;        // PB
+  uint64_t* dq_full = pds_free + PB;        // 1
   uint64_t* dq_free = dq_full + 1;          // 1 (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_free + 1);
 
@@ -87,8 +92,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       mbar_init(qdo_empty + i, 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(pds_full, 128);
-    mbar_init(pds_free, 1);
+    mbar_init(pds_full, 256);
+    for (int i = 0; i < PB; ++i) mbar_init(pds_free + i, 1);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, 128);
     mbar_fence_init();
@@ -133,7 +138,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       constexpr uint32_t idesc_acc = make_idesc_bf16(kBK, DH, 0, 1);   // dV, dK: A K-major, B MN-major
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, DQT ? BM : DH, 1, 1);
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
-      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+      const uint32_t p_base = smem_u32(sP), ds_base = smem_u32(sDS);
       auto issue_s_dp = [&](int i) {
         const int st = i % STAGES;
         mbar_wait(qdo_full + st, (i / STAGES) & 1);
@@ -155,6 +160,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       };
       auto issue_acc = [&](int i) {
         const int st = i % STAGES;
+        const uint32_t p_addr = p_base + (i % PB) * Cfg::kPBytes, ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
         const uint32_t qa = q_addr + st * Cfg::kQBytes + half * 2 * (BM * 128);
         const uint32_t da = do_addr + st * Cfg::kQBytes + half * 2 * (BM * 128);
 #pragma unroll
@@ -186,7 +192,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           umma_ss(tmem_base + Cfg::kTmDQ, a, bd, idesc_dq, kk > 0);
         }
         umma_commit(qdo_empty + st);
-        umma_commit(pds_free);
+        umma_commit(pds_free + (i % PB));
         umma_commit(dq_full);
       };
       mbar_wait(kv_full, 0);
@@ -203,16 +209,21 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================================================== softmax-backward warps: thread <-> key row
+  } else if (warp >= 4 && warp < 12) {
+    // ===================================================== softmax-backward warps: thread <-> key row.
+    // Two warpgroups split the query columns of every tile (no row reduction is needed in backward, so the
+    // halves are independent); two warps per SM sub-partition hide each other's MUFU / FMA latencies.
     const int quad = warp & 3;
+    const int hcol = (warp - 4) >> 2;                    // 0: first half of the columns, 1: second half
     const int r = quad * 32 + (int)lane_id();
-    const int t = threadIdx.x - 128;                     // 0..127 within this warpgroup
+    const int t = threadIdx.x - 128;                     // 0..255 over both warpgroups
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const bool key_ok = k0 + r < nk;
     const float scale_log2 = scale * kLog2eB;
     const float* lse_b = lse + (size_t)b * N;
     const float* delta_b = delta + (size_t)b * N;
+    const uint32_t lse_addr = smem_u32(sLse), delta_addr = smem_u32(sDelta);
+    const uint32_t p_base = smem_u32(sP), ds_base = smem_u32(sDS);
     auto fetch = [&](int i, float& l2, float& dl) {
       const int qi = i * BM + t;
       const bool ok = (t < BM) && (qi < N);
@@ -221,58 +232,66 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     };
     float nl2, ndl;
     fetch(0, nl2, ndl);
+    constexpr int kChunksPerThread = BM / 64;            // 32-column chunks per thread
     uint32_t s[32], dp[32];
     for (int i = 0; i < T; ++i) {
-      float* my_lse = sLse + (i & 1) * BM;
-      float* my_delta = sDelta + (i & 1) * BM;
+      const uint32_t my_lse = lse_addr + (i & 1) * BM * 4, my_delta = delta_addr + (i & 1) * BM * 4;
       if (t < BM) {
-        my_lse[t] = nl2;
-        my_delta[t] = ndl;
+        st_shared_f32(my_lse + t * 4, nl2);
+        st_shared_f32(my_delta + t * 4, ndl);
       }
       if (i + 1 < T) fetch(i + 1, nl2, ndl);
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-      if (i > 0) mbar_wait(pds_free, (i - 1) & 1);       // previous tile's MMAs no longer read sP / sDS
+      // the MMAs that last read this P^T / dS^T buffer (tile i - PB) must have completed
+      if (i >= PB) mbar_wait(pds_free + (i % PB), ((i / PB) - 1) & 1);
+      const uint32_t p_addr = p_base + (i % PB) * Cfg::kPBytes, ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
 #pragma unroll
-      for (int c = 0; c < BM / 32; ++c) {
+      for (int cc = 0; cc < kChunksPerThread; ++cc) {
+        const int c = hcol * kChunksPerThread + cc;      // 32-column chunk index within the tile
         tmem_ld32(lane_base + Cfg::kTmS + c * 32, s);
         tmem_ld32(lane_base + Cfg::kTmDP + c * 32, dp);
         tmem_wait_ld();
         uint32_t pk[16], dk[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float2 l2 = *reinterpret_cast<const float2*>(my_lse + c * 32 + 2 * e);
-          const float2 dl = *reinterpret_cast<const float2*>(my_delta + c * 32 + 2 * e);
-          float p0 = fast_exp2(fmaf(__uint_as_float(s[2 * e]), scale_log2, -l2.x));
-          float p1 = fast_exp2(fmaf(__uint_as_float(s[2 * e + 1]), scale_log2, -l2.y));
-          if (!key_ok) p0 = p1 = 0.f;
-          const float d0 = p0 * (__uint_as_float(dp[2 * e]) - dl.x);
-          const float d1 = p1 * (__uint_as_float(dp[2 * e + 1]) - dl.y);
-          pk[e] = pack_bf16(p0, p1);
-          dk[e] = pack_bf16(d0, d1);
+        for (int e = 0; e < 8; ++e) {
+          const float4 l2 = ld_shared_v4f(my_lse + (c * 32 + 4 * e) * 4);
+          const float4 dl = ld_shared_v4f(my_delta + (c * 32 + 4 * e) * 4);
+          float p0 = fast_exp2(fmaf(__uint_as_float(s[4 * e + 0]), scale_log2, -l2.x));
+          float p1 = fast_exp2(fmaf(__uint_as_float(s[4 * e + 1]), scale_log2, -l2.y));
+          float p2 = fast_exp2(fmaf(__uint_as_float(s[4 * e + 2]), scale_log2, -l2.z));
+          float p3 = fast_exp2(fmaf(__uint_as_float(s[4 * e + 3]), scale_log2, -l2.w));
+          if (!key_ok) p0 = p1 = p2 = p3 = 0.f;
+          const float d0 = p0 * (__uint_as_float(dp[4 * e + 0]) - dl.x);
+          const float d1 = p1 * (__uint_as_float(dp[4 * e + 1]) - dl.y);
+          const float d2 = p2 * (__uint_as_float(dp[4 * e + 2]) - dl.z);
+          const float d3 = p3 * (__uint_as_float(dp[4 * e + 3]) - dl.w);
+          pk[2 * e] = pack_bf16(p0, p1);
+          pk[2 * e + 1] = pack_bf16(p2, p3);
+          dk[2 * e] = pack_bf16(d0, d1);
+          dk[2 * e + 1] = pack_bf16(d2, d3);
         }
-        uint8_t* prow = sP + (c >> 1) * (kBK * 128) + r * 128;
-        uint8_t* drow = sDS + (c >> 1) * (kBK * 128) + r * 128;
+        const uint32_t row_off = (c >> 1) * (kBK * 128) + r * 128;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const int chunk = ((c & 1) * 4 + ch) ^ (r & 7);
-          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
-          *reinterpret_cast<uint4*>(drow + chunk * 16) = make_uint4(dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
+          const uint32_t chunk = (((c & 1) * 4 + ch) ^ (r & 7)) * 16;
+          st_shared_v4(p_addr + row_off + chunk, pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+          st_shared_v4(ds_addr + row_off + chunk, dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
         }
       }
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(pds_full);
     }
-    // ---- epilogue: dV_j, dK_j out of TMEM (rows of kept keys only)
-    mbar_wait(pds_free, (T - 1) & 1);
+    // ---- epilogue: dV_j (first warpgroup) and dK_j (second) out of TMEM, rows of kept keys only
+    mbar_wait(pds_free + ((T - 1) % PB), ((T - 1) / PB) & 1);   // last tile's MMAs (and all before) are done
     tc_fence_after();
     // dense token-space outputs: key row r of this tile goes back to token keep_idx[k0 + r]
     const int tok = key_ok ? keep_idx[(size_t)b * N + k0 + r] : 0;
     const size_t row_off = ((size_t)b * N + tok) * D + half * DH;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
+    {
+      const int which = hcol;
       __nv_bfloat16* dst = (which == 0 ? dv : dk) + row_off;
       const float mul = which == 0 ? 1.f : scale;
       const int col0 = which == 0 ? Cfg::kTmDV : Cfg::kTmDK;
@@ -293,7 +312,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ===================================================== dQ reduction warps
     const int quad = warp & 3;
     const int r = quad * 32 + (int)lane_id();
@@ -360,18 +379,18 @@ __global__ void dq_convert_kernel(const float4* __restrict__ acc, uint2* __restr
   }
 }
 
-template <int D, int BM, int DH, int STAGES>
+template <int D, int BM, int DH, int STAGES, int PB>
 static int run(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const int32_t* keep_idx,
                const void* d_o, const float* lse, const float* delta, void* dq, void* dkc, void* dvc, float* dq_acc,
                int B, int N, int NKP, cudaStream_t s) {
-  using Cfg = BwdCfg<D, BM, DH, STAGES>;
+  using Cfg = BwdCfg<D, BM, DH, STAGES, PB>;
   CUtensorMap tq, tdo, tk, tv;
   int rc;
   if ((rc = make_tmap_bf16_3d(&tq, q, D, N, B, BM))) return rc;
   if ((rc = make_tmap_bf16_3d(&tdo, d_o, D, N, B, BM))) return rc;
   if ((rc = make_tmap_bf16_3d(&tk, kc, D, NKP, B, kBK))) return rc;
   if ((rc = make_tmap_bf16_3d(&tv, vc, D, NKP, B, kBK))) return rc;
-  auto kern = attn_bwd_sm100_kernel<D, BM, DH, STAGES>;
+  auto kern = attn_bwd_sm100_kernel<D, BM, DH, STAGES, PB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("attn_bwd_sm100: cudaFuncSetAttribute(%d bytes): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
@@ -404,11 +423,11 @@ int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const i
   float* acc = (float*)workspace;
   switch (C) {
     case 64:
-      return run<64, 128, 64, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+      return run<64, 128, 64, 2, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
     case 128:
-      return run<128, 64, 128, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+      return run<128, 64, 128, 2, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
     case 256:
-      return run<256, 64, 128, 1>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+      return run<256, 64, 128, 1, 1>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
     default:
       set_error("attn_bwd_sm100: channels must be 64, 128 or 256 (got %d)", C);
       return MU_ERR_BAD_SHAPE;

@@ -156,6 +156,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const int r = quad * 32 + (int)lane_id();       // query row within the tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const bool row_ok = q0 + r < N;
+    const uint32_t p_saddr = smem_u32(sP);
     __nv_bfloat16* orow = o + ((size_t)b * N + q0 + r) * D;
     if (T == 0) {  // every key masked: the reference yields NaN (softmax over all -inf)
       if (row_ok) {
@@ -224,11 +225,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             pk[i] = pack_bf16(p0, p1);
           }
           // columns [c*32, c*32+32) = 16-byte chunks (c&1)*4 .. +3 of 64-column block c>>1
-          uint8_t* prow = sP + (c >> 1) * (kBM * 128) + r * 128;
+          const uint32_t prow = p_saddr + (c >> 1) * (kBM * 128) + r * 128;
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
-            const int chunk = ((c & 1) * 4 + ch) ^ (r & 7);
-            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+            const uint32_t chunk = (((c & 1) * 4 + ch) ^ (r & 7)) * 16;
+            st_shared_v4(prow + chunk, pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
           }
         }
         tc_fence_before();

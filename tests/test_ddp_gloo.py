@@ -1,0 +1,62 @@
+"""CPU, world_size 2 over gloo: the bucketed gradient reducer (host logic of the data-parallel path)."""
+import importlib.util
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load_ddp():
+    # loaded by path: the reducer is plain torch.distributed and must be testable without a GPU
+    spec = importlib.util.spec_from_file_location("maskunet_ddp", os.path.join(ROOT, "maskunet_b200", "ddp.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ddp = _load_ddp()
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.GELU(), torch.nn.Linear(64, 64), torch.nn.GELU(),
+                              torch.nn.Linear(64, 8))
+    dead = torch.nn.Linear(4, 4)                       # like the reference's emb_layer: never used in forward
+    params = list(net.parameters()) + list(dead.parameters())
+    if rank == 1:                                      # de-synchronise, then broadcast must repair it
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(1.0)
+    red = ddp.GradReducer(params, bucket_bytes=8 * 1024)
+    red.broadcast_parameters(net)
+    gen = torch.Generator().manual_seed(123)
+    x_all = torch.randn(3, 8, 16, generator=gen)       # 3 steps, global batch 8
+    y_all = torch.randn(3, 8, 8, generator=gen)
+    ref = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.GELU(), torch.nn.Linear(64, 64), torch.nn.GELU(),
+                              torch.nn.Linear(64, 8))
+    ref.load_state_dict(net.state_dict())
+    for step in range(3):
+        for p in params:
+            p.grad = None
+        xs, ys = x_all[step].chunk(world)[rank], y_all[step].chunk(world)[rank]
+        torch.nn.functional.mse_loss(net(xs), ys).backward()
+        red.finish()
+        ref.zero_grad()
+        torch.nn.functional.mse_loss(ref(x_all[step]), y_all[step]).backward()
+        for p, q in zip(net.parameters(), ref.parameters()):
+            assert torch.allclose(p.grad, q.grad, atol=1e-6), f"rank {rank} step {step}"
+        assert all(p.grad is None for p in dead.parameters())
+    assert len(red.buckets) >= 2 and red.launched == 3 * len(red.buckets)
+    torch.save(torch.tensor(1), os.path.join(tmp, f"ok{rank}"))
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_world2_gloo(tmp_path):
+    port = 29600 + os.getpid() % 300
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")

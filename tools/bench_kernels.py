@@ -26,11 +26,11 @@ def make(B, N, C, p_keep=0.5, seed=0):
     kc = torch.randn(B, NKP, C, device=DEV, generator=g).bfloat16()
     vc = torch.randn(B, NKP, C, device=DEV, generator=g).bfloat16()
     bits = (torch.rand(B, N, device=DEV, generator=g) < p_keep).to(torch.int64)
-    _, n_keep, _, _ = ops.mask_binarize(bits)
+    _, n_keep, keep_idx, _ = ops.mask_binarize(bits)
     for b in range(B):
         kc[b, int(n_keep[b]):] = 0
         vc[b, int(n_keep[b]):] = 0
-    return q, kc, vc, n_keep
+    return q, kc, vc, n_keep, keep_idx
 
 
 def time_fn(fn, iters=10, warm=3):
@@ -51,7 +51,7 @@ def time_fn(fn, iters=10, warm=3):
 
 
 def run(B, N, C, bwd, peak):
-    q, kc, vc, n_keep = make(B, N, C)
+    q, kc, vc, n_keep, keep_idx = make(B, N, C)
     nk = float(n_keep.sum())
     ms = time_fn(lambda: ops.attn_fwd(q, kc, vc, n_keep))
     tf = 4 * N * nk * C / (ms * 1e-3) / 1e12
@@ -60,7 +60,7 @@ def run(B, N, C, bwd, peak):
         o, lse = ops.attn_fwd(q, kc, vc, n_keep)
         d_o = torch.randn_like(o)
         delta = (d_o.float() * o.float()).sum(-1)
-        ms = time_fn(lambda: ops.attn_bwd(q, kc, vc, n_keep, d_o, lse, delta), iters=5, warm=2)
+        ms = time_fn(lambda: ops.attn_bwd(q, kc, vc, n_keep, keep_idx, d_o, lse, delta), iters=5, warm=2)
         tf = 8 * N * nk * C / (ms * 1e-3) / 1e12
         rec.update({"bwd_ms": round(ms, 4), "bwd_tflops": round(tf, 1), "bwd_frac": round(tf / peak, 3)})
     print(json.dumps(rec), flush=True)
