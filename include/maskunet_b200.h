@@ -150,6 +150,32 @@ int mu_bn_act_bwd(const void* dy, const void* x, const void* r, const float* a, 
                   const float* rstd, float* sums, void* dx, void* dr, int64_t M, int32_t C, int32_t act,
                   int32_t dtype, mu_stream_t stream);
 
+/* K9. MaxPool2d(2) on channels-last [B, H, W, C] (:216).  bwd = 0: out [B, H/2, W/2, C] = max over 2x2;
+ * bwd = 1: dy [B, H/2, W/2, C] -> out = dx [B, H, W, C], gradient to the first maximum in scan order. */
+int mu_maxpool2(const void* x, const void* dy, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t bwd,
+                int32_t dtype, mu_stream_t stream);
+
+/* K10. Upsample(scale 2, bilinear, align_corners=True) of x [B, H, W, Cx] fused with cat([skip, up], channel)
+ * (:235, :252): out [B, 2H, 2W, Cs + Cx].  Backward splits dout into dskip [B, 2H, 2W, Cs] and dx [B, H, W, Cx]. */
+int mu_upsample_concat_fwd(const void* skip, const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t Cs,
+                           int32_t Cx, int32_t dtype, mu_stream_t stream);
+int mu_upsample_concat_bwd(const void* dout, void* dskip, void* dx, int32_t B, int32_t H, int32_t W, int32_t Cs,
+                           int32_t Cx, int32_t dtype, mu_stream_t stream);
+
+/* K11. LayerNorm over all L = C*H*W elements of each sample (nn.LayerNorm([64, 128, 128]), :281, :311).
+ * x, y [B, L] in channels-last element order; gamma, beta f32 [L] in the SAME order; sums f32 [2B] scratch. */
+int mu_sample_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, float* mean,
+                            float* rstd, float* sums, int32_t B, int64_t L, int32_t dtype, mu_stream_t stream);
+int mu_sample_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                            float* sums, void* dx, float* dgamma, float* dbeta, int32_t B, int64_t L, int32_t dtype,
+                            mu_stream_t stream);
+
+/* A14. nn.CrossEntropyLoss(mean, ignore_index) forward fused with its gradient (:377, :399): logits [M, C]
+ * (channels-last rows), labels int64 [M], valid_count f32 [1] = number of labels != ignore_index.
+ * loss_sum f32 [1] receives the mean loss; dlogits [M, C] = (softmax - onehot) / valid_count. */
+int mu_cross_entropy_fused(const void* logits, const int64_t* labels, const float* valid_count, int64_t ignore_index,
+                           void* dlogits, float* loss_sum, int64_t M, int32_t C, int32_t dtype, mu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,12 @@ SIGNATURES = {
     "mu_attn_bwd_cudacore": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "mu_qkv_project_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "mu_transpose": [_P, _P, _I, _I, _I, _I, _P],
+    "mu_maxpool2": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mu_upsample_concat_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mu_upsample_concat_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mu_sample_layernorm_fwd": [_P, _P, _P, _F, _P, _P, _P, _P, _I, ctypes.c_int64, _I, _P],
+    "mu_sample_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, ctypes.c_int64, _I, _P],
+    "mu_cross_entropy_fused": [_P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int64, _I, _I, _P],
     "mu_bn_act_fwd": [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
     "mu_bn_act_apply": [_P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
     "mu_bn_act_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],

@@ -212,4 +212,53 @@ int mu_bn_act_bwd(const void* dy, const void* x, const void* r, const float* a, 
   return launch_bn_backward(dy, x, r, a, b, mean, rstd, sums, dx, dr, (long)M, C, act, dtype, (cudaStream_t)stream);
 }
 
+#define MU_DTYPE_OK(fn) \
+  MU_REQUIRE(dtype == MU_F32 || dtype == MU_BF16, MU_ERR_BAD_DTYPE, fn ": unknown dtype code %d", dtype)
+
+int mu_maxpool2(const void* x, const void* dy, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t bwd,
+                int32_t dtype, mu_stream_t stream) {
+  MU_DTYPE_OK("mu_maxpool2");
+  MU_PTRS("mu_maxpool2", x, out);
+  if (bwd) MU_PTRS("mu_maxpool2", dy);
+  return launch_maxpool2(x, dy, out, B, H, W, C, bwd, dtype, (cudaStream_t)stream);
+}
+
+int mu_upsample_concat_fwd(const void* skip, const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t Cs,
+                           int32_t Cx, int32_t dtype, mu_stream_t stream) {
+  MU_DTYPE_OK("mu_upsample_concat_fwd");
+  MU_PTRS("mu_upsample_concat_fwd", skip, x, out);
+  return launch_upcat_fwd(skip, x, out, B, H, W, Cs, Cx, dtype, (cudaStream_t)stream);
+}
+
+int mu_upsample_concat_bwd(const void* dout, void* dskip, void* dx, int32_t B, int32_t H, int32_t W, int32_t Cs,
+                           int32_t Cx, int32_t dtype, mu_stream_t stream) {
+  MU_DTYPE_OK("mu_upsample_concat_bwd");
+  MU_PTRS("mu_upsample_concat_bwd", dout, dskip, dx);
+  return launch_upcat_bwd(dout, dskip, dx, B, H, W, Cs, Cx, dtype, (cudaStream_t)stream);
+}
+
+int mu_sample_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, float* mean,
+                            float* rstd, float* sums, int32_t B, int64_t L, int32_t dtype, mu_stream_t stream) {
+  MU_DTYPE_OK("mu_sample_layernorm_fwd");
+  MU_PTRS("mu_sample_layernorm_fwd", x, gamma, beta, y, mean, rstd, sums);
+  return launch_sample_ln_fwd(x, gamma, beta, eps, y, mean, rstd, sums, B, (long)L, dtype, (cudaStream_t)stream);
+}
+
+int mu_sample_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                            float* sums, void* dx, float* dgamma, float* dbeta, int32_t B, int64_t L, int32_t dtype,
+                            mu_stream_t stream) {
+  MU_DTYPE_OK("mu_sample_layernorm_bwd");
+  MU_PTRS("mu_sample_layernorm_bwd", dy, x, gamma, mean, rstd, sums, dx, dgamma, dbeta);
+  return launch_sample_ln_bwd(dy, x, gamma, mean, rstd, sums, dx, dgamma, dbeta, B, (long)L, dtype,
+                              (cudaStream_t)stream);
+}
+
+int mu_cross_entropy_fused(const void* logits, const int64_t* labels, const float* valid_count, int64_t ignore_index,
+                           void* dlogits, float* loss_sum, int64_t M, int32_t C, int32_t dtype, mu_stream_t stream) {
+  MU_DTYPE_OK("mu_cross_entropy_fused");
+  MU_PTRS("mu_cross_entropy_fused", logits, labels, valid_count, dlogits, loss_sum);
+  return launch_ce_fused(logits, labels, valid_count, (long)ignore_index, dlogits, loss_sum, (long)M, C, dtype,
+                         (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -84,6 +84,18 @@ int launch_bn_apply(const void* x, const void* r, const float* a, const float* b
 int launch_bn_backward(const void* dy, const void* x, const void* r, const float* a, const float* b, const float* mean,
                        const float* rstd, float* sums, void* dx, void* dr, long M, int C, int act, int dtype,
                        cudaStream_t s);
+int launch_maxpool2(const void* x, const void* dy, void* out, int B, int H, int W, int C, int bwd, int dtype,
+                    cudaStream_t s);
+int launch_upcat_fwd(const void* skip, const void* x, void* out, int B, int H, int W, int Cs, int Cx, int dtype,
+                     cudaStream_t s);
+int launch_upcat_bwd(const void* dout, void* dskip, void* dx, int B, int H, int W, int Cs, int Cx, int dtype,
+                     cudaStream_t s);
+int launch_sample_ln_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, float* mean,
+                         float* rstd, float* sums, int B, long L, int dtype, cudaStream_t s);
+int launch_sample_ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                         float* sums, void* dx, float* dgamma, float* dbeta, int B, long L, int dtype, cudaStream_t s);
+int launch_ce_fused(const void* logits, const int64_t* labels, const float* valid_count, long ignore_index,
+                    void* dlogits, float* loss_sum, long M, int C, int dtype, cudaStream_t s);
 int launch_transpose(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t s);
 
 }  // namespace mu

@@ -1,0 +1,490 @@
+// K9 / K10 / K11 / A14: the remaining HBM-bound pieces of the U-Net on channels-last activations.
+//   K9   MaxPool2d(2)                                   /root/reference/code/ade20k/ade_semantic.py:216
+//   K10  Upsample(x2, bilinear, align_corners=True) + cat([skip, up], 1)              :235, :252
+//   K11  LayerNorm([C, H, W]) over each sample (1 Mi elements at [64,128,128])        :281, :311
+//   A14  CrossEntropyLoss(mean, ignore_index) fused forward + gradient                :377, :399
+// Every kernel maps a thread to an 8-channel (16-byte) group of one pixel so that loads and stores are
+// coalesced 16-byte vectors along the contiguous channel axis; reductions use fp32 partials, warp shuffles and
+// one atomicAdd per CTA.
+#include "common.cuh"
+
+namespace mu {
+
+// ---- 8-wide vector helpers (bf16 or fp32 storage, fp32 math) ---------------------------------------
+template <typename T> struct V8;
+template <> struct V8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] = __uint_as_float(w[e] << 16);
+      v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(v[0], v[1]); u.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[2], v[3]); u.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[4], v[5]); u.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v[6], v[7]); u.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <> struct V8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+
+// ============================================================================ K9: MaxPool2d(2), NHWC
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256) maxpool2_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                       T* __restrict__ out, int B, int H, int W, int C) {
+  const int G = C / 8, Ho = H / 2, Wo = W / 2;
+  const long total = (long)B * Ho * Wo * G;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    long p = idx / G;
+    const int wo = (int)(p % Wo);
+    p /= Wo;
+    const int ho = (int)(p % Ho), b = (int)(p / Ho);
+    const long in0 = (((long)b * H + 2 * ho) * W + 2 * wo) * C + g * 8;
+    float v[4][8];
+    V8<T>::load(x + in0, v[0]);
+    V8<T>::load(x + in0 + C, v[1]);
+    V8<T>::load(x + in0 + (long)W * C, v[2]);
+    V8<T>::load(x + in0 + (long)W * C + C, v[3]);
+    if (!BWD) {
+      float m[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m[e] = fmaxf(fmaxf(v[0][e], v[1][e]), fmaxf(v[2][e], v[3][e]));
+      V8<T>::store(out + (((long)b * Ho + ho) * Wo + wo) * C + g * 8, m);
+    } else {  // gradient goes to the first maximum in scan order (0,0) (0,1) (1,0) (1,1), as ATen does
+      float g_[8], d[4][8];
+      V8<T>::load(dy + (((long)b * Ho + ho) * Wo + wo) * C + g * 8, g_);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int arg = 0;
+        float best = v[0][e];
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+          if (v[k][e] > best) { best = v[k][e]; arg = k; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[k][e] = (k == arg) ? g_[e] : 0.f;
+      }
+      V8<T>::store(out + in0, d[0]);
+      V8<T>::store(out + in0 + C, d[1]);
+      V8<T>::store(out + in0 + (long)W * C, d[2]);
+      V8<T>::store(out + in0 + (long)W * C + C, d[3]);
+    }
+  }
+}
+
+// ============================================================================ K10: bilinear x2 + concat, NHWC
+// out[b, h2, w2, 0:Cs] = skip;  out[b, h2, w2, Cs:Cs+Cx] = bilinear(x) with align_corners=True.
+__device__ __forceinline__ void src_index(int dst, float ratio, int in_size, int& i0, int& ip, float& l0, float& l1) {
+  const float r = ratio * dst;          // ATen: area_pixel_compute_source_index(align_corners=True)
+  i0 = (int)r;
+  ip = (i0 < in_size - 1) ? 1 : 0;
+  l1 = r - i0;
+  l0 = 1.f - l1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upcat_fwd_kernel(const T* __restrict__ skip, const T* __restrict__ x,
+                                                        T* __restrict__ out, int B, int H, int W, int Cs, int Cx) {
+  const int H2 = 2 * H, W2 = 2 * W, Ct = Cs + Cx, G = Ct / 8, Gs = Cs / 8;
+  const float rh = H2 > 1 ? (float)(H - 1) / (H2 - 1) : 0.f, rw = W2 > 1 ? (float)(W - 1) / (W2 - 1) : 0.f;
+  const long total = (long)B * H2 * W2 * G;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    long p = idx / G;
+    const int w2 = (int)(p % W2);
+    p /= W2;
+    const int h2 = (int)(p % H2), b = (int)(p / H2);
+    float o[8];
+    if (g < Gs) {
+      V8<T>::load(skip + (((long)b * H2 + h2) * W2 + w2) * Cs + g * 8, o);
+    } else {
+      int h1, hp, w1, wp;
+      float h0l, h1l, w0l, w1l;
+      src_index(h2, rh, H, h1, hp, h0l, h1l);
+      src_index(w2, rw, W, w1, wp, w0l, w1l);
+      const long base = (((long)b * H + h1) * W + w1) * Cx + (g - Gs) * 8;
+      float a[8], bq[8], c[8], d[8];
+      V8<T>::load(x + base, a);
+      V8<T>::load(x + base + (long)wp * Cx, bq);
+      V8<T>::load(x + base + (long)hp * W * Cx, c);
+      V8<T>::load(x + base + (long)hp * W * Cx + (long)wp * Cx, d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = h0l * (w0l * a[e] + w1l * bq[e]) + h1l * (w0l * c[e] + w1l * d[e]);
+    }
+    V8<T>::store(out + (((long)b * H2 + h2) * W2 + w2) * Ct + g * 8, o);
+  }
+}
+
+// backward: dskip = dout[..., :Cs];  dx[b, h, w, :] = sum over the <= 4x4 output pixels whose stencil touches (h, w)
+template <typename T>
+__global__ void __launch_bounds__(256) upcat_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dskip,
+                                                        T* __restrict__ dx, int B, int H, int W, int Cs, int Cx) {
+  const int H2 = 2 * H, W2 = 2 * W, Ct = Cs + Cx, Gs = Cs / 8, Gx = Cx / 8;
+  const float rh = H2 > 1 ? (float)(H - 1) / (H2 - 1) : 0.f, rw = W2 > 1 ? (float)(W - 1) / (W2 - 1) : 0.f;
+  const long n_skip = (long)B * H2 * W2 * Gs, n_x = (long)B * H * W * Gx;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n_skip + n_x;
+       idx += (long)gridDim.x * blockDim.x) {
+    float v[8];
+    if (idx < n_skip) {
+      const int g = (int)(idx % Gs);
+      const long pix = idx / Gs;
+      V8<T>::load(dout + pix * Ct + g * 8, v);
+      V8<T>::store(dskip + pix * Cs + g * 8, v);
+      continue;
+    }
+    long p = idx - n_skip;
+    const int g = (int)(p % Gx);
+    p /= Gx;
+    const int w = (int)(p % W);
+    p /= W;
+    const int h = (int)(p % H), b = (int)(p / H);
+    float acc[8] = {};
+    // candidate output rows: those with source row h (weight h0l) or h - 1 (weight h1l, when its hp == 1)
+    const int h2_lo = max(0, 2 * h - 2), h2_hi = min(H2 - 1, 2 * h + 2);
+    const int w2_lo = max(0, 2 * w - 2), w2_hi = min(W2 - 1, 2 * w + 2);
+    for (int h2 = h2_lo; h2 <= h2_hi; ++h2) {
+      int h1, hp;
+      float h0l, h1l;
+      src_index(h2, rh, H, h1, hp, h0l, h1l);
+      float wh = 0.f;
+      if (h1 == h) wh += h0l;
+      if (h1 + hp == h) wh += h1l;       // (hp == 0: both taps hit row h1, as in the forward)
+      if (wh == 0.f) continue;
+      for (int w2 = w2_lo; w2 <= w2_hi; ++w2) {
+        int w1, wp;
+        float w0l, w1l;
+        src_index(w2, rw, W, w1, wp, w0l, w1l);
+        float ww = 0.f;
+        if (w1 == w) ww += w0l;
+        if (w1 + wp == w) ww += w1l;
+        if (ww == 0.f) continue;
+        V8<T>::load(dout + (((long)b * H2 + h2) * W2 + w2) * Ct + Cs + g * 8, v);
+        const float wgt = wh * ww;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, v[e], acc[e]);
+      }
+    }
+    V8<T>::store(dx + (((long)b * H + h) * W + w) * Cx + g * 8, acc);
+  }
+}
+
+// ============================================================================ K11: LayerNorm over (C, H, W) per sample
+// x, y: [B][L] with L = H*W*C in NHWC order; gamma / beta: f32 [L] in the same order.
+template <typename T>
+__global__ void __launch_bounds__(256) sample_stats_kernel(const T* __restrict__ x, float* __restrict__ sums, long L) {
+  // grid (chunks, B); sums[b] = (sum, sumsq)
+  __shared__ float red[2][8];
+  const int b = blockIdx.y;
+  const T* xb = x + (long)b * L;
+  float s1 = 0.f, s2 = 0.f;
+  for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < L; i += (long)gridDim.x * blockDim.x * 8) {
+    float v[8];
+    V8<T>::load(xb + i, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s1 += v[e];
+      s2 = fmaf(v[e], v[e], s2);
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    atomicAdd(sums + 2 * b + threadIdx.x, t);
+  }
+}
+
+__global__ void sample_finalize_kernel(const float* __restrict__ sums, float* __restrict__ mean,
+                                       float* __restrict__ rstd, int B, long L, float eps) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double mu_ = (double)sums[2 * b] / (double)L;
+  double var = (double)sums[2 * b + 1] / (double)L - mu_ * mu_;
+  if (var < 0.0) var = 0.0;
+  mean[b] = (float)mu_;
+  rstd[b] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sample_ln_apply_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd, T* __restrict__ y, int B,
+                                                              long L) {
+  // thread owns 8 consecutive positions and walks over the batch: gamma / beta are read once per thread
+  for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < L; i += (long)gridDim.x * blockDim.x * 8) {
+    float g[8], bt[8];
+    V8<float>::load(gamma + i, g);
+    V8<float>::load(beta + i, bt);
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+      const float mu_ = mean[b], rs = rstd[b];
+      float v[8];
+      V8<T>::load(x + (long)b * L + i, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (v[e] - mu_) * rs * g[e] + bt[e];
+      V8<T>::store(y + (long)b * L + i, v);
+    }
+  }
+}
+
+// backward pass A: per-sample s1 = sum(dy*gamma), s2 = sum(dy*gamma*xhat)
+template <typename T>
+__global__ void __launch_bounds__(256) sample_ln_bwd_stats_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd,
+                                                                  float* __restrict__ sums, long L) {
+  __shared__ float red[2][8];
+  const int b = blockIdx.y;
+  const float mu_ = mean[b], rs = rstd[b];
+  float s1 = 0.f, s2 = 0.f;
+  for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < L; i += (long)gridDim.x * blockDim.x * 8) {
+    float d[8], v[8], g[8];
+    V8<T>::load(dy + (long)b * L + i, d);
+    V8<T>::load(x + (long)b * L + i, v);
+    V8<float>::load(gamma + i, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float t = d[e] * g[e];
+      s1 += t;
+      s2 = fmaf(t, (v[e] - mu_) * rs, s2);
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    atomicAdd(sums + 2 * b + threadIdx.x, t);
+  }
+}
+
+// backward pass B: dx, and dgamma / dbeta reduced over the batch by the thread that owns the position
+template <typename T>
+__global__ void __launch_bounds__(256) sample_ln_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd,
+                                                                  const float* __restrict__ sums, T* __restrict__ dx,
+                                                                  float* __restrict__ dgamma,
+                                                                  float* __restrict__ dbeta, int B, long L) {
+  const float invL = 1.f / (float)L;
+  for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < L; i += (long)gridDim.x * blockDim.x * 8) {
+    float g[8], dg[8] = {}, db[8] = {};
+    V8<float>::load(gamma + i, g);
+    for (int b = 0; b < B; ++b) {
+      const float mu_ = mean[b], rs = rstd[b], c1 = sums[2 * b] * invL, c2 = sums[2 * b + 1] * invL;
+      float d[8], v[8], o[8];
+      V8<T>::load(dy + (long)b * L + i, d);
+      V8<T>::load(x + (long)b * L + i, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (v[e] - mu_) * rs;
+        dg[e] = fmaf(d[e], xh, dg[e]);
+        db[e] += d[e];
+        o[e] = rs * (d[e] * g[e] - c1 - xh * c2);
+      }
+      V8<T>::store(dx + (long)b * L + i, o);
+    }
+    V8<float>::store(dgamma + i, dg);
+    V8<float>::store(dbeta + i, db);
+  }
+}
+
+// ============================================================================ A14: fused cross-entropy (mean) fwd + grad
+// logits [M rows][C classes] (channels-last), labels int64 [M].  One warp per row.
+//   loss_sum += lse(row) - logit[label];   dlogits = (softmax - onehot) * inv_count   (0 for ignored rows)
+template <typename T>
+__global__ void __launch_bounds__(256) ce_fused_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                       const float* __restrict__ valid_count, long ignore_index,
+                                                       T* __restrict__ dlogits, float* __restrict__ loss_sum, long M,
+                                                       int C) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const float inv = 1.f / fmaxf(valid_count[0], 1.f);
+  float local = 0.f;
+  for (long row = (long)blockIdx.x * 8 + wib; row < M; row += (long)gridDim.x * 8) {
+    const T* lr = logits + row * C;
+    T* dr = dlogits + row * C;
+    const long lab = labels[row];
+    if (lab == ignore_index) {
+      for (int c = lane; c < C; c += 32) st_f(dr + c, 0.f);
+      continue;
+    }
+    float v[8];  // C <= 256
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane + 32 * k;
+      v[k] = (c < C) ? ld_f(lr + c) : -INFINITY;
+      mx = fmaxf(mx, v[k]);
+    }
+    mx = warp_max(mx);
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = __expf(v[k] - mx);       // exp(-inf) = 0 for the padding lanes
+      se += v[k];
+    }
+    se = warp_sum(se);
+    const float inv_se = 1.f / se;
+    float picked = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane + 32 * k;
+      if (c < C) {
+        const float p = v[k] * inv_se;
+        if (c == lab) picked = p;
+        st_f(dr + c, (p - (c == lab ? 1.f : 0.f)) * inv);
+      }
+    }
+    picked = warp_sum(picked);        // exactly one lane holds it
+    if (lane == 0) local += -__logf(fmaxf(picked, 1e-38f));
+  }
+  __shared__ float red[8];
+  if (lane == 0) red[wib] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(loss_sum, t * inv);
+  }
+}
+
+// ============================================================================ launchers
+static int grid_for(long items, int threads = 256) {
+  long blocks = (items + threads - 1) / threads;
+  const long cap = 148L * 16;
+  return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+#define MU_T(dtype, CALL_F32, CALL_BF16) \
+  if ((dtype) == MU_F32) { CALL_F32; } else { CALL_BF16; }
+
+int launch_maxpool2(const void* x, const void* dy, void* out, int B, int H, int W, int C, int bwd, int dtype,
+                    cudaStream_t s) {
+  if (C % 8 || H % 2 || W % 2) {
+    set_error("maxpool2: needs C %% 8 == 0 and even H, W (C=%d H=%d W=%d)", C, H, W);
+    return MU_ERR_BAD_SHAPE;
+  }
+  const int grid = grid_for((long)B * (H / 2) * (W / 2) * (C / 8));
+  if (!bwd) {
+    MU_T(dtype, (maxpool2_kernel<float, false><<<grid, 256, 0, s>>>((const float*)x, nullptr, (float*)out, B, H, W, C)),
+         (maxpool2_kernel<__nv_bfloat16, false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, nullptr,
+                                                                    (__nv_bfloat16*)out, B, H, W, C)));
+  } else {
+    MU_T(dtype, (maxpool2_kernel<float, true><<<grid, 256, 0, s>>>((const float*)x, (const float*)dy, (float*)out, B, H, W, C)),
+         (maxpool2_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
+                                                                   (__nv_bfloat16*)out, B, H, W, C)));
+  }
+  return check_launch("maxpool2");
+}
+
+int launch_upcat_fwd(const void* skip, const void* x, void* out, int B, int H, int W, int Cs, int Cx, int dtype,
+                     cudaStream_t s) {
+  if (Cs % 8 || Cx % 8) {
+    set_error("upsample_concat: channel counts must be multiples of 8 (Cs=%d Cx=%d)", Cs, Cx);
+    return MU_ERR_BAD_SHAPE;
+  }
+  const int grid = grid_for((long)B * 4 * H * W * ((Cs + Cx) / 8));
+  MU_T(dtype, (upcat_fwd_kernel<float><<<grid, 256, 0, s>>>((const float*)skip, (const float*)x, (float*)out, B, H, W, Cs, Cx)),
+       (upcat_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)skip, (const __nv_bfloat16*)x,
+                                                             (__nv_bfloat16*)out, B, H, W, Cs, Cx)));
+  return check_launch("upsample_concat_fwd");
+}
+
+int launch_upcat_bwd(const void* dout, void* dskip, void* dx, int B, int H, int W, int Cs, int Cx, int dtype,
+                     cudaStream_t s) {
+  if (Cs % 8 || Cx % 8) {
+    set_error("upsample_concat: channel counts must be multiples of 8 (Cs=%d Cx=%d)", Cs, Cx);
+    return MU_ERR_BAD_SHAPE;
+  }
+  const int grid = grid_for((long)B * 4 * H * W * (Cs / 8) + (long)B * H * W * (Cx / 8));
+  MU_T(dtype, (upcat_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)dout, (float*)dskip, (float*)dx, B, H, W, Cs, Cx)),
+       (upcat_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dskip,
+                                                             (__nv_bfloat16*)dx, B, H, W, Cs, Cx)));
+  return check_launch("upsample_concat_bwd");
+}
+
+int launch_sample_ln_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, float* mean,
+                         float* rstd, float* sums, int B, long L, int dtype, cudaStream_t s) {
+  if (L % 8) {
+    set_error("sample_layernorm: normalized size must be a multiple of 8 (L=%ld)", L);
+    return MU_ERR_BAD_SHAPE;
+  }
+  cudaMemsetAsync(sums, 0, 2 * (size_t)B * sizeof(float), s);
+  int chunks = (int)((L / 8 + 255) / 256);
+  if (chunks > 64) chunks = 64;
+  dim3 g1(chunks, B);
+  MU_T(dtype, (sample_stats_kernel<float><<<g1, 256, 0, s>>>((const float*)x, sums, L)),
+       (sample_stats_kernel<__nv_bfloat16><<<g1, 256, 0, s>>>((const __nv_bfloat16*)x, sums, L)));
+  sample_finalize_kernel<<<(B + 127) / 128, 128, 0, s>>>(sums, mean, rstd, B, L, eps);
+  int pos_blocks = (int)((L / 8 + 255) / 256);
+  int by = 1;
+  while ((long)pos_blocks * by < 148 * 4 && by < B) by *= 2;
+  dim3 g2(pos_blocks, by);
+  MU_T(dtype, (sample_ln_apply_kernel<float><<<g2, 256, 0, s>>>((const float*)x, gamma, beta, mean, rstd, (float*)y, B, L)),
+       (sample_ln_apply_kernel<__nv_bfloat16><<<g2, 256, 0, s>>>((const __nv_bfloat16*)x, gamma, beta, mean, rstd,
+                                                                 (__nv_bfloat16*)y, B, L)));
+  return check_launch("sample_layernorm_fwd");
+}
+
+int launch_sample_ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                         float* sums, void* dx, float* dgamma, float* dbeta, int B, long L, int dtype,
+                         cudaStream_t s) {
+  if (L % 8) {
+    set_error("sample_layernorm: normalized size must be a multiple of 8 (L=%ld)", L);
+    return MU_ERR_BAD_SHAPE;
+  }
+  cudaMemsetAsync(sums, 0, 2 * (size_t)B * sizeof(float), s);
+  int chunks = (int)((L / 8 + 255) / 256);
+  if (chunks > 64) chunks = 64;
+  dim3 g1(chunks, B);
+  MU_T(dtype, (sample_ln_bwd_stats_kernel<float><<<g1, 256, 0, s>>>((const float*)dy, (const float*)x, gamma, mean, rstd, sums, L)),
+       (sample_ln_bwd_stats_kernel<__nv_bfloat16><<<g1, 256, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                                                                     gamma, mean, rstd, sums, L)));
+  const int pos_blocks = (int)((L / 8 + 255) / 256);
+  MU_T(dtype, (sample_ln_bwd_apply_kernel<float><<<pos_blocks, 256, 0, s>>>((const float*)dy, (const float*)x, gamma, mean, rstd,
+                                                                         sums, (float*)dx, dgamma, dbeta, B, L)),
+       (sample_ln_bwd_apply_kernel<__nv_bfloat16><<<pos_blocks, 256, 0, s>>>(
+           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, gamma, mean, rstd, sums, (__nv_bfloat16*)dx, dgamma, dbeta,
+           B, L)));
+  return check_launch("sample_layernorm_bwd");
+}
+
+int launch_ce_fused(const void* logits, const int64_t* labels, const float* valid_count, long ignore_index,
+                    void* dlogits, float* loss_sum, long M, int C, int dtype, cudaStream_t s) {
+  if (C > 256 || C < 1) {
+    set_error("cross_entropy: class count must be in [1, 256] (got %d)", C);
+    return MU_ERR_BAD_SHAPE;
+  }
+  cudaMemsetAsync(loss_sum, 0, sizeof(float), s);
+  const int grid = grid_for((M + 7) / 8, 1);
+  MU_T(dtype, (ce_fused_kernel<float><<<grid, 256, 0, s>>>((const float*)logits, labels, valid_count, ignore_index,
+                                                        (float*)dlogits, loss_sum, M, C)),
+       (ce_fused_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)logits, labels, valid_count,
+                                                            ignore_index, (__nv_bfloat16*)dlogits, loss_sum, M, C)));
+  return check_launch("cross_entropy_fused");
+}
+
+}  // namespace mu

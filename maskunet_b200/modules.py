@@ -115,6 +115,12 @@ class Mask2FormerAttention(nn.Module):
         return y.view(batch, channels, height, width)                               # :190
 
 
+def _fast_layout(x: torch.Tensor, channel_multiple: int = 8) -> bool:
+    """True when x is a CUDA channels-last activation our NHWC kernels take."""
+    return (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16)
+            and x.shape[1] % channel_multiple == 0 and x.is_contiguous(memory_format=torch.channels_last))
+
+
 def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Optional[torch.Tensor] = None):
     """act(BatchNorm2d(x) [+ residual]) -- the BN / GELU / ReLU / residual chains of ade_semantic.py:198-210,
     :219, :240 and :283-287.
@@ -193,7 +199,11 @@ class DownSample(nn.Module):
 
     def forward(self, x):
         pool, block1, block2, bn = self.maxpool_conv
-        return fused_bn_act(block2(block1(pool(x))), bn, ops.ACT_NONE)
+        if _fast_layout(x) and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+            h = ops.maxpool2(x)                      # K9, channels-last kernel
+        else:
+            h = pool(x)
+        return fused_bn_act(block2(block1(h)), bn, ops.ACT_NONE)
 
 
 class UpSample(nn.Module):
@@ -210,9 +220,12 @@ class UpSample(nn.Module):
         self.emb_layer = _dead_embedding(emb_dim, out_channels)
 
     def forward(self, x, skip_x):
-        up = self.upsample(x)
         block1, block2, bn = self.conv
-        h = torch.cat([skip_x, up.to(skip_x.dtype)], dim=1)
+        if _fast_layout(x) and _fast_layout(skip_x) and x.dtype == skip_x.dtype:
+            h = ops.upsample_concat(skip_x, x)       # K10: bilinear x2 + concat in one pass
+        else:
+            up = self.upsample(x)
+            h = torch.cat([skip_x, up.to(skip_x.dtype)], dim=1)
         return fused_bn_act(block2(block1(h)), bn, ops.ACT_NONE)
 
 
@@ -270,6 +283,11 @@ class UNet(nn.Module):
         h = self.self_attention4(self.dropout(self.upsample1(x4, x3)))
         h = self.self_attention5(self.dropout(self.upsample2(h, x2)))
         h = self.self_attention6(self.upsample3(h, x1))
+        if _fast_layout(h) and tuple(h.shape[1:]) == tuple(self.norm.normalized_shape):
+            # K11: LayerNorm([C, H, W]) on channels-last memory; parameters viewed in the same element order
+            gamma = self.norm.weight.float().permute(1, 2, 0).contiguous()
+            beta = self.norm.bias.float().permute(1, 2, 0).contiguous()
+            return ops.sample_layernorm(h, gamma, beta, self.norm.eps)[0]
         return self.norm(h)
 
     @staticmethod

@@ -409,6 +409,196 @@ def _bn_backward(ctx, dy, *unused):
 bn_act_fwd.register_autograd(_bn_backward, setup_context=_bn_setup)
 
 
+# ------------------------------------------------------------------ K9: MaxPool2d(2), channels-last
+def _nhwc(x: Tensor):
+    if not (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)):
+        raise RuntimeError("this maskunet op takes 4-D channels-last tensors")
+    return x.shape[0], x.shape[1], x.shape[2], x.shape[3]          # B, C, H, W
+
+
+def _empty_cl(x: Tensor, B, C, H, W):
+    return torch.empty((B, C, H, W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+
+
+@torch.library.custom_op("maskunet::maxpool2", mutates_args=(), device_types="cuda")
+def maxpool2(x: Tensor) -> Tensor:
+    B, C, H, W = _nhwc(x)
+    y = _empty_cl(x, B, C, H // 2, W // 2)
+    with torch.cuda.device(x.device):
+        _count(1)
+        check(_L.mu_maxpool2(_p(x), _optp(None), _p(y), B, H, W, C, 0, _code(x), _stream(x)), "mu_maxpool2")
+    return y
+
+
+@maxpool2.register_fake
+def _(x):
+    B, C, H, W = x.shape
+    return _empty_cl(x, B, C, H // 2, W // 2)
+
+
+@torch.library.custom_op("maskunet::maxpool2_bwd", mutates_args=(), device_types="cuda")
+def maxpool2_bwd(x: Tensor, dy: Tensor) -> Tensor:
+    B, C, H, W = _nhwc(x)
+    _nhwc(dy)
+    dx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _count(1)
+        check(_L.mu_maxpool2(_p(x), _p(dy), _p(dx), B, H, W, C, 1, _code(x), _stream(x)), "mu_maxpool2")
+    return dx
+
+
+@maxpool2_bwd.register_fake
+def _(x, dy):
+    return torch.empty_like(x)
+
+
+maxpool2.register_autograd(
+    lambda ctx, g: maxpool2_bwd(ctx.saved_tensors[0], g.contiguous(memory_format=torch.channels_last)),
+    setup_context=lambda ctx, inputs, output: ctx.save_for_backward(inputs[0]))
+
+
+# ------------------------------------------------------------------ K10: bilinear x2 (align_corners) + concat
+@torch.library.custom_op("maskunet::upsample_concat", mutates_args=(), device_types="cuda")
+def upsample_concat(skip: Tensor, x: Tensor) -> Tensor:
+    """cat([skip, Upsample(2, bilinear, align_corners=True)(x)], dim=1) on channels-last tensors."""
+    B, Cx, H, W = _nhwc(x)
+    Bs, Cs, H2, W2 = _nhwc(skip)
+    assert (Bs, H2, W2) == (B, 2 * H, 2 * W) and skip.dtype == x.dtype
+    out = _empty_cl(x, B, Cs + Cx, H2, W2)
+    with torch.cuda.device(x.device):
+        _count(1)
+        check(_L.mu_upsample_concat_fwd(_p(skip), _p(x), _p(out), B, H, W, Cs, Cx, _code(x), _stream(x)),
+              "mu_upsample_concat_fwd")
+    return out
+
+
+@upsample_concat.register_fake
+def _(skip, x):
+    B, Cx, H, W = x.shape
+    return _empty_cl(x, B, skip.shape[1] + Cx, 2 * H, 2 * W)
+
+
+@torch.library.custom_op("maskunet::upsample_concat_bwd", mutates_args=(), device_types="cuda")
+def upsample_concat_bwd(dout: Tensor, cs: int) -> Tuple[Tensor, Tensor]:
+    B, Ct, H2, W2 = _nhwc(dout)
+    cx, H, W = Ct - cs, H2 // 2, W2 // 2
+    dskip = _empty_cl(dout, B, cs, H2, W2)
+    dx = _empty_cl(dout, B, cx, H, W)
+    with torch.cuda.device(dout.device):
+        _count(1)
+        check(_L.mu_upsample_concat_bwd(_p(dout), _p(dskip), _p(dx), B, H, W, cs, cx, _code(dout), _stream(dout)),
+              "mu_upsample_concat_bwd")
+    return dskip, dx
+
+
+@upsample_concat_bwd.register_fake
+def _(dout, cs):
+    B, Ct, H2, W2 = dout.shape
+    return _empty_cl(dout, B, cs, H2, W2), _empty_cl(dout, B, Ct - cs, H2 // 2, W2 // 2)
+
+
+def _upcat_setup(ctx, inputs, output):
+    ctx.cs = inputs[0].shape[1]
+
+
+upsample_concat.register_autograd(
+    lambda ctx, g: upsample_concat_bwd(g.contiguous(memory_format=torch.channels_last), ctx.cs),
+    setup_context=_upcat_setup)
+
+
+# ------------------------------------------------------------------ K11: LayerNorm over (C, H, W) per sample
+@torch.library.custom_op("maskunet::sample_layernorm", mutates_args=(), device_types="cuda")
+def sample_layernorm(x: Tensor, gamma_nhwc: Tensor, beta_nhwc: Tensor, eps: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """x channels-last [B, C, H, W]; gamma / beta f32 [H, W, C] (the [C, H, W] parameters permuted)."""
+    B, C, H, W = _nhwc(x)
+    _cuda(gamma_nhwc, beta_nhwc)
+    L = C * H * W
+    y = torch.empty_like(x)
+    f32 = dict(dtype=torch.float32, device=x.device)
+    mean, rstd, sums = torch.empty((B,), **f32), torch.empty((B,), **f32), torch.empty((2 * B,), **f32)
+    with torch.cuda.device(x.device):
+        _count(3)
+        check(_L.mu_sample_layernorm_fwd(_p(x), _p(gamma_nhwc), _p(beta_nhwc), eps, _p(y), _p(mean), _p(rstd),
+                                         _p(sums), B, L, _code(x), _stream(x)), "mu_sample_layernorm_fwd")
+    return y, mean, rstd
+
+
+@sample_layernorm.register_fake
+def _(x, gamma_nhwc, beta_nhwc, eps):
+    v = x.new_empty((x.shape[0],), dtype=torch.float32)
+    return torch.empty_like(x), v, torch.empty_like(v)
+
+
+@torch.library.custom_op("maskunet::sample_layernorm_bwd", mutates_args=(), device_types="cuda")
+def sample_layernorm_bwd(dy: Tensor, x: Tensor, gamma_nhwc: Tensor, mean: Tensor, rstd: Tensor
+                         ) -> Tuple[Tensor, Tensor, Tensor]:
+    B, C, H, W = _nhwc(x)
+    _nhwc(dy)
+    L = C * H * W
+    dx = torch.empty_like(x)
+    dgamma, dbeta = torch.empty_like(gamma_nhwc), torch.empty_like(gamma_nhwc)
+    sums = torch.empty((2 * B,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _count(2)
+        check(_L.mu_sample_layernorm_bwd(_p(dy), _p(x), _p(gamma_nhwc), _p(mean), _p(rstd), _p(sums), _p(dx),
+                                         _p(dgamma), _p(dbeta), B, L, _code(x), _stream(x)),
+              "mu_sample_layernorm_bwd")
+    return dx, dgamma, dbeta
+
+
+@sample_layernorm_bwd.register_fake
+def _(dy, x, gamma_nhwc, mean, rstd):
+    return torch.empty_like(x), torch.empty_like(gamma_nhwc), torch.empty_like(gamma_nhwc)
+
+
+def _sln_setup(ctx, inputs, output):
+    x, gamma, beta, eps = inputs
+    ctx.save_for_backward(x, gamma, output[1], output[2])
+
+
+def _sln_backward(ctx, dy, *unused):
+    x, gamma, mean, rstd = ctx.saved_tensors
+    dx, dg, db = sample_layernorm_bwd(dy.contiguous(memory_format=torch.channels_last), x, gamma, mean, rstd)
+    return dx, dg, db, None
+
+
+sample_layernorm.register_autograd(_sln_backward, setup_context=_sln_setup)
+
+
+# ------------------------------------------------------------------ A14: fused cross-entropy (mean) + gradient
+@torch.library.custom_op("maskunet::cross_entropy_fused", mutates_args=(), device_types="cuda")
+def cross_entropy_fused(logits: Tensor, labels: Tensor, ignore_index: int) -> Tuple[Tensor, Tensor]:
+    """logits channels-last [B, C, H, W], labels int64 [B, H, W] -> (mean loss [1] f32, dlogits like logits)."""
+    B, C, H, W = _nhwc(logits)
+    _cuda(labels)
+    assert labels.dtype == torch.int64 and labels.shape == (B, H, W)
+    dlogits = torch.empty_like(logits)
+    loss = torch.empty((1,), dtype=torch.float32, device=logits.device)
+    count = (labels != ignore_index).sum().to(torch.float32).reshape(1)
+    with torch.cuda.device(logits.device):
+        _count(1)
+        check(_L.mu_cross_entropy_fused(_p(logits), _p(labels), _p(count), ignore_index, _p(dlogits), _p(loss),
+                                        B * H * W, C, _code(logits), _stream(logits)), "mu_cross_entropy_fused")
+    return loss, dlogits
+
+
+@cross_entropy_fused.register_fake
+def _(logits, labels, ignore_index):
+    return logits.new_empty((1,), dtype=torch.float32), torch.empty_like(logits)
+
+
+def _ce_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+
+
+def _ce_backward(ctx, dloss, *unused):
+    (dlogits,) = ctx.saved_tensors
+    return dlogits * dloss.to(dlogits.dtype), None, None
+
+
+cross_entropy_fused.register_autograd(_ce_backward, setup_context=_ce_setup)
+
+
 # ------------------------------------------------------------------ the module-level op (A3-A9 of SURVEY.md 8(a))
 @torch.library.custom_op("maskunet::mask_attention", mutates_args=(), device_types="cuda")
 def mask_attention(x: Tensor, w_qkv: Tensor, b_qkv: Tensor, gamma: Tensor, beta: Tensor, keep_rank: Tensor,

@@ -14,6 +14,7 @@ from typing import Optional
 import torch
 import torch.nn.functional as F
 
+from . import ops
 from .ddp import GradReducer
 
 
@@ -39,7 +40,12 @@ class Trainer:
         self.optimizer.zero_grad(set_to_none=True)
         out = self.model(images)
         logits = out[0] if isinstance(out, tuple) else out
-        loss = F.cross_entropy(logits.float(), labels, ignore_index=self.ignore_index)
+        if (logits.is_cuda and logits.shape[1] <= 256 and logits.dtype in (torch.float32, torch.bfloat16)
+                and logits.is_contiguous(memory_format=torch.channels_last)):
+            # fused CrossEntropyLoss(mean) forward + gradient on channels-last logits (one read, one write)
+            loss = ops.cross_entropy_fused(logits, labels, self.ignore_index)[0].squeeze(0)
+        else:
+            loss = F.cross_entropy(logits.float(), labels, ignore_index=self.ignore_index)
         loss.backward()
         if self.reducer is not None:
             self.reducer.finish()

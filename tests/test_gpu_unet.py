@@ -170,3 +170,78 @@ def test_unet_fp32_channels_last_uses_fused_kernels_and_matches_reference():
             continue
         g = float(p.grad.double().norm())
         assert abs(g - r) < 2e-3 * r + 1e-7, (name, g, r)
+
+
+# ------------------------------------------------------------------ K9 / K10 / K11 / A14 kernels vs the stock torch ops
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-2)])
+def test_maxpool2_matches_torch(dtype, tol):
+    from maskunet_b200 import ops
+    torch.manual_seed(0)
+    x = _cl(torch.randn(3, 64, 20, 12, device=DEV).to(dtype)).requires_grad_(True)
+    xr = x.detach().float().requires_grad_(True)
+    dy = _cl(torch.randn(3, 64, 10, 6, device=DEV).to(dtype))
+    y = ops.maxpool2(x)
+    yr = torch.nn.functional.max_pool2d(xr, 2)
+    assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(y.float(), yr)
+    y.backward(dy)
+    yr.backward(dy.float())
+    assert torch.equal(x.grad.float(), xr.grad)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("H,W", [(16, 16), (8, 12)])
+def test_upsample_concat_matches_torch(dtype, tol, H, W):
+    from maskunet_b200 import ops
+    torch.manual_seed(1)
+    x = _cl(torch.randn(2, 32, H, W, device=DEV).to(dtype)).requires_grad_(True)
+    sk = _cl(torch.randn(2, 16, 2 * H, 2 * W, device=DEV).to(dtype)).requires_grad_(True)
+    xr, skr = x.detach().float().requires_grad_(True), sk.detach().float().requires_grad_(True)
+    dy = _cl(torch.randn(2, 48, 2 * H, 2 * W, device=DEV).to(dtype))
+    y = ops.upsample_concat(sk, x)
+    yr = torch.cat([skr, torch.nn.functional.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=True)], 1)
+    assert float((y.float() - yr).norm() / yr.norm()) < tol
+    y.backward(dy)
+    yr.backward(dy.float())
+    assert float((x.grad.float() - xr.grad).norm() / xr.grad.norm()) < tol
+    assert float((sk.grad.float() - skr.grad).norm() / skr.grad.norm()) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_sample_layernorm_matches_torch(dtype, tol):
+    from maskunet_b200 import ops
+    torch.manual_seed(2)
+    B, C, H, W = 5, 64, 16, 24
+    x = _cl((torch.randn(B, C, H, W, device=DEV) * 1.5 + 0.3).to(dtype)).requires_grad_(True)
+    g = (torch.rand(C, H, W, device=DEV) + 0.5).requires_grad_(True)
+    bt = torch.randn(C, H, W, device=DEV).requires_grad_(True)
+    xr, gr, br = (t.detach().float().requires_grad_(True) for t in (x, g, bt))
+    dy = _cl(torch.randn(B, C, H, W, device=DEV).to(dtype))
+    y = ops.sample_layernorm(x, g.permute(1, 2, 0).contiguous(), bt.permute(1, 2, 0).contiguous(), 1e-5)[0]
+    yr = torch.nn.functional.layer_norm(xr, [C, H, W], gr, br, 1e-5)
+    assert float((y.float() - yr).norm() / yr.norm()) < tol
+    y.backward(dy)
+    yr.backward(dy.float())
+    for a, b in ((x.grad, xr.grad), (g.grad, gr.grad), (bt.grad, br.grad)):
+        assert float((a.float() - b).norm() / b.norm()) < tol
+
+
+@pytest.mark.parametrize("C", [150, 19, 133])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_cross_entropy_fused_matches_torch(C, dtype, tol):
+    from maskunet_b200 import ops
+    torch.manual_seed(3)
+    logits = _cl((torch.randn(3, C, 16, 20, device=DEV) * 3).to(dtype)).requires_grad_(True)
+    lr = logits.detach().float().requires_grad_(True)
+    labels = torch.randint(0, C, (3, 16, 20), device=DEV)
+    labels[0, :4] = 255
+    loss = ops.cross_entropy_fused(logits, labels, 255)[0]
+    ref = torch.nn.functional.cross_entropy(lr, labels, ignore_index=255)
+    assert abs(float(loss) - float(ref)) < tol * max(1.0, abs(float(ref)))
+    (loss.squeeze() * 2.0).backward()
+    (ref * 2.0).backward()
+    assert float((logits.grad.float() - lr.grad).norm() / lr.grad.norm()) < tol
+    assert (logits.grad[0, :, :4] == 0).all()
