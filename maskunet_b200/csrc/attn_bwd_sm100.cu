@@ -24,7 +24,8 @@ constexpr float kLog2eB = 1.4426950408889634f;
 
 template <int D, int BM, int DH, int STAGES, int PB>
 struct BwdCfg {
-  static constexpr bool kDQT = (D >= 128);               // dQ tile computed transposed
+  static constexpr bool kDQT = (D >= 128);               // dQ tile computed transposed (dQ^T = K_j^T dS)
+  static constexpr int kDQM = 128;
   static constexpr int kKBytes = kBK * D * 2;            // K_j or V_j
   static constexpr int kQBytes = BM * D * 2;             // Q_i or dO_i
   static constexpr int kPBytes = kBK * BM * 2;           // P^T or dS^T
@@ -35,7 +36,10 @@ struct BwdCfg {
   static constexpr int kStatBytes = 2 * 2 * BM * 4;       // lse2, delta, double-buffered over tiles
   // PB = 2 double-buffers the P^T / dS^T tiles so that the exp / dS work of query tile i+1 overlaps the
   // dV / dK / dQ MMAs of tile i.  Dynamic shared memory is declared __align__(1024), no alignment slack.
-  static constexpr int kSmemBytes = 2 * kKBytes + 2 * STAGES * kQBytes + 2 * PB * kPBytes + kStatBytes + 256;
+  static constexpr bool kDQTma = (D <= 128);             // dQ tile leaves through a TMA reduce-add (smem permitting)
+  static constexpr int kDQStageBytes = kDQTma ? BM * DH * 4 : 0;   // fp32 dQ tile staged for the TMA reduce-add
+  static constexpr int kSmemBytes =
+      2 * kKBytes + 2 * STAGES * kQBytes + (1 + PB) * kPBytes + kDQStageBytes + kStatBytes + 256;
   static_assert(kSmemBytes <= 232448, "shared memory overflow");
 };
 
@@ -50,7 +54,8 @@ template <int D, int BM, int DH, int STAGES, int PB>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                       const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
-                      const int32_t* __restrict__ n_keep, const int32_t* __restrict__ keep_idx,
+                      const __grid_constant__ CUtensorMap tmap_dq, const int32_t* __restrict__ n_keep,
+                      const int32_t* __restrict__ keep_idx,
                       const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
                       __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int N, int NKP, float scale) {
   using Cfg = BwdCfg<D, BM, DH, STAGES, PB>;
@@ -64,9 +69,10 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   uint8_t* sV = sK + Cfg::kKBytes;
   uint8_t* sQ = sV + Cfg::kKBytes;                       // STAGES x Q_i
   uint8_t* sDO = sQ + STAGES * Cfg::kQBytes;             // STAGES x dO_i
-  uint8_t* sP = sDO + STAGES * Cfg::kQBytes;              // PB x P^T
-  uint8_t* sDS = sP + PB * Cfg::kPBytes;                  // PB x dS^T
-  float* sLse = reinterpret_cast<float*>(sDS + PB * Cfg::kPBytes);   // [2][BM], already * log2e
+  uint8_t* sP = sDO + STAGES * Cfg::kQBytes;              // P^T (single: only the dV MMA reads it)
+  uint8_t* sDS = sP + Cfg::kPBytes;                       // PB x dS^T
+  uint8_t* sDQ = sDS + PB * Cfg::kPBytes;                 // fp32 dQ staging (D = 64 only)
+  float* sLse = reinterpret_cast<float*>(sDQ + Cfg::kDQStageBytes);   // [2][BM], already * log2e
   float* sDelta = sLse + 2 * BM;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * BM);
   uint64_t* kv_full = bars;                 // 1
@@ -77,7 +83,9 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   uint64_t* pds_free = pds_full + 1;        // PB
   uint64_t* dq_full = pds_free + PB;        // 1
   uint64_t* dq_free = dq_full + 1;          // 1 (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_free + 1);
+  uint64_t* sdp_free = dq_free + 1;         // 1 (256 arrivals): S^T / dP^T of this tile are in registers
+  uint64_t* p_free = sdp_free + 1;          // 1: the dV MMAs have consumed P^T
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 1);
 
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.y, k0 = blockIdx.x * kBK, half = blockIdx.z;
@@ -96,6 +104,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     for (int i = 0; i < PB; ++i) mbar_init(pds_free + i, 1);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, 128);
+    mbar_init(sdp_free, 256);
+    mbar_init(p_free, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -113,6 +123,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // 512 threads start with 128 registers each; data-movement and reduction warpgroups hand registers to the two
+  // softmax warpgroups, which hold a whole S^T / dP^T half-row (the TMEM buffers are released right after the
+  // loads, so the next tile's S^T / dP^T MMAs run underneath the exp / dS arithmetic of this one).
+  if (warp < 4) {
+  reg_dealloc<56>();
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane_id() == 0) {
@@ -160,7 +175,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       };
       auto issue_acc = [&](int i) {
         const int st = i % STAGES;
-        const uint32_t p_addr = p_base + (i % PB) * Cfg::kPBytes, ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
+        const uint32_t p_addr = p_base, ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
         const uint32_t qa = q_addr + st * Cfg::kQBytes + half * 2 * (BM * 128);
         const uint32_t da = do_addr + st * Cfg::kQBytes + half * 2 * (BM * 128);
 #pragma unroll
@@ -169,6 +184,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           const uint64_t bd = make_smem_desc(da + kk * 2048, BM * 128, 1024);
           umma_ss(tmem_base + Cfg::kTmDV, a, bd, idesc_acc, (i > 0) || (kk > 0));
         }
+        umma_commit(p_free);
 #pragma unroll
         for (int kk = 0; kk < BM / 16; ++kk) {   // dK += dS^T Q_i
           const uint64_t a = make_smem_desc(ds_addr + (kk >> 2) * (kBK * 128) + (kk & 3) * 32, 0, 1024);
@@ -198,18 +214,24 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       mbar_wait(kv_full, 0);
       issue_s_dp(0);
       for (int i = 0; i < T; ++i) {
-        mbar_wait(pds_full, i & 1);          // P^T / dS^T of tile i in smem, S^T / dP^T TMEM drained
-        tc_fence_after();
         if (STAGES >= 2) {
-          if (i + 1 < T) issue_s_dp(i + 1);
+          mbar_wait(sdp_free, i & 1);        // S^T / dP^T of tile i drained into registers
+          tc_fence_after();
+          if (i + 1 < T) issue_s_dp(i + 1);  // runs underneath the softmax arithmetic of tile i
+          mbar_wait(pds_full, i & 1);        // P^T / dS^T of tile i are in shared memory
+          tc_fence_after();
           issue_acc(i);
-        } else {
+        } else {                             // single Q/dO stage: tile i+1 can only load after acc(i) released it
+          mbar_wait(pds_full, i & 1);
+          tc_fence_after();
           issue_acc(i);
           if (i + 1 < T) issue_s_dp(i + 1);
         }
       }
     }
-  } else if (warp >= 4 && warp < 12) {
+  }
+  } else if (warp < 12) {
+    reg_alloc<184>();
     // ===================================================== softmax-backward warps: thread <-> key row.
     // Two warpgroups split the query columns of every tile (no row reduction is needed in backward, so the
     // halves are independent); two warps per SM sub-partition hide each other's MUFU / FMA latencies.
@@ -233,7 +255,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     float nl2, ndl;
     fetch(0, nl2, ndl);
     constexpr int kChunksPerThread = BM / 64;            // 32-column chunks per thread
-    uint32_t s[32], dp[32];
+    uint32_t s[kChunksPerThread][32], dp[kChunksPerThread][32];
+    const bool tile_partial = k0 + kBK > nk;
     for (int i = 0; i < T; ++i) {
       const uint32_t my_lse = lse_addr + (i & 1) * BM * 4, my_delta = delta_addr + (i & 1) * BM * 4;
       if (t < BM) {
@@ -244,29 +267,41 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       named_bar_sync(1, 256);
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-      // the MMAs that last read this P^T / dS^T buffer (tile i - PB) must have completed
-      if (i >= PB) mbar_wait(pds_free + (i % PB), ((i / PB) - 1) & 1);
-      const uint32_t p_addr = p_base + (i % PB) * Cfg::kPBytes, ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
 #pragma unroll
       for (int cc = 0; cc < kChunksPerThread; ++cc) {
         const int c = hcol * kChunksPerThread + cc;      // 32-column chunk index within the tile
-        tmem_ld32(lane_base + Cfg::kTmS + c * 32, s);
-        tmem_ld32(lane_base + Cfg::kTmDP + c * 32, dp);
-        tmem_wait_ld();
+        tmem_ld32(lane_base + Cfg::kTmS + c * 32, s[cc]);
+        tmem_ld32(lane_base + Cfg::kTmDP + c * 32, dp[cc]);
+      }
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(sdp_free);
+      if (tile_partial && !key_ok) {                     // rows past n_keep in the last key tile: p = exp2(-inf) = 0
+#pragma unroll
+        for (int cc = 0; cc < kChunksPerThread; ++cc)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) s[cc][e] = 0xff800000u;
+      }
+      // the MMAs that last read this P^T / dS^T buffer (tile i - PB) must have completed
+      if (i >= PB) mbar_wait(pds_free + (i % PB), ((i / PB) - 1) & 1);
+      if (i > 0) mbar_wait(p_free, (i - 1) & 1);         // dV MMAs of tile i-1 are done with P^T
+      const uint32_t p_addr = p_base, ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
+#pragma unroll
+      for (int cc = 0; cc < kChunksPerThread; ++cc) {
+        const int c = hcol * kChunksPerThread + cc;
         uint32_t pk[16], dk[16];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float4 l2 = ld_shared_v4f(my_lse + (c * 32 + 4 * e) * 4);
           const float4 dl = ld_shared_v4f(my_delta + (c * 32 + 4 * e) * 4);
-          float p0 = fast_exp2(fmaf(__uint_as_float(s[4 * e + 0]), scale_log2, -l2.x));
-          float p1 = fast_exp2(fmaf(__uint_as_float(s[4 * e + 1]), scale_log2, -l2.y));
-          float p2 = fast_exp2(fmaf(__uint_as_float(s[4 * e + 2]), scale_log2, -l2.z));
-          float p3 = fast_exp2(fmaf(__uint_as_float(s[4 * e + 3]), scale_log2, -l2.w));
-          if (!key_ok) p0 = p1 = p2 = p3 = 0.f;
-          const float d0 = p0 * (__uint_as_float(dp[4 * e + 0]) - dl.x);
-          const float d1 = p1 * (__uint_as_float(dp[4 * e + 1]) - dl.y);
-          const float d2 = p2 * (__uint_as_float(dp[4 * e + 2]) - dl.z);
-          const float d3 = p3 * (__uint_as_float(dp[4 * e + 3]) - dl.w);
+          const float p0 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 0]), scale_log2, -l2.x));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 1]), scale_log2, -l2.y));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 2]), scale_log2, -l2.z));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 3]), scale_log2, -l2.w));
+          const float d0 = p0 * (__uint_as_float(dp[cc][4 * e + 0]) - dl.x);
+          const float d1 = p1 * (__uint_as_float(dp[cc][4 * e + 1]) - dl.y);
+          const float d2 = p2 * (__uint_as_float(dp[cc][4 * e + 2]) - dl.z);
+          const float d3 = p3 * (__uint_as_float(dp[cc][4 * e + 3]) - dl.w);
           pk[2 * e] = pack_bf16(p0, p1);
           pk[2 * e + 1] = pack_bf16(p2, p3);
           dk[2 * e] = pack_bf16(d0, d1);
@@ -297,22 +332,24 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       const int col0 = which == 0 ? Cfg::kTmDV : Cfg::kTmDK;
 #pragma unroll
       for (int c = 0; c < DH / 32; ++c) {
-        tmem_ld32(lane_base + col0 + c * 32, s);
+        uint32_t(&sv)[32] = s[0];
+        tmem_ld32(lane_base + col0 + c * 32, sv);
         tmem_wait_ld();
         if (key_ok) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 w;
-            w.x = pack_bf16(__uint_as_float(s[8 * g + 0]) * mul, __uint_as_float(s[8 * g + 1]) * mul);
-            w.y = pack_bf16(__uint_as_float(s[8 * g + 2]) * mul, __uint_as_float(s[8 * g + 3]) * mul);
-            w.z = pack_bf16(__uint_as_float(s[8 * g + 4]) * mul, __uint_as_float(s[8 * g + 5]) * mul);
-            w.w = pack_bf16(__uint_as_float(s[8 * g + 6]) * mul, __uint_as_float(s[8 * g + 7]) * mul);
+            w.x = pack_bf16(__uint_as_float(sv[8 * g + 0]) * mul, __uint_as_float(sv[8 * g + 1]) * mul);
+            w.y = pack_bf16(__uint_as_float(sv[8 * g + 2]) * mul, __uint_as_float(sv[8 * g + 3]) * mul);
+            w.z = pack_bf16(__uint_as_float(sv[8 * g + 4]) * mul, __uint_as_float(sv[8 * g + 5]) * mul);
+            w.w = pack_bf16(__uint_as_float(sv[8 * g + 6]) * mul, __uint_as_float(sv[8 * g + 7]) * mul);
             *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = w;
           }
         }
       }
     }
-  } else if (warp >= 12) {
+  } else {
+    reg_dealloc<72>();
     // ===================================================== dQ reduction warps
     const int quad = warp & 3;
     const int r = quad * 32 + (int)lane_id();
@@ -321,7 +358,38 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     for (int i = 0; i < T; ++i) {
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
-      if (DQT) {
+      if (DQT && Cfg::kDQTma) {
+        // dQ^T tile: lanes = channels, columns = queries.  Staged transposed ([query][channel], 128-byte rows,
+        // TMA swizzle; a warp's 32 lanes fill one row segment per store) and added by the TMA unit.
+        const uint32_t stage = smem_u32(sDQ);
+        const bool issuer = (threadIdx.x == kBwdThreads - 128);
+        if (issuer) tma_store_wait_read<0>();
+        named_bar_sync(2, 128);
+        const uint32_t sub = stage + (r >> 5) * (BM * 128);      // sub-tile = 32 channels
+        const uint32_t cj = (uint32_t)((r & 31) >> 2), cw = (uint32_t)(r & 3) * 4;
+#pragma unroll
+        for (int c = 0; c < BM / 32; ++c) {
+          tmem_ld32(lane_base + Cfg::kTmDQ + c * 32, v);
+          tmem_wait_ld();
+          if (c == BM / 32 - 1) {
+            tc_fence_before();
+            mbar_arrive(dq_free);
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const uint32_t qrow = (uint32_t)(c * 32 + e);
+            st_shared_f32(sub + qrow * 128 + ((cj ^ (qrow & 7)) * 16) + cw, __uint_as_float(v[e]) * scale);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (issuer) {
+#pragma unroll
+          for (int c = 0; c < DH / 32; ++c)
+            tma_reduce_add_3d(&tmap_dq, stage + c * (BM * 128), half * DH + c * 32, i * BM, b);
+          tma_store_commit();
+        }
+      } else if (DQT) {
         // lanes = channel (half * 128 + r), columns = queries of tile i: coalesced scalar reductions
         float* base = dq_acc + ((size_t)b * N + (size_t)i * BM) * D + half * DH + r;
 #pragma unroll
@@ -337,9 +405,13 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             if (i * BM + c * 32 + e < N) atomicAdd(base + (size_t)(c * 32 + e) * D, __uint_as_float(v[e]) * scale);
         }
       } else {
-        // lanes = query row, columns = channels
-        const bool ok = i * BM + r < N;
-        float* base = dq_acc + ((size_t)b * N + (size_t)i * BM + r) * D;
+        // lanes = query row, columns = channels.  The fp32 tile is staged in shared memory (128-byte rows,
+        // TMA swizzle) and added into the dQ accumulator by the TMA unit (cp.reduce.async.bulk.tensor .add):
+        // no LSU atomics, which were the dominant load on the L1 data pipe.
+        const uint32_t stage = smem_u32(sDQ);
+        const bool issuer = (threadIdx.x == kBwdThreads - 128);
+        if (issuer) tma_store_wait_read<0>();          // the previous tile's reduce has finished reading the stage
+        named_bar_sync(2, 128);
 #pragma unroll
         for (int c = 0; c < DH / 32; ++c) {
           tmem_ld32(lane_base + Cfg::kTmDQ + c * 32, v);
@@ -348,15 +420,26 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             tc_fence_before();
             mbar_arrive(dq_free);
           }
-          if (ok) {
+          const uint32_t row = stage + c * (BM * 128) + r * 128;   // sub-tile c = channels [32c, 32c+32)
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              red_add_v4(base + c * 32 + 4 * e, __uint_as_float(v[4 * e]) * scale, __uint_as_float(v[4 * e + 1]) * scale,
-                         __uint_as_float(v[4 * e + 2]) * scale, __uint_as_float(v[4 * e + 3]) * scale);
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t chunk = ((uint32_t)(ch ^ (r & 7))) * 16;
+            st_shared_v4(row + chunk, __float_as_uint(__uint_as_float(v[4 * ch]) * scale),
+                         __float_as_uint(__uint_as_float(v[4 * ch + 1]) * scale),
+                         __float_as_uint(__uint_as_float(v[4 * ch + 2]) * scale),
+                         __float_as_uint(__uint_as_float(v[4 * ch + 3]) * scale));
           }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (issuer) {
+#pragma unroll
+          for (int c = 0; c < DH / 32; ++c) tma_reduce_add_3d(&tmap_dq, stage + c * (BM * 128), c * 32, i * BM, b);
+          tma_store_commit();
         }
       }
     }
+    if (Cfg::kDQTma && threadIdx.x == kBwdThreads - 128) tma_store_wait<0>();   // all reduce-adds landed before exit
   }
   tc_fence_before();
   __syncthreads();
@@ -384,8 +467,9 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
                const void* d_o, const float* lse, const float* delta, void* dq, void* dkc, void* dvc, float* dq_acc,
                int B, int N, int NKP, cudaStream_t s) {
   using Cfg = BwdCfg<D, BM, DH, STAGES, PB>;
-  CUtensorMap tq, tdo, tk, tv;
+  CUtensorMap tq, tdo, tk, tv, tdq;
   int rc;
+  if ((rc = make_tmap_f32_3d(&tdq, dq_acc, D, N, B, BM))) return rc;
   if ((rc = make_tmap_bf16_3d(&tq, q, D, N, B, BM))) return rc;
   if ((rc = make_tmap_bf16_3d(&tdo, d_o, D, N, B, BM))) return rc;
   if ((rc = make_tmap_bf16_3d(&tk, kc, D, NKP, B, kBK))) return rc;
@@ -402,7 +486,7 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
   cudaMemsetAsync(dvc, 0, n * 2, s);
   dim3 grid(NKP / kBK, B, D / DH);
   const float scale = 1.f / sqrtf((float)D);
-  kern<<<grid, kBwdThreads, Cfg::kSmemBytes, s>>>(tq, tdo, tk, tv, n_keep, keep_idx, lse, delta, dq_acc, (__nv_bfloat16*)dkc,
+  kern<<<grid, kBwdThreads, Cfg::kSmemBytes, s>>>(tq, tdo, tk, tv, tdq, n_keep, keep_idx, lse, delta, dq_acc, (__nv_bfloat16*)dkc,
                                                   (__nv_bfloat16*)dvc, N, NKP, scale);
   if ((rc = check_launch("attn_bwd_sm100"))) return rc;
   const size_t n4 = n / 4;

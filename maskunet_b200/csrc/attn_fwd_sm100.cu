@@ -7,7 +7,7 @@
 // One CTA = one 128-query tile of one sample.  Warp roles:
 //   warp 0   TMA producer: Q once, then K_j / V_j tiles through a ring of shared-memory slots
 //   warp 1   allocates TMEM, single thread issues tcgen05.mma:  S_j = Q K_j^T,   O += P_j V_j
-//   warp 2-5 softmax: thread <-> query row (TMEM lane); online max / exp2 / row sum in fp32,
+//   warp 4-7 softmax: thread <-> query row (TMEM lane); online max / exp2 / row sum in fp32,
 //            P_j written to shared memory as bf16 in the UMMA K-major 128B-swizzled layout,
 //            O rescaled in TMEM when the running max moves, final O / l and LSE written out.
 // Shared-memory operand tiles are [rows][64 bf16] blocks as TMA SWIZZLE_128B writes them
@@ -19,7 +19,7 @@
 namespace mu {
 
 constexpr int kBM = 128;                 // queries per CTA
-constexpr int kFwdThreads = 192;         // 6 warps
+constexpr int kFwdThreads = 256;         // warpgroup 0: TMA, MMA, 2 idle warps; warpgroup 1: softmax
 constexpr float kLog2eF = 1.4426950408889634f;
 
 template <int D, int BN, int SBUFS, int SLOTS>
@@ -92,6 +92,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+    // 2 CTAs / SM start with 128 registers per thread; the data-movement warpgroup hands most of its share to the
+    // softmax warpgroup, which keeps a whole score row in registers
+    if (MINB > 1) reg_dealloc<40>();
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane_id() == 0 && T > 0) {
@@ -150,8 +154,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         umma_commit(o_done);
       }
     }
+  }
   } else {
     // ===================================================== softmax / correction / epilogue
+    if (MINB > 1) reg_alloc<208>();
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
     const int r = quad * 32 + (int)lane_id();       // query row within the tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -165,63 +171,67 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       }
     } else {
       float m = -INFINITY, l = 0.f;
-      uint32_t v[32];
+      uint32_t v[BN / 32][32];                      // the whole S row of this thread, one TMEM pass per tile
       for (int j = 0; j < T; ++j) {
         const int buf = j % SBUFS;
         const uint32_t s_addr = lane_base + Cfg::kTmemS + buf * BN;
-        const int limit = nk - j * BN;  // valid key columns in this tile (>= 1)
+        const int limit = nk - j * BN;              // valid key columns in this tile (>= 1)
         mbar_wait(s_full + buf, (j / SBUFS) & 1);
         tc_fence_after();
-        // ---- pass 1: row max
-        float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-          tmem_ld32(s_addr + c * 32, v);
-          tmem_wait_ld();
-          if (limit >= BN) {
+        for (int c = 0; c < BN / 32; ++c) tmem_ld32(s_addr + c * 32, v[c]);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(s_free + buf);                  // S lives in registers now: the next QK^T may overwrite TMEM
+        if (limit < BN) {                           // tail of the last key tile
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-          } else {
+          for (int c = 0; c < BN / 32; ++c)
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < limit) mx = fmaxf(mx, __uint_as_float(v[i]));
-          }
+              if (c * 32 + i >= limit) v[c][i] = 0xff800000u;   // -inf
         }
-        const float m_new = fmaxf(m, mx);
+        // ---- row max: independent FMNMX3 chains
+        float mx[BN / 32];
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          mx[c] = max3(__uint_as_float(v[c][0]), __uint_as_float(v[c][1]), __uint_as_float(v[c][2]));
+#pragma unroll
+          for (int i = 3; i + 1 < 32; i += 2)
+            mx[c] = max3(mx[c], __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
+          mx[c] = fmaxf(mx[c], __uint_as_float(v[c][31]));
+        }
+        float m_new = m;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) m_new = fmaxf(m_new, mx[c]);
         const float alpha = fast_exp2((m - m_new) * scale_log2);
         // ---- rescale O once the previous PV has landed
         if (j > 0) {
           mbar_wait(o_done, (j - 1) & 1);
           tc_fence_after();
           if (__any_sync(0xffffffffu, m_new > m)) {
+            uint32_t ov[32];
 #pragma unroll
             for (int c = 0; c < D / 32; ++c) {
-              tmem_ld32(lane_base + Cfg::kTmemO + c * 32, v);
+              tmem_ld32(lane_base + Cfg::kTmemO + c * 32, ov);
               tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-              tmem_st32(lane_base + Cfg::kTmemO + c * 32, v);
+              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st32(lane_base + Cfg::kTmemO + c * 32, ov);
             }
             tmem_wait_st();
           }
         }
-        // ---- pass 2: p = exp2((s - m) * scale * log2e), bf16 P tile into shared memory
+        // ---- p = exp2((s - m) * scale * log2e), bf16 P tile into shared memory
         const float mb = m_new * scale_log2;
-        float sum = 0.f;
+        float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
-          tmem_ld32(s_addr + c * 32, v);
-          tmem_wait_ld();
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), scale_log2, -mb));
-            float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, -mb));
-            if (limit < BN) {
-              if (c * 32 + 2 * i >= limit) p0 = 0.f;
-              if (c * 32 + 2 * i + 1 >= limit) p1 = 0.f;
-            }
-            sum += p0 + p1;
+            const float p0 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i]), scale_log2, -mb));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i + 1]), scale_log2, -mb));
+            sum[i & 3] += p0 + p1;
             pk[i] = pack_bf16(p0, p1);
           }
           // columns [c*32, c*32+32) = 16-byte chunks (c&1)*4 .. +3 of 64-column block c>>1
@@ -233,28 +243,28 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           }
         }
         tc_fence_before();
-        mbar_arrive(s_free + buf);
         fence_proxy_async_smem();
         mbar_arrive(p_full);
-        l = l * alpha + sum;
+        l = l * alpha + ((sum[0] + sum[1]) + (sum[2] + sum[3]));
         m = m_new;
       }
       // ---- epilogue: O / l, LSE
       mbar_wait(o_done, (T - 1) & 1);
       tc_fence_after();
       const float inv = 1.f / l;
+      uint32_t(&vo)[32] = v[0];
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
-        tmem_ld32(lane_base + Cfg::kTmemO + c * 32, v);
+        tmem_ld32(lane_base + Cfg::kTmemO + c * 32, vo);
         tmem_wait_ld();
         if (row_ok) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 w;
-            w.x = pack_bf16(__uint_as_float(v[8 * g + 0]) * inv, __uint_as_float(v[8 * g + 1]) * inv);
-            w.y = pack_bf16(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv);
-            w.z = pack_bf16(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv);
-            w.w = pack_bf16(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv);
+            w.x = pack_bf16(__uint_as_float(vo[8 * g + 0]) * inv, __uint_as_float(vo[8 * g + 1]) * inv);
+            w.y = pack_bf16(__uint_as_float(vo[8 * g + 2]) * inv, __uint_as_float(vo[8 * g + 3]) * inv);
+            w.z = pack_bf16(__uint_as_float(vo[8 * g + 4]) * inv, __uint_as_float(vo[8 * g + 5]) * inv);
+            w.w = pack_bf16(__uint_as_float(vo[8 * g + 6]) * inv, __uint_as_float(vo[8 * g + 7]) * inv);
             *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = w;
           }
         }

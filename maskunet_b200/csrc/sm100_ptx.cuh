@@ -94,6 +94,12 @@ MU_DEVICE void tma_store_3d(const void* tmap, const void* smem_src, int32_t c0, 
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// smem tile -> global with element-wise add performed by the TMA unit (no LSU atomics)
+MU_DEVICE void tma_reduce_add_3d(const void* tmap, uint32_t smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 MU_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 MU_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -206,6 +212,12 @@ MU_DEVICE void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ------------------------------------------------------------------ per-warpgroup register budget
+// All 4 warps of a warpgroup must execute these together.  Lets the data-movement warpgroup hand its registers
+// to the softmax warpgroup(s) so that a full score row fits in registers at 2 CTAs / SM.
+template <int kRegs> MU_DEVICE void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> MU_DEVICE void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+
 // ------------------------------------------------------------------ explicit shared-space accesses
 // (generic-pointer accesses compile to LD.E / ST.E, which take the slow generic path and the long scoreboard)
 MU_DEVICE void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -219,14 +231,19 @@ MU_DEVICE float4 ld_shared_v4f(uint32_t addr) {
 MU_DEVICE void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
 // ------------------------------------------------------------------ misc math
+MU_DEVICE float max3(float a, float b, float c) {   // FMNMX3 on sm_100
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 MU_DEVICE float fast_exp2(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 MU_DEVICE uint32_t pack_bf16(float lo, float hi) {
   uint32_t r;
-  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 

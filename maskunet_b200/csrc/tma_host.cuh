@@ -47,4 +47,24 @@ inline int make_tmap_bf16_3d(CUtensorMap* map, const void* base, int cols, int r
   return 0;
 }
 
+// fp32 tensor [batch][rows][cols]; box = [1][box_rows][32 cols] (128-byte rows), 128-byte swizzle.
+// Used as the destination of TMA reduce-add stores (rows past `rows` are dropped).
+inline int make_tmap_f32_3d(CUtensorMap* map, const void* base, int cols, int rows, int batch, int box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return MU_ERR_DRIVER;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)cols * 4 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(f32) failed: CUresult %d (cols %d rows %d batch %d box_rows %d)", (int)r, cols,
+              rows, batch, box_rows);
+    return MU_ERR_DRIVER;
+  }
+  return 0;
+}
+
 }  // namespace mu
