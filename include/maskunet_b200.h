@@ -176,6 +176,36 @@ int mu_sample_layernorm_bwd(const void* dy, const void* x, const float* gamma, c
 int mu_cross_entropy_fused(const void* logits, const int64_t* labels, const float* valid_count, int64_t ignore_index,
                            void* dlogits, float* loss_sum, int64_t M, int32_t C, int32_t dtype, mu_stream_t stream);
 
+/* K7. 3x3 convolution, stride 1, zero padding 1, no bias (nn.Conv2d(cin, cout, kernel_size=3, padding=1,
+ * bias=False), :199 and :202, inside ConvBlock :192-210) on tcgen05 tensor cores.  bf16 channels-last
+ * activations [B, H, W, C], fp32 accumulation; W in {16, 32, 64, 128}, H a multiple of 128 / W, channel counts
+ * multiples of 64 in [64, 512].  MU_BF16 only (fp32 validation mode keeps the stock NCHW convolution).
+ *
+ * mu_conv_prep_weights: w f32 [Cout, Cin, taps] (the parameter as nn.Conv2d holds it, taps = 9 or 1) ->
+ *   wf bf16 [taps, Cout, Cin] (forward operand) and wd bf16 [taps, Cin, Cout] with the tap order reversed
+ *   (data-gradient operand; wd may be NULL).
+ * mu_conv3x3_fwd: y [B, H, W, Cout] = conv(x [B, H, W, Cin], wf).  stats (may be NULL): f32 [2 * Cout],
+ *   ADDED to: per-channel sum and sum of squares of the (rounded) outputs -- the statistics pass of the
+ *   training-mode BatchNorm2d that always follows (:200, :203), so the caller zeroes it first and passes it to
+ *   mu_bn_act_fwd_stats.
+ * mu_conv3x3_bwd_data: dx [B, H, W, Cin] = conv(dy [B, H, W, Cout], wd).
+ * mu_conv3x3_bwd_weight: dw f32 [Cout, Cin, 3, 3] = sum over pixels of dy (x) shifted x; workspace of
+ *   mu_conv3x3_workspace_bytes(Cin, Cout) bytes (f32 [9, Cin, Cout] split-K accumulator, cleared inside). */
+int mu_conv_prep_weights(const float* w, void* wf, void* wd, int32_t Cout, int32_t Cin, int32_t taps,
+                         mu_stream_t stream);
+int mu_conv3x3_fwd(const void* x, const void* wf, void* y, float* stats, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                   int32_t Cout, int32_t dtype, mu_stream_t stream);
+int mu_conv3x3_bwd_data(const void* dy, const void* wd, void* dx, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                        int32_t Cout, int32_t dtype, mu_stream_t stream);
+size_t mu_conv3x3_workspace_bytes(int32_t Cin, int32_t Cout);
+int mu_conv3x3_bwd_weight(const void* x, const void* dy, void* workspace, size_t workspace_bytes, float* dw, int32_t B,
+                          int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t dtype, mu_stream_t stream);
+/* mu_bn_act_fwd with the statistics pass already done (sums f32 [2C] = per-channel sum, sum of squares over the
+ * M rows, e.g. from mu_conv3x3_fwd): finalize + apply only. */
+int mu_bn_act_fwd_stats(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y,
+                        float* mean, float* rstd, float* a, float* b, const float* sums, int64_t M, int32_t C,
+                        int32_t act, int32_t dtype, mu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,11 @@ SIGNATURES = {
     "mu_cross_entropy_fused": [_P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int64, _I, _I, _P],
     "mu_bn_act_fwd": [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
     "mu_bn_act_apply": [_P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
+    "mu_bn_act_fwd_stats": [_P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
+    "mu_conv_prep_weights": [_P, _P, _P, _I, _I, _I, _P],
+    "mu_conv3x3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mu_conv3x3_bwd_data": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mu_conv3x3_bwd_weight": [_P, _P, _P, ctypes.c_size_t, _P, _I, _I, _I, _I, _I, _I, _P],
     "mu_bn_act_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
 }
 
@@ -59,6 +64,8 @@ def load() -> ctypes.CDLL:
     lib.mu_device_supported.argtypes = []
     lib.mu_attn_bwd_workspace_bytes.restype = ctypes.c_size_t
     lib.mu_attn_bwd_workspace_bytes.argtypes = [_I, _I, _I, _I]
+    lib.mu_conv3x3_workspace_bytes.restype = ctypes.c_size_t
+    lib.mu_conv3x3_workspace_bytes.argtypes = [_I, _I]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int32

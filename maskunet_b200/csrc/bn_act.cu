@@ -360,6 +360,22 @@ int launch_bn_forward(const void* x, const void* r, const float* gamma, const fl
                          : bn_apply_t<__nv_bfloat16>(x, r, a, b, y, M, C, act, s);
 }
 
+// statistics already reduced by the producer (the convolution epilogue): finalize + apply
+int launch_bn_forward_stats(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y,
+                            float* mean, float* rstd, float* a, float* b, const float* sums, long M, int C, int act,
+                            int dtype, cudaStream_t s) {
+  if (!bn_shape_ok(M, C)) {
+    set_error("bn_forward_stats: unsupported shape M=%ld C=%d", M, C);
+    return MU_ERR_BAD_SHAPE;
+  }
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, gamma, beta, nullptr, nullptr, M, C, 0.f, eps, mean, rstd, a,
+                                                    b);
+  int rc;
+  if ((rc = check_launch("bn_finalize"))) return rc;
+  return dtype == MU_F32 ? bn_apply_t<float>(x, r, a, b, y, M, C, act, s)
+                         : bn_apply_t<__nv_bfloat16>(x, r, a, b, y, M, C, act, s);
+}
+
 int launch_bn_apply(const void* x, const void* r, const float* a, const float* b, void* y, long M, int C, int act,
                     int dtype, cudaStream_t s) {
   if (!bn_shape_ok(M, C)) {

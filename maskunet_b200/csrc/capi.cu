@@ -261,4 +261,55 @@ int mu_cross_entropy_fused(const void* logits, const int64_t* labels, const floa
                          (cudaStream_t)stream);
 }
 
+#define MU_BF16_ONLY(fn) \
+  MU_REQUIRE(dtype == MU_BF16, MU_ERR_BAD_DTYPE, fn ": tensor-core convolution takes MU_BF16 activations (got %d)", dtype)
+#define MU_SM100_ONLY(fn) \
+  MU_REQUIRE(device_cc_major() == 10, MU_ERR_ARCH, fn ": needs an sm_100 device (tcgen05 / TMEM)")
+
+int mu_conv_prep_weights(const float* w, void* wf, void* wd, int32_t Cout, int32_t Cin, int32_t taps,
+                         mu_stream_t stream) {
+  MU_REQUIRE(Cout > 0 && Cin > 0 && (taps == 9 || taps == 1), MU_ERR_BAD_SHAPE,
+             "mu_conv_prep_weights: bad shape (Cout=%d Cin=%d taps=%d)", Cout, Cin, taps);
+  MU_PTRS("mu_conv_prep_weights", w, wf);
+  return launch_conv_prep_weights(w, wf, wd, Cout, Cin, taps, (cudaStream_t)stream);
+}
+
+int mu_conv3x3_fwd(const void* x, const void* wf, void* y, float* stats, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                   int32_t Cout, int32_t dtype, mu_stream_t stream) {
+  MU_BF16_ONLY("mu_conv3x3_fwd");
+  MU_PTRS("mu_conv3x3_fwd", x, wf, y);
+  MU_SM100_ONLY("mu_conv3x3_fwd");
+  return launch_conv_fprop_sm100(x, wf, y, stats, B, H, W, Cin, Cout, 9, (cudaStream_t)stream);
+}
+
+int mu_conv3x3_bwd_data(const void* dy, const void* wd, void* dx, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                        int32_t Cout, int32_t dtype, mu_stream_t stream) {
+  MU_BF16_ONLY("mu_conv3x3_bwd_data");
+  MU_PTRS("mu_conv3x3_bwd_data", dy, wd, dx);
+  MU_SM100_ONLY("mu_conv3x3_bwd_data");
+  return launch_conv_fprop_sm100(dy, wd, dx, nullptr, B, H, W, Cout, Cin, 9, (cudaStream_t)stream);
+}
+
+size_t mu_conv3x3_workspace_bytes(int32_t Cin, int32_t Cout) { return (size_t)9 * Cin * Cout * sizeof(float); }
+
+int mu_conv3x3_bwd_weight(const void* x, const void* dy, void* workspace, size_t workspace_bytes, float* dw, int32_t B,
+                          int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t dtype, mu_stream_t stream) {
+  MU_BF16_ONLY("mu_conv3x3_bwd_weight");
+  MU_PTRS("mu_conv3x3_bwd_weight", x, dy, workspace, dw);
+  MU_REQUIRE(workspace_bytes >= mu_conv3x3_workspace_bytes(Cin, Cout), MU_ERR_WORKSPACE,
+             "mu_conv3x3_bwd_weight: workspace too small (%zu < %zu)", workspace_bytes,
+             mu_conv3x3_workspace_bytes(Cin, Cout));
+  MU_SM100_ONLY("mu_conv3x3_bwd_weight");
+  return launch_conv_wgrad_sm100(x, dy, (float*)workspace, dw, B, H, W, Cin, Cout, (cudaStream_t)stream);
+}
+
+int mu_bn_act_fwd_stats(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y,
+                        float* mean, float* rstd, float* a, float* b, const float* sums, int64_t M, int32_t C,
+                        int32_t act, int32_t dtype, mu_stream_t stream) {
+  MU_DTYPE_OK("mu_bn_act_fwd_stats");
+  MU_PTRS("mu_bn_act_fwd_stats", x, gamma, beta, y, mean, rstd, a, b, sums);
+  return launch_bn_forward_stats(x, r, gamma, beta, eps, y, mean, rstd, a, b, sums, (long)M, C, act, dtype,
+                                 (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -84,6 +84,15 @@ int launch_bn_apply(const void* x, const void* r, const float* a, const float* b
 int launch_bn_backward(const void* dy, const void* x, const void* r, const float* a, const float* b, const float* mean,
                        const float* rstd, float* sums, void* dx, void* dr, long M, int C, int act, int dtype,
                        cudaStream_t s);
+int launch_bn_forward_stats(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y,
+                            float* mean, float* rstd, float* a, float* b, const float* sums, long M, int C, int act,
+                            int dtype, cudaStream_t s);
+// K7 (tcgen05, bf16 channels-last)
+int launch_conv_fprop_sm100(const void* x, const void* wt, void* y, float* stats, int B, int H, int W, int K, int N,
+                            int taps, cudaStream_t s);
+int launch_conv_wgrad_sm100(const void* x, const void* dy, float* ws, float* dw, int B, int H, int W, int Cin, int Cout,
+                            cudaStream_t s);
+int launch_conv_prep_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int taps, cudaStream_t s);
 int launch_maxpool2(const void* x, const void* dy, void* out, int B, int H, int W, int C, int bwd, int dtype,
                     cudaStream_t s);
 int launch_upcat_fwd(const void* skip, const void* x, void* out, int B, int H, int W, int Cs, int Cx, int dtype,

@@ -1,0 +1,607 @@
+// K7: 3x3 convolution (stride 1, zero padding 1, no bias) of the reference's DoubleConv blocks on tcgen05 tensor
+// cores, channels-last bf16 activations, fp32 accumulation.  Replaces nn.Conv2d(.., kernel_size=3, padding=1,
+// bias=False) and its autograd, /root/reference/code/ade20k/ade_semantic.py:199, :202 (ConvBlock) as used by
+// DownSample :212-229, UpSample :231-256 and the bottom blocks :268-270.
+//
+// Implicit GEMM, no im2col buffer:  y[p, co] = sum_{tap, ci} x[p + off(tap), ci] * w[co, ci, tap]
+//   forward / data gradient  (one kernel; dX is the same convolution of dY with flipped, transposed weights):
+//     M = 128 pixels (TH image rows x the full width W), N = up to 256 output channels, K = 9 taps x Cin.
+//     The A operand is ONE TMA box with halo per 64-channel chunk -- the 4-D tensor map zero-fills what falls
+//     outside the image, which is the convolution's padding -- and each tap is the same shared-memory tile
+//     addressed through a UMMA descriptor whose start is shifted by whole 128-byte pixel rows
+//     (SWIZZLE_128B is a function of the absolute shared-memory address, so a row-shifted start reads exactly
+//     what TMA wrote; tools/desc_probe.cu is the hardware check).  W = 128: one [3 x 130 pixel] box serves all 9
+//     taps; W < 128: one [(TH + 2) x W] box per horizontal tap serves the 3 vertical taps.  So the activation
+//     tile crosses L2 -> SMEM 1.0 / 1.5 - 3 times instead of 9.
+//     Weights stream as [N x 64] K-major tiles per (tap, chunk).  Persistent CTAs, double-buffered TMEM
+//     accumulator: the epilogue of tile i (TMEM -> bf16 -> swizzled staging -> TMA store, BatchNorm partial sums)
+//     overlaps the main loop of tile i + 1.
+//   weight gradient:  dw[tap, ci, co] = sum_p x[p + off(tap), ci] * dy[p, co]
+//     contraction over pixels: both operands MN-major (pixel rows = K), the tap again a row shift of one x tile
+//     with halo; 3 taps x 128 ci x 128 co accumulate in TMEM over the CTA's pixel range (split-K), then
+//     red.global.add.v4.f32 into an fp32 [9][Cin][Cout] workspace; a small kernel permutes to the parameter layout.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+#include "tma_host.cuh"
+
+namespace mu {
+
+constexpr int kConvThreads = 192;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int kMaxRing = 8;
+constexpr int kSmemLimit = 232448;  // 227 KB
+
+enum { CONV_W128 = 0, CONV_ROWS = 1, CONV_1X1 = 2 };
+
+struct ConvArgs {
+  int B, H, W, K, N;       // K = contraction channels, N = output channels of this GEMM
+  int TH, tiles_y, m_tiles, n_tiles;
+  int mode, groups, taps;  // A loads per 64-channel chunk, taps served by each
+  int a_bytes, a_stride, SA, SB, SO;  // ring geometry; SO = output staging buffers (1 or 2)
+};
+
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void red_add_v4f(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// ============================================================================ forward / data gradient
+// One CTA step ("super tile") = MT vertically adjacent 128-pixel tiles of one image x NT output channels: every
+// weight tile fetched from L2 feeds MT MMAs, and the activation box with halo is shared by the MT tiles.
+//   TMEM: NBUF accumulator sets of MT * NT fp32 columns (NBUF = 2 when 2 * MT * NT <= 512).
+template <int NT, int MT, int MODE>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                        const __grid_constant__ CUtensorMap tmap_y, float* __restrict__ stats, const ConvArgs p) {
+  constexpr int kBBytes = NT * 128;
+  constexpr int GROUPS = MODE == CONV_ROWS ? 3 : 1;
+  constexpr int TAPS = MODE == CONV_W128 ? 9 : (MODE == CONV_ROWS ? 3 : 1);
+  constexpr int NBUF = (2 * MT * NT <= 512) ? 2 : 1;
+  constexpr int kTmemCols = NBUF * MT * NT;
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation must be a power of two <= 512");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + p.SA * p.a_stride;
+  uint8_t* sO = sB + p.SB * kBBytes;
+  float* s_stats = reinterpret_cast<float*>(sO + p.SO * 16384);       // [2][512]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + 1024);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + kMaxRing;
+  uint64_t* b_full = bars + 2 * kMaxRing;
+  uint64_t* b_empty = bars + 3 * kMaxRing;
+  uint64_t* acc_full = bars + 4 * kMaxRing;       // 2
+  uint64_t* acc_empty = acc_full + 2;             // 2 (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5;
+  const int total = p.m_tiles * p.n_tiles;        // m_tiles counts super tiles
+  const int kchunks = p.K / 64;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxRing; ++i) {
+      mbar_init(a_full + i, 1);
+      mbar_init(a_empty + i, 1);
+      mbar_init(b_full + i, 1);
+      mbar_init(b_empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(acc_full + i, 1);
+      mbar_init(acc_empty + i, 128);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_y);
+  }
+  if (warp == 1) {
+    tmem_alloc<kTmemCols>(tmem_slot);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 1024; i += kConvThreads) s_stats[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Ring protocol: consumer waits full[s] with its phase bit, producer waits empty[s] with phase ^ 1 (a fresh
+  // barrier passes a parity-1 wait), both flip the bit when the stage index wraps.
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane_id() == 0) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      const int SA = p.SA, SB = p.SB, a_stride = p.a_stride, a_bytes = p.a_bytes;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+        const int b = mt / p.tiles_y, y0 = (mt - b * p.tiles_y) * (MT * p.TH);
+        const int n0 = nt * NT;
+        for (int ch = 0; ch < kchunks; ++ch) {
+#pragma unroll
+          for (int g = 0; g < GROUPS; ++g) {
+            mbar_wait(a_empty + sa, pa ^ 1);
+            mbar_expect_tx(a_full + sa, a_bytes);
+            const int cx = MODE == CONV_W128 ? -1 : (MODE == CONV_ROWS ? g - 1 : 0);
+            const int cy = MODE == CONV_1X1 ? y0 : y0 - 1;
+            tma_load_4d(sA + sa * a_stride, &tmap_x, a_full + sa, ch * 64, cx, cy, b);
+            if (++sa == SA) { sa = 0; pa ^= 1; }
+#pragma unroll
+            for (int j = 0; j < TAPS; ++j) {
+              const int tap = MODE == CONV_ROWS ? j * 3 + g : j;
+              mbar_wait(b_empty + sb, pb ^ 1);
+              mbar_expect_tx(b_full + sb, kBBytes);
+              tma_load_3d(sB + sb * kBBytes, &tmap_w, b_full + sb, ch * 64, n0, tap);
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane_id() == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
+      const uint64_t desc_hi = make_smem_desc(0, 0, 1024);
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      const int SA = p.SA, SB = p.SB, a_stride = p.a_stride;
+      const uint32_t tile_pitch = (MODE == CONV_W128 ? 130 : 128) * 128;   // bytes between the MT tiles' first rows
+      const uint32_t row_w = p.W * 128;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        mbar_wait(acc_empty + buf, pacc ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * (MT * NT);
+        uint32_t accumulate = 0;
+        for (int ch = 0; ch < kchunks; ++ch) {
+#pragma unroll
+          for (int g = 0; g < GROUPS; ++g) {
+            mbar_wait(a_full + sa, pa);
+            const uint32_t a_tile = a_base + sa * a_stride;
+#pragma unroll
+            for (int j = 0; j < TAPS; ++j) {
+              const uint32_t row_off = MODE == CONV_W128 ? ((j / 3) * 130 + (j % 3)) * 128
+                                                         : (MODE == CONV_ROWS ? j * row_w : 0);
+              mbar_wait(b_full + sb, pb);
+              tc_fence_after();
+              const uint64_t b_desc = desc_hi | (uint64_t)(((b_base + sb * kBBytes) & 0x3FFFF) >> 4);
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                const uint64_t a_desc = desc_hi | (uint64_t)(((a_tile + row_off + m * tile_pitch) & 0x3FFFF) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_ss(d_tmem + m * NT, a_desc + 2 * kk, b_desc + 2 * kk, idesc, accumulate | (uint32_t)(kk > 0));
+              }
+              accumulate = 1;
+              umma_commit(b_empty + sb);
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+            }
+            umma_commit(a_empty + sa);
+            if (++sa == SA) { sa = 0; pa ^= 1; }
+          }
+        }
+        umma_commit(acc_full + buf);
+        if (++buf == NBUF) { buf = 0; pacc ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int e = threadIdx.x - 64;
+    const int quad = warp & 3;
+    const int r = quad * 32 + (int)lane_id();              // pixel row of the tile == TMEM lane
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t so_base = smem_u32(sO);
+    const int sq = e >> 5, cp = e & 31;                    // statistics: rows sq*32.., channel pair cp
+    const int SO = p.SO;
+    uint32_t buf = 0, pacc = 0, so_idx = 0;
+    uint32_t v[32];
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+      const int b = mt / p.tiles_y, y0 = (mt - b * p.tiles_y) * (MT * p.TH);
+      mbar_wait(acc_full + buf, pacc);
+      tc_fence_after();
+#pragma unroll 1
+      for (int blk = 0; blk < MT * (NT / 64); ++blk) {
+        const int m = blk / (NT / 64), cb = blk - m * (NT / 64);
+        const uint32_t so = so_base + so_idx * 16384;
+        if (e == 0) {                                      // the store that last read this staging buffer is done
+          if (SO == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+        }
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          tmem_ld32(lane_base + buf * (MT * NT) + m * NT + cb * 64 + h * 32, v);
+          tmem_wait_ld();
+          if (h == 1 && blk == MT * (NT / 64) - 1) {
+            tc_fence_before();
+            mbar_arrive(acc_empty + buf);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t c = h * 4 + g;
+            st_shared_v4(so + r * 128 + ((c ^ (r & 7)) << 4),
+                         pack_bf16(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])),
+                         pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                         pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                         pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (e == 0) {
+          tma_store_4d(&tmap_y, so, nt * NT + cb * 64, 0, y0 + m * p.TH, b);
+          tma_store_commit();
+        }
+        if (stats != nullptr) {
+          // BatchNorm partial sums of the ROUNDED outputs (what the normalisation will read back)
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int rr = sq * 32 + i;
+            const uint32_t w = ld_shared_u32(so + rr * 128 + ((((uint32_t)cp >> 2) ^ (rr & 7)) << 4) + (cp & 3) * 4);
+            const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+            s0 += lo;
+            s1 += hi;
+            q0 = fmaf(lo, lo, q0);
+            q1 = fmaf(hi, hi, q1);
+          }
+          const int chn = nt * NT + cb * 64 + 2 * cp;
+          atomicAdd(s_stats + chn, s0);
+          atomicAdd(s_stats + chn + 1, s1);
+          atomicAdd(s_stats + 512 + chn, q0);
+          atomicAdd(s_stats + 512 + chn + 1, q1);
+        }
+        if (++so_idx == (uint32_t)SO) so_idx = 0;
+      }
+      if (++buf == NBUF) { buf = 0; pacc ^= 1; }
+    }
+    if (e == 0) tma_store_wait<0>();
+    if (stats != nullptr) {
+      named_bar_sync(1, 128);
+      for (int i = e; i < p.N; i += 128) {
+        const float a = s_stats[i], q = s_stats[512 + i];
+        if (a != 0.f || q != 0.f) {
+          atomicAdd(stats + i, a);
+          atomicAdd(stats + p.N + i, q);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ============================================================================ weight gradient
+struct WgradArgs {
+  int B, H, W, Cin, Cout;
+  int TH, tiles_y, m_tiles;
+  int mode;                 // CONV_W128: tap group = ky, taps along kx (row step 1); CONV_ROWS: group = kx, step W rows
+  int x_bytes, x_stride;    // one 64-channel x tile with halo
+  int ci_blocks;            // 64-channel x blocks per CTA: 2 (Cin % 128 == 0) or 1 (two taps share an M tile)
+  int n_cb, n_nb;           // ci / co blocks over the grid
+  int S, chunks_per_cta;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                        float* __restrict__ ws, const WgradArgs p) {
+  constexpr int kDyBytes = (NB / 64) * 16384;
+  constexpr int kTmemCols = NB == 128 ? 512 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int x_tile_bytes = p.ci_blocks * p.x_stride;
+  const int stage_bytes = x_tile_bytes + kDyBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.S * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxRing;
+  uint64_t* acc_full = bars + 2 * kMaxRing;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5;
+
+  int combo = blockIdx.x;
+  const int g = combo % 3;
+  combo /= 3;
+  const int cb = combo % p.n_cb, nb = combo / p.n_cb;
+  const int c_begin = blockIdx.y * p.chunks_per_cta;
+  const int c_end = min(p.m_tiles, c_begin + p.chunks_per_cta);
+  const int nchunks = c_end - c_begin;
+  if (nchunks <= 0) return;
+  const int row_step = p.mode == CONV_W128 ? 1 : p.W;
+  const int ci0 = cb * p.ci_blocks * 64;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxRing; ++i) {
+      mbar_init(full + i, 1);
+      mbar_init(empty + i, 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_dy);
+  }
+  if (warp == 1) {
+    tmem_alloc<kTmemCols>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane_id() == 0) {
+      for (int j = 0; j < nchunks; ++j) {
+        const int st = j % p.S, use = j / p.S;
+        if (use > 0) mbar_wait(empty + st, (use - 1) & 1);
+        const int mt = c_begin + j;
+        const int b = mt / p.tiles_y, y0 = (mt - b * p.tiles_y) * p.TH;
+        uint8_t* sX = smem + st * stage_bytes;
+        uint8_t* sD = sX + x_tile_bytes;
+        mbar_expect_tx(full + st, p.ci_blocks * p.x_bytes + kDyBytes);
+        const int cx = p.mode == CONV_W128 ? -1 : g - 1;
+        const int cy = p.mode == CONV_W128 ? y0 + g - 1 : y0 - 1;
+        for (int blk = 0; blk < p.ci_blocks; ++blk)
+          tma_load_4d(sX + blk * p.x_stride, &tmap_x, full + st, ci0 + blk * 64, cx, cy, b);
+        for (int blk = 0; blk < NB / 64; ++blk)
+          tma_load_4d(sD + blk * 16384, &tmap_dy, full + st, nb * NB + blk * 64, 0, y0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane_id() == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, NB, 1, 1);   // both operands MN-major (contraction over pixels)
+      const int m_tiles_cta = p.ci_blocks == 2 ? 3 : 2;
+      for (int j = 0; j < nchunks; ++j) {
+        const int st = j % p.S;
+        mbar_wait(full + st, (j / p.S) & 1);
+        tc_fence_after();
+        const uint32_t x_addr = smem_u32(smem + st * stage_bytes), d_addr = x_addr + x_tile_bytes;
+        for (int m = 0; m < m_tiles_cta; ++m) {
+          uint32_t a_start, a_lbo;
+          if (p.ci_blocks == 2) {
+            a_start = x_addr + m * row_step * 128;              // tap m, 128 input channels = two 64-wide blocks
+            a_lbo = p.x_stride;
+          } else if (m == 0) {
+            a_start = x_addr;                                   // taps 0 and 1 of 64 input channels side by side
+            a_lbo = row_step * 128;
+          } else {
+            a_start = x_addr + 2 * row_step * 128;              // tap 2; rows 64..127 of the tile are ignored
+            a_lbo = 0;
+          }
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ss(tmem_base + m * NB, make_smem_desc(a_start + kk * 2048, a_lbo, 1024),
+                    make_smem_desc(d_addr + kk * 2048, 16384, 1024), idesc, (j > 0) || (kk > 0));
+        }
+        umma_commit(empty + st);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + (int)lane_id();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int m_tiles_cta = p.ci_blocks == 2 ? 3 : 2;
+    uint32_t v[32];
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    for (int m = 0; m < m_tiles_cta; ++m) {
+      int j, ci;
+      bool valid = true;
+      if (p.ci_blocks == 2) {
+        j = m;
+        ci = ci0 + r;
+      } else {
+        j = m == 0 ? (r >> 6) : 2;
+        ci = ci0 + (r & 63);
+        valid = m == 0 || r < 64;
+      }
+      const int tap = p.mode == CONV_W128 ? g * 3 + j : j * 3 + g;
+      float* dst = ws + ((size_t)tap * p.Cin + ci) * p.Cout + nb * NB;
+#pragma unroll
+      for (int c = 0; c < NB / 32; ++c) {
+        tmem_ld32(lane_base + m * NB + c * 32, v);
+        tmem_wait_ld();
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            red_add_v4f(dst + c * 32 + q * 4, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                        __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ============================================================================ small helpers
+// w f32 [Cout][Cin][taps] (the nn.Conv2d parameter) -> wf bf16 [taps][Cout][Cin] (forward operand) and
+// wd bf16 [taps][Cin][Cout] with the taps reversed (the data-gradient operand).
+__global__ void conv_prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                         __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int taps) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * Cin) return;
+  const int co = idx / Cin, ci = idx - co * Cin;
+  const float* src = w + (size_t)idx * taps;
+  for (int t = 0; t < taps; ++t) {
+    const __nv_bfloat16 v = __float2bfloat16_rn(src[t]);
+    wf[((size_t)t * Cout + co) * Cin + ci] = v;
+    if (wd != nullptr) wd[((size_t)(taps - 1 - t) * Cin + ci) * Cout + co] = v;
+  }
+}
+
+// ws f32 [taps][Cin][Cout] -> dw f32 [Cout][Cin][taps]
+__global__ void conv_wgrad_finish_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin,
+                                         int taps) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // co fastest: coalesced reads
+  if (idx >= Cout * Cin) return;
+  const int ci = idx / Cout, co = idx - ci * Cout;
+  float* dst = dw + ((size_t)co * Cin + ci) * taps;
+  for (int t = 0; t < taps; ++t) dst[t] = ws[((size_t)t * Cin + ci) * Cout + co];
+}
+
+// ============================================================================ launchers
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int conv_geometry_ok(const char* fn, int B, int H, int W, int K, int N) {
+  MU_REQUIRE(B > 0 && H > 0, MU_ERR_BAD_SHAPE, "%s: bad batch / height (B=%d H=%d)", fn, B, H);
+  MU_REQUIRE(W == 16 || W == 32 || W == 64 || W == 128, MU_ERR_BAD_SHAPE,
+             "%s: width must be 16, 32, 64 or 128 (got %d)", fn, W);
+  MU_REQUIRE(H % (128 / W) == 0, MU_ERR_BAD_SHAPE, "%s: height %d must be a multiple of %d", fn, H, 128 / W);
+  MU_REQUIRE(K % 64 == 0 && N % 64 == 0 && K >= 64 && N >= 64 && K <= 512 && N <= 512, MU_ERR_BAD_SHAPE,
+             "%s: channel counts must be multiples of 64 in [64, 512] (got %d -> %d)", fn, K, N);
+  return 0;
+}
+
+template <int NT, int MT, int MODE>
+static int run_fprop(const void* x, const void* wt, void* y, float* stats, int B, int H, int W, int K, int N, int taps,
+                     cudaStream_t s) {
+  ConvArgs p;
+  p.B = B; p.H = H; p.W = W; p.K = K; p.N = N;
+  p.TH = 128 / W;
+  p.tiles_y = H / (p.TH * MT);          // super tiles per image
+  p.m_tiles = B * p.tiles_y;
+  p.n_tiles = N / NT;
+  p.mode = MODE;
+  int box_w, box_h;
+  if (MODE == CONV_1X1) {
+    p.groups = 1; p.taps = 1; box_w = W; box_h = p.TH * MT;
+  } else if (MODE == CONV_W128) {
+    p.groups = 1; p.taps = 9; box_w = 130; box_h = MT + 2;
+  } else {
+    p.groups = 3; p.taps = 3; box_w = W; box_h = p.TH * MT + 2;
+  }
+  p.a_bytes = box_w * box_h * 128;
+  p.a_stride = round_up(p.a_bytes, 1024);
+  const int fixed = 1024 + 4096 + 512;
+  p.SA = 2;
+  p.SO = 2;
+  p.SB = (kSmemLimit - fixed - p.SO * 16384 - p.SA * p.a_stride) / (NT * 128);
+  if (p.SB < 3) {                        // a deep enough weight ring matters more than a second staging buffer
+    p.SO = 1;
+    p.SB = (kSmemLimit - fixed - p.SO * 16384 - p.SA * p.a_stride) / (NT * 128);
+  }
+  if (p.SB > kMaxRing) p.SB = kMaxRing;
+  if (p.SB < 2) {
+    set_error("conv_fprop: shared memory budget exceeded (a_stride %d NT %d)", p.a_stride, NT);
+    return MU_ERR_BAD_SHAPE;
+  }
+  const int smem = fixed + p.SO * 16384 + p.SA * p.a_stride + p.SB * NT * 128;
+  CUtensorMap tx, tw, ty;
+  int rc;
+  if ((rc = make_tmap_bf16_nhwc(&tx, x, K, W, H, B, box_w, box_h))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tw, wt, K, N, taps, NT))) return rc;
+  if ((rc = make_tmap_bf16_nhwc(&ty, y, N, W, H, B, W, p.TH))) return rc;
+  auto kern = conv_fprop_sm100_kernel<NT, MT, MODE>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < sm_count() ? total : sm_count();
+  kern<<<grid, kConvThreads, smem, s>>>(tx, tw, ty, stats, p);
+  return check_launch("conv_fprop_sm100");
+}
+
+template <int NT, int MT>
+static int run_fprop_mode(const void* x, const void* wt, void* y, float* stats, int B, int H, int W, int K, int N,
+                          int taps, cudaStream_t s) {
+  if (taps == 1) return run_fprop<NT, MT, CONV_1X1>(x, wt, y, stats, B, H, W, K, N, taps, s);
+  if (W == 128) return run_fprop<NT, MT, CONV_W128>(x, wt, y, stats, B, H, W, K, N, taps, s);
+  return run_fprop<NT, MT, CONV_ROWS>(x, wt, y, stats, B, H, W, K, N, taps, s);
+}
+
+// y [B,H,W,N] = conv(x [B,H,W,K], wt [taps][N][K]); stats (optional) f32 [2N] += (sum, sum of squares) per channel
+int launch_conv_fprop_sm100(const void* x, const void* wt, void* y, float* stats, int B, int H, int W, int K, int N,
+                            int taps, cudaStream_t s) {
+  int rc;
+  if ((rc = conv_geometry_ok("conv_fprop_sm100", B, H, W, K, N))) return rc;
+  MU_REQUIRE(taps == 9 || taps == 1, MU_ERR_BAD_SHAPE, "conv_fprop_sm100: taps must be 9 or 1 (got %d)", taps);
+  const bool pair = H % (2 * (128 / W)) == 0;       // two vertically adjacent tiles per CTA step
+  if (N % 256 == 0)
+    return pair ? run_fprop_mode<256, 2>(x, wt, y, stats, B, H, W, K, N, taps, s)
+                : run_fprop_mode<256, 1>(x, wt, y, stats, B, H, W, K, N, taps, s);
+  if (N % 128 == 0)
+    return pair ? run_fprop_mode<128, 2>(x, wt, y, stats, B, H, W, K, N, taps, s)
+                : run_fprop_mode<128, 1>(x, wt, y, stats, B, H, W, K, N, taps, s);
+  return pair ? run_fprop_mode<64, 2>(x, wt, y, stats, B, H, W, K, N, taps, s)
+              : run_fprop_mode<64, 1>(x, wt, y, stats, B, H, W, K, N, taps, s);
+}
+
+template <int NB>
+static int run_wgrad(const void* x, const void* dy, float* ws, int B, int H, int W, int Cin, int Cout, cudaStream_t s) {
+  WgradArgs p;
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.TH = 128 / W;
+  p.tiles_y = H / p.TH;
+  p.m_tiles = B * p.tiles_y;
+  int box_w, box_h;
+  if (W == 128) {
+    p.mode = CONV_W128; box_w = 130; box_h = 1;
+  } else {
+    p.mode = CONV_ROWS; box_w = W; box_h = p.TH + 2;
+  }
+  p.x_bytes = box_w * box_h * 128;
+  p.x_stride = round_up(p.x_bytes, 1024);
+  p.ci_blocks = Cin % 128 == 0 ? 2 : 1;
+  p.n_cb = Cin / (64 * p.ci_blocks);
+  p.n_nb = Cout / NB;
+  const int stage = p.ci_blocks * p.x_stride + (NB / 64) * 16384;
+  p.S = (kSmemLimit - 1024 - 512) / stage;
+  if (p.S > kMaxRing) p.S = kMaxRing;
+  if (p.S < 2) {
+    set_error("conv_wgrad: shared memory budget exceeded (stage %d)", stage);
+    return MU_ERR_BAD_SHAPE;
+  }
+  const int smem = 1024 + 512 + p.S * stage;
+  const int combos = 3 * p.n_cb * p.n_nb;
+  int splits = (2 * sm_count() + combos - 1) / combos;      // about two CTAs' worth of work queued per SM
+  if (splits > p.m_tiles) splits = p.m_tiles;
+  if (splits < 1) splits = 1;
+  p.chunks_per_cta = (p.m_tiles + splits - 1) / splits;
+  splits = (p.m_tiles + p.chunks_per_cta - 1) / p.chunks_per_cta;
+  CUtensorMap tx, td;
+  int rc;
+  if ((rc = make_tmap_bf16_nhwc(&tx, x, Cin, W, H, B, box_w, box_h))) return rc;
+  if ((rc = make_tmap_bf16_nhwc(&td, dy, Cout, W, H, B, W, p.TH))) return rc;
+  auto kern = conv_wgrad_sm100_kernel<NB>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  kern<<<dim3(combos, splits), kConvThreads, smem, s>>>(tx, td, ws, p);
+  return check_launch("conv_wgrad_sm100");
+}
+
+// dw f32 [Cout][Cin][3][3] = sum over pixels; ws f32 [9][Cin][Cout] scratch (cleared here)
+int launch_conv_wgrad_sm100(const void* x, const void* dy, float* ws, float* dw, int B, int H, int W, int Cin, int Cout,
+                            cudaStream_t s) {
+  int rc;
+  if ((rc = conv_geometry_ok("conv_wgrad_sm100", B, H, W, Cin, Cout))) return rc;
+  cudaMemsetAsync(ws, 0, (size_t)9 * Cin * Cout * sizeof(float), s);
+  rc = Cout % 128 == 0 ? run_wgrad<128>(x, dy, ws, B, H, W, Cin, Cout, s) : run_wgrad<64>(x, dy, ws, B, H, W, Cin, Cout, s);
+  if (rc) return rc;
+  const int n = Cin * Cout;
+  conv_wgrad_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(ws, dw, Cout, Cin, 9);
+  return check_launch("conv_wgrad_finish");
+}
+
+int launch_conv_prep_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int taps, cudaStream_t s) {
+  const int n = Cin * Cout;
+  conv_prep_weights_kernel<<<(n + 255) / 256, 256, 0, s>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, Cout, Cin, taps);
+  return check_launch("conv_prep_weights");
+}
+
+}  // namespace mu

@@ -67,4 +67,25 @@ inline int make_tmap_f32_3d(CUtensorMap* map, const void* base, int cols, int ro
   return 0;
 }
 
+// bf16 channels-last activation [B][H][W][C] as a 4-D tensor (C, W, H, B); box = [1][box_h][box_w][64 channels],
+// 128-byte swizzle.  Coordinates may be negative / past the edge: those elements are zero-filled on load (the
+// zero padding of a 3x3 convolution) and dropped on store.
+inline int make_tmap_bf16_nhwc(CUtensorMap* map, const void* base, int C, int W, int H, int B, int box_w, int box_h) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return MU_ERR_DRIVER;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(nhwc) failed: CUresult %d (C %d W %d H %d B %d box %dx%d)", (int)r, C, W, H, B,
+              box_w, box_h);
+    return MU_ERR_DRIVER;
+  }
+  return 0;
+}
+
 }  // namespace mu

@@ -121,9 +121,11 @@ def _fast_layout(x: torch.Tensor, channel_multiple: int = 8) -> bool:
             and x.shape[1] % channel_multiple == 0 and x.is_contiguous(memory_format=torch.channels_last))
 
 
-def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Optional[torch.Tensor] = None):
+def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Optional[torch.Tensor] = None,
+                 sums: Optional[torch.Tensor] = None):
     """act(BatchNorm2d(x) [+ residual]) -- the BN / GELU / ReLU / residual chains of ade_semantic.py:198-210,
-    :219, :240 and :283-287.
+    :219, :240 and :283-287.  ``sums`` = per-channel (sum, sum of squares) of x already reduced by the producer
+    (the epilogue of our convolution kernel), which removes the statistics pass.
 
     Channels-last CUDA activations (the bf16 production layout) run on our fused sm_100a kernels
     (csrc/bn_act.cu: one statistics pass, one apply pass; backward one reduce + one apply pass).  Any other
@@ -146,7 +148,10 @@ def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Option
         residual = residual.to(x.dtype).contiguous(memory_format=torch.channels_last)
     gamma, beta = bn.weight.float(), bn.bias.float()
     if bn.training:
-        y, mean, rstd, _, _ = ops.bn_act_fwd(x, residual, gamma, beta, bn.eps, act)
+        if sums is not None and sums.numel() == 2 * x.shape[1]:
+            y, mean, rstd, _, _ = ops.bn_act_fwd_stats(x, residual, gamma, beta, sums, bn.eps, act)
+        else:
+            y, mean, rstd, _, _ = ops.bn_act_fwd(x, residual, gamma, beta, bn.eps, act)
         if bn.track_running_stats:
             with torch.no_grad():
                 count = x.shape[0] * x.shape[2] * x.shape[3]
@@ -162,6 +167,29 @@ def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Option
         return ops.bn_act_apply(x, residual, a, b, act)
 
 
+def _own_conv3x3(conv: nn.Conv2d, x: torch.Tensor) -> bool:
+    """True when K7 (csrc/conv_sm100.cu) takes this convolution: the reference's conv3x3(bias=False, padding=1) on a
+    bf16 channels-last activation whose geometry the tcgen05 tiling covers (all of them at 128x128 inputs except the
+    3-channel stem)."""
+    return (x.is_cuda and x.dim() == 4 and x.dtype == torch.bfloat16
+            and x.is_contiguous(memory_format=torch.channels_last)
+            and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1)
+            and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None
+            and conv.weight.dtype == torch.float32
+            and ops.conv3x3_shape_ok(x.shape[0], conv.in_channels, conv.out_channels, x.shape[2], x.shape[3]))
+
+
+def conv_bn_act(conv: nn.Conv2d, bn: nn.BatchNorm2d, x: torch.Tensor, act: int,
+                residual: Optional[torch.Tensor] = None):
+    """act(BN(conv(x)) [+ residual]): one conv3x3 -> BatchNorm2d -> activation link of ade_semantic.py:198-210.
+    On the production layout the convolution is our implicit-GEMM kernel and its epilogue hands the BatchNorm
+    batch statistics to the fused normalise + activate kernel."""
+    if _own_conv3x3(conv, x):
+        y, sums, _ = ops.conv3x3(x, conv.weight, bn.training)
+        return fused_bn_act(y, bn, act, residual, sums=sums if bn.training else None)
+    return fused_bn_act(conv(x), bn, act, residual)
+
+
 class ConvBlock(nn.Module):
     """conv3x3 -> BN -> GELU(erf) -> conv3x3 -> BN, optionally gelu(x + block(x)).  ade_semantic.py:192-210."""
 
@@ -175,11 +203,10 @@ class ConvBlock(nn.Module):
 
     def forward(self, x):
         conv1, bn1, _, conv2, bn2 = self.conv_block
-        h = fused_bn_act(conv1(x), bn1, ops.ACT_GELU)
-        h = conv2(h)
+        h = conv_bn_act(conv1, bn1, x, ops.ACT_GELU)
         if self.residual:
-            return fused_bn_act(h, bn2, ops.ACT_GELU, residual=x)
-        return fused_bn_act(h, bn2, ops.ACT_NONE)
+            return conv_bn_act(conv2, bn2, h, ops.ACT_GELU, residual=x)
+        return conv_bn_act(conv2, bn2, h, ops.ACT_NONE)
 
 
 def _dead_embedding(emb_dim, out_channels):

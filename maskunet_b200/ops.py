@@ -409,6 +409,178 @@ def _bn_backward(ctx, dy, *unused):
 bn_act_fwd.register_autograd(_bn_backward, setup_context=_bn_setup)
 
 
+# ------------------------------------------------------------------ K8 with the statistics pass done by the producer
+@torch.library.custom_op("maskunet::bn_act_fwd_stats", mutates_args=(), device_types="cuda")
+def bn_act_fwd_stats(x: Tensor, residual: Tensor | None, gamma: Tensor, beta: Tensor, sums: Tensor, eps: float,
+                     act: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """bn_act_fwd where ``sums`` f32 [2C] (per-channel sum, sum of squares of x over B*H*W) was already reduced
+    by the convolution epilogue (mu_conv3x3_fwd): finalize + apply only, one HBM pass less."""
+    M, C = _rows(x)
+    if residual is not None:
+        _rows(residual)
+    _cuda(sums)
+    y = torch.empty_like(x)
+    f32 = dict(dtype=torch.float32, device=x.device)
+    mean, rstd, a, b = (torch.empty((C,), **f32) for _ in range(4))
+    with torch.cuda.device(x.device):
+        _count(2)
+        check(_L.mu_bn_act_fwd_stats(_p(x), _optp(residual), _p(gamma), _p(beta), eps, _p(y), _p(mean), _p(rstd),
+                                     _p(a), _p(b), _p(sums), M, C, act, _code(x), _stream(x)), "mu_bn_act_fwd_stats")
+    return y, mean, rstd, a, b
+
+
+@bn_act_fwd_stats.register_fake
+def _(x, residual, gamma, beta, sums, eps, act):
+    C = x.shape[1]
+    v = lambda: x.new_empty((C,), dtype=torch.float32)
+    return torch.empty_like(x), v(), v(), v(), v()
+
+
+def _bns_setup(ctx, inputs, output):
+    x, residual, gamma, beta, sums, eps, act = inputs
+    _bn_setup(ctx, (x, residual, gamma, beta, eps, act), output)
+
+
+def _bns_backward(ctx, dy, *unused):
+    dx, dr, dgamma, dbeta, _, _ = _bn_backward(ctx, dy)
+    return dx, dr, dgamma, dbeta, None, None, None
+
+
+bn_act_fwd_stats.register_autograd(_bns_backward, setup_context=_bns_setup)
+
+
+# ------------------------------------------------------------------ K7: conv3x3 on tcgen05 (bf16 channels-last)
+CONV_WIDTHS = (16, 32, 64, 128)
+
+
+def conv3x3_shape_ok(B: int, Cin: int, Cout: int, H: int, W: int) -> bool:
+    return (W in CONV_WIDTHS and H % (128 // W) == 0 and Cin % 64 == 0 and Cout % 64 == 0
+            and 64 <= Cin <= 512 and 64 <= Cout <= 512)
+
+
+@torch.library.custom_op("maskunet::conv_prep_weights", mutates_args=(), device_types="cuda")
+def conv_prep_weights(w: Tensor, with_wd: bool) -> Tuple[Tensor, Tensor]:
+    """w f32 [Cout, Cin, kh, kw] -> wf bf16 [taps, Cout, Cin], wd bf16 [taps (reversed), Cin, Cout]."""
+    _cuda(w)
+    assert w.dtype == torch.float32 and w.dim() == 4
+    Cout, Cin, kh, kw = w.shape
+    taps = kh * kw
+    wf = torch.empty((taps, Cout, Cin), dtype=torch.bfloat16, device=w.device)
+    wd = torch.empty((taps, Cin, Cout) if with_wd else (0,), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        _count(1)
+        check(_L.mu_conv_prep_weights(_p(w), _p(wf), _p(wd) if with_wd else _optp(None), Cout, Cin, taps, _stream(w)),
+              "mu_conv_prep_weights")
+    return wf, wd
+
+
+@conv_prep_weights.register_fake
+def _(w, with_wd):
+    Cout, Cin, kh, kw = w.shape
+    return (w.new_empty((kh * kw, Cout, Cin), dtype=torch.bfloat16),
+            w.new_empty((kh * kw, Cin, Cout) if with_wd else (0,), dtype=torch.bfloat16))
+
+
+@torch.library.custom_op("maskunet::conv3x3_fwd", mutates_args=(), device_types="cuda")
+def conv3x3_fwd(x: Tensor, wf: Tensor, want_stats: bool) -> Tuple[Tensor, Tensor]:
+    """y = conv3x3(x) for bf16 channels-last x [B, Cin, H, W]; sums f32 [2 Cout] = per-channel (sum, sum of squares)
+    of y from the epilogue (empty when not wanted)."""
+    B, Cin, H, W = _nhwc(x)
+    _cuda(wf)
+    Cout = wf.shape[1]
+    assert x.dtype == torch.bfloat16 and wf.shape == (9, Cout, Cin)
+    y = _empty_cl(x, B, Cout, H, W)
+    sums = torch.zeros((2 * Cout,), dtype=torch.float32, device=x.device) if want_stats else \
+        torch.empty((0,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _timed("mu_conv3x3_fwd", (B, H, W, Cin, Cout)):
+        _count(1)
+        check(_L.mu_conv3x3_fwd(_p(x), _p(wf), _p(y), _p(sums) if want_stats else _optp(None), B, H, W, Cin, Cout,
+                                MU_BF16, _stream(x)), "mu_conv3x3_fwd")
+    return y, sums
+
+
+@conv3x3_fwd.register_fake
+def _(x, wf, want_stats):
+    B, Cin, H, W = x.shape
+    Cout = wf.shape[1]
+    return _empty_cl(x, B, Cout, H, W), x.new_empty((2 * Cout if want_stats else 0,), dtype=torch.float32)
+
+
+@torch.library.custom_op("maskunet::conv3x3_bwd_data", mutates_args=(), device_types="cuda")
+def conv3x3_bwd_data(dy: Tensor, wd: Tensor) -> Tensor:
+    B, Cout, H, W = _nhwc(dy)
+    _cuda(wd)
+    Cin = wd.shape[1]
+    assert dy.dtype == torch.bfloat16 and wd.shape == (9, Cin, Cout)
+    dx = _empty_cl(dy, B, Cin, H, W)
+    with torch.cuda.device(dy.device), _timed("mu_conv3x3_bwd_data", (B, H, W, Cin, Cout)):
+        _count(1)
+        check(_L.mu_conv3x3_bwd_data(_p(dy), _p(wd), _p(dx), B, H, W, Cin, Cout, MU_BF16, _stream(dy)),
+              "mu_conv3x3_bwd_data")
+    return dx
+
+
+@conv3x3_bwd_data.register_fake
+def _(dy, wd):
+    B, Cout, H, W = dy.shape
+    return _empty_cl(dy, B, wd.shape[1], H, W)
+
+
+@torch.library.custom_op("maskunet::conv3x3_bwd_weight", mutates_args=(), device_types="cuda")
+def conv3x3_bwd_weight(x: Tensor, dy: Tensor) -> Tensor:
+    """dw f32 [Cout, Cin, 3, 3]."""
+    B, Cin, H, W = _nhwc(x)
+    _, Cout, _, _ = _nhwc(dy)
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16
+    dw = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=x.device)
+    ws_bytes = int(_L.mu_conv3x3_workspace_bytes(Cin, Cout))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device), _timed("mu_conv3x3_bwd_weight", (B, H, W, Cin, Cout)):
+        _count(2)
+        check(_L.mu_conv3x3_bwd_weight(_p(x), _p(dy), _p(ws), ws_bytes, _p(dw), B, H, W, Cin, Cout, MU_BF16,
+                                       _stream(x)), "mu_conv3x3_bwd_weight")
+    return dw
+
+
+@conv3x3_bwd_weight.register_fake
+def _(x, dy):
+    return x.new_empty((dy.shape[1], x.shape[1], 3, 3), dtype=torch.float32)
+
+
+@torch.library.custom_op("maskunet::conv3x3", mutates_args=(), device_types="cuda")
+def conv3x3(x: Tensor, weight: Tensor, want_stats: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """nn.Conv2d(Cin, Cout, 3, padding=1, bias=False) on our tcgen05 kernels.  x bf16 channels-last, weight the fp32
+    parameter.  Returns (y, BatchNorm partial sums, wd) -- wd is the operand of the data gradient."""
+    wf, wd = conv_prep_weights(weight.contiguous(), True)
+    y, sums = conv3x3_fwd(x, wf, want_stats)
+    return y, sums, wd
+
+
+@conv3x3.register_fake
+def _(x, weight, want_stats):
+    B, Cin, H, W = x.shape
+    Cout = weight.shape[0]
+    return (_empty_cl(x, B, Cout, H, W), x.new_empty((2 * Cout if want_stats else 0,), dtype=torch.float32),
+            x.new_empty((9, Cin, Cout), dtype=torch.bfloat16))
+
+
+def _conv_setup(ctx, inputs, output):
+    x, weight, want_stats = inputs
+    ctx.save_for_backward(x, output[2])
+    ctx.x_needs_grad = x.requires_grad
+
+
+def _conv_backward(ctx, dy, *unused):
+    x, wd = ctx.saved_tensors
+    dy = dy.contiguous(memory_format=torch.channels_last)
+    dx = conv3x3_bwd_data(dy, wd) if ctx.needs_input_grad[0] else None
+    dw = conv3x3_bwd_weight(x, dy) if ctx.needs_input_grad[1] else None
+    return dx, dw, None
+
+
+conv3x3.register_autograd(_conv_backward, setup_context=_conv_setup)
+
+
 # ------------------------------------------------------------------ K9: MaxPool2d(2), channels-last
 def _nhwc(x: Tensor):
     if not (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)):

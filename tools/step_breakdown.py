@@ -12,6 +12,7 @@ def classify(n):
     if "attn_bwd" in n or "dq_convert" in n: return "mu attn_bwd"
     if "attn_fwd" in n: return "mu attn_fwd"
     if "mu::qkv" in n or "zero_pad" in n: return "mu qkv projections"
+    if "mu::conv_" in n: return "mu conv3x3"
     if "mu::bn_" in n: return "mu bn+act"
     if "mu::residual_ln" in n: return "mu residual LN"
     if "mu::transpose" in n: return "mu transpose"
