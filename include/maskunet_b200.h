@@ -200,6 +200,11 @@ int mu_conv3x3_bwd_data(const void* dy, const void* wd, void* dx, int32_t B, int
 size_t mu_conv3x3_workspace_bytes(int32_t Cin, int32_t Cout);
 int mu_conv3x3_bwd_weight(const void* x, const void* dy, void* workspace, size_t workspace_bytes, float* dw, int32_t B,
                           int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t dtype, mu_stream_t stream);
+/* nn.BatchNorm2d running-statistics update from the batch statistics mu_bn_act_fwd produced:
+ * running_mean = (1 - momentum) running_mean + momentum mean; running_var likewise with the unbiased batch
+ * variance (1 / rstd^2 - eps) M / (M - 1).  In place on running_mean / running_var (f32 [C]). */
+int mu_bn_update_running(float* running_mean, float* running_var, const float* mean, const float* rstd, float momentum,
+                         float eps, int64_t M, int32_t C, mu_stream_t stream);
 /* mu_bn_act_fwd with the statistics pass already done (sums f32 [2C] = per-channel sum, sum of squares over the
  * M rows, e.g. from mu_conv3x3_fwd): finalize + apply only. */
 int mu_bn_act_fwd_stats(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y,

@@ -360,6 +360,24 @@ int launch_bn_forward(const void* x, const void* r, const float* gamma, const fl
                          : bn_apply_t<__nv_bfloat16>(x, r, a, b, y, M, C, act, s);
 }
 
+__global__ void bn_update_running_kernel(float* __restrict__ running_mean, float* __restrict__ running_var,
+                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                         float momentum, float eps, long M, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float rs = rstd[c];
+  float var = fmaxf(1.f / (rs * rs) - eps, 0.f);
+  if (M > 1) var *= (float)((double)M / (double)(M - 1));
+  running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean[c];
+  running_var[c] = (1.f - momentum) * running_var[c] + momentum * var;
+}
+
+int launch_bn_update_running(float* running_mean, float* running_var, const float* mean, const float* rstd,
+                             float momentum, float eps, long M, int C, cudaStream_t s) {
+  bn_update_running_kernel<<<(C + 127) / 128, 128, 0, s>>>(running_mean, running_var, mean, rstd, momentum, eps, M, C);
+  return check_launch("bn_update_running");
+}
+
 // statistics already reduced by the producer (the convolution epilogue): finalize + apply
 int launch_bn_forward_stats(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y,
                             float* mean, float* rstd, float* a, float* b, const float* sums, long M, int C, int act,

@@ -303,6 +303,13 @@ int mu_conv3x3_bwd_weight(const void* x, const void* dy, void* workspace, size_t
   return launch_conv_wgrad_sm100(x, dy, (float*)workspace, dw, B, H, W, Cin, Cout, (cudaStream_t)stream);
 }
 
+int mu_bn_update_running(float* running_mean, float* running_var, const float* mean, const float* rstd, float momentum,
+                         float eps, int64_t M, int32_t C, mu_stream_t stream) {
+  MU_REQUIRE(C > 0 && M > 0, MU_ERR_BAD_SHAPE, "mu_bn_update_running: bad shape (M=%ld C=%d)", (long)M, C);
+  MU_PTRS("mu_bn_update_running", running_mean, running_var, mean, rstd);
+  return launch_bn_update_running(running_mean, running_var, mean, rstd, momentum, eps, (long)M, C, (cudaStream_t)stream);
+}
+
 int mu_bn_act_fwd_stats(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y,
                         float* mean, float* rstd, float* a, float* b, const float* sums, int64_t M, int32_t C,
                         int32_t act, int32_t dtype, mu_stream_t stream) {

@@ -84,6 +84,8 @@ int launch_bn_apply(const void* x, const void* r, const float* a, const float* b
 int launch_bn_backward(const void* dy, const void* x, const void* r, const float* a, const float* b, const float* mean,
                        const float* rstd, float* sums, void* dx, void* dr, long M, int C, int act, int dtype,
                        cudaStream_t s);
+int launch_bn_update_running(float* running_mean, float* running_var, const float* mean, const float* rstd,
+                             float momentum, float eps, long M, int C, cudaStream_t s);
 int launch_bn_forward_stats(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y,
                             float* mean, float* rstd, float* a, float* b, const float* sums, long M, int C, int act,
                             int dtype, cudaStream_t s);

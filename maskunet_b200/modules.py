@@ -121,6 +121,11 @@ def _fast_layout(x: torch.Tensor, channel_multiple: int = 8) -> bool:
             and x.shape[1] % channel_multiple == 0 and x.is_contiguous(memory_format=torch.channels_last))
 
 
+# BatchNorm `num_batches_tracked += 1` is one tiny kernel per layer; UNet.forward collects the counters here and
+# bumps them with a single multi-tensor add.  None outside a UNet forward (each layer then updates its own).
+_NBT_PENDING: Optional[list] = None
+
+
 def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Optional[torch.Tensor] = None,
                  sums: Optional[torch.Tensor] = None):
     """act(BatchNorm2d(x) [+ residual]) -- the BN / GELU / ReLU / residual chains of ade_semantic.py:198-210,
@@ -152,14 +157,15 @@ def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Option
             y, mean, rstd, _, _ = ops.bn_act_fwd_stats(x, residual, gamma, beta, sums, bn.eps, act)
         else:
             y, mean, rstd, _, _ = ops.bn_act_fwd(x, residual, gamma, beta, bn.eps, act)
-        if bn.track_running_stats:
+        if bn.track_running_stats:      # nn.BatchNorm2d's running-statistics update (:200), one small kernel
             with torch.no_grad():
-                count = x.shape[0] * x.shape[2] * x.shape[3]
-                var = (1.0 / (rstd * rstd) - bn.eps).clamp_min_(0.0) * (count / max(count - 1, 1))
-                momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
-                bn.running_mean.lerp_(mean, momentum)
-                bn.running_var.lerp_(var, momentum)
-                bn.num_batches_tracked += 1
+                if _NBT_PENDING is not None and bn.momentum is not None:
+                    _NBT_PENDING.append(bn.num_batches_tracked)
+                else:
+                    bn.num_batches_tracked += 1
+                momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                ops.bn_update_running(bn.running_mean, bn.running_var, mean, rstd, momentum, bn.eps,
+                                      x.shape[0] * x.shape[2] * x.shape[3])
         return y
     with torch.no_grad():
         a = gamma * torch.rsqrt(bn.running_var.float() + bn.eps)
@@ -330,12 +336,21 @@ class UNet(nn.Module):
         return semantic, boundary, embeddings
 
     def forward(self, x):
+        global _NBT_PENDING
         if self.channels_last:
             x = x.contiguous(memory_format=torch.channels_last)
-        if self.compute_dtype == torch.bfloat16:
-            with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
-                return self._heads(self._trunk(x.to(torch.bfloat16)))
-        return self._heads(self._trunk(x))
+        _NBT_PENDING = [] if self.training else None
+        try:
+            if self.compute_dtype == torch.bfloat16:
+                with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+                    out = self._heads(self._trunk(x.to(torch.bfloat16)))
+            else:
+                out = self._heads(self._trunk(x))
+            if _NBT_PENDING:
+                torch._foreach_add_(_NBT_PENDING, 1)
+        finally:
+            _NBT_PENDING = None
+        return out
 
 
 class InstanceUNet(UNet):

@@ -386,6 +386,7 @@ def _(dy, x, residual, a, b, mean, rstd, act):
 
 
 def _bn_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)   # unused outputs get None, not dense zero gradients
     x, residual, gamma, beta, eps, act = inputs
     y, mean, rstd, a, b = output
     ctx.act = act
@@ -407,6 +408,20 @@ def _bn_backward(ctx, dy, *unused):
 
 
 bn_act_fwd.register_autograd(_bn_backward, setup_context=_bn_setup)
+
+
+@torch.library.custom_op("maskunet::bn_update_running", mutates_args=("running_mean", "running_var"),
+                         device_types="cuda")
+def bn_update_running(running_mean: Tensor, running_var: Tensor, mean: Tensor, rstd: Tensor, momentum: float,
+                      eps: float, count: int) -> None:
+    """nn.BatchNorm2d's running-statistics update (momentum, unbiased variance) from the batch mean / rstd that
+    bn_act_fwd returned: one small kernel instead of six elementwise launches per layer."""
+    _cuda(running_mean, running_var, mean, rstd)
+    C = mean.numel()
+    with torch.cuda.device(mean.device):
+        _count(1)
+        check(_L.mu_bn_update_running(_p(running_mean), _p(running_var), _p(mean), _p(rstd), momentum, eps, count, C,
+                                      _stream(mean)), "mu_bn_update_running")
 
 
 # ------------------------------------------------------------------ K8 with the statistics pass done by the producer
@@ -565,6 +580,7 @@ def _(x, weight, want_stats):
 
 
 def _conv_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)   # unused outputs get None, not dense zero gradients
     x, weight, want_stats = inputs
     ctx.save_for_backward(x, output[2])
     ctx.x_needs_grad = x.requires_grad
@@ -670,6 +686,7 @@ def _(dout, cs):
 
 
 def _upcat_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)   # unused outputs get None, not dense zero gradients
     ctx.cs = inputs[0].shape[1]
 
 
@@ -724,6 +741,7 @@ def _(dy, x, gamma_nhwc, mean, rstd):
 
 
 def _sln_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)   # unused outputs get None, not dense zero gradients
     x, gamma, beta, eps = inputs
     ctx.save_for_backward(x, gamma, output[1], output[2])
 
@@ -760,6 +778,7 @@ def _(logits, labels, ignore_index):
 
 
 def _ce_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)   # unused outputs get None, not dense zero gradients
     ctx.save_for_backward(output[1])
 
 
@@ -811,6 +830,7 @@ def _(dy, x, w_qkv, gamma, keep_idx, n_keep, q, kc, vc, o, lse, mean, rstd, toke
 
 
 def _ma_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)   # unused outputs get None, not dense zero gradients
     x, w_qkv, b_qkv, gamma, beta, keep_rank, keep_idx, n_keep, eps, token_major = inputs
     y, q, kc, vc, o, lse, mean, rstd = output
     ctx.token_major = token_major

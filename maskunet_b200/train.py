@@ -43,10 +43,15 @@ class Trainer:
         if (logits.is_cuda and logits.shape[1] <= 256 and logits.dtype in (torch.float32, torch.bfloat16)
                 and logits.is_contiguous(memory_format=torch.channels_last)):
             # fused CrossEntropyLoss(mean) forward + gradient on channels-last logits (one read, one write)
-            loss = ops.cross_entropy_fused(logits, labels, self.ignore_index)[0].squeeze(0)
+            # and start backward from d(loss)/d(logits) directly: the fused kernel already produced it, so the
+            # loss node and its `dlogits * dloss` pass are skipped
+            with torch.no_grad():
+                loss, dlogits = ops.cross_entropy_fused(logits.detach(), labels, self.ignore_index)
+            loss = loss.squeeze(0)
+            logits.backward(dlogits)
         else:
             loss = F.cross_entropy(logits.float(), labels, ignore_index=self.ignore_index)
-        loss.backward()
+            loss.backward()
         if self.reducer is not None:
             self.reducer.finish()
         self.optimizer.step()
