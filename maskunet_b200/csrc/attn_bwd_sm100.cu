@@ -31,7 +31,8 @@ struct BwdCfg {
   static constexpr int kPBytes = kBK * BM * 2;           // P^T or dS^T
   static constexpr int kTmS = 0, kTmDP = BM, kTmDV = 2 * BM, kTmDK = 2 * BM + DH, kTmDQ = 2 * BM + 2 * DH;
   static constexpr int kDQCols = kDQT ? BM : DH;
-  static constexpr int kTmemUsed = kTmDQ + kDQCols;
+  static constexpr int kTmP = kTmDQ + kDQCols;           // bf16 P^T tile, two queries per 32-bit column (A of the dV MMA)
+  static constexpr int kTmemUsed = kTmP + BM / 2;
   static_assert(kTmemUsed <= 512, "TMEM overflow");
   static constexpr int kStatBytes = 2 * 2 * BM * 4;       // lse2, delta, double-buffered over tiles
   // PB = 2 double-buffers the P^T / dS^T tiles so that the exp / dS work of query tile i+1 overlaps the
@@ -39,7 +40,7 @@ struct BwdCfg {
   static constexpr bool kDQTma = (D <= 128);             // dQ tile leaves through a TMA reduce-add (smem permitting)
   static constexpr int kDQStageBytes = kDQTma ? BM * DH * 4 : 0;   // fp32 dQ tile staged for the TMA reduce-add
   static constexpr int kSmemBytes =
-      2 * kKBytes + 2 * STAGES * kQBytes + (1 + PB) * kPBytes + kDQStageBytes + kStatBytes + 256;
+      2 * kKBytes + 2 * STAGES * kQBytes + PB * kPBytes + kDQStageBytes + kStatBytes + 256;
   static_assert(kSmemBytes <= 232448, "shared memory overflow");
 };
 
@@ -66,8 +67,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   uint8_t* sV = sK + Cfg::kKBytes;
   uint8_t* sQ = sV + Cfg::kKBytes;                       // STAGES x Q_i
   uint8_t* sDO = sQ + STAGES * Cfg::kQBytes;             // STAGES x dO_i
-  uint8_t* sP = sDO + STAGES * Cfg::kQBytes;              // P^T (single: only the dV MMA reads it)
-  uint8_t* sDS = sP + Cfg::kPBytes;                       // PB x dS^T
+  uint8_t* sDS = sDO + STAGES * Cfg::kQBytes;             // PB x dS^T (P^T lives in TMEM: only the dV MMA reads it)
   uint8_t* sDQ = sDS + PB * Cfg::kPBytes;                 // fp32 dQ staging (D = 64 only)
   float* sLse = reinterpret_cast<float*>(sDQ + Cfg::kDQStageBytes);   // [2][BM], already * log2e
   float* sDelta = sLse + 2 * BM;
@@ -150,7 +150,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       constexpr uint32_t idesc_acc = make_idesc_bf16(kBK, DH, 0, 1);   // dV, dK: A K-major, B MN-major
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, DQT ? BM : DH, 1, 1);
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
-      const uint32_t p_base = smem_u32(sP), ds_base = smem_u32(sDS);
+      const uint32_t ds_base = smem_u32(sDS);
       auto issue_s_dp = [&](int i) {
         const int st = i % STAGES;
         mbar_wait(qdo_full + st, (i / STAGES) & 1);
@@ -172,14 +172,13 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       };
       auto issue_acc = [&](int i) {
         const int st = i % STAGES;
-        const uint32_t p_addr = p_base, ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
+        const uint32_t ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
         const uint32_t qa = q_addr + st * Cfg::kQBytes + half * 2 * (BM * 128);
         const uint32_t da = do_addr + st * Cfg::kQBytes + half * 2 * (BM * 128);
 #pragma unroll
-        for (int kk = 0; kk < BM / 16; ++kk) {   // dV += P^T dO_i
-          const uint64_t a = make_smem_desc(p_addr + (kk >> 2) * (kBK * 128) + (kk & 3) * 32, 0, 1024);
+        for (int kk = 0; kk < BM / 16; ++kk) {   // dV += P^T dO_i, A = P^T from TMEM (16 queries = 8 columns)
           const uint64_t bd = make_smem_desc(da + kk * 2048, BM * 128, 1024);
-          umma_ss(tmem_base + Cfg::kTmDV, a, bd, idesc_acc, (i > 0) || (kk > 0));
+          umma_ts(tmem_base + Cfg::kTmDV, tmem_base + Cfg::kTmP + kk * 8, bd, idesc_acc, (i > 0) || (kk > 0));
         }
         umma_commit(p_free);
 #pragma unroll
@@ -242,11 +241,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const float* lse_b = lse + (size_t)b * N;
     const float* delta_b = delta + (size_t)b * N;
     const uint32_t lse_addr = smem_u32(sLse), delta_addr = smem_u32(sDelta);
-    const uint32_t p_base = smem_u32(sP), ds_base = smem_u32(sDS);
+    const uint32_t ds_base = smem_u32(sDS);
     auto fetch = [&](int i, float& l2, float& dl) {
       const int qi = i * BM + t;
       const bool ok = (t < BM) && (qi < N);
-      l2 = ok ? lse_b[qi] * kLog2eB : INFINITY;          // +inf -> p = 0 for rows past N
+      l2 = ok ? lse_b[qi] : INFINITY;                    // +inf -> p = 0 for rows past N (scaled by log2e when staged)
       dl = ok ? delta_b[qi] : 0.f;
     };
     float nl2, ndl;
@@ -257,7 +256,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     for (int i = 0; i < T; ++i) {
       const uint32_t my_lse = lse_addr + (i & 1) * BM * 4, my_delta = delta_addr + (i & 1) * BM * 4;
       if (t < BM) {
-        st_shared_f32(my_lse + t * 4, nl2);
+        st_shared_f32(my_lse + t * 4, nl2 * kLog2eB);
         st_shared_f32(my_delta + t * 4, ndl);
       }
       if (i + 1 < T) fetch(i + 1, nl2, ndl);
@@ -282,7 +281,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       // the MMAs that last read this P^T / dS^T buffer (tile i - PB) must have completed
       if (i >= PB) mbar_wait(pds_free + (i % PB), ((i / PB) - 1) & 1);
       if (i > 0) mbar_wait(p_free, (i - 1) & 1);         // dV MMAs of tile i-1 are done with P^T
-      const uint32_t p_addr = p_base, ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
+      const uint32_t ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
 #pragma unroll
       for (int cc = 0; cc < kChunksPerThread; ++cc) {
         const int c = hcol * kChunksPerThread + cc;
@@ -308,10 +307,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const uint32_t chunk = (((c & 1) * 4 + ch) ^ (r & 7)) * 16;
-          st_shared_v4(p_addr + row_off + chunk, pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
           st_shared_v4(ds_addr + row_off + chunk, dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
         }
+        tmem_st16(lane_base + Cfg::kTmP + c * 16, pk);   // 32 queries = 16 packed columns of the TMEM P^T tile
       }
+      tmem_wait_st();
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(pds_full);

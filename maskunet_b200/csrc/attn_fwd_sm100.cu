@@ -21,6 +21,7 @@ namespace mu {
 constexpr int kBM = 128;                 // queries per CTA
 constexpr int kFwdThreads = 256;         // warpgroup 0: TMA, MMA, 2 idle warps; warpgroup 1: softmax
 constexpr float kLog2eF = 1.4426950408889634f;
+constexpr float kLazyLog2 = 8.f;         // rescale O only when the row maximum grew by more than 2^8
 
 template <int D, int BN, int SBUFS, int SLOTS>
 struct FwdCfg {
@@ -30,10 +31,11 @@ struct FwdCfg {
   static constexpr int kPBytes = kBM * BN * 2;
   static constexpr int kTmemS = 0;
   static constexpr int kTmemO = SBUFS * BN;
-  static constexpr int kTmemUsed = SBUFS * BN + D;
+  static constexpr int kTmemP = SBUFS * BN + D;              // bf16 P tile, two keys per 32-bit column (A operand of PV)
+  static constexpr int kTmemUsed = SBUFS * BN + D + BN / 2;
   static constexpr int kTmemCols = kTmemUsed <= 256 ? 256 : 512;
   static constexpr int kBarBytes = 8 * (1 + 2 * SLOTS + 2 * SBUFS + 2) + 8;
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kQBytes + SLOTS * kKVBytes + kPBytes + 256;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kQBytes + SLOTS * kKVBytes + 256;
   static_assert(kBarBytes <= 256, "barrier block too small");
   static_assert(kTmemUsed <= 512, "TMEM overflow");
 };
@@ -48,8 +50,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Cfg::kQBytes;
-  uint8_t* sP = sKV + SLOTS * Cfg::kKVBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + SLOTS * Cfg::kKVBytes);
   uint64_t* q_full = bars;                  // 1
   uint64_t* kv_full = bars + 1;             // SLOTS
   uint64_t* kv_empty = kv_full + SLOTS;     // SLOTS
@@ -116,7 +117,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     if (lane_id() == 0 && T > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(kBM, BN, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(kBM, D, 0, 1);
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP), kv_addr = smem_u32(sKV);
+      const uint32_t q_addr = smem_u32(sQ), kv_addr = smem_u32(sKV);
       auto issue_s = [&](int j) {
         const int t = 2 * j, slot = t % SLOTS, buf = j % SBUFS;
         mbar_wait(kv_full + slot, (t / SLOTS) & 1);
@@ -145,10 +146,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         tc_fence_after();
         const uint32_t v_addr = kv_addr + slot * Cfg::kKVBytes;
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk) {
-          const uint64_t da = make_smem_desc(p_addr + (kk >> 2) * (kBM * 128) + (kk & 3) * 32, 0, 1024);
+        for (int kk = 0; kk < BN / 16; ++kk) {   // A = P straight from TMEM (16 keys = 8 columns per step)
           const uint64_t db = make_smem_desc(v_addr + kk * 2048, BN * 128, 1024);
-          umma_ss(tmem_base + Cfg::kTmemO, da, db, idesc_o, (j > 0) || (kk > 0));
+          umma_ts(tmem_base + Cfg::kTmemO, tmem_base + Cfg::kTmemP + kk * 8, db, idesc_o, (j > 0) || (kk > 0));
         }
         umma_commit(kv_empty + slot);
         umma_commit(o_done);
@@ -162,7 +162,6 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const int r = quad * 32 + (int)lane_id();       // query row within the tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const bool row_ok = q0 + r < N;
-    const uint32_t p_saddr = smem_u32(sP);
     __nv_bfloat16* orow = o + ((size_t)b * N + q0 + r) * D;
     if (T == 0) {  // every key masked: the reference yields NaN (softmax over all -inf)
       if (row_ok) {
@@ -203,12 +202,17 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         float m_new = m;
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) m_new = fmaxf(m_new, mx[c]);
-        const float alpha = fast_exp2((m - m_new) * scale_log2);
-        // ---- rescale O once the previous PV has landed
-        if (j > 0) {
-          mbar_wait(o_done, (j - 1) & 1);
-          tc_fence_after();
-          if (__any_sync(0xffffffffu, m_new > m)) {
+        // ---- lazy rescale: the exponent offset m only follows the running maximum when it has moved by more than
+        // 2^kLazyLog2 (P then stays below 2^kLazyLog2, harmless in bf16 / fp32), so after the first tiles the
+        // softmax warps neither wait for the previous PV nor touch O in TMEM.  O / l and the LSE use the same m.
+        float alpha = 1.f;
+        const bool grow = (m_new - m) * scale_log2 > kLazyLog2;       // true on the first tile (m = -inf)
+        if (__any_sync(0xffffffffu, grow)) {
+          alpha = fast_exp2((m - m_new) * scale_log2);
+          m = m_new;
+          if (j > 0) {
+            mbar_wait(o_done, (j - 1) & 1);                            // the previous PV has landed in TMEM
+            tc_fence_after();
             uint32_t ov[32];
 #pragma unroll
             for (int c = 0; c < D / 32; ++c) {
@@ -222,7 +226,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           }
         }
         // ---- p = exp2((s - m) * scale * log2e), bf16 P tile into shared memory
-        const float mb = m_new * scale_log2;
+        const float mb = m * scale_log2;
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
@@ -234,19 +238,18 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             sum[i & 3] += p0 + p1;
             pk[i] = pack_bf16(p0, p1);
           }
-          // columns [c*32, c*32+32) = 16-byte chunks (c&1)*4 .. +3 of 64-column block c>>1
-          const uint32_t prow = p_saddr + (c >> 1) * (kBM * 128) + r * 128;
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const uint32_t chunk = (((c & 1) * 4 + ch) ^ (r & 7)) * 16;
-            st_shared_v4(prow + chunk, pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+          // P never touches shared memory: 32 keys = 16 packed columns of the TMEM P tile.  The previous PV must
+          // have consumed the tile first (normally long done: it was issued a whole exp phase ago).
+          if (c == 0 && j > 0) {
+            mbar_wait(o_done, (j - 1) & 1);
+            tc_fence_after();
           }
+          tmem_st16(lane_base + Cfg::kTmemP + c * 16, pk);
         }
+        tmem_wait_st();
         tc_fence_before();
-        fence_proxy_async_smem();
         mbar_arrive(p_full);
         l = l * alpha + ((sum[0] + sum[1]) + (sum[2] + sum[3]));
-        m = m_new;
       }
       // ---- epilogue: O / l, LSE
       mbar_wait(o_done, (T - 1) & 1);
