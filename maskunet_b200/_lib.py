@@ -10,7 +10,8 @@ import os
 from ctypes import c_float, c_int32, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmaskunet_b200.so")
+# MASKUNET_B200_LIB selects another build of the same library (A/B experiments with tools/); default: in-tree
+LIB_PATH = os.environ.get("MASKUNET_B200_LIB") or os.path.join(HERE, "libmaskunet_b200.so")
 
 MU_F32, MU_BF16 = 0, 1
 

@@ -44,6 +44,25 @@ def compile_one(src, force, hm, log):
     return obj, True
 
 
+def build_variant(out: str, defines, objdir: str) -> str:
+    """A/B build: the same sources with extra -D flags into another .so (select it with MASKUNET_B200_LIB)."""
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    def one(src):
+        obj = os.path.join(objdir, src[:-3] + ".o")
+        cmd = [NVCC, *ARCH, *FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stderr}")
+        return obj
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(one, sources()))
+    r = subprocess.run([NVCC, *ARCH, "-shared", "-o", out, *objs, "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stderr}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     hm = headers_mtime()
@@ -66,4 +85,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:       # python build.py --variant out.so DEF1=V1 DEF2=V2 ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:], OBJ + "_variant"))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

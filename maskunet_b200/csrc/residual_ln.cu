@@ -146,6 +146,188 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Production layout (bf16, token-major x): C / 8 lanes own one token, each lane one 16-byte vector of 8 channels,
+// so a warp covers 32 / (C / 8) tokens per step; kLnUnroll independent steps are in flight per thread (the kernel
+// is a pure HBM stream: 3 or 4 tensor passes, statistics by xor-shuffles inside the token's lane group).
+constexpr int kLnUnroll = 4;
+
+__device__ __forceinline__ void unpack8(const uint4 u, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = __uint_as_float(w[e] << 16);
+    v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack2_bf16(v[0], v[1]), pack2_bf16(v[2], v[3]), pack2_bf16(v[4], v[5]), pack2_bf16(v[6], v[7]));
+}
+template <int LPT>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPT / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kLnThreads) residual_ln_fwd_tok_kernel(
+    const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
+    float* __restrict__ rstd, long M) {
+  constexpr int LPT = C / 8, TPB = kLnThreads / LPT;          // lanes per token, tokens per CTA step
+  const int g = threadIdx.x % LPT, tl = threadIdx.x / LPT;
+  float gm[8], bt[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    gm[e] = gamma[g * 8 + e];
+    bt[e] = beta[g * 8 + e];
+  }
+  const long stride = (long)gridDim.x * TPB;
+  for (long t0 = (long)blockIdx.x * TPB + tl; t0 < M; t0 += stride * kLnUnroll) {
+    uint4 uo[kLnUnroll], ux[kLnUnroll];
+#pragma unroll
+    for (int u = 0; u < kLnUnroll; ++u) {
+      const long t = t0 + u * stride;
+      uo[u] = ux[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (t < M) {
+        uo[u] = *reinterpret_cast<const uint4*>(o + t * C + g * 8);
+        ux[u] = *reinterpret_cast<const uint4*>(x + t * C + g * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kLnUnroll; ++u) {
+      const long t = t0 + u * stride;
+      const bool ok = t < M;              // no early exit: the shuffles below need every lane of the warp
+      float a[8], b[8], z[8];
+      unpack8(uo[u], a);
+      unpack8(ux[u], b);
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        z[e] = a[e] + b[e];
+        s += z[e];
+      }
+      const float mu_ = group_sum<LPT>(s) * (1.f / C);
+      float v = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = z[e] - mu_;
+        v = fmaf(d, d, v);
+      }
+      const float rs = rsqrtf(group_sum<LPT>(v) * (1.f / C) + eps);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) z[e] = fmaf((z[e] - mu_) * rs, gm[e], bt[e]);
+      if (ok) *reinterpret_cast<uint4*>(y + t * C + g * 8) = pack8(z);
+      if (ok && g == 0) {
+        mean[t] = mu_;
+        rstd[t] = rs;
+      }
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_tok_kernel(
+    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ x,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+    __nv_bfloat16* __restrict__ dz, float* __restrict__ delta, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    long M) {
+  constexpr int LPT = C / 8, TPB = kLnThreads / LPT;
+  __shared__ float red[2 * C];
+  const int g = threadIdx.x % LPT, tl = threadIdx.x / LPT;
+  for (int i = threadIdx.x; i < 2 * C; i += kLnThreads) red[i] = 0.f;
+  float gm[8], dg[8], db[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    gm[e] = gamma[g * 8 + e];
+    dg[e] = db[e] = 0.f;
+  }
+  const long stride = (long)gridDim.x * TPB;
+  for (long t0 = (long)blockIdx.x * TPB + tl; t0 < M; t0 += stride * kLnUnroll) {
+    uint4 ud[kLnUnroll], uo[kLnUnroll], ux[kLnUnroll];
+    float mu_[kLnUnroll], rs[kLnUnroll];
+#pragma unroll
+    for (int u = 0; u < kLnUnroll; ++u) {
+      const long t = t0 + u * stride;
+      ud[u] = uo[u] = ux[u] = make_uint4(0u, 0u, 0u, 0u);
+      mu_[u] = rs[u] = 0.f;
+      if (t < M) {
+        ud[u] = *reinterpret_cast<const uint4*>(dy + t * C + g * 8);
+        uo[u] = *reinterpret_cast<const uint4*>(o + t * C + g * 8);
+        ux[u] = *reinterpret_cast<const uint4*>(x + t * C + g * 8);
+        mu_[u] = mean[t];
+        rs[u] = rstd[t];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kLnUnroll; ++u) {
+      const long t = t0 + u * stride;
+      const bool ok = t < M;              // masked tokens carry zeros: they add nothing to dgamma / dbeta
+      float d[8], ov[8], xv[8], zh[8], gg[8];
+      unpack8(ud[u], d);
+      unpack8(uo[u], ov);
+      unpack8(ux[u], xv);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        zh[e] = (ov[e] + xv[e] - mu_[u]) * rs[u];
+        gg[e] = d[e] * gm[e];
+        dg[e] = fmaf(d[e], zh[e], dg[e]);
+        db[e] += d[e];
+        s1 += gg[e];
+        s2 = fmaf(gg[e], zh[e], s2);
+      }
+      s1 = group_sum<LPT>(s1) * (1.f / C);
+      s2 = group_sum<LPT>(s2) * (1.f / C);
+      float r[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = rs[u] * (gg[e] - s1 - zh[e] * s2);
+      const uint4 packed = pack8(r);
+      if (ok) *reinterpret_cast<uint4*>(dz + t * C + g * 8) = packed;
+      float rr[8], dl = 0.f;
+      unpack8(packed, rr);                                    // delta uses the stored (rounded) gradient
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dl = fmaf(rr[e], ov[e], dl);
+      dl = group_sum<LPT>(dl);
+      if (ok && g == 0) delta[t] = dl;
+    }
+  }
+  // per-channel parameter gradients: lanes with the same channel group inside the warp first, then the CTA
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+#pragma unroll
+    for (int off = 16; off >= LPT; off >>= 1) {
+      dg[e] += __shfl_xor_sync(0xffffffffu, dg[e], off);
+      db[e] += __shfl_xor_sync(0xffffffffu, db[e], off);
+    }
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) < LPT) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(red + g * 8 + e, dg[e]);
+      atomicAdd(red + C + g * 8 + e, db[e]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kLnThreads) {
+    atomicAdd(dgamma + c, red[c]);
+    atomicAdd(dbeta + c, red[C + c]);
+  }
+}
+
+static int ln_tok_grid(long M, int C) {
+  const long per = kLnThreads / (C / 8) * kLnUnroll;
+  long blocks = (M + per - 1) / per;
+  const long cap = 148L * 8;
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
 static size_t ln_smem(int C) { return sizeof(float) * (size_t)C * 33; }  // >= 16*C for C >= 32
 
 template <typename T>
@@ -176,12 +358,33 @@ static int run_bwd(const void* dy, const void* o, const void* x, const float* me
 
 int launch_residual_ln_fwd(const void* o, const void* x, const float* gamma, const float* beta, float eps, void* y,
                            float* mean, float* rstd, int B, int C, int N, int dtype, int tok, cudaStream_t s) {
+  if (dtype == MU_BF16 && tok && (C == 64 || C == 128 || C == 256)) {
+    const long M = (long)B * N;
+    const int grid = ln_tok_grid(M, C);
+#define MU_LN_FWD(CC)                                                                                              \
+  residual_ln_fwd_tok_kernel<CC><<<grid, kLnThreads, 0, s>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)x, gamma, \
+                                                             beta, eps, (__nv_bfloat16*)y, mean, rstd, M)
+    if (C == 64) MU_LN_FWD(64); else if (C == 128) MU_LN_FWD(128); else MU_LN_FWD(256);
+#undef MU_LN_FWD
+    return check_launch("residual_ln_fwd_tok");
+  }
   if (dtype == MU_F32) return run_fwd<float>(o, x, gamma, beta, eps, y, mean, rstd, B, C, N, tok, s);
   return run_fwd<__nv_bfloat16>(o, x, gamma, beta, eps, y, mean, rstd, B, C, N, tok, s);
 }
 int launch_residual_ln_bwd(const void* dy, const void* o, const void* x, const float* mean, const float* rstd,
                            const float* gamma, void* dz, float* delta, float* dgamma, float* dbeta, int B, int C, int N,
                            int dtype, int tok, cudaStream_t s) {
+  if (dtype == MU_BF16 && tok && (C == 64 || C == 128 || C == 256)) {
+    const long M = (long)B * N;
+    const int grid = ln_tok_grid(M, C);
+#define MU_LN_BWD(CC)                                                                                               \
+  residual_ln_bwd_tok_kernel<CC><<<grid, kLnThreads, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)o,        \
+                                                             (const __nv_bfloat16*)x, mean, rstd, gamma,              \
+                                                             (__nv_bfloat16*)dz, delta, dgamma, dbeta, M)
+    if (C == 64) MU_LN_BWD(64); else if (C == 128) MU_LN_BWD(128); else MU_LN_BWD(256);
+#undef MU_LN_BWD
+    return check_launch("residual_ln_bwd_tok");
+  }
   if (dtype == MU_F32) return run_bwd<float>(dy, o, x, mean, rstd, gamma, dz, delta, dgamma, dbeta, B, C, N, tok, s);
   return run_bwd<__nv_bfloat16>(dy, o, x, mean, rstd, gamma, dz, delta, dgamma, dbeta, B, C, N, tok, s);
 }

@@ -265,6 +265,18 @@ MU_DEVICE float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic fit of 2^f
+// (max relative error 1.9e-4, well under the bf16 rounding of the consumer), exponent added through the integer
+// bits.  Used for a fraction of the softmax exponentials so that MUFU.EX2 is no longer the only pipe they load.
+MU_DEVICE float poly_exp2(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                 // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.05489881f, 0.24193298f);
+  p = fmaf(p, f, 0.69324847f);
+  p = fmaf(p, f, 0.99997654f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 MU_DEVICE uint32_t pack_bf16(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
