@@ -109,7 +109,7 @@ struct RowMap {
 // block reduction of per-thread [VEC] partials over row lanes, then one atomicAdd per channel
 template <int VEC>
 __device__ __forceinline__ void block_reduce_add(float* red /*[kBnThreads*VEC]*/, const float (&a)[VEC], const RowMap& m,
-                                                 float* out, int C) {
+                                                 float* out, int C, int Cper) {
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < VEC; ++e) red[threadIdx.x * VEC + e] = m.active ? a[e] : 0.f;
@@ -118,14 +118,14 @@ __device__ __forceinline__ void block_reduce_add(float* red /*[kBnThreads*VEC]*/
     const int g = c / VEC, e = c - g * VEC;
     float s = 0.f;
     for (int rl = 0; rl < m.RL; ++rl) s += red[(rl * m.G + g) * VEC + e];
-    atomicAdd(out + c, s);
+    atomicAdd(out + (c % Cper), s);      // folded rows: column c of the wide row is channel c mod Cper
   }
 }
 
 // ------------------------------------------------------------------ forward: statistics
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restrict__ x, float* __restrict__ sums, long M,
-                                                              int C) {
+                                                              int C, int Cper) {
   __shared__ float red[kBnThreads * VEC];
   const RowMap m(C, VEC);
   float s1[VEC], s2[VEC];
@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
       }
     }
   }
-  block_reduce_add<VEC>(red, s1, m, sums, C);
-  block_reduce_add<VEC>(red, s2, m, sums + C, C);
+  block_reduce_add<VEC>(red, s1, m, sums, C, Cper);
+  block_reduce_add<VEC>(red, s2, m, sums + Cper, C, Cper);
 }
 
 // ------------------------------------------------------------------ forward: finalize ([C] work, one CTA)
@@ -174,14 +174,14 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* 
 template <typename T, int VEC, int ACT, bool RES>
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ r,
                                                               const float* __restrict__ a, const float* __restrict__ b,
-                                                              T* __restrict__ y, long M, int C) {
+                                                              T* __restrict__ y, long M, int C, int Cper) {
   const RowMap m(C, VEC);
   if (!m.active) return;
   float av[VEC], bv[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
-    av[e] = a[m.g * VEC + e];
-    bv[e] = b[m.g * VEC + e];
+    av[e] = a[(m.g * VEC + e) % Cper];
+    bv[e] = b[(m.g * VEC + e) % Cper];
   }
   for (long row = (long)blockIdx.x * m.RL + m.rl; row < M; row += (long)gridDim.x * m.RL) {
     const long off = row * C + m.g * VEC;
@@ -203,14 +203,14 @@ template <typename T, int VEC, int ACT, bool RES>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
     const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ a,
     const float* __restrict__ b, const float* __restrict__ mean, const float* __restrict__ rstd,
-    float* __restrict__ sums, long M, int C) {
+    float* __restrict__ sums, long M, int C, int Cper) {
   __shared__ float red[kBnThreads * VEC];
   const RowMap m(C, VEC);
   float s1[VEC], s2[VEC], av[VEC], bv[VEC], mv[VEC], rsv[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
     s1[e] = s2[e] = 0.f;
-    const int c = m.active ? m.g * VEC + e : 0;
+    const int c = m.active ? (m.g * VEC + e) % Cper : 0;
     av[e] = a[c]; bv[e] = b[c]; mv[e] = mean[c]; rsv[e] = rstd[c];
   }
   if (m.active) {
@@ -233,8 +233,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
       }
     }
   }
-  block_reduce_add<VEC>(red, s1, m, sums, C);
-  block_reduce_add<VEC>(red, s2, m, sums + C, C);
+  block_reduce_add<VEC>(red, s1, m, sums, C, Cper);
+  block_reduce_add<VEC>(red, s2, m, sums + Cper, C, Cper);
 }
 
 // ------------------------------------------------------------------ backward: apply
@@ -242,17 +242,17 @@ template <typename T, int VEC, int ACT, bool RES>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ a,
     const float* __restrict__ b, const float* __restrict__ mean, const float* __restrict__ rstd,
-    const float* __restrict__ sums, T* __restrict__ dx, T* __restrict__ dr, long M, int C) {
+    const float* __restrict__ sums, T* __restrict__ dx, T* __restrict__ dr, long M, int C, int Cper) {
   const RowMap m(C, VEC);
   if (!m.active) return;
   float av[VEC], bv[VEC], mv[VEC], rsv[VEC], c1[VEC], c2[VEC];
-  const float invM = 1.f / (float)M;
+  const float invM = 1.f / ((float)M * (float)(C / Cper));      // true row count = M wide rows x fold
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
-    const int c = m.g * VEC + e;
+    const int c = (m.g * VEC + e) % Cper;
     av[e] = a[c]; bv[e] = b[c]; mv[e] = mean[c]; rsv[e] = rstd[c];
     c1[e] = sums[c] * invM;
-    c2[e] = sums[C + c] * invM;
+    c2[e] = sums[Cper + c] * invM;
   }
   for (long row = (long)blockIdx.x * m.RL + m.rl; row < M; row += (long)gridDim.x * m.RL) {
     const long off = row * C + m.g * VEC;
@@ -279,6 +279,15 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
 
 // ------------------------------------------------------------------ dispatch
 static int pick_vec(int C) { return (C % 8 == 0) ? 8 : (C % 2 == 0 ? 2 : 1); }
+// Channel counts that are not a multiple of 8 (the 150-class head) would fall back to 2- or 4-byte accesses.  Instead
+// `fold` consecutive rows are treated as one wide row of fold * C columns (a multiple of 8): every thread still owns
+// fixed columns, and column c is channel c mod C for the parameters and the reductions.
+static int pick_fold(long M, int C) {
+  if (C % 8 == 0) return 1;
+  for (int f = 2; f <= 8; f *= 2)
+    if ((f * C) % 8 == 0 && M % f == 0 && f * C / 8 <= kBnThreads) return f;
+  return 1;
+}
 static int pick_grid(long M, int C, int VEC) {
   const int RL = kBnThreads / (C / VEC);
   long blocks = (M + RL - 1) / RL;
@@ -315,31 +324,40 @@ static bool bn_shape_ok(long M, int C) {
 
 template <typename T>
 static int bn_stats_t(const void* x, float* sums, long M, int C, cudaStream_t s) {
+  const int Cper = C, fold = pick_fold(M, C);
+  M /= fold;
+  C *= fold;
   const int vec = pick_vec(C), grid = pick_grid(M, C, vec);
-  MU_BN_VEC(vec, (bn_stats_kernel<T, VEC><<<grid, kBnThreads, 0, s>>>((const T*)x, sums, M, C)));
+  MU_BN_VEC(vec, (bn_stats_kernel<T, VEC><<<grid, kBnThreads, 0, s>>>((const T*)x, sums, M, C, Cper)));
   return check_launch("bn_stats");
 }
 template <typename T>
 static int bn_apply_t(const void* x, const void* r, const float* a, const float* b, void* y, long M, int C, int act,
                       cudaStream_t s) {
+  const int Cper = C, fold = pick_fold(M, C);
+  M /= fold;
+  C *= fold;
   const int vec = pick_vec(C), grid = pick_grid(M, C, vec);
   const bool res = r != nullptr;
   MU_BN_VEC(vec, MU_BN_ACT(act, res, (bn_apply_kernel<T, VEC, ACT, RES><<<grid, kBnThreads, 0, s>>>(
-                                         (const T*)x, (const T*)r, a, b, (T*)y, M, C))));
+                                         (const T*)x, (const T*)r, a, b, (T*)y, M, C, Cper))));
   return check_launch("bn_apply");
 }
 template <typename T>
 static int bn_bwd_t(const void* dy, const void* x, const void* r, const float* a, const float* b, const float* mean,
                     const float* rstd, float* sums, void* dx, void* dr, long M, int C, int act, cudaStream_t s) {
+  const int Cper = C, fold = pick_fold(M, C);
+  M /= fold;
+  C *= fold;
   const int vec = pick_vec(C), grid = pick_grid(M, C, vec);
   const bool res = r != nullptr;
   MU_BN_VEC(vec, MU_BN_ACT(act, res, (bn_bwd_reduce_kernel<T, VEC, ACT, RES><<<grid, kBnThreads, 0, s>>>(
-                                         (const T*)dy, (const T*)x, (const T*)r, a, b, mean, rstd, sums, M, C))));
+                                         (const T*)dy, (const T*)x, (const T*)r, a, b, mean, rstd, sums, M, C, Cper))));
   int rc = check_launch("bn_bwd_reduce");
   if (rc) return rc;
   MU_BN_VEC(vec, MU_BN_ACT(act, res, (bn_bwd_apply_kernel<T, VEC, ACT, RES><<<grid, kBnThreads, 0, s>>>(
                                          (const T*)dy, (const T*)x, (const T*)r, a, b, mean, rstd, sums, (T*)dx,
-                                         (T*)dr, M, C))));
+                                         (T*)dr, M, C, Cper))));
   return check_launch("bn_bwd_apply");
 }
 

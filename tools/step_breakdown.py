@@ -5,7 +5,17 @@ lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
 rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
 names = [r["Kernel Name"] for r in rows]
 idx = [i for i, n in enumerate(names) if "multi_tensor_apply" in n and "adam" in n.lower()]
-step = rows[: idx[-1] + 1] if idx else rows
+# one step = the launches after the previous AdamW group up to and including the last AdamW group
+groups = []
+for i in idx:
+    if groups and i - groups[-1][1] <= 2:
+        groups[-1][1] = i
+    else:
+        groups.append([i, i])
+if len(groups) >= 2:
+    step = rows[groups[-2][1] + 1: groups[-1][1] + 1]
+else:
+    step = rows[: idx[-1] + 1] if idx else rows
 
 
 def classify(n):
