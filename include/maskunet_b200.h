@@ -174,7 +174,10 @@ int mu_sample_layernorm_bwd(const void* dy, const void* x, const float* gamma, c
  * (channels-last rows), labels int64 [M], valid_count f32 [1] = number of labels != ignore_index.
  * loss_sum f32 [1] receives the mean loss; dlogits [M, C] = (softmax - onehot) / valid_count. */
 int mu_cross_entropy_fused(const void* logits, const int64_t* labels, const float* valid_count, int64_t ignore_index,
-                           void* dlogits, float* loss_sum, int64_t M, int32_t C, int32_t dtype, mu_stream_t stream);
+                           void* dlogits, float* loss_sum, int64_t M, int32_t C, int32_t pitch, int32_t dtype,
+                           mu_stream_t stream);
+/* (pitch >= C: row stride of logits / dlogits in elements -- the class-padded buffers of mu_conv1x1_fwd; the
+ * pad columns of dlogits are written as zeros.) */
 
 /* K7. 3x3 convolution, stride 1, zero padding 1, no bias (nn.Conv2d(cin, cout, kernel_size=3, padding=1,
  * bias=False), :199 and :202, inside ConvBlock :192-210) on tcgen05 tensor cores.  bf16 channels-last
@@ -210,6 +213,27 @@ int mu_bn_update_running(float* running_mean, float* running_var, const float* m
 int mu_bn_act_fwd_stats(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y,
                         float* mean, float* rstd, float* a, float* b, const float* sums, int64_t M, int32_t C,
                         int32_t act, int32_t dtype, mu_stream_t stream);
+
+/* K12. 1x1 convolution heads (nn.Conv2d(64, c_out, kernel_size=1) with bias, :284; the embedding head
+ * cityscapes/city_instance.py:248) on the same tcgen05 implicit-GEMM kernels as K7.  Output channels are padded
+ * to Np in {32, 64, 128, 160, 256} so that the activation rows are TMA-addressable (150 classes -> 160: 320-byte
+ * pitch): y, dy are [B, H, W, Np] with channels >= Cout equal to zero; the caller exposes the first Cout channels.
+ *   mu_conv1x1_prep:       w f32 [Cout, Cin], bias f32 [Cout] or NULL -> wf bf16 [Np, roundup(Cin, 64)],
+ *                          wd bf16 [Cin, roundup(Np, 64)] (data-gradient operand), bias_p f32 [Np], all zero padded
+ *   mu_conv1x1_fwd:        y = x [B, H, W, Cin] . wf^T + bias_p
+ *   mu_conv1x1_bwd_data:   dx [B, H, W, Cin] = dy [B, H, W, Np] . wd^T    (Cin in {32, 64, 128, 160, 256})
+ *   mu_conv1x1_bwd_weight: dw f32 [Np, Cin] = dy^T x   (Cin a multiple of 64); workspace f32 [Cin, Np]
+ * mu_column_sums: per-channel sum and sum of squares of x [M, C] -> sums f32 [2C] (the bias gradient of the head). */
+int mu_conv1x1_prep(const float* w, const float* bias, void* wf, void* wd, float* bias_p, int32_t Cout, int32_t Cin,
+                    int32_t Np, mu_stream_t stream);
+int mu_conv1x1_fwd(const void* x, const void* wf, const float* bias_p, void* y, int32_t B, int32_t H, int32_t W,
+                   int32_t Cin, int32_t Np, int32_t dtype, mu_stream_t stream);
+int mu_conv1x1_bwd_data(const void* dy, const void* wd, void* dx, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                        int32_t Np, int32_t dtype, mu_stream_t stream);
+size_t mu_conv1x1_workspace_bytes(int32_t Cin, int32_t Np);
+int mu_conv1x1_bwd_weight(const void* x, const void* dy, void* workspace, size_t workspace_bytes, float* dw, int32_t B,
+                          int32_t H, int32_t W, int32_t Cin, int32_t Np, int32_t dtype, mu_stream_t stream);
+int mu_column_sums(const void* x, float* sums, int64_t M, int32_t C, int32_t dtype, mu_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,12 @@ SIGNATURES = {
     "mu_upsample_concat_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "mu_sample_layernorm_fwd": [_P, _P, _P, _F, _P, _P, _P, _P, _I, ctypes.c_int64, _I, _P],
     "mu_sample_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, ctypes.c_int64, _I, _P],
-    "mu_cross_entropy_fused": [_P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int64, _I, _I, _P],
+    "mu_cross_entropy_fused": [_P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
+    "mu_column_sums": [_P, _P, ctypes.c_int64, _I, _I, _P],
+    "mu_conv1x1_prep": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "mu_conv1x1_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mu_conv1x1_bwd_data": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mu_conv1x1_bwd_weight": [_P, _P, _P, ctypes.c_size_t, _P, _I, _I, _I, _I, _I, _I, _P],
     "mu_bn_act_fwd": [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
     "mu_bn_act_apply": [_P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
     "mu_bn_act_fwd_stats": [_P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
@@ -68,6 +73,8 @@ def load() -> ctypes.CDLL:
     lib.mu_attn_bwd_workspace_bytes.argtypes = [_I, _I, _I, _I]
     lib.mu_conv3x3_workspace_bytes.restype = ctypes.c_size_t
     lib.mu_conv3x3_workspace_bytes.argtypes = [_I, _I]
+    lib.mu_conv1x1_workspace_bytes.restype = ctypes.c_size_t
+    lib.mu_conv1x1_workspace_bytes.argtypes = [_I, _I]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int32

@@ -361,6 +361,16 @@ static int bn_bwd_t(const void* dy, const void* x, const void* r, const float* a
   return check_launch("bn_bwd_apply");
 }
 
+// per-channel sum and sum of squares of x [M, C] into sums f32 [2C] (cleared here): the statistics pass on its own
+int launch_column_sums(const void* x, float* sums, long M, int C, int dtype, cudaStream_t s) {
+  if (!bn_shape_ok(M, C)) {
+    set_error("column_sums: unsupported shape M=%ld C=%d", M, C);
+    return MU_ERR_BAD_SHAPE;
+  }
+  cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), s);
+  return dtype == MU_F32 ? bn_stats_t<float>(x, sums, M, C, s) : bn_stats_t<__nv_bfloat16>(x, sums, M, C, s);
+}
+
 int launch_bn_forward(const void* x, const void* r, const float* gamma, const float* beta, float* running_mean,
                       float* running_var, float momentum, float eps, void* y, float* mean, float* rstd, float* a,
                       float* b, float* sums, long M, int C, int act, int dtype, cudaStream_t s) {

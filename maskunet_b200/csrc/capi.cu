@@ -212,6 +212,11 @@ int mu_bn_act_bwd(const void* dy, const void* x, const void* r, const float* a, 
   return launch_bn_backward(dy, x, r, a, b, mean, rstd, sums, dx, dr, (long)M, C, act, dtype, (cudaStream_t)stream);
 }
 
+#define MU_BF16_ONLY(fn) \
+  MU_REQUIRE(dtype == MU_BF16, MU_ERR_BAD_DTYPE, fn ": tensor-core convolution takes MU_BF16 activations (got %d)", dtype)
+#define MU_SM100_ONLY(fn) \
+  MU_REQUIRE(device_cc_major() == 10, MU_ERR_ARCH, fn ": needs an sm_100 device (tcgen05 / TMEM)")
+
 #define MU_DTYPE_OK(fn) \
   MU_REQUIRE(dtype == MU_F32 || dtype == MU_BF16, MU_ERR_BAD_DTYPE, fn ": unknown dtype code %d", dtype)
 
@@ -254,17 +259,56 @@ int mu_sample_layernorm_bwd(const void* dy, const void* x, const float* gamma, c
 }
 
 int mu_cross_entropy_fused(const void* logits, const int64_t* labels, const float* valid_count, int64_t ignore_index,
-                           void* dlogits, float* loss_sum, int64_t M, int32_t C, int32_t dtype, mu_stream_t stream) {
+                           void* dlogits, float* loss_sum, int64_t M, int32_t C, int32_t pitch, int32_t dtype,
+                           mu_stream_t stream) {
   MU_DTYPE_OK("mu_cross_entropy_fused");
   MU_PTRS("mu_cross_entropy_fused", logits, labels, valid_count, dlogits, loss_sum);
-  return launch_ce_fused(logits, labels, valid_count, (long)ignore_index, dlogits, loss_sum, (long)M, C, dtype,
+  return launch_ce_fused(logits, labels, valid_count, (long)ignore_index, dlogits, loss_sum, (long)M, C, pitch, dtype,
                          (cudaStream_t)stream);
 }
 
-#define MU_BF16_ONLY(fn) \
-  MU_REQUIRE(dtype == MU_BF16, MU_ERR_BAD_DTYPE, fn ": tensor-core convolution takes MU_BF16 activations (got %d)", dtype)
-#define MU_SM100_ONLY(fn) \
-  MU_REQUIRE(device_cc_major() == 10, MU_ERR_ARCH, fn ": needs an sm_100 device (tcgen05 / TMEM)")
+int mu_column_sums(const void* x, float* sums, int64_t M, int32_t C, int32_t dtype, mu_stream_t stream) {
+  MU_DTYPE_OK("mu_column_sums");
+  MU_PTRS("mu_column_sums", x, sums);
+  return launch_column_sums(x, sums, (long)M, C, dtype, (cudaStream_t)stream);
+}
+
+int mu_conv1x1_prep(const float* w, const float* bias, void* wf, void* wd, float* bias_p, int32_t Cout, int32_t Cin,
+                    int32_t Np, mu_stream_t stream) {
+  MU_REQUIRE(Cout > 0 && Cin > 0 && Np >= Cout, MU_ERR_BAD_SHAPE, "mu_conv1x1_prep: bad shape (Cout=%d Cin=%d Np=%d)",
+             Cout, Cin, Np);
+  MU_PTRS("mu_conv1x1_prep", w, wf, wd, bias_p);
+  return launch_conv1x1_prep(w, bias, wf, wd, bias_p, Cout, Cin, Np, (cudaStream_t)stream);
+}
+
+int mu_conv1x1_fwd(const void* x, const void* wf, const float* bias_p, void* y, int32_t B, int32_t H, int32_t W,
+                   int32_t Cin, int32_t Np, int32_t dtype, mu_stream_t stream) {
+  MU_BF16_ONLY("mu_conv1x1_fwd");
+  MU_PTRS("mu_conv1x1_fwd", x, wf, y);
+  MU_SM100_ONLY("mu_conv1x1_fwd");
+  return launch_conv1x1_fprop_sm100(x, wf, bias_p, y, B, H, W, Cin, Np, (cudaStream_t)stream);
+}
+
+int mu_conv1x1_bwd_data(const void* dy, const void* wd, void* dx, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                        int32_t Np, int32_t dtype, mu_stream_t stream) {
+  MU_BF16_ONLY("mu_conv1x1_bwd_data");
+  MU_PTRS("mu_conv1x1_bwd_data", dy, wd, dx);
+  MU_SM100_ONLY("mu_conv1x1_bwd_data");
+  return launch_conv1x1_fprop_sm100(dy, wd, nullptr, dx, B, H, W, Np, Cin, (cudaStream_t)stream);
+}
+
+size_t mu_conv1x1_workspace_bytes(int32_t Cin, int32_t Np) { return (size_t)Cin * Np * sizeof(float); }
+
+int mu_conv1x1_bwd_weight(const void* x, const void* dy, void* workspace, size_t workspace_bytes, float* dw, int32_t B,
+                          int32_t H, int32_t W, int32_t Cin, int32_t Np, int32_t dtype, mu_stream_t stream) {
+  MU_BF16_ONLY("mu_conv1x1_bwd_weight");
+  MU_PTRS("mu_conv1x1_bwd_weight", x, dy, workspace, dw);
+  MU_REQUIRE(workspace_bytes >= mu_conv1x1_workspace_bytes(Cin, Np), MU_ERR_WORKSPACE,
+             "mu_conv1x1_bwd_weight: workspace too small (%zu < %zu)", workspace_bytes,
+             mu_conv1x1_workspace_bytes(Cin, Np));
+  MU_SM100_ONLY("mu_conv1x1_bwd_weight");
+  return launch_conv1x1_wgrad_sm100(x, dy, (float*)workspace, dw, B, H, W, Cin, Np, (cudaStream_t)stream);
+}
 
 int mu_conv_prep_weights(const float* w, void* wf, void* wd, int32_t Cout, int32_t Cin, int32_t taps,
                          mu_stream_t stream) {

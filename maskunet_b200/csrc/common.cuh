@@ -106,7 +106,14 @@ int launch_sample_ln_fwd(const void* x, const float* gamma, const float* beta, f
 int launch_sample_ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                          float* sums, void* dx, float* dgamma, float* dbeta, int B, long L, int dtype, cudaStream_t s);
 int launch_ce_fused(const void* logits, const int64_t* labels, const float* valid_count, long ignore_index,
-                    void* dlogits, float* loss_sum, long M, int C, int dtype, cudaStream_t s);
+                    void* dlogits, float* loss_sum, long M, int C, int pitch, int dtype, cudaStream_t s);
+int launch_conv1x1_fprop_sm100(const void* x, const void* wt, const float* bias, void* y, int B, int H, int W, int K,
+                               int Np, cudaStream_t s);
+int launch_conv1x1_wgrad_sm100(const void* x, const void* dy, float* ws, float* dw, int B, int H, int W, int Cin, int Np,
+                               cudaStream_t s);
+int launch_conv1x1_prep(const float* w, const float* bias, void* wf, void* wd, float* bias_p, int Cout, int Cin, int Np,
+                        cudaStream_t s);
+int launch_column_sums(const void* x, float* sums, long M, int C, int dtype, cudaStream_t s);
 int launch_transpose(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t s);
 
 }  // namespace mu

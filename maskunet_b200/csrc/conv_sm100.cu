@@ -55,13 +55,16 @@ __device__ __forceinline__ void red_add_v4f(float* p, float a, float b, float c,
 template <int NT, int MT, int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                        const __grid_constant__ CUtensorMap tmap_y, float* __restrict__ stats, const ConvArgs p) {
+                        const __grid_constant__ CUtensorMap tmap_y, float* __restrict__ stats,
+                        const float* __restrict__ bias, const ConvArgs p) {
   constexpr int kBBytes = NT * 128;
   constexpr int GROUPS = MODE == CONV_ROWS ? 3 : 1;
   constexpr int TAPS = MODE == CONV_W128 ? 9 : (MODE == CONV_ROWS ? 3 : 1);
   constexpr int NBUF = (2 * MT * NT <= 512) ? 2 : 1;
-  constexpr int kTmemCols = NBUF * MT * NT;
-  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation must be a power of two <= 512");
+  constexpr int kTmemUsed = NBUF * MT * NT;
+  constexpr int kTmemCols = kTmemUsed <= 32 ? 32 : kTmemUsed <= 64 ? 64 : kTmemUsed <= 128 ? 128 : kTmemUsed <= 256 ? 256 : 512;
+  constexpr int kBlocks = (NT + 63) / 64;          // 64-channel output blocks per tile (the last may be half)
+  static_assert(kTmemUsed <= 512, "TMEM overflow");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -78,7 +81,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   const int warp = threadIdx.x >> 5;
   const int total = p.m_tiles * p.n_tiles;        // m_tiles counts super tiles
-  const int kchunks = p.K / 64;
+  const int kchunks = (p.K + 63) / 64;            // a partial last chunk is zero-filled by TMA (1x1 heads)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxRing; ++i) {
@@ -191,6 +194,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     const int r = quad * 32 + (int)lane_id();              // pixel row of the tile == TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t so_base = smem_u32(sO);
+    // (the BatchNorm partial sums below assume full 64-channel blocks: NT = 32 / 160 launches pass stats = NULL)
     const int sq = e >> 5, cp = e & 31;                    // statistics: rows sq*32.., channel pair cp
     const int SO = p.SO;
     uint32_t buf = 0, pacc = 0, so_idx = 0;
@@ -201,8 +205,8 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       mbar_wait(acc_full + buf, pacc);
       tc_fence_after();
 #pragma unroll 1
-      for (int blk = 0; blk < MT * (NT / 64); ++blk) {
-        const int m = blk / (NT / 64), cb = blk - m * (NT / 64);
+      for (int blk = 0; blk < MT * kBlocks; ++blk) {
+        const int m = blk / kBlocks, cb = blk - m * kBlocks;
         const uint32_t so = so_base + so_idx * 16384;
         if (e == 0) {                                      // the store that last read this staging buffer is done
           if (SO == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
@@ -210,21 +214,28 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         named_bar_sync(1, 128);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          tmem_ld32(lane_base + buf * (MT * NT) + m * NT + cb * 64 + h * 32, v);
-          tmem_wait_ld();
-          if (h == 1 && blk == MT * (NT / 64) - 1) {
-            tc_fence_before();
-            mbar_arrive(acc_empty + buf);
-          }
+          if (cb * 64 + h * 32 < NT) {                     // NT = 32 / 160: the last block is only half wide
+            tmem_ld32(lane_base + buf * (MT * NT) + m * NT + cb * 64 + h * 32, v);
+            tmem_wait_ld();
+            if (bias != nullptr) {
+              const float* bp = bias + nt * NT + cb * 64 + h * 32;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t c = h * 4 + g;
-            st_shared_v4(so + r * 128 + ((c ^ (r & 7)) << 4),
-                         pack_bf16(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])),
-                         pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
-                         pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
-                         pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __ldg(bp + i));
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t c = h * 4 + g;
+              st_shared_v4(so + r * 128 + ((c ^ (r & 7)) << 4),
+                           pack_bf16(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])),
+                           pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                           pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                           pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+            }
           }
+        }
+        if (blk == MT * kBlocks - 1) {                     // accumulator drained: the next tile's MMAs may start
+          tc_fence_before();
+          mbar_arrive(acc_empty + buf);
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
@@ -290,8 +301,9 @@ template <int NB>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                         float* __restrict__ ws, const WgradArgs p) {
-  constexpr int kDyBytes = (NB / 64) * 16384;
-  constexpr int kTmemCols = NB == 128 ? 512 : 256;
+  constexpr int kDyBlocks = (NB + 63) / 64;
+  constexpr int kDyBytes = kDyBlocks * 16384;
+  constexpr int kTmemCols = NB == 128 ? 512 : 256;       // 3 taps x 128 | 3 x 64 | 1 x 160 (1x1 mode) | 1 x 32
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int x_tile_bytes = p.ci_blocks * p.x_stride;
@@ -304,15 +316,17 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   const int warp = threadIdx.x >> 5;
 
   int combo = blockIdx.x;
-  const int g = combo % 3;
-  combo /= 3;
+  const int g = p.mode == CONV_1X1 ? 0 : combo % 3;
+  if (p.mode != CONV_1X1) combo /= 3;
   const int cb = combo % p.n_cb, nb = combo / p.n_cb;
   const int c_begin = blockIdx.y * p.chunks_per_cta;
   const int c_end = min(p.m_tiles, c_begin + p.chunks_per_cta);
   const int nchunks = c_end - c_begin;
   if (nchunks <= 0) return;
-  const int row_step = p.mode == CONV_W128 ? 1 : p.W;
+  const int row_step = p.mode == CONV_W128 ? 1 : (p.mode == CONV_ROWS ? p.W : 0);
   const int ci0 = cb * p.ci_blocks * 64;
+  // M tiles of this CTA: 3 taps (128 input channels each), 2 (64 channels: taps 0|1 paired, tap 2), 1 for a 1x1 conv
+  const int m_tiles_cta = p.mode == CONV_1X1 ? 1 : (p.ci_blocks == 2 ? 3 : 2);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxRing; ++i) {
@@ -343,18 +357,17 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         uint8_t* sX = smem + st * stage_bytes;
         uint8_t* sD = sX + x_tile_bytes;
         mbar_expect_tx(full + st, p.ci_blocks * p.x_bytes + kDyBytes);
-        const int cx = p.mode == CONV_W128 ? -1 : g - 1;
-        const int cy = p.mode == CONV_W128 ? y0 + g - 1 : y0 - 1;
+        const int cx = p.mode == CONV_W128 ? -1 : (p.mode == CONV_ROWS ? g - 1 : 0);
+        const int cy = p.mode == CONV_W128 ? y0 + g - 1 : (p.mode == CONV_ROWS ? y0 - 1 : y0);
         for (int blk = 0; blk < p.ci_blocks; ++blk)
           tma_load_4d(sX + blk * p.x_stride, &tmap_x, full + st, ci0 + blk * 64, cx, cy, b);
-        for (int blk = 0; blk < NB / 64; ++blk)
+        for (int blk = 0; blk < kDyBlocks; ++blk)     // channels past Cout (NB = 160: 160..191) arrive as zeros
           tma_load_4d(sD + blk * 16384, &tmap_dy, full + st, nb * NB + blk * 64, 0, y0, b);
       }
     }
   } else if (warp == 1) {
     if (lane_id() == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, NB, 1, 1);   // both operands MN-major (contraction over pixels)
-      const int m_tiles_cta = p.ci_blocks == 2 ? 3 : 2;
       for (int j = 0; j < nchunks; ++j) {
         const int st = j % p.S;
         mbar_wait(full + st, (j / p.S) & 1);
@@ -367,7 +380,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             a_lbo = p.x_stride;
           } else if (m == 0) {
             a_start = x_addr;                                   // taps 0 and 1 of 64 input channels side by side
-            a_lbo = row_step * 128;
+            a_lbo = row_step * 128;                             // (1x1: row_step = 0, rows 64..127 duplicate, ignored)
           } else {
             a_start = x_addr + 2 * row_step * 128;              // tap 2; rows 64..127 of the tile are ignored
             a_lbo = 0;
@@ -385,7 +398,6 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     const int quad = warp & 3;
     const int r = quad * 32 + (int)lane_id();
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int m_tiles_cta = p.ci_blocks == 2 ? 3 : 2;
     uint32_t v[32];
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -398,9 +410,9 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       } else {
         j = m == 0 ? (r >> 6) : 2;
         ci = ci0 + (r & 63);
-        valid = m == 0 || r < 64;
+        valid = (m == 0 && p.mode != CONV_1X1) || r < 64;
       }
-      const int tap = p.mode == CONV_W128 ? g * 3 + j : j * 3 + g;
+      const int tap = p.mode == CONV_1X1 ? 0 : (p.mode == CONV_W128 ? g * 3 + j : j * 3 + g);
       float* dst = ws + ((size_t)tap * p.Cin + ci) * p.Cout + nb * NB;
 #pragma unroll
       for (int c = 0; c < NB / 32; ++c) {
@@ -472,8 +484,8 @@ static int conv_geometry_ok(const char* fn, int B, int H, int W, int K, int N) {
 }
 
 template <int NT, int MT, int MODE>
-static int run_fprop(const void* x, const void* wt, void* y, float* stats, int B, int H, int W, int K, int N, int taps,
-                     cudaStream_t s) {
+static int run_fprop(const void* x, const void* wt, void* y, float* stats, const float* bias, int B, int H, int W, int K,
+                     int N, int taps, cudaStream_t s) {
   ConvArgs p;
   p.B = B; p.H = H; p.W = W; p.K = K; p.N = N;
   p.TH = 128 / W;
@@ -508,22 +520,22 @@ static int run_fprop(const void* x, const void* wt, void* y, float* stats, int B
   CUtensorMap tx, tw, ty;
   int rc;
   if ((rc = make_tmap_bf16_nhwc(&tx, x, K, W, H, B, box_w, box_h))) return rc;
-  if ((rc = make_tmap_bf16_3d(&tw, wt, K, N, taps, NT))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tw, wt, round_up(K, 64), N, taps, NT))) return rc;   // weight rows are padded to 64 K
   if ((rc = make_tmap_bf16_nhwc(&ty, y, N, W, H, B, W, p.TH))) return rc;
   auto kern = conv_fprop_sm100_kernel<NT, MT, MODE>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
-  kern<<<grid, kConvThreads, smem, s>>>(tx, tw, ty, stats, p);
+  kern<<<grid, kConvThreads, smem, s>>>(tx, tw, ty, stats, bias, p);
   return check_launch("conv_fprop_sm100");
 }
 
 template <int NT, int MT>
 static int run_fprop_mode(const void* x, const void* wt, void* y, float* stats, int B, int H, int W, int K, int N,
                           int taps, cudaStream_t s) {
-  if (taps == 1) return run_fprop<NT, MT, CONV_1X1>(x, wt, y, stats, B, H, W, K, N, taps, s);
-  if (W == 128) return run_fprop<NT, MT, CONV_W128>(x, wt, y, stats, B, H, W, K, N, taps, s);
-  return run_fprop<NT, MT, CONV_ROWS>(x, wt, y, stats, B, H, W, K, N, taps, s);
+  if (taps == 1) return run_fprop<NT, MT, CONV_1X1>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
+  if (W == 128) return run_fprop<NT, MT, CONV_W128>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
+  return run_fprop<NT, MT, CONV_ROWS>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
 }
 
 // y [B,H,W,N] = conv(x [B,H,W,K], wt [taps][N][K]); stats (optional) f32 [2N] += (sum, sum of squares) per channel
@@ -543,15 +555,55 @@ int launch_conv_fprop_sm100(const void* x, const void* wt, void* y, float* stats
               : run_fprop_mode<64, 1>(x, wt, y, stats, B, H, W, K, N, taps, s);
 }
 
+// ---- K12: 1x1 convolution heads (nn.Conv2d(64, c_out, kernel_size=1), ade_semantic.py:284; the embedding head
+// city_instance.py:248).  Output channels are padded to Np in {32, 64, 128, 160, 256} (a single N tile; the
+// activation buffers carry Np channels, the extra ones are zero), K may be any multiple of 8 (TMA zero-fills the
+// last 64-channel chunk): this is what lets the 150-class logits live in a 320-byte-pitch, TMA-addressable buffer.
+static int conv1x1_geometry_ok(const char* fn, int B, int H, int W, int K, int Np) {
+  MU_REQUIRE(B > 0 && H > 0, MU_ERR_BAD_SHAPE, "%s: bad batch / height (B=%d H=%d)", fn, B, H);
+  MU_REQUIRE(W == 16 || W == 32 || W == 64 || W == 128, MU_ERR_BAD_SHAPE,
+             "%s: width must be 16, 32, 64 or 128 (got %d)", fn, W);
+  MU_REQUIRE(H % (128 / W) == 0, MU_ERR_BAD_SHAPE, "%s: height %d must be a multiple of %d", fn, H, 128 / W);
+  MU_REQUIRE(K % 8 == 0 && K >= 8 && K <= 512, MU_ERR_BAD_SHAPE, "%s: input channels must be a multiple of 8 in [8, 512] (got %d)", fn, K);
+  MU_REQUIRE(Np == 32 || Np == 64 || Np == 128 || Np == 160 || Np == 256, MU_ERR_BAD_SHAPE,
+             "%s: padded output channels must be 32, 64, 128, 160 or 256 (got %d)", fn, Np);
+  return 0;
+}
+
+template <int NT>
+static int run_conv1x1(const void* x, const void* wt, const float* bias, void* y, int B, int H, int W, int K,
+                       cudaStream_t s) {
+  const bool pair = H % (2 * (128 / W)) == 0;
+  return pair ? run_fprop<NT, 2, CONV_1X1>(x, wt, y, nullptr, bias, B, H, W, K, NT, 1, s)
+              : run_fprop<NT, 1, CONV_1X1>(x, wt, y, nullptr, bias, B, H, W, K, NT, 1, s);
+}
+
+// y [B,H,W,Np] = x [B,H,W,K] . wt[Np][Kpad]^T + bias[Np]
+int launch_conv1x1_fprop_sm100(const void* x, const void* wt, const float* bias, void* y, int B, int H, int W, int K,
+                               int Np, cudaStream_t s) {
+  int rc;
+  if ((rc = conv1x1_geometry_ok("conv1x1_fprop_sm100", B, H, W, K, Np))) return rc;
+  switch (Np) {
+    case 32: return run_conv1x1<32>(x, wt, bias, y, B, H, W, K, s);
+    case 64: return run_conv1x1<64>(x, wt, bias, y, B, H, W, K, s);
+    case 128: return run_conv1x1<128>(x, wt, bias, y, B, H, W, K, s);
+    case 160: return run_conv1x1<160>(x, wt, bias, y, B, H, W, K, s);
+    default: return run_conv1x1<256>(x, wt, bias, y, B, H, W, K, s);
+  }
+}
+
 template <int NB>
-static int run_wgrad(const void* x, const void* dy, float* ws, int B, int H, int W, int Cin, int Cout, cudaStream_t s) {
+static int run_wgrad(const void* x, const void* dy, float* ws, int B, int H, int W, int Cin, int Cout, int taps,
+                     cudaStream_t s) {
   WgradArgs p;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.TH = 128 / W;
   p.tiles_y = H / p.TH;
   p.m_tiles = B * p.tiles_y;
   int box_w, box_h;
-  if (W == 128) {
+  if (taps == 1) {
+    p.mode = CONV_1X1; box_w = W; box_h = p.TH;
+  } else if (W == 128) {
     p.mode = CONV_W128; box_w = 130; box_h = 1;
   } else {
     p.mode = CONV_ROWS; box_w = W; box_h = p.TH + 2;
@@ -561,7 +613,7 @@ static int run_wgrad(const void* x, const void* dy, float* ws, int B, int H, int
   p.ci_blocks = Cin % 128 == 0 ? 2 : 1;
   p.n_cb = Cin / (64 * p.ci_blocks);
   p.n_nb = Cout / NB;
-  const int stage = p.ci_blocks * p.x_stride + (NB / 64) * 16384;
+  const int stage = p.ci_blocks * p.x_stride + ((NB + 63) / 64) * 16384;
   p.S = (kSmemLimit - 1024 - 512) / stage;
   if (p.S > kMaxRing) p.S = kMaxRing;
   if (p.S < 2) {
@@ -569,7 +621,7 @@ static int run_wgrad(const void* x, const void* dy, float* ws, int B, int H, int
     return MU_ERR_BAD_SHAPE;
   }
   const int smem = 1024 + 512 + p.S * stage;
-  const int combos = 3 * p.n_cb * p.n_nb;
+  const int combos = (taps == 1 ? 1 : 3) * p.n_cb * p.n_nb;
   int splits = (2 * sm_count() + combos - 1) / combos;      // about two CTAs' worth of work queued per SM
   if (splits > p.m_tiles) splits = p.m_tiles;
   if (splits < 1) splits = 1;
@@ -591,11 +643,60 @@ int launch_conv_wgrad_sm100(const void* x, const void* dy, float* ws, float* dw,
   int rc;
   if ((rc = conv_geometry_ok("conv_wgrad_sm100", B, H, W, Cin, Cout))) return rc;
   cudaMemsetAsync(ws, 0, (size_t)9 * Cin * Cout * sizeof(float), s);
-  rc = Cout % 128 == 0 ? run_wgrad<128>(x, dy, ws, B, H, W, Cin, Cout, s) : run_wgrad<64>(x, dy, ws, B, H, W, Cin, Cout, s);
+  rc = Cout % 128 == 0 ? run_wgrad<128>(x, dy, ws, B, H, W, Cin, Cout, 9, s)
+                       : run_wgrad<64>(x, dy, ws, B, H, W, Cin, Cout, 9, s);
   if (rc) return rc;
   const int n = Cin * Cout;
   conv_wgrad_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(ws, dw, Cout, Cin, 9);
   return check_launch("conv_wgrad_finish");
+}
+
+// dw f32 [Np][Cin] of a 1x1 convolution whose output gradient dy carries Np (padded) channels; ws f32 [Cin][Np]
+int launch_conv1x1_wgrad_sm100(const void* x, const void* dy, float* ws, float* dw, int B, int H, int W, int Cin, int Np,
+                               cudaStream_t s) {
+  int rc;
+  if ((rc = conv1x1_geometry_ok("conv1x1_wgrad_sm100", B, H, W, Cin, Np))) return rc;
+  MU_REQUIRE(Cin % 64 == 0, MU_ERR_BAD_SHAPE, "conv1x1_wgrad_sm100: input channels must be a multiple of 64 (got %d)", Cin);
+  cudaMemsetAsync(ws, 0, (size_t)Cin * Np * sizeof(float), s);
+  switch (Np) {
+    case 32: rc = run_wgrad<32>(x, dy, ws, B, H, W, Cin, Np, 1, s); break;
+    case 64: rc = run_wgrad<64>(x, dy, ws, B, H, W, Cin, Np, 1, s); break;
+    case 128: rc = run_wgrad<128>(x, dy, ws, B, H, W, Cin, Np, 1, s); break;
+    case 160: rc = run_wgrad<160>(x, dy, ws, B, H, W, Cin, Np, 1, s); break;
+    default: rc = run_wgrad<128>(x, dy, ws, B, H, W, Cin, Np, 1, s); break;   // 256 = two 128-channel blocks
+  }
+  if (rc) return rc;
+  const int n = Cin * Np;
+  conv_wgrad_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(ws, dw, Np, Cin, 1);
+  return check_launch("conv1x1_wgrad_finish");
+}
+
+// w f32 [Cout][Cin] -> wf bf16 [Np][Kp = roundup(Cin, 64)] (rows >= Cout and columns >= Cin zero) and
+// wd bf16 [Cin][Dp = roundup(Np, 64)] (the data-gradient operand: wd[ci][co] = w[co][ci], zero padded);
+// bias f32 [Cout] -> bias_p f32 [Np] (zero padded).
+__global__ void conv1x1_prep_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                    __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd,
+                                    float* __restrict__ bias_p, int Cout, int Cin, int Np, int Kp, int Dp) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < Np * Kp) {
+    const int co = idx / Kp, ci = idx - co * Kp;
+    wf[idx] = __float2bfloat16_rn((co < Cout && ci < Cin) ? w[(size_t)co * Cin + ci] : 0.f);
+  }
+  if (idx < Cin * Dp) {
+    const int ci = idx / Dp, co = idx - ci * Dp;
+    wd[idx] = __float2bfloat16_rn(co < Cout ? w[(size_t)co * Cin + ci] : 0.f);
+  }
+  if (idx < Np) bias_p[idx] = (bias != nullptr && idx < Cout) ? bias[idx] : 0.f;
+}
+
+int launch_conv1x1_prep(const float* w, const float* bias, void* wf, void* wd, float* bias_p, int Cout, int Cin, int Np,
+                        cudaStream_t s) {
+  const int Kp = round_up(Cin, 64), Dp = round_up(Np, 64);
+  int n = Np * Kp > Cin * Dp ? Np * Kp : Cin * Dp;
+  if (n < Np) n = Np;
+  conv1x1_prep_kernel<<<(n + 255) / 256, 256, 0, s>>>(w, bias, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, bias_p, Cout, Cin,
+                                                     Np, Kp, Dp);
+  return check_launch("conv1x1_prep");
 }
 
 int launch_conv_prep_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int taps, cudaStream_t s) {

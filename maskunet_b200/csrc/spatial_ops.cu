@@ -320,14 +320,16 @@ template <typename T>
 __global__ void __launch_bounds__(256) ce_fused_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels,
                                                        const float* __restrict__ valid_count, long ignore_index,
                                                        T* __restrict__ dlogits, float* __restrict__ loss_sum, long M,
-                                                       int C) {
+                                                       int C, int pitch) {
+  // pitch >= C: row stride in elements (class-padded logits of the 1x1 head); gradient pad columns are zeroed
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const float inv = 1.f / fmaxf(valid_count[0], 1.f);
   float local = 0.f;
   for (long row = (long)blockIdx.x * 8 + wib; row < M; row += (long)gridDim.x * 8) {
-    const T* lr = logits + row * C;
-    T* dr = dlogits + row * C;
+    const T* lr = logits + row * pitch;
+    T* dr = dlogits + row * pitch;
     const long lab = labels[row];
+    for (int c = C + lane; c < pitch; c += 32) st_f(dr + c, 0.f);
     if (lab == ignore_index) {
       for (int c = lane; c < C; c += 32) st_f(dr + c, 0.f);
       continue;
@@ -473,7 +475,11 @@ int launch_sample_ln_bwd(const void* dy, const void* x, const float* gamma, cons
 }
 
 int launch_ce_fused(const void* logits, const int64_t* labels, const float* valid_count, long ignore_index,
-                    void* dlogits, float* loss_sum, long M, int C, int dtype, cudaStream_t s) {
+                    void* dlogits, float* loss_sum, long M, int C, int pitch, int dtype, cudaStream_t s) {
+  if (pitch < C) {
+    set_error("cross_entropy: row pitch %d smaller than the class count %d", pitch, C);
+    return MU_ERR_BAD_SHAPE;
+  }
   if (C > 256 || C < 1) {
     set_error("cross_entropy: class count must be in [1, 256] (got %d)", C);
     return MU_ERR_BAD_SHAPE;
@@ -481,9 +487,9 @@ int launch_ce_fused(const void* logits, const int64_t* labels, const float* vali
   cudaMemsetAsync(loss_sum, 0, sizeof(float), s);
   const int grid = grid_for((M + 7) / 8, 1);
   MU_T(dtype, (ce_fused_kernel<float><<<grid, 256, 0, s>>>((const float*)logits, labels, valid_count, ignore_index,
-                                                        (float*)dlogits, loss_sum, M, C)),
+                                                        (float*)dlogits, loss_sum, M, C, pitch)),
        (ce_fused_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)logits, labels, valid_count,
-                                                            ignore_index, (__nv_bfloat16*)dlogits, loss_sum, M, C)));
+                                                            ignore_index, (__nv_bfloat16*)dlogits, loss_sum, M, C, pitch)));
   return check_launch("cross_entropy_fused");
 }
 

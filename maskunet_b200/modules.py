@@ -152,6 +152,9 @@ def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Option
     if residual is not None:
         residual = residual.to(x.dtype).contiguous(memory_format=torch.channels_last)
     gamma, beta = bn.weight.float(), bn.bias.float()
+    n_feat, n_pad = bn.num_features, x.shape[1] - bn.num_features
+    if n_pad > 0:       # class-padded output of our 1x1 head: the pad channels are zero and stay zero (gamma = beta = 0)
+        gamma, beta = F.pad(gamma, (0, n_pad)), F.pad(beta, (0, n_pad))
     if bn.training:
         if sums is not None and sums.numel() == 2 * x.shape[1]:
             y, mean, rstd, _, _ = ops.bn_act_fwd_stats(x, residual, gamma, beta, sums, bn.eps, act)
@@ -164,12 +167,16 @@ def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Option
                 else:
                     bn.num_batches_tracked += 1
                 momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                if n_pad > 0:
+                    mean, rstd = mean[:n_feat].contiguous(), rstd[:n_feat].contiguous()
                 ops.bn_update_running(bn.running_mean, bn.running_var, mean, rstd, momentum, bn.eps,
                                       x.shape[0] * x.shape[2] * x.shape[3])
         return y
     with torch.no_grad():
-        a = gamma * torch.rsqrt(bn.running_var.float() + bn.eps)
-        b = beta - bn.running_mean.float() * a
+        a = gamma[:n_feat] * torch.rsqrt(bn.running_var.float() + bn.eps)
+        b = beta[:n_feat] - bn.running_mean.float() * a
+        if n_pad > 0:
+            a, b = F.pad(a, (0, n_pad)), F.pad(b, (0, n_pad))
         return ops.bn_act_apply(x, residual, a, b, act)
 
 
@@ -303,6 +310,7 @@ class UNet(nn.Module):
             self.embedding_head = nn.Sequential(nn.Conv2d(64, embed_dim, kernel_size=1),
                                                 nn.BatchNorm2d(embed_dim), nn.ReLU())
         self.compute_dtype = compute_dtype
+        self._padded_logits = None     # class-padded logits buffer of the last forward (see _conv_bn_relu)
 
     def attention_sites(self):
         return [getattr(self, f"self_attention{i}") for i in range(1, 7)]
@@ -324,14 +332,35 @@ class UNet(nn.Module):
         return self.norm(h)
 
     @staticmethod
-    def _conv_bn_relu(seq, h):
-        return fused_bn_act(seq[0](h), seq[1], ops.ACT_RELU)
+    def _own_conv1x1(conv, h):
+        """K12: the 1x1 heads run on the tcgen05 kernels when the activation is bf16 channels-last."""
+        return (h.is_cuda and h.dim() == 4 and h.dtype == torch.bfloat16
+                and h.is_contiguous(memory_format=torch.channels_last)
+                and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.padding == (0, 0)
+                and conv.groups == 1 and conv.weight.dtype == torch.float32
+                and ops.conv1x1_shape_ok(conv.in_channels, conv.out_channels, h.shape[2], h.shape[3]))
+
+    def _conv_bn_relu(self, seq, h, keep_padded=False):
+        """ReLU(BN(conv(h))) of the output heads (ade_semantic.py:283-287).  On the production layout the 1x1
+        convolution writes a class-padded buffer ([B, 160, H, W] for 150 classes, pad channels zero); the result is
+        the first c_out channels of it, as a view."""
+        conv, bn = seq[0], seq[1]
+        if self._own_conv1x1(conv, h):
+            n_pad = ops.pad_channels(conv.out_channels)
+            bias = conv.bias.float() if conv.bias is not None else None
+            y_pad = ops.conv1x1(h, conv.weight, bias, n_pad)[0]
+            out_pad = fused_bn_act(y_pad, bn, ops.ACT_RELU)
+            if keep_padded:
+                self._padded_logits = out_pad       # train.Trainer starts backward from the padded tensor
+            return out_pad[:, :conv.out_channels] if n_pad > conv.out_channels else out_pad
+        return fused_bn_act(conv(h), bn, ops.ACT_RELU)
 
     def _heads(self, h):
+        self._padded_logits = None
         if not self.instance_variant:
-            return self._conv_bn_relu(self.final_layer, h)
+            return self._conv_bn_relu(self.final_layer, h, keep_padded=True)
         embeddings = self._conv_bn_relu(self.embedding_head, h)          # city_instance.py:273-276 order
-        semantic = self._conv_bn_relu(self.final_layer, h)
+        semantic = self._conv_bn_relu(self.final_layer, h, keep_padded=True)
         boundary = self.boundary_head[3](self._conv_bn_relu(self.boundary_head, semantic))
         return semantic, boundary, embeddings
 

@@ -597,6 +597,115 @@ def _conv_backward(ctx, dy, *unused):
 conv3x3.register_autograd(_conv_backward, setup_context=_conv_setup)
 
 
+# ------------------------------------------------------------------ K12: 1x1 convolution heads (class-padded outputs)
+HEAD_PADS = (32, 64, 128, 160, 256)
+
+
+def pad_channels(c: int) -> int:
+    """Padded channel count of a 1x1 head output (TMA needs a 16-byte row pitch; 150 classes -> 160)."""
+    for n in HEAD_PADS:
+        if c <= n:
+            return n
+    raise ValueError(f"1x1 head with {c} output channels is not supported (max {HEAD_PADS[-1]})")
+
+
+def conv1x1_shape_ok(Cin: int, Cout: int, H: int, W: int) -> bool:
+    return (W in CONV_WIDTHS and H % (128 // W) == 0 and Cin in (64, 128, 256) and 1 <= Cout <= HEAD_PADS[-1])
+
+
+@torch.library.custom_op("maskunet::column_sums", mutates_args=(), device_types="cuda")
+def column_sums(x: Tensor) -> Tensor:
+    """x channels-last [B, C, H, W] -> f32 [2C]: per-channel sum and sum of squares."""
+    M, C = _rows(x)
+    sums = torch.empty((2 * C,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _count(1)
+        check(_L.mu_column_sums(_p(x), _p(sums), M, C, _code(x), _stream(x)), "mu_column_sums")
+    return sums
+
+
+@column_sums.register_fake
+def _(x):
+    return x.new_empty((2 * x.shape[1],), dtype=torch.float32)
+
+
+@torch.library.custom_op("maskunet::conv1x1", mutates_args=(), device_types="cuda")
+def conv1x1(x: Tensor, weight: Tensor, bias: Tensor | None, n_pad: int) -> Tuple[Tensor, Tensor]:
+    """nn.Conv2d(Cin, Cout, 1) on tcgen05: x bf16 channels-last [B, Cin, H, W], weight f32 [Cout, Cin, 1, 1],
+    bias f32 [Cout].  Returns (y [B, n_pad, H, W] with channels >= Cout zero, wd = data-gradient operand)."""
+    B, Cin, H, W = _nhwc(x)
+    _cuda(weight)
+    Cout = weight.shape[0]
+    assert x.dtype == torch.bfloat16 and weight.dtype == torch.float32 and weight.shape[1] == Cin and n_pad >= Cout
+    dev = x.device
+    wf = torch.empty((n_pad, (Cin + 63) // 64 * 64), dtype=torch.bfloat16, device=dev)
+    wd = torch.empty((Cin, (n_pad + 63) // 64 * 64), dtype=torch.bfloat16, device=dev)
+    bias_p = torch.empty((n_pad,), dtype=torch.float32, device=dev)
+    y = _empty_cl(x, B, n_pad, H, W)
+    with torch.cuda.device(dev), _timed("mu_conv1x1_fwd", (B, H, W, Cin, n_pad)):
+        _count(2)
+        check(_L.mu_conv1x1_prep(_p(weight.contiguous()), _optp(bias), _p(wf), _p(wd), _p(bias_p), Cout, Cin, n_pad,
+                                 _stream(x)), "mu_conv1x1_prep")
+        check(_L.mu_conv1x1_fwd(_p(x), _p(wf), _p(bias_p), _p(y), B, H, W, Cin, n_pad, MU_BF16, _stream(x)),
+              "mu_conv1x1_fwd")
+    return y, wd
+
+
+@conv1x1.register_fake
+def _(x, weight, bias, n_pad):
+    B, Cin, H, W = x.shape
+    return _empty_cl(x, B, n_pad, H, W), x.new_empty((Cin, (n_pad + 63) // 64 * 64), dtype=torch.bfloat16)
+
+
+@torch.library.custom_op("maskunet::conv1x1_bwd", mutates_args=(), device_types="cuda")
+def conv1x1_bwd(x: Tensor, dy: Tensor, wd: Tensor, want_dx: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (dx [B, Cin, H, W] (empty when not wanted), dw f32 [n_pad, Cin], db f32 [n_pad])."""
+    B, Cin, H, W = _nhwc(x)
+    _, n_pad, _, _ = _nhwc(dy)
+    dev = x.device
+    dx = _empty_cl(x, B, Cin, H, W) if want_dx else x.new_empty((0,))
+    dw = torch.empty((n_pad, Cin), dtype=torch.float32, device=dev)
+    ws_bytes = int(_L.mu_conv1x1_workspace_bytes(Cin, n_pad))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    sums = torch.empty((2 * n_pad,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _timed("mu_conv1x1_bwd", (B, H, W, Cin, n_pad)):
+        _count(4 if want_dx else 3)
+        if want_dx:
+            check(_L.mu_conv1x1_bwd_data(_p(dy), _p(wd), _p(dx), B, H, W, Cin, n_pad, MU_BF16, _stream(x)),
+                  "mu_conv1x1_bwd_data")
+        check(_L.mu_conv1x1_bwd_weight(_p(x), _p(dy), _p(ws), ws_bytes, _p(dw), B, H, W, Cin, n_pad, MU_BF16,
+                                       _stream(x)), "mu_conv1x1_bwd_weight")
+        check(_L.mu_column_sums(_p(dy), _p(sums), B * H * W, n_pad, MU_BF16, _stream(x)), "mu_column_sums")
+    return dx, dw, sums[:n_pad].clone()
+
+
+@conv1x1_bwd.register_fake
+def _(x, dy, wd, want_dx):
+    n_pad = dy.shape[1]
+    return (torch.empty_like(x) if want_dx else x.new_empty((0,)), x.new_empty((n_pad, x.shape[1]), dtype=torch.float32),
+            x.new_empty((n_pad,), dtype=torch.float32))
+
+
+def _c1_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    x, weight, bias, n_pad = inputs
+    ctx.save_for_backward(x, output[1])
+    ctx.cout = weight.shape[0]
+    ctx.has_bias = bias is not None
+
+
+def _c1_backward(ctx, dy, *unused):
+    x, wd = ctx.saved_tensors
+    dy = dy.contiguous(memory_format=torch.channels_last)
+    dx, dw, db = conv1x1_bwd(x, dy, wd, bool(ctx.needs_input_grad[0]))
+    cout = ctx.cout
+    return (dx if ctx.needs_input_grad[0] else None, dw[:cout].reshape(cout, x.shape[1], 1, 1).contiguous(),
+            db[:cout].contiguous() if ctx.has_bias else None, None)
+
+
+conv1x1.register_autograd(_c1_backward, setup_context=_c1_setup)
+
+
 # ------------------------------------------------------------------ K9: MaxPool2d(2), channels-last
 def _nhwc(x: Tensor):
     if not (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)):
@@ -757,23 +866,26 @@ sample_layernorm.register_autograd(_sln_backward, setup_context=_sln_setup)
 
 # ------------------------------------------------------------------ A14: fused cross-entropy (mean) + gradient
 @torch.library.custom_op("maskunet::cross_entropy_fused", mutates_args=(), device_types="cuda")
-def cross_entropy_fused(logits: Tensor, labels: Tensor, ignore_index: int) -> Tuple[Tensor, Tensor]:
-    """logits channels-last [B, C, H, W], labels int64 [B, H, W] -> (mean loss [1] f32, dlogits like logits)."""
-    B, C, H, W = _nhwc(logits)
+def cross_entropy_fused(logits: Tensor, labels: Tensor, ignore_index: int, n_classes: int = -1) -> Tuple[Tensor, Tensor]:
+    """logits channels-last [B, P, H, W], labels int64 [B, H, W] -> (mean loss [1] f32, dlogits like logits).
+    n_classes > 0: only the first n_classes of the P channels are classes (the class-padded output of the 1x1
+    head); the pad channels of dlogits are zero."""
+    B, P, H, W = _nhwc(logits)
+    C = n_classes if n_classes > 0 else P
     _cuda(labels)
-    assert labels.dtype == torch.int64 and labels.shape == (B, H, W)
+    assert labels.dtype == torch.int64 and labels.shape == (B, H, W) and C <= P
     dlogits = torch.empty_like(logits)
     loss = torch.empty((1,), dtype=torch.float32, device=logits.device)
     count = (labels != ignore_index).sum().to(torch.float32).reshape(1)
     with torch.cuda.device(logits.device):
         _count(1)
         check(_L.mu_cross_entropy_fused(_p(logits), _p(labels), _p(count), ignore_index, _p(dlogits), _p(loss),
-                                        B * H * W, C, _code(logits), _stream(logits)), "mu_cross_entropy_fused")
+                                        B * H * W, C, P, _code(logits), _stream(logits)), "mu_cross_entropy_fused")
     return loss, dlogits
 
 
 @cross_entropy_fused.register_fake
-def _(logits, labels, ignore_index):
+def _(logits, labels, ignore_index, n_classes=-1):
     return logits.new_empty((1,), dtype=torch.float32), torch.empty_like(logits)
 
 
@@ -784,7 +896,7 @@ def _ce_setup(ctx, inputs, output):
 
 def _ce_backward(ctx, dloss, *unused):
     (dlogits,) = ctx.saved_tensors
-    return dlogits * dloss.to(dlogits.dtype), None, None
+    return dlogits * dloss.to(dlogits.dtype), None, None, None
 
 
 cross_entropy_fused.register_autograd(_ce_backward, setup_context=_ce_setup)

@@ -40,11 +40,19 @@ class Trainer:
         self.optimizer.zero_grad(set_to_none=True)
         out = self.model(images)
         logits = out[0] if isinstance(out, tuple) else out
-        if (logits.is_cuda and logits.shape[1] <= 256 and logits.dtype in (torch.float32, torch.bfloat16)
-                and logits.is_contiguous(memory_format=torch.channels_last)):
-            # fused CrossEntropyLoss(mean) forward + gradient on channels-last logits (one read, one write)
-            # and start backward from d(loss)/d(logits) directly: the fused kernel already produced it, so the
-            # loss node and its `dlogits * dloss` pass are skipped
+        fused_ok = logits.is_cuda and logits.shape[1] <= 256 and logits.dtype in (torch.float32, torch.bfloat16)
+        padded = getattr(self.model, "_padded_logits", None)
+        if (fused_ok and padded is not None and padded.requires_grad and padded.data_ptr() == logits.data_ptr()
+                and padded.is_contiguous(memory_format=torch.channels_last)):
+            # logits are the first c_out channels of the head's class-padded buffer: run the fused loss on the
+            # buffer itself and start backward there (no narrow / pad passes, no loss node)
+            with torch.no_grad():
+                loss, dpad = ops.cross_entropy_fused(padded.detach(), labels, self.ignore_index, logits.shape[1])
+            loss = loss.squeeze(0)
+            padded.backward(dpad)
+        elif fused_ok and logits.is_contiguous(memory_format=torch.channels_last):
+            # fused CrossEntropyLoss(mean) forward + gradient on channels-last logits (one read, one write), and
+            # backward starts from d(loss)/d(logits) directly: the loss node and its `dlogits * dloss` pass are skipped
             with torch.no_grad():
                 loss, dlogits = ops.cross_entropy_fused(logits.detach(), labels, self.ignore_index)
             loss = loss.squeeze(0)

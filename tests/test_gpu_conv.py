@@ -88,3 +88,55 @@ def test_bn_act_with_epilogue_statistics_matches_two_pass():
     b = ops.bn_act_fwd_stats(y, None, gamma, beta, sums, 1e-5, ops.ACT_GELU)
     assert rel_err(b[0].float(), a[0].float()) < 1e-3
     assert rel_err(b[1], a[1]) < 1e-5 and rel_err(b[2], a[2]) < 1e-5
+
+
+# ---- K12: 1x1 heads with class-padded outputs ----------------------------------------------------------------
+HEAD_CASES = [(2, 64, 150, 128, 128), (2, 64, 19, 64, 64), (3, 64, 16, 32, 32), (2, 128, 133, 16, 16),
+              (2, 64, 64, 4, 128), (1, 256, 200, 16, 16)]
+
+
+@pytest.mark.parametrize("case", HEAD_CASES, ids=lambda c: "b%d_%dto%d_%dx%d" % c)
+def test_conv1x1_head_forward_and_gradients(case):
+    from maskunet_b200 import ops
+    B, Cin, Cout, H, W = case
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.randn(B, Cin, H, W, generator=g).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    n_pad = ops.pad_channels(Cout)
+    dy = torch.randn(B, n_pad, H, W, generator=g).to(DEV).to(torch.bfloat16)
+    dy[:, Cout:] = 0                                            # what the padded pipeline guarantees
+    dy = dy.contiguous(memory_format=torch.channels_last)
+
+    xr = x.float().requires_grad_(True)
+    wr = w.to(torch.bfloat16).float().requires_grad_(True)
+    br = bias.clone().requires_grad_(True)
+    y_ref = F.conv2d(xr, wr, br)
+    y_ref.backward(dy[:, :Cout].float())
+
+    xq, wq, bq = x.clone().requires_grad_(True), w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    y_pad = ops.conv1x1(xq, wq, bq, n_pad)[0]
+    assert y_pad.shape == (B, n_pad, H, W) and y_pad.is_contiguous(memory_format=torch.channels_last)
+    assert rel_err(y_pad[:, :Cout].float(), y_ref) < 6e-3
+    if n_pad > Cout:
+        assert float(y_pad[:, Cout:].float().abs().max()) == 0.0     # pad channels are exactly zero
+    y_pad.backward(dy)
+    assert rel_err(xq.grad.float(), xr.grad) < 6e-3
+    assert rel_err(wq.grad, wr.grad) < 2e-3
+    assert rel_err(bq.grad, br.grad) < 2e-3
+
+
+def test_cross_entropy_on_class_padded_logits():
+    from maskunet_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(11)
+    B, C, P, H, W = 2, 150, 160, 16, 16
+    logits = torch.randn(B, P, H, W, generator=g).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    labels = torch.randint(0, C, (B, H, W), generator=g).to(DEV)
+    labels[0, 0, :4] = 255
+    loss, dl = ops.cross_entropy_fused(logits, labels, 255, C)
+    ref_in = logits[:, :C].float().requires_grad_(True)
+    ref = F.cross_entropy(ref_in, labels, ignore_index=255)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 2e-3 * abs(float(ref))
+    assert rel_err(dl[:, :C].float(), ref_in.grad) < 1e-2
+    assert float(dl[:, C:].float().abs().max()) == 0.0
