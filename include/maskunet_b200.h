@@ -184,9 +184,11 @@ int mu_cross_entropy_fused(const void* logits, const int64_t* labels, const floa
  * activations [B, H, W, C], fp32 accumulation; W in {16, 32, 64, 128}, H a multiple of 128 / W, channel counts
  * multiples of 64 in [64, 512].  MU_BF16 only (fp32 validation mode keeps the stock NCHW convolution).
  *
+ * The 3-channel stem (:259 -> ConvBlock(3, 64)) runs on the same kernels with its input zero-padded to 8 channels
+ * (Cin < 64 must be a multiple of 8; TMA zero-fills the rest of the 64-channel operand tile).
  * mu_conv_prep_weights: w f32 [Cout, Cin, taps] (the parameter as nn.Conv2d holds it, taps = 9 or 1) ->
- *   wf bf16 [taps, Cout, Cin] (forward operand) and wd bf16 [taps, Cin, Cout] with the tap order reversed
- *   (data-gradient operand; wd may be NULL).
+ *   wf bf16 [taps, Cout, roundup(Cin, 64)] (forward operand, zero padded) and wd bf16 [taps, Cin, Cout] with the tap
+ *   order reversed (data-gradient operand; wd may be NULL).
  * mu_conv3x3_fwd: y [B, H, W, Cout] = conv(x [B, H, W, Cin], wf).  stats (may be NULL): f32 [2 * Cout],
  *   ADDED to: per-channel sum and sum of squares of the (rounded) outputs -- the statistics pass of the
  *   training-mode BatchNorm2d that always follows (:200, :203), so the caller zeroes it first and passes it to

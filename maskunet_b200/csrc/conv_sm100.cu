@@ -157,6 +157,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         const uint32_t d_tmem = tmem_base + buf * (MT * NT);
         uint32_t accumulate = 0;
         for (int ch = 0; ch < kchunks; ++ch) {
+          const int kk_n = min(4, (p.K - ch * 64 + 15) / 16);     // 16-channel MMA steps with data in this chunk
 #pragma unroll
           for (int g = 0; g < GROUPS; ++g) {
             mbar_wait(a_full + sa, pa);
@@ -173,7 +174,8 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                 const uint64_t a_desc = desc_hi | (uint64_t)(((a_tile + row_off + m * tile_pitch) & 0x3FFFF) >> 4);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                  umma_ss(d_tmem + m * NT, a_desc + 2 * kk, b_desc + 2 * kk, idesc, accumulate | (uint32_t)(kk > 0));
+                  if (kk < kk_n)
+                    umma_ss(d_tmem + m * NT, a_desc + 2 * kk, b_desc + 2 * kk, idesc, accumulate | (uint32_t)(kk > 0));
               }
               accumulate = 1;
               umma_commit(b_empty + sb);
@@ -412,6 +414,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         ci = ci0 + (r & 63);
         valid = (m == 0 && p.mode != CONV_1X1) || r < 64;
       }
+      valid = valid && ci < p.Cin;                            // stem: 8 (3 + padding) of the 64 tile rows exist
       const int tap = p.mode == CONV_1X1 ? 0 : (p.mode == CONV_W128 ? g * 3 + j : j * 3 + g);
       float* dst = ws + ((size_t)tap * p.Cin + ci) * p.Cout + nb * NB;
 #pragma unroll
@@ -436,18 +439,19 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 }
 
 // ============================================================================ small helpers
-// w f32 [Cout][Cin][taps] (the nn.Conv2d parameter) -> wf bf16 [taps][Cout][Cin] (forward operand) and
-// wd bf16 [taps][Cin][Cout] with the taps reversed (the data-gradient operand).
+// w f32 [Cout][Cin][taps] (the nn.Conv2d parameter) -> wf bf16 [taps][Cout][Kp] (forward operand; Kp = Cin rounded
+// up to 64, extra columns zero) and wd bf16 [taps][Cin][Cout] with the taps reversed (the data-gradient operand).
 __global__ void conv_prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
-                                         __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int taps) {
+                                         __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int Kp, int taps) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Cout * Cin) return;
-  const int co = idx / Cin, ci = idx - co * Cin;
-  const float* src = w + (size_t)idx * taps;
+  if (idx >= Cout * Kp) return;
+  const int co = idx / Kp, ci = idx - co * Kp;
+  const bool real = ci < Cin;
+  const float* src = w + ((size_t)co * Cin + (real ? ci : 0)) * taps;
   for (int t = 0; t < taps; ++t) {
-    const __nv_bfloat16 v = __float2bfloat16_rn(src[t]);
-    wf[((size_t)t * Cout + co) * Cin + ci] = v;
-    if (wd != nullptr) wd[((size_t)(taps - 1 - t) * Cin + ci) * Cout + co] = v;
+    const __nv_bfloat16 v = __float2bfloat16_rn(real ? src[t] : 0.f);
+    wf[((size_t)t * Cout + co) * Kp + ci] = v;
+    if (wd != nullptr && real) wd[((size_t)(taps - 1 - t) * Cin + ci) * Cout + co] = v;
   }
 }
 
@@ -478,8 +482,10 @@ static int conv_geometry_ok(const char* fn, int B, int H, int W, int K, int N) {
   MU_REQUIRE(W == 16 || W == 32 || W == 64 || W == 128, MU_ERR_BAD_SHAPE,
              "%s: width must be 16, 32, 64 or 128 (got %d)", fn, W);
   MU_REQUIRE(H % (128 / W) == 0, MU_ERR_BAD_SHAPE, "%s: height %d must be a multiple of %d", fn, H, 128 / W);
-  MU_REQUIRE(K % 64 == 0 && N % 64 == 0 && K >= 64 && N >= 64 && K <= 512 && N <= 512, MU_ERR_BAD_SHAPE,
-             "%s: channel counts must be multiples of 64 in [64, 512] (got %d -> %d)", fn, K, N);
+  MU_REQUIRE((K % 64 == 0 || (K < 64 && K % 8 == 0)) && N % 64 == 0 && K >= 8 && N >= 64 && K <= 512 && N <= 512,
+             MU_ERR_BAD_SHAPE,
+             "%s: channel counts must be multiples of 64 in [64, 512] (input side: also 8..56 in steps of 8; got %d -> %d)",
+             fn, K, N);
   return 0;
 }
 
@@ -611,7 +617,7 @@ static int run_wgrad(const void* x, const void* dy, float* ws, int B, int H, int
   p.x_bytes = box_w * box_h * 128;
   p.x_stride = round_up(p.x_bytes, 1024);
   p.ci_blocks = Cin % 128 == 0 ? 2 : 1;
-  p.n_cb = Cin / (64 * p.ci_blocks);
+  p.n_cb = (Cin + 64 * p.ci_blocks - 1) / (64 * p.ci_blocks);
   p.n_nb = Cout / NB;
   const int stage = p.ci_blocks * p.x_stride + ((NB + 63) / 64) * 16384;
   p.S = (kSmemLimit - 1024 - 512) / stage;
@@ -700,8 +706,8 @@ int launch_conv1x1_prep(const float* w, const float* bias, void* wf, void* wd, f
 }
 
 int launch_conv_prep_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int taps, cudaStream_t s) {
-  const int n = Cin * Cout;
-  conv_prep_weights_kernel<<<(n + 255) / 256, 256, 0, s>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, Cout, Cin, taps);
+  const int Kp = round_up(Cin, 64), n = Kp * Cout;
+  conv_prep_weights_kernel<<<(n + 255) / 256, 256, 0, s>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, Cout, Cin, Kp, taps);
   return check_launch("conv_prep_weights");
 }
 

@@ -180,7 +180,7 @@ def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Option
         return ops.bn_act_apply(x, residual, a, b, act)
 
 
-def _own_conv3x3(conv: nn.Conv2d, x: torch.Tensor) -> bool:
+def _own_conv3x3(conv: nn.Conv2d, x: torch.Tensor, weight: Optional[torch.Tensor] = None) -> bool:
     """True when K7 (csrc/conv_sm100.cu) takes this convolution: the reference's conv3x3(bias=False, padding=1) on a
     bf16 channels-last activation whose geometry the tcgen05 tiling covers (all of them at 128x128 inputs except the
     3-channel stem)."""
@@ -189,7 +189,7 @@ def _own_conv3x3(conv: nn.Conv2d, x: torch.Tensor) -> bool:
             and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1)
             and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None
             and conv.weight.dtype == torch.float32
-            and ops.conv3x3_shape_ok(x.shape[0], conv.in_channels, conv.out_channels, x.shape[2], x.shape[3]))
+            and ops.conv3x3_shape_ok(x.shape[0], x.shape[1], conv.out_channels, x.shape[2], x.shape[3]))
 
 
 def conv_bn_act(conv: nn.Conv2d, bn: nn.BatchNorm2d, x: torch.Tensor, act: int,
@@ -197,10 +197,18 @@ def conv_bn_act(conv: nn.Conv2d, bn: nn.BatchNorm2d, x: torch.Tensor, act: int,
     """act(BN(conv(x)) [+ residual]): one conv3x3 -> BatchNorm2d -> activation link of ade_semantic.py:198-210.
     On the production layout the convolution is our implicit-GEMM kernel and its epilogue hands the BatchNorm
     batch statistics to the fused normalise + activate kernel."""
-    if _own_conv3x3(conv, x):
-        y, sums, _ = ops.conv3x3(x, conv.weight, bn.training)
+    weight = conv.weight
+    if (conv.in_channels < 8 and x.dim() == 4 and x.is_cuda and x.dtype == torch.bfloat16 and conv.bias is None
+            and conv.kernel_size == (3, 3) and x.is_contiguous(memory_format=torch.channels_last)):
+        # the 3-channel stem: zero-pad image and weight to 8 input channels (16-byte pixels, TMA-addressable);
+        # autograd slices the weight gradient back
+        extra = 8 - conv.in_channels
+        x = F.pad(x, (0, 0, 0, 0, 0, extra)).contiguous(memory_format=torch.channels_last)
+        weight = F.pad(weight, (0, 0, 0, 0, 0, extra))
+    if _own_conv3x3(conv, x, weight):
+        y, sums, _ = ops.conv3x3(x, weight, bn.training)
         return fused_bn_act(y, bn, act, residual, sums=sums if bn.training else None)
-    return fused_bn_act(conv(x), bn, act, residual)
+    return fused_bn_act(conv(x[:, :conv.in_channels]), bn, act, residual)
 
 
 class ConvBlock(nn.Module):

@@ -469,8 +469,8 @@ CONV_WIDTHS = (16, 32, 64, 128)
 
 
 def conv3x3_shape_ok(B: int, Cin: int, Cout: int, H: int, W: int) -> bool:
-    return (W in CONV_WIDTHS and H % (128 // W) == 0 and Cin % 64 == 0 and Cout % 64 == 0
-            and 64 <= Cin <= 512 and 64 <= Cout <= 512)
+    return (W in CONV_WIDTHS and H % (128 // W) == 0 and Cout % 64 == 0 and 64 <= Cout <= 512
+            and ((Cin % 64 == 0 and 64 <= Cin <= 512) or (Cin % 8 == 0 and 8 <= Cin < 64)))
 
 
 @torch.library.custom_op("maskunet::conv_prep_weights", mutates_args=(), device_types="cuda")
@@ -480,7 +480,7 @@ def conv_prep_weights(w: Tensor, with_wd: bool) -> Tuple[Tensor, Tensor]:
     assert w.dtype == torch.float32 and w.dim() == 4
     Cout, Cin, kh, kw = w.shape
     taps = kh * kw
-    wf = torch.empty((taps, Cout, Cin), dtype=torch.bfloat16, device=w.device)
+    wf = torch.empty((taps, Cout, (Cin + 63) // 64 * 64), dtype=torch.bfloat16, device=w.device)
     wd = torch.empty((taps, Cin, Cout) if with_wd else (0,), dtype=torch.bfloat16, device=w.device)
     with torch.cuda.device(w.device):
         _count(1)
@@ -492,7 +492,7 @@ def conv_prep_weights(w: Tensor, with_wd: bool) -> Tuple[Tensor, Tensor]:
 @conv_prep_weights.register_fake
 def _(w, with_wd):
     Cout, Cin, kh, kw = w.shape
-    return (w.new_empty((kh * kw, Cout, Cin), dtype=torch.bfloat16),
+    return (w.new_empty((kh * kw, Cout, (Cin + 63) // 64 * 64), dtype=torch.bfloat16),
             w.new_empty((kh * kw, Cin, Cout) if with_wd else (0,), dtype=torch.bfloat16))
 
 
@@ -503,7 +503,7 @@ def conv3x3_fwd(x: Tensor, wf: Tensor, want_stats: bool) -> Tuple[Tensor, Tensor
     B, Cin, H, W = _nhwc(x)
     _cuda(wf)
     Cout = wf.shape[1]
-    assert x.dtype == torch.bfloat16 and wf.shape == (9, Cout, Cin)
+    assert x.dtype == torch.bfloat16 and wf.shape == (9, Cout, (Cin + 63) // 64 * 64)
     y = _empty_cl(x, B, Cout, H, W)
     sums = torch.zeros((2 * Cout,), dtype=torch.float32, device=x.device) if want_stats else \
         torch.empty((0,), dtype=torch.float32, device=x.device)

@@ -17,7 +17,8 @@ torch.backends.cuda.matmul.allow_tf32 = False
 # Cin = 64 (paired-tap weight gradient) and Cin >= 128, non-square H
 CASES = [(2, 64, 64, 128, 128), (1, 128, 128, 128, 128), (2, 128, 64, 4, 128), (2, 64, 128, 64, 64),
          (3, 128, 128, 64, 64), (2, 256, 256, 32, 32), (3, 128, 256, 32, 32), (2, 512, 256, 16, 16),
-         (4, 256, 512, 16, 16), (2, 512, 512, 16, 16), (2, 64, 64, 8, 32), (5, 192, 320, 16, 16)]
+         (4, 256, 512, 16, 16), (2, 512, 512, 16, 16), (2, 64, 64, 8, 32), (5, 192, 320, 16, 16),
+         (2, 8, 64, 128, 128), (2, 8, 64, 64, 64)]       # stem: 3 input channels zero-padded to 8
 
 
 def _inputs(B, Cin, Cout, H, W, seed=0):
@@ -40,7 +41,8 @@ def test_conv3x3_forward_stats_and_gradients(case):
     y_ref = F.conv2d(xr, wr, padding=1)
     y_ref.backward(dy.float())
 
-    xq = x.clone().requires_grad_(True)
+    stem = Cin < 64                                          # the padded image needs no gradient (and has no kernel for it)
+    xq = x.clone().requires_grad_(not stem)
     wq = w.clone().requires_grad_(True)
     y, sums, _ = ops.conv3x3(xq, wq, True)
     assert y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
@@ -51,10 +53,11 @@ def test_conv3x3_forward_stats_and_gradients(case):
     s_ref = torch.cat([yf.sum((0, 2, 3)), (yf * yf).sum((0, 2, 3))])
     assert rel_err(sums, s_ref) < 1e-4
     y.backward(dy)
-    assert rel_err(xq.grad.float(), xr.grad) < 2e-2
     assert rel_err(wq.grad, wr.grad) < 2e-2
-    assert rel_err(xq.grad.float(), xr.grad) < 6e-3
     assert rel_err(wq.grad, wr.grad) < 2e-3                  # fp32 accumulation, fp32 output
+    if not stem:
+        assert rel_err(xq.grad.float(), xr.grad) < 2e-2
+        assert rel_err(xq.grad.float(), xr.grad) < 6e-3
 
 
 def test_conv3x3_border_is_zero_padding():
