@@ -226,10 +226,18 @@ def run_ours(args):
         cand = dict(kernel=name, ms=avg_ms, achieved=flops / (avg_ms * 1e-3) / 1e12)
         if best is None or cand["ms"] > best["ms"]:
             best = cand
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "attn_b256_dram_traffic.json")   # from tools/ncu_traffic.py (ncu --set full)
+    if best is not None and os.path.isfile(tpath):
+        try:
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(best["kernel"], {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
     if best is not None:
         peak = peaks["tf_sustained"]
         roof = {"bound": "tensor", "achieved": best["achieved"], "peak": peak, "unit": "TFLOP/s",
-                "frac": best["achieved"] / peak, "traffic": None, "kernel": best["kernel"],
+                "frac": best["achieved"] / peak, "traffic": traffic, "kernel": best["kernel"],
                 "kernel_ms": best["ms"], "peak_source": peaks["source"] + ", sustained (kernel timed inside the step)",
                 "flops_counted": "useful: kept keys only (4 N n_keep C fwd, 8 N n_keep C bwd), site N=16384 C=64"}
 
