@@ -374,6 +374,71 @@ __global__ void __launch_bounds__(256) ce_fused_kernel(const T* __restrict__ log
   }
 }
 
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+
+// bf16 rows whose pitch is a multiple of 8 (every production shape: 160-pitch padded logits, 32 for the instance
+// heads): lane l owns the 16-byte vector of classes [8l, 8l + 8) -- one vector load and one vector store per row and
+// lane instead of up to eight 2-byte accesses.
+__global__ void __launch_bounds__(256) ce_fused_vec_kernel(const __nv_bfloat16* __restrict__ logits,
+                                                           const int64_t* __restrict__ labels,
+                                                           const float* __restrict__ valid_count, long ignore_index,
+                                                           __nv_bfloat16* __restrict__ dlogits,
+                                                           float* __restrict__ loss_sum, long M, int C, int pitch) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const float inv = 1.f / fmaxf(valid_count[0], 1.f);
+  const bool in_row = lane * 8 < pitch;
+  float local = 0.f;
+  for (long row = (long)blockIdx.x * 8 + wib; row < M; row += (long)gridDim.x * 8) {
+    const long lab = labels[row];
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (in_row && lab != ignore_index) u = *reinterpret_cast<const uint4*>(logits + row * pitch + lane * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float v[8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float f = __uint_as_float((e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16));
+      v[e] = (lane * 8 + e < C) ? f : -INFINITY;
+      mx = fmaxf(mx, v[e]);
+    }
+    mx = warp_max(mx);
+    float se = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = __expf(v[e] - mx);
+      se += v[e];
+    }
+    se = warp_sum(se);
+    const float inv_se = 1.f / se;
+    float picked = 0.f, o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = lane * 8 + e;
+      const float p = v[e] * inv_se;                       // 0 for the pad classes
+      if (c == lab) picked = p;
+      o[e] = (lab == ignore_index || c >= C) ? 0.f : (p - (c == lab ? 1.f : 0.f)) * inv;
+    }
+    if (in_row) {
+      uint4 r;
+      r.x = pack2(o[0], o[1]); r.y = pack2(o[2], o[3]); r.z = pack2(o[4], o[5]); r.w = pack2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dlogits + row * pitch + lane * 8) = r;
+    }
+    picked = warp_sum(picked);
+    if (lane == 0 && lab != ignore_index) local += -__logf(fmaxf(picked, 1e-38f));
+  }
+  __shared__ float red[8];
+  if (lane == 0) red[wib] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w2 = 0; w2 < 8; ++w2) t += red[w2];
+    atomicAdd(loss_sum, t * inv);
+  }
+}
+
 // ============================================================================ launchers
 static int grid_for(long items, int threads = 256) {
   long blocks = (items + threads - 1) / threads;
@@ -486,6 +551,11 @@ int launch_ce_fused(const void* logits, const int64_t* labels, const float* vali
   }
   cudaMemsetAsync(loss_sum, 0, sizeof(float), s);
   const int grid = grid_for((M + 7) / 8, 1);
+  if (dtype == MU_BF16 && pitch % 8 == 0) {
+    ce_fused_vec_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)logits, labels, valid_count, ignore_index,
+                                             (__nv_bfloat16*)dlogits, loss_sum, M, C, pitch);
+    return check_launch("cross_entropy_fused_vec");
+  }
   MU_T(dtype, (ce_fused_kernel<float><<<grid, 256, 0, s>>>((const float*)logits, labels, valid_count, ignore_index,
                                                         (float*)dlogits, loss_sum, M, C, pitch)),
        (ce_fused_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)logits, labels, valid_count,
