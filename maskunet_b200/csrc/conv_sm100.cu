@@ -628,9 +628,13 @@ static int run_wgrad(const void* x, const void* dy, float* ws, int B, int H, int
   }
   const int smem = 1024 + 512 + p.S * stage;
   const int combos = (taps == 1 ? 1 : 3) * p.n_cb * p.n_nb;
-  int splits = (2 * sm_count() + combos - 1) / combos;      // about two CTAs' worth of work queued per SM
-  if (splits > p.m_tiles) splits = p.m_tiles;
+  // split-K: whole waves only.  One CTA per SM is resident (shared memory), so combos * splits must not exceed a
+  // multiple of the SM count by a few CTAs (297 CTAs on 148 SMs ran as three waves, the last with one CTA).
+  const int sms = sm_count();
+  int waves = 2;
+  int splits = waves * sms / combos;
   if (splits < 1) splits = 1;
+  if (splits > p.m_tiles) splits = p.m_tiles;
   p.chunks_per_cta = (p.m_tiles + splits - 1) / splits;
   splits = (p.m_tiles + p.chunks_per_cta - 1) / p.chunks_per_cta;
   CUtensorMap tx, td;
