@@ -201,14 +201,37 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     const int SO = p.SO;
     uint32_t buf = 0, pacc = 0, so_idx = 0;
     uint32_t v[32];
+    // BatchNorm partial sums of this thread's channel pair (cp) and row group (sq), one set per 64-channel block
+    float acc[kBlocks][4];
+#pragma unroll
+    for (int i = 0; i < kBlocks; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    int acc_nt = -1;
+    auto flush_stats = [&](int nt_done) {
+      if (nt_done < 0) return;
+#pragma unroll
+      for (int i = 0; i < kBlocks; ++i) {
+        const int chn = nt_done * NT + i * 64 + 2 * cp;
+        atomicAdd(s_stats + chn, acc[i][0]);
+        atomicAdd(s_stats + chn + 1, acc[i][1]);
+        atomicAdd(s_stats + 512 + chn, acc[i][2]);
+        atomicAdd(s_stats + 512 + chn + 1, acc[i][3]);
+        acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+      }
+    };
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
       const int b = mt / p.tiles_y, y0 = (mt - b * p.tiles_y) * (MT * p.TH);
       mbar_wait(acc_full + buf, pacc);
       tc_fence_after();
+      if (stats != nullptr && nt != acc_nt) {             // (rare: at most once per CTA) new channel range
+        flush_stats(acc_nt);
+        acc_nt = nt;
+      }
 #pragma unroll 1
-      for (int blk = 0; blk < MT * kBlocks; ++blk) {
-        const int m = blk / kBlocks, cb = blk - m * kBlocks;
+      for (int m = 0; m < MT; ++m) {
+#pragma unroll
+      for (int cb = 0; cb < kBlocks; ++cb) {
+        const int blk = m * kBlocks + cb;
         const uint32_t so = so_base + so_idx * 16384;
         if (e == 0) {                                      // the store that last read this staging buffer is done
           if (SO == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
@@ -258,18 +281,21 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             q0 = fmaf(lo, lo, q0);
             q1 = fmaf(hi, hi, q1);
           }
-          const int chn = nt * NT + cb * 64 + 2 * cp;
-          atomicAdd(s_stats + chn, s0);
-          atomicAdd(s_stats + chn + 1, s1);
-          atomicAdd(s_stats + 512 + chn, q0);
-          atomicAdd(s_stats + 512 + chn + 1, q1);
+          // registers, not shared-memory atomics: float atomics on shared memory are CAS loops, and four row
+          // groups hitting every address made this block cost ~1900 cycles per 64 channels
+          acc[cb][0] += s0;
+          acc[cb][1] += s1;
+          acc[cb][2] += q0;
+          acc[cb][3] += q1;
         }
         if (++so_idx == (uint32_t)SO) so_idx = 0;
+      }
       }
       if (++buf == NBUF) { buf = 0; pacc ^= 1; }
     }
     if (e == 0) tma_store_wait<0>();
     if (stats != nullptr) {
+      flush_stats(acc_nt);
       named_bar_sync(1, 128);
       for (int i = e; i < p.N; i += 128) {
         const float a = s_stats[i], q = s_stats[512 + i];
