@@ -237,6 +237,15 @@ int mu_conv1x1_bwd_weight(const void* x, const void* dy, void* workspace, size_t
                           int32_t H, int32_t W, int32_t Cin, int32_t Np, int32_t dtype, mu_stream_t stream);
 int mu_column_sums(const void* x, float* sums, int64_t M, int32_t C, int32_t dtype, mu_stream_t stream);
 
+/* Logit post-processing on the device: the class map `argmax(softmax(y_pred / 0.5, dim=1), dim=1)`
+ * (:130-131; cityscapes/city_instance.py:461-462) -- softmax is monotone, so argmax of the logits with torch's tie
+ * rule (lowest index) -- and mean_iou (:128-146) without its per-class host syncs.
+ * logits [M, pitch >= C] rows (channels-last, class-padded allowed); labels int64 [M] or NULL; pred int64 [M] or NULL;
+ * hist int32 [3C] scratch (predicted / labelled / matching pixels per class, cleared inside); miou f32 [1] or NULL:
+ * mean over classes with a non-empty union of (intersection + smooth) / (union + smooth). */
+int mu_argmax_iou(const void* logits, const int64_t* labels, int64_t* pred, int32_t* hist, float* miou, int64_t M,
+                  int32_t C, int32_t pitch, float smooth, int32_t dtype, mu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

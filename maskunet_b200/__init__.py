@@ -12,5 +12,9 @@ from . import ops  # noqa: E402  (registers the maskunet:: operators)
 from .modules import (ConvBlock, DownSample, InstanceUNet, Mask2FormerAttention, UNet,  # noqa: E402
                       UpSample)
 
-__all__ = ["Mask2FormerAttention", "ConvBlock", "DownSample", "UpSample", "UNet", "InstanceUNet", "ops"]
+from . import checkpoint  # noqa: E402
+from .ops import mean_iou, segmentation_argmax  # noqa: E402  (device versions of ade_semantic.py:128-146)
+
+__all__ = ["Mask2FormerAttention", "ConvBlock", "DownSample", "UpSample", "UNet", "InstanceUNet", "ops",
+           "mean_iou", "segmentation_argmax", "checkpoint"]
 __version__ = "0.1.0"

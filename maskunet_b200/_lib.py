@@ -35,6 +35,7 @@ SIGNATURES = {
     "mu_sample_layernorm_fwd": [_P, _P, _P, _F, _P, _P, _P, _P, _I, ctypes.c_int64, _I, _P],
     "mu_sample_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, ctypes.c_int64, _I, _P],
     "mu_cross_entropy_fused": [_P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
+    "mu_argmax_iou": [_P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _F, _I, _P],
     "mu_column_sums": [_P, _P, ctypes.c_int64, _I, _I, _P],
     "mu_conv1x1_prep": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mu_conv1x1_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

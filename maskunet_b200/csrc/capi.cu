@@ -267,6 +267,15 @@ int mu_cross_entropy_fused(const void* logits, const int64_t* labels, const floa
                          (cudaStream_t)stream);
 }
 
+int mu_argmax_iou(const void* logits, const int64_t* labels, int64_t* pred, int32_t* hist, float* miou, int64_t M,
+                  int32_t C, int32_t pitch, float smooth, int32_t dtype, mu_stream_t stream) {
+  MU_DTYPE_OK("mu_argmax_iou");
+  MU_PTRS("mu_argmax_iou", logits);
+  MU_REQUIRE(pred != nullptr || labels != nullptr, MU_ERR_NULL, "mu_argmax_iou: nothing to produce (pred and labels NULL)");
+  MU_REQUIRE(labels == nullptr || hist != nullptr, MU_ERR_NULL, "mu_argmax_iou: labels given without a histogram buffer");
+  return launch_argmax_iou(logits, labels, pred, hist, miou, (long)M, C, pitch, smooth, dtype, (cudaStream_t)stream);
+}
+
 int mu_column_sums(const void* x, float* sums, int64_t M, int32_t C, int32_t dtype, mu_stream_t stream) {
   MU_DTYPE_OK("mu_column_sums");
   MU_PTRS("mu_column_sums", x, sums);

@@ -114,6 +114,8 @@ int launch_conv1x1_wgrad_sm100(const void* x, const void* dy, float* ws, float* 
 int launch_conv1x1_prep(const float* w, const float* bias, void* wf, void* wd, float* bias_p, int Cout, int Cin, int Np,
                         cudaStream_t s);
 int launch_column_sums(const void* x, float* sums, long M, int C, int dtype, cudaStream_t s);
+int launch_argmax_iou(const void* logits, const int64_t* labels, int64_t* pred, int32_t* hist, float* miou, long M, int C,
+                      int pitch, float smooth, int dtype, cudaStream_t s);
 int launch_transpose(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t s);
 
 }  // namespace mu

@@ -439,6 +439,89 @@ __global__ void __launch_bounds__(256) ce_fused_vec_kernel(const __nv_bfloat16* 
   }
 }
 
+// ============================================================================ logit post-processing
+// ade_semantic.py:130-131 `argmax(softmax(y_pred / 0.5, dim=1), dim=1)` and the per-class IoU loop :135-143 that runs
+// inside every training step (:403) with a host sync per class.  softmax(x / 0.5) is strictly monotone in x, so the
+// class map is argmax(x) with torch's tie rule (lowest index); one pass also histograms prediction, label and match
+// counts per class (shared-memory integer atomics), a second tiny kernel forms mean IoU on the device.
+//   hist i32 [3][C]: [0] pixels predicted c, [1] pixels labelled c, [2] pixels predicted = labelled = c
+template <typename T, bool VEC8>
+__global__ void __launch_bounds__(256) argmax_hist_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                          int64_t* __restrict__ pred, int32_t* __restrict__ hist,
+                                                          long M, int C, int pitch) {
+  extern __shared__ int32_t sh[];   // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += 256) sh[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (long row = (long)blockIdx.x * 8 + wib; row < M; row += (long)gridDim.x * 8) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    if (VEC8) {
+      if (lane * 8 < pitch) {
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(logits) + row * pitch + lane * 8);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float f = __uint_as_float((e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16));
+          const int c = lane * 8 + e;
+          if (c < C && (f > best || (f != f && best == best))) { best = f; bi = c; }   // first maximum; NaN wins like torch
+        }
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        const float f = ld_f(logits + row * pitch + c);
+        if (f > best || (f != f && best == best)) { best = f; bi = c; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const bool take = (ob > best) || (ob != ob && best == best) || (ob == best && oi < bi) || (ob != ob && best != best && oi < bi);
+      if (take) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+      if (bi == 0x7fffffff) bi = 0;
+      if (pred != nullptr) pred[row] = bi;
+      if (labels != nullptr) {
+        const long lab = labels[row];
+        atomicAdd(sh + bi, 1);
+        if (lab >= 0 && lab < C) {
+          atomicAdd(sh + C + (int)lab, 1);
+          if (lab == bi) atomicAdd(sh + 2 * C + bi, 1);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (labels != nullptr)
+    for (int i = threadIdx.x; i < 3 * C; i += 256)
+      if (sh[i] != 0) atomicAdd(hist + i, sh[i]);
+}
+
+// mean over the classes with a non-empty union of (intersection + smooth) / (union + smooth)   (:137-146)
+__global__ void mean_iou_finalize_kernel(const int32_t* __restrict__ hist, float* __restrict__ out, int C, float smooth) {
+  __shared__ float s_sum[32], s_cnt[32];
+  float acc = 0.f, cnt = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float inter = (float)hist[2 * C + c];
+    const float uni = (float)(hist[c] + hist[C + c] - hist[2 * C + c]);
+    if (uni > 0.f) {
+      acc += (inter + smooth) / (uni + smooth);
+      cnt += 1.f;
+    }
+  }
+  acc = warp_sum(acc);
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = acc; s_cnt[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, n = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_sum[w]; n += s_cnt[w]; }
+    out[0] = a / n;            // no class present: 0 / 0 = NaN, as torch.mean of an empty stack
+  }
+}
+
 // ============================================================================ launchers
 static int grid_for(long items, int threads = 256) {
   long blocks = (items + threads - 1) / threads;
@@ -561,6 +644,28 @@ int launch_ce_fused(const void* logits, const int64_t* labels, const float* vali
        (ce_fused_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)logits, labels, valid_count,
                                                             ignore_index, (__nv_bfloat16*)dlogits, loss_sum, M, C, pitch)));
   return check_launch("cross_entropy_fused");
+}
+
+// pred i64 [M] (optional), hist i32 [3C] scratch (cleared here), miou f32 [1] (optional, needs labels)
+int launch_argmax_iou(const void* logits, const int64_t* labels, int64_t* pred, int32_t* hist, float* miou, long M, int C,
+                      int pitch, float smooth, int dtype, cudaStream_t s) {
+  if (C < 1 || C > 4096 || pitch < C) {
+    set_error("argmax_iou: bad class count / pitch (C=%d pitch=%d)", C, pitch);
+    return MU_ERR_BAD_SHAPE;
+  }
+  if (labels != nullptr) cudaMemsetAsync(hist, 0, 3 * (size_t)C * sizeof(int32_t), s);
+  const int grid = grid_for((M + 7) / 8, 1);
+  const size_t smem = 3 * (size_t)C * sizeof(int32_t);
+  if (dtype == MU_BF16 && pitch % 8 == 0 && pitch <= 256)
+    argmax_hist_kernel<__nv_bfloat16, true><<<grid, 256, smem, s>>>((const __nv_bfloat16*)logits, labels, pred, hist, M, C, pitch);
+  else if (dtype == MU_BF16)
+    argmax_hist_kernel<__nv_bfloat16, false><<<grid, 256, smem, s>>>((const __nv_bfloat16*)logits, labels, pred, hist, M, C, pitch);
+  else
+    argmax_hist_kernel<float, false><<<grid, 256, smem, s>>>((const float*)logits, labels, pred, hist, M, C, pitch);
+  int rc = check_launch("argmax_hist");
+  if (rc || labels == nullptr || miou == nullptr) return rc;
+  mean_iou_finalize_kernel<<<1, 256, 0, s>>>(hist, miou, C, smooth);
+  return check_launch("mean_iou_finalize");
 }
 
 }  // namespace mu

@@ -902,6 +902,58 @@ def _ce_backward(ctx, dloss, *unused):
 cross_entropy_fused.register_autograd(_ce_backward, setup_context=_ce_setup)
 
 
+# ------------------------------------------------------------------ logit post-processing
+def _class_rows(logits: Tensor):
+    """(tensor to pass, pitch): channels-last logits, possibly the [:, :C] view of a class-padded buffer."""
+    B, C, H, W = logits.shape
+    st = logits.stride()
+    if logits.is_contiguous(memory_format=torch.channels_last):
+        return logits, C
+    if st[1] == 1 and st[3] >= C and st[2] == W * st[3] and st[0] == H * W * st[3]:
+        return logits, st[3]                                  # rows of pitch st[3], first C entries are the classes
+    return logits.contiguous(memory_format=torch.channels_last), C
+
+
+@torch.library.custom_op("maskunet::argmax_iou", mutates_args=(), device_types="cuda")
+def argmax_iou(logits: Tensor, labels: Tensor | None, pitch: int, smooth: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """logits [B, C, H, W] whose memory is rows of `pitch` >= C channels -> (pred int64 [B, H, W], mean IoU f32 [1]
+    (NaN without labels), hist int32 [3, C]: predicted / labelled / matching pixels per class)."""
+    B, C, H, W = logits.shape
+    dev = logits.device
+    pred = torch.empty((B, H, W), dtype=torch.int64, device=dev)
+    hist = torch.zeros((3, C), dtype=torch.int32, device=dev)
+    miou = torch.full((1,), float("nan"), dtype=torch.float32, device=dev)
+    if labels is not None:
+        _cuda(labels)
+        assert labels.dtype == torch.int64 and labels.shape == (B, H, W)
+    with torch.cuda.device(dev):
+        _count(2 if labels is not None else 1)
+        check(_L.mu_argmax_iou(_p(logits), _optp(labels), _p(pred), _p(hist), _p(miou) if labels is not None else _optp(None),
+                               B * H * W, C, pitch, smooth, _code(logits), _stream(logits)), "mu_argmax_iou")
+    return pred, miou, hist
+
+
+@argmax_iou.register_fake
+def _(logits, labels, pitch, smooth):
+    B, C, H, W = logits.shape
+    return (logits.new_empty((B, H, W), dtype=torch.int64), logits.new_empty((1,), dtype=torch.float32),
+            logits.new_empty((3, C), dtype=torch.int32))
+
+
+def segmentation_argmax(y_pred: Tensor) -> Tensor:
+    """argmax(softmax(y_pred / 0.5, dim=1), dim=1) (ade_semantic.py:130-131) on the device, one pass."""
+    t, pitch = _class_rows(y_pred.detach())
+    return argmax_iou(t, None, pitch, 0.0)[0]
+
+
+def mean_iou(y_pred: Tensor, y_true: Tensor, num_classes: int, smooth: float = 1e-6) -> Tensor:
+    """Drop-in for the reference's mean_iou (ade_semantic.py:128-146): same signature, same value, no host syncs."""
+    if y_pred.shape[1] != num_classes:
+        raise ValueError("mean_iou: y_pred must have num_classes channels")
+    t, pitch = _class_rows(y_pred.detach())
+    return argmax_iou(t, y_true.contiguous(), pitch, smooth)[1][0]
+
+
 # ------------------------------------------------------------------ the module-level op (A3-A9 of SURVEY.md 8(a))
 @torch.library.custom_op("maskunet::mask_attention", mutates_args=(), device_types="cuda")
 def mask_attention(x: Tensor, w_qkv: Tensor, b_qkv: Tensor, gamma: Tensor, beta: Tensor, keep_rank: Tensor,

@@ -49,3 +49,21 @@ def load_reference_classes(script: str = "ade_semantic", names=MODEL_CLASSES) ->
     module = ast.Module(body=wanted, type_ignores=[])
     exec(compile(module, path, "exec"), ns)
     return SimpleNamespace(**{k: ns[k] for k in names})
+
+
+def load_reference_functions(script: str = "ade_semantic", names=("mean_iou",)) -> SimpleNamespace:
+    """The reference's own module-level FUNCTIONS ``names`` (e.g. mean_iou, ade_semantic.py:128-146), same mechanism."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    path = os.path.join(REFERENCE_ROOT, SCRIPTS.get(script, script))
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    wanted = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    missing = set(names) - {n.name for n in wanted}
+    if missing:
+        raise RuntimeError(f"{path}: functions not found: {sorted(missing)}")
+    ns = {"torch": torch, "nn": nn, "F": F, "__name__": f"reference_{script}"}
+    exec(compile(ast.Module(body=wanted, type_ignores=[]), path, "exec"), ns)
+    return SimpleNamespace(**{k: ns[k] for k in names})

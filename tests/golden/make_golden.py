@@ -118,7 +118,28 @@ def make_unet(script, variant, c_out, fname, batch=2):
     print(fname, "out0 stats", store["out0.stats"], "loss", loss.item())
 
 
+def make_postproc():
+    """mean_iou and the class map of the reference's own function (ade_semantic.py:128-146) on seeded logits:
+    ReLU'd logits (exact zeros and ties, as the head produces), an ignore label, a class that never occurs."""
+    from oracle.ref_loader import load_reference_functions
+    fn = load_reference_functions("ade_semantic", ("mean_iou",)).mean_iou
+    for name, B, C, H, W, seed in (("postproc_c150", 2, 150, 16, 16, 7), ("postproc_c19", 3, 19, 8, 32, 8)):
+        g = torch.Generator().manual_seed(seed)
+        logits = torch.relu(torch.randn(B, C, H, W, generator=g)).to(torch.bfloat16).float()   # bf16-representable
+        labels = torch.randint(0, C - 1, (B, H, W), generator=g)                               # class C-1 never labelled
+        labels[0, 0, :5] = 255
+        miou = fn(logits, labels, C)
+        pred = torch.argmax(torch.softmax(logits / 0.5, dim=1), dim=1)                          # :130-131 verbatim recipe
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), logits=np32(logits), labels=labels.numpy(),
+                            pred=pred.numpy().astype(np.int16), miou=np.array([float(miou)], dtype=np.float64))
+        print(name, float(miou))
+
+
 def main():
+    if "--postproc-only" in sys.argv:
+        make_postproc()
+        return
+    make_postproc()
     ref = load_reference_classes("ade_semantic")
     make_attention(ref)
     make_unet("ade_semantic", "semantic", 150, "unet_semantic")

@@ -90,3 +90,17 @@ def test_unet_oracle_matches_reference_golden(fname, variant):
     safe = margin > 1e-3
     assert (am[safe] == z["argmax"][safe]).all()
     assert (am == z["argmax"]).mean() > 0.999
+
+
+@pytest.mark.parametrize("name,C", [("postproc_c150", 150), ("postproc_c19", 19)])
+def test_metrics_oracle_matches_reference_golden(name, C):
+    """oracle/metrics_oracle.py against outputs of the reference's own mean_iou (ade_semantic.py:128-146)."""
+    import os
+    import numpy as np
+    import torch
+    from conftest import GOLDEN
+    from oracle import metrics_oracle as mo
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    logits, labels = torch.from_numpy(z["logits"]), torch.from_numpy(z["labels"])
+    assert torch.equal(mo.class_map(logits), torch.from_numpy(z["pred"].astype(np.int64)))   # bit-exact class map
+    assert abs(float(mo.mean_iou(logits, labels, C)) - float(z["miou"][0])) < 1e-6

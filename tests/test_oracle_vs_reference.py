@@ -61,3 +61,15 @@ def test_unet_init_and_keys_identical(script, variant, c_out):
     rsd = model.state_dict()
     assert list(rsd.keys()) == list(sd.keys())
     assert all(torch.equal(rsd[k], sd[k]) for k in sd)
+
+
+def test_mean_iou_live():
+    from oracle import metrics_oracle as mo
+    from oracle.ref_loader import load_reference_functions
+    fn = load_reference_functions("ade_semantic", ("mean_iou",)).mean_iou
+    g = torch.Generator().manual_seed(3)
+    for C in (5, 150):
+        logits = torch.relu(torch.randn(2, C, 12, 12, generator=g))
+        labels = torch.randint(0, C, (2, 12, 12), generator=g)
+        assert abs(float(fn(logits, labels, C)) - float(mo.mean_iou(logits, labels, C))) < 1e-6
+        assert torch.equal(torch.argmax(torch.softmax(logits / 0.5, dim=1), dim=1), mo.class_map(logits))
