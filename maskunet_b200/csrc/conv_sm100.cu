@@ -79,7 +79,9 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   uint64_t* acc_full = bars + 4 * kMaxRing;       // 2
   uint64_t* acc_empty = acc_full + 2;             // 2 (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows the role branches are warp-uniform and keeps the MMA
+  // issuer's address arithmetic on the uniform datapath (no per-MMA ELECT / R2UR.BROADCAST loops)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int total = p.m_tiles * p.n_tiles;        // m_tiles counts super tiles
   const int kchunks = (p.K + 63) / 64;            // a partial last chunk is zero-filled by TMA (1x1 heads)
 
@@ -142,14 +144,16 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane_id() == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp walks the loop,
+    // one elected lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
-      const uint64_t desc_hi = make_smem_desc(0, 0, 1024);
-      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-      const int SA = p.SA, SB = p.SB, a_stride = p.a_stride;
-      const uint32_t tile_pitch = (MODE == CONV_W128 ? 130 : 128) * 128;   // bytes between the MT tiles' first rows
-      const uint32_t row_w = p.W * 128;
+      constexpr uint32_t hi = desc_hi_sbo(1024);
+      const uint32_t a_base = desc_lo(smem_u32(sA)), b_base = desc_lo(smem_u32(sB));
+      const int SA = p.SA, SB = p.SB;
+      const uint32_t a_stride16 = p.a_stride >> 4;
+      constexpr uint32_t tile_pitch16 = (MODE == CONV_W128 ? 130 : 128) * 8;   // (bytes >> 4) between the MT tiles' rows
+      const uint32_t row_w16 = p.W * 8;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         mbar_wait(acc_empty + buf, pacc ^ 1);
@@ -161,31 +165,31 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 #pragma unroll
           for (int g = 0; g < GROUPS; ++g) {
             mbar_wait(a_full + sa, pa);
-            const uint32_t a_tile = a_base + sa * a_stride;
+            const uint32_t a_tile = a_base + sa * a_stride16;
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) {
-              const uint32_t row_off = MODE == CONV_W128 ? ((j / 3) * 130 + (j % 3)) * 128
-                                                         : (MODE == CONV_ROWS ? j * row_w : 0);
+              const uint32_t row_off = MODE == CONV_W128 ? ((j / 3) * 130 + (j % 3)) * 8
+                                                         : (MODE == CONV_ROWS ? j * row_w16 : 0);
               mbar_wait(b_full + sb, pb);
               tc_fence_after();
-              const uint64_t b_desc = desc_hi | (uint64_t)(((b_base + sb * kBBytes) & 0x3FFFF) >> 4);
+              const uint32_t b_lo = b_base + sb * (kBBytes >> 4);
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
-                const uint64_t a_desc = desc_hi | (uint64_t)(((a_tile + row_off + m * tile_pitch) & 0x3FFFF) >> 4);
+                const uint32_t a_lo = a_tile + row_off + m * tile_pitch16;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                  if (kk < kk_n)
-                    umma_ss(d_tmem + m * NT, a_desc + 2 * kk, b_desc + 2 * kk, idesc, accumulate | (uint32_t)(kk > 0));
+                  if (kk < kk_n && elect_one())
+                    umma_ss_lo(d_tmem + m * NT, a_lo + 2 * kk, b_lo + 2 * kk, hi, idesc, kk > 0 ? 1u : accumulate);
               }
               accumulate = 1;
-              umma_commit(b_empty + sb);
+              if (elect_one()) umma_commit(b_empty + sb);
               if (++sb == SB) { sb = 0; pb ^= 1; }
             }
-            umma_commit(a_empty + sa);
+            if (elect_one()) umma_commit(a_empty + sa);
             if (++sa == SA) { sa = 0; pa ^= 1; }
           }
         }
-        umma_commit(acc_full + buf);
+        if (elect_one()) umma_commit(acc_full + buf);
         if (++buf == NBUF) { buf = 0; pacc ^= 1; }
       }
     }
@@ -341,7 +345,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   uint64_t* empty = bars + kMaxRing;
   uint64_t* acc_full = bars + 2 * kMaxRing;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
 
   int combo = blockIdx.x;
   const int g = p.mode == CONV_1X1 ? 0 : combo % 3;
@@ -394,33 +398,48 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       }
     }
   } else if (warp == 1) {
-    if (lane_id() == 0) {
+    {   // whole warp walks the loop, one elected lane issues (see conv_fprop_sm100_kernel)
       constexpr uint32_t idesc = make_idesc_bf16(128, NB, 1, 1);   // both operands MN-major (contraction over pixels)
-      for (int j = 0; j < nchunks; ++j) {
-        const int st = j % p.S;
-        mbar_wait(full + st, (j / p.S) & 1);
-        tc_fence_after();
-        const uint32_t x_addr = smem_u32(smem + st * stage_bytes), d_addr = x_addr + x_tile_bytes;
-        for (int m = 0; m < m_tiles_cta; ++m) {
-          uint32_t a_start, a_lbo;
-          if (p.ci_blocks == 2) {
-            a_start = x_addr + m * row_step * 128;              // tap m, 128 input channels = two 64-wide blocks
-            a_lbo = p.x_stride;
-          } else if (m == 0) {
-            a_start = x_addr;                                   // taps 0 and 1 of 64 input channels side by side
-            a_lbo = row_step * 128;                             // (1x1: row_step = 0, rows 64..127 duplicate, ignored)
-          } else {
-            a_start = x_addr + 2 * row_step * 128;              // tap 2; rows 64..127 of the tile are ignored
-            a_lbo = 0;
-          }
+      constexpr uint32_t hi = desc_hi_sbo(1024);
+      const int S = p.S;
+      const uint32_t x_base = smem_u32(smem), stage16 = (uint32_t)stage_bytes >> 4;
+      // per M tile: start offset (>> 4) inside the x tile and LBO of the A operand; all loop-invariant
+      uint32_t a_off[3], a_lbo[3];
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_ss(tmem_base + m * NB, make_smem_desc(a_start + kk * 2048, a_lbo, 1024),
-                    make_smem_desc(d_addr + kk * 2048, 16384, 1024), idesc, (j > 0) || (kk > 0));
+      for (int m = 0; m < 3; ++m) {
+        if (p.ci_blocks == 2) {
+          a_off[m] = (uint32_t)(m * row_step * 128) >> 4;        // tap m, 128 input channels = two 64-wide blocks
+          a_lbo[m] = (uint32_t)p.x_stride;
+        } else if (m == 0) {
+          a_off[m] = 0;                                          // taps 0 and 1 of 64 input channels side by side
+          a_lbo[m] = (uint32_t)(row_step * 128);                 // (1x1: row_step = 0, rows 64..127 duplicate, ignored)
+        } else {
+          a_off[m] = (uint32_t)(2 * row_step * 128) >> 4;        // tap 2; rows 64..127 of the tile are ignored
+          a_lbo[m] = 0;
         }
-        umma_commit(empty + st);
+        a_lbo[m] = ((a_lbo[m] >> 4) & 0x3FFFu) << 16;
       }
-      umma_commit(acc_full);
+      const uint32_t b_lbo = ((16384u >> 4) & 0x3FFFu) << 16;
+      uint32_t st = 0, ph = 0;
+      for (int j = 0; j < nchunks; ++j) {
+        mbar_wait(full + st, ph);
+        tc_fence_after();
+        const uint32_t x_lo = desc_lo(x_base) + st * stage16;
+        const uint32_t d_lo = (x_lo + ((uint32_t)x_tile_bytes >> 4)) | b_lbo;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          if (m < m_tiles_cta) {
+            const uint32_t a_lo = (x_lo + a_off[m]) | a_lbo[m];
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              if (elect_one())
+                umma_ss_lo(tmem_base + m * NB, a_lo + kk * 128, d_lo + kk * 128, hi, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        if (elect_one()) umma_commit(empty + st);
+        if (++st == (uint32_t)S) { st = 0; ph ^= 1; }
+      }
+      if (elect_one()) umma_commit(acc_full);
     }
   } else {
     const int quad = warp & 3;

@@ -212,6 +212,36 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Lean issue path for hot MMA loops: both shared-memory descriptors share their high word (SBO, version, swizzle;
+// LBO = 0 for K-major operands, or a loop-invariant LBO for MN-major ones) and differ only in the 14-bit start-address
+// field of the low word, so a loop carries two 32-bit values and adds small immediates -- a single thread issues
+// every MMA of the CTA, and at ~26 instructions per MMA that thread, not the tensor pipe, was the limit for N <= 128.
+MU_DEVICE uint32_t desc_lo(uint32_t smem_addr) { return (smem_addr & 0x3FFFFu) >> 4; }
+MU_DEVICE uint32_t desc_lo_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi_sbo(uint32_t sbo_bytes) {     // high word: SBO | version 1 | SWIZZLE_128B
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (kSwizzle128B << 29);
+}
+MU_DEVICE void umma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+MU_DEVICE void umma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem];  one thread issues for the CTA.
 MU_DEVICE void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
