@@ -84,7 +84,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   uint64_t* p_free = sdp_free + 1;          // 1: the dV MMAs have consumed P^T
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int b = blockIdx.y, k0 = blockIdx.x * kBK, half = blockIdx.z;
   const int nk = n_keep[b];
   if (k0 >= nk) return;                      // whole CTA: nothing kept in this tile
@@ -144,48 +144,52 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane_id() == 0) {
+    // ===================================================== MMA issuer: the whole warp walks the loop, one elected lane
+    // issues; every descriptor is a loop-invariant 32-bit low word plus an immediate (see umma_ss_lo): the single
+    // issuing thread feeds 32 MMAs per query tile
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(kBK, BM, 0, 0);     // S^T, dP^T
       constexpr uint32_t idesc_acc = make_idesc_bf16(kBK, DH, 0, 1);   // dV, dK: A K-major, B MN-major
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, DQT ? BM : DH, 1, 1);
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
-      const uint32_t ds_base = smem_u32(sDS);
+      constexpr uint32_t hi = desc_hi_sbo(1024);
+      const uint32_t k_lo = desc_lo(smem_u32(sK)), v_lo = desc_lo(smem_u32(sV));
+      const uint32_t q_lo0 = desc_lo(smem_u32(sQ)), do_lo0 = desc_lo(smem_u32(sDO)), ds_lo0 = desc_lo(smem_u32(sDS));
+      constexpr uint32_t kLboQ = (((uint32_t)(BM * 128) >> 4) & 0x3FFFu) << 16;     // MN-major tiles of BM rows
+      constexpr uint32_t kLboK = (((uint32_t)(kBK * 128) >> 4) & 0x3FFFu) << 16;    // MN-major tiles of 128 rows
       auto issue_s_dp = [&](int i) {
         const int st = i % STAGES;
         mbar_wait(qdo_full + st, (i / STAGES) & 1);
         tc_fence_after();
-        const uint32_t qa = q_addr + st * Cfg::kQBytes, da = do_addr + st * Cfg::kQBytes;
+        const uint32_t qa = q_lo0 + st * (Cfg::kQBytes >> 4), da = do_lo0 + st * (Cfg::kQBytes >> 4);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t offa = (kk >> 2) * (kBK * 128) + (kk & 3) * 32, offb = (kk >> 2) * (BM * 128) + (kk & 3) * 32;
-          umma_ss(tmem_base + Cfg::kTmS, make_smem_desc(k_addr + offa, 0, 1024), make_smem_desc(qa + offb, 0, 1024),
-                  idesc_s, kk > 0);
+          const uint32_t offa = ((kk >> 2) * (kBK * 128) + (kk & 3) * 32) >> 4, offb = ((kk >> 2) * (BM * 128) + (kk & 3) * 32) >> 4;
+          if (elect_one()) umma_ss_lo(tmem_base + Cfg::kTmS, k_lo + offa, qa + offb, hi, idesc_s, kk > 0 ? 1u : 0u);
         }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t offa = (kk >> 2) * (kBK * 128) + (kk & 3) * 32, offb = (kk >> 2) * (BM * 128) + (kk & 3) * 32;
-          umma_ss(tmem_base + Cfg::kTmDP, make_smem_desc(v_addr + offa, 0, 1024), make_smem_desc(da + offb, 0, 1024),
-                  idesc_s, kk > 0);
+          const uint32_t offa = ((kk >> 2) * (kBK * 128) + (kk & 3) * 32) >> 4, offb = ((kk >> 2) * (BM * 128) + (kk & 3) * 32) >> 4;
+          if (elect_one()) umma_ss_lo(tmem_base + Cfg::kTmDP, v_lo + offa, da + offb, hi, idesc_s, kk > 0 ? 1u : 0u);
         }
-        umma_commit(s_full);
+        if (elect_one()) umma_commit(s_full);
       };
       auto issue_acc = [&](int i) {
         const int st = i % STAGES;
-        const uint32_t ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
-        const uint32_t qa = q_addr + st * Cfg::kQBytes + half * 2 * (BM * 128);
-        const uint32_t da = do_addr + st * Cfg::kQBytes + half * 2 * (BM * 128);
+        const uint32_t ds_lo = ds_lo0 + (i % PB) * (Cfg::kPBytes >> 4);
+        const uint32_t qa = q_lo0 + st * (Cfg::kQBytes >> 4) + ((half * 2 * (BM * 128)) >> 4);
+        const uint32_t da = do_lo0 + st * (Cfg::kQBytes >> 4) + ((half * 2 * (BM * 128)) >> 4);
+        const uint32_t acc = i > 0 ? 1u : 0u;
 #pragma unroll
-        for (int kk = 0; kk < BM / 16; ++kk) {   // dV += P^T dO_i, A = P^T from TMEM (16 queries = 8 columns)
-          const uint64_t bd = make_smem_desc(da + kk * 2048, BM * 128, 1024);
-          umma_ts(tmem_base + Cfg::kTmDV, tmem_base + Cfg::kTmP + kk * 8, bd, idesc_acc, (i > 0) || (kk > 0));
-        }
-        umma_commit(p_free);
+        for (int kk = 0; kk < BM / 16; ++kk)     // dV += P^T dO_i, A = P^T from TMEM (16 queries = 8 columns)
+          if (elect_one())
+            umma_ts_lo(tmem_base + Cfg::kTmDV, tmem_base + Cfg::kTmP + kk * 8, (da + kk * 128) | kLboQ, hi, idesc_acc,
+                       kk > 0 ? 1u : acc);
+        if (elect_one()) umma_commit(p_free);
 #pragma unroll
         for (int kk = 0; kk < BM / 16; ++kk) {   // dK += dS^T Q_i
-          const uint64_t a = make_smem_desc(ds_addr + (kk >> 2) * (kBK * 128) + (kk & 3) * 32, 0, 1024);
-          const uint64_t bd = make_smem_desc(qa + kk * 2048, BM * 128, 1024);
-          umma_ss(tmem_base + Cfg::kTmDK, a, bd, idesc_acc, (i > 0) || (kk > 0));
+          const uint32_t offa = ((kk >> 2) * (kBK * 128) + (kk & 3) * 32) >> 4;
+          if (elect_one())
+            umma_ss_lo(tmem_base + Cfg::kTmDK, ds_lo + offa, (qa + kk * 128) | kLboQ, hi, idesc_acc, kk > 0 ? 1u : acc);
         }
         if (i > 0) {
           mbar_wait(dq_free, (i - 1) & 1);
@@ -193,19 +197,21 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
 #pragma unroll
         for (int kk = 0; kk < kBK / 16; ++kk) {  // dQ tile: contraction over the 128 keys of this CTA
-          uint64_t a, bd;
+          uint32_t a, bd;
           if (DQT) {  // dQ^T [channels x queries] = K_j^T (MN-major A) . dS (MN-major B)
-            a = make_smem_desc(k_addr + half * 2 * (kBK * 128) + kk * 2048, kBK * 128, 1024);
-            bd = make_smem_desc(ds_addr + kk * 2048, kBK * 128, 1024);
+            a = (k_lo + ((half * 2 * (kBK * 128)) >> 4) + kk * 128) | kLboK;
+            bd = (ds_lo + kk * 128) | kLboK;
           } else {    // dQ [queries x channels] = dS (MN-major A over queries) . K_j (MN-major B)
-            a = make_smem_desc(ds_addr + kk * 2048, kBK * 128, 1024);
-            bd = make_smem_desc(k_addr + kk * 2048, kBK * 128, 1024);
+            a = (ds_lo + kk * 128) | kLboK;
+            bd = (k_lo + kk * 128) | kLboK;
           }
-          umma_ss(tmem_base + Cfg::kTmDQ, a, bd, idesc_dq, kk > 0);
+          if (elect_one()) umma_ss_lo(tmem_base + Cfg::kTmDQ, a, bd, hi, idesc_dq, kk > 0 ? 1u : 0u);
         }
-        umma_commit(qdo_empty + st);
-        umma_commit(pds_free + (i % PB));
-        umma_commit(dq_full);
+        if (elect_one()) {
+          umma_commit(qdo_empty + st);
+          umma_commit(pds_free + (i % PB));
+          umma_commit(dq_full);
+        }
       };
       mbar_wait(kv_full, 0);
       issue_s_dp(0);

@@ -66,7 +66,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   uint64_t* o_done = p_full + 1;            // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int b = blockIdx.y, q0 = blockIdx.x * kBM;
   const int nk = n_keep[b];
   const int T = (nk + BN - 1) / BN;  // key tiles
@@ -119,24 +119,29 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane_id() == 0 && T > 0) {
+    // ===================================================== MMA issuer: the whole warp walks the loop, one elected
+    // lane issues; descriptors are 32-bit low words + immediates (see umma_ss_lo)
+    if (T > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(kBM, BN, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(kBM, D, 0, 1);
-      const uint32_t q_addr = smem_u32(sQ), kv_addr = smem_u32(sKV);
+      constexpr uint32_t hi = desc_hi_sbo(1024);
+      const uint32_t q_lo = desc_lo(smem_u32(sQ)), kv_lo = desc_lo(smem_u32(sKV));
       auto issue_s = [&](int j) {
         const int t = 2 * j, slot = t % SLOTS, buf = j % SBUFS;
         mbar_wait(kv_full + slot, (t / SLOTS) & 1);
         tc_fence_after();
-        const uint32_t k_addr = kv_addr + slot * Cfg::kKVBytes;
+        const uint32_t k_lo = kv_lo + slot * (Cfg::kKVBytes >> 4);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint64_t da = make_smem_desc(q_addr + (kk >> 2) * (kBM * 128) + (kk & 3) * 32, 0, 1024);
-          const uint64_t db = make_smem_desc(k_addr + (kk >> 2) * (BN * 128) + (kk & 3) * 32, 0, 1024);
-          umma_ss(tmem_base + Cfg::kTmemS + buf * BN, da, db, idesc_s, kk > 0);
+          const uint32_t offa = ((kk >> 2) * (kBM * 128) + (kk & 3) * 32) >> 4;
+          const uint32_t offb = ((kk >> 2) * (BN * 128) + (kk & 3) * 32) >> 4;
+          if (elect_one())
+            umma_ss_lo(tmem_base + Cfg::kTmemS + buf * BN, q_lo + offa, k_lo + offb, hi, idesc_s, kk > 0 ? 1u : 0u);
         }
-        umma_commit(kv_empty + slot);
-        umma_commit(s_full + buf);
+        if (elect_one()) {
+          umma_commit(kv_empty + slot);
+          umma_commit(s_full + buf);
+        }
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -150,14 +155,16 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         mbar_wait(kv_full + slot, (t / SLOTS) & 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const uint32_t v_addr = kv_addr + slot * Cfg::kKVBytes;
+        const uint32_t v_lo = desc_lo_lbo(smem_u32(sKV) + slot * Cfg::kKVBytes, BN * 128);
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk) {   // A = P straight from TMEM (16 keys = 8 columns per step)
-          const uint64_t db = make_smem_desc(v_addr + kk * 2048, BN * 128, 1024);
-          umma_ts(tmem_base + Cfg::kTmemO, tmem_base + Cfg::kTmemP + kk * 8, db, idesc_o, (j > 0) || (kk > 0));
+        for (int kk = 0; kk < BN / 16; ++kk)     // A = P straight from TMEM (16 keys = 8 columns per step)
+          if (elect_one())
+            umma_ts_lo(tmem_base + Cfg::kTmemO, tmem_base + Cfg::kTmemP + kk * 8, v_lo + kk * 128, hi, idesc_o,
+                       (j > 0 || kk > 0) ? 1u : 0u);
+        if (elect_one()) {
+          umma_commit(kv_empty + slot);
+          umma_commit(o_done);
         }
-        umma_commit(kv_empty + slot);
-        umma_commit(o_done);
       }
     }
   }
