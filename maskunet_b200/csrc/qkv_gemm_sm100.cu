@@ -47,7 +47,7 @@ qkv_project_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   uint64_t* acc_full = bars + 5;    // 2
   uint64_t* acc_free = bars + 7;    // 2 (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int t0 = blockIdx.x * 128;
 
   if (threadIdx.x == 0) {
@@ -82,23 +82,26 @@ qkv_project_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       }
     }
   } else if (warp == 1) {
-    if (lane_id() == 0) {
+    {   // whole warp walks the loop, one elected lane issues; 32-bit descriptor words (see umma_ss_lo)
       constexpr uint32_t idesc = make_idesc_bf16(128, NC, 0, 0);
-      const uint32_t x_addr = smem_u32(sX), w_addr = smem_u32(sW);
+      constexpr uint32_t hi = desc_hi_sbo(1024);
+      const uint32_t x_lo = desc_lo(smem_u32(sX)), w_lo0 = desc_lo(smem_u32(sW));
       mbar_wait(x_full, 0);
       for (int j = 0; j < Cfg::kChunks; ++j) {
         const int st = j & 1, use = j >> 1;
         mbar_wait(w_full + st, use & 1);
         if (use > 0) mbar_wait(acc_free + st, (use - 1) & 1);
         tc_fence_after();
+        const uint32_t w_lo = w_lo0 + st * (Cfg::kWBytes >> 4);
 #pragma unroll
-        for (int kk = 0; kk < C / 16; ++kk) {
-          const uint64_t da = make_smem_desc(x_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
-          const uint64_t db = make_smem_desc(w_addr + st * Cfg::kWBytes + (kk >> 2) * (NC * 128) + (kk & 3) * 32, 0, 1024);
-          umma_ss(tmem_base + st * NC, da, db, idesc, kk > 0);
+        for (int kk = 0; kk < C / 16; ++kk)
+          if (elect_one())
+            umma_ss_lo(tmem_base + st * NC, x_lo + (((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                       w_lo + (((kk >> 2) * (NC * 128) + (kk & 3) * 32) >> 4), hi, idesc, kk > 0 ? 1u : 0u);
+        if (elect_one()) {
+          umma_commit(w_empty + st);
+          umma_commit(acc_full + st);
         }
-        umma_commit(w_empty + st);
-        umma_commit(acc_full + st);
       }
     }
   } else {
@@ -180,7 +183,7 @@ qkv_dx_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
   uint64_t* empty = bars + S;     // S
   uint64_t* acc_full = bars + 2 * S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int t0 = blockIdx.x * 128;
 
   if (threadIdx.x == 0) {
@@ -215,22 +218,22 @@ qkv_dx_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane_id() == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, C, 0, 1);   // A K-major, B (= W rows) MN-major
+      constexpr uint32_t hi = desc_hi_sbo(1024);
+      constexpr uint32_t kLboW = ((8192u >> 4) & 0x3FFFu) << 16;
+      const uint32_t base_lo = desc_lo(smem_u32(smem));
       for (int j = 0; j < Cfg::kKChunks; ++j) {
         const int st = j % S;
         mbar_wait(full + st, (j / S) & 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + st * Cfg::kStageBytes), w_addr = a_addr + Cfg::kABytes;
+        const uint32_t a_lo = base_lo + st * (Cfg::kStageBytes >> 4), w_lo = (a_lo + (Cfg::kABytes >> 4)) | kLboW;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t da = make_smem_desc(a_addr + kk * 32, 0, 1024);
-          const uint64_t db = make_smem_desc(w_addr + kk * 2048, 8192, 1024);
-          umma_ss(tmem_base, da, db, idesc, (j > 0) || (kk > 0));
-        }
-        umma_commit(empty + st);
+        for (int kk = 0; kk < 4; ++kk)
+          if (elect_one()) umma_ss_lo(tmem_base, a_lo + kk * 2, w_lo + kk * 128, hi, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+        if (elect_one()) umma_commit(empty + st);
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(acc_full);
     }
   } else {
     const int quad = warp & 3;
@@ -297,7 +300,7 @@ qkv_dw_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
   uint64_t* empty = bars + S;
   uint64_t* acc_full = bars + 2 * S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int m = blockIdx.y;
   const int total_chunks = (Mtot + 127) / 128;
   const int c_begin = blockIdx.x * chunks_per_cta;
@@ -348,22 +351,23 @@ qkv_dw_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane_id() == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, C, 1, 1);   // both operands MN-major (contraction over tokens)
+      constexpr uint32_t hi = desc_hi_sbo(1024);
+      constexpr uint32_t kLbo = ((16384u >> 4) & 0x3FFFu) << 16;
+      const uint32_t base_lo = desc_lo(smem_u32(smem));
       for (int j = 0; j < nchunks; ++j) {
         const int st = j % S;
         mbar_wait(full + st, (j / S) & 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + st * Cfg::kStageBytes), x_addr = a_addr + Cfg::kABytes;
+        const uint32_t a_lo = (base_lo + st * (Cfg::kStageBytes >> 4)) | kLbo;
+        const uint32_t x_lo = (base_lo + st * (Cfg::kStageBytes >> 4) + (Cfg::kABytes >> 4)) | kLbo;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t da = make_smem_desc(a_addr + kk * 2048, 16384, 1024);
-          const uint64_t db = make_smem_desc(x_addr + kk * 2048, 16384, 1024);
-          umma_ss(tmem_base, da, db, idesc, (j > 0) || (kk > 0));
-        }
-        umma_commit(empty + st);
+        for (int kk = 0; kk < 8; ++kk)
+          if (elect_one()) umma_ss_lo(tmem_base, a_lo + kk * 128, x_lo + kk * 128, hi, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+        if (elect_one()) umma_commit(empty + st);
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(acc_full);
     }
   } else {
     const int quad = warp & 3;
