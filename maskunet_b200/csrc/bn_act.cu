@@ -41,13 +41,41 @@ __device__ __forceinline__ float gelu_grad_f(float z) {
   gelu_parts(z, cdf, e);
   return fmaf(z * 0.3989422804014327f, e, cdf);
 }
-template <int ACT> __device__ __forceinline__ float act_f(float z) {
-  if (ACT == ACT_GELU) return gelu_f(z);
+// bf16 activations: Phi(z) = sigmoid(z (a + b z^2 + c z^4)) fitted to the normal CDF on [-8, 8] (clamped outside):
+// |Phi error| <= 1.9e-5, |gelu error| <= 5.5e-5, |gelu' error| <= 1.4e-4 -- 1/70 .. 1/30 of the bf16 rounding of the
+// stored result -- at 10 (forward) / 15 (gradient) instructions instead of ~20 / ~24 with the erf form above, which
+// kept these HBM kernels at the instruction limit (3.7 TB/s against 5.6 TB/s without GELU).  fp32 activations (the
+// validation configuration, tolerance 1e-4) keep the erf form.
+constexpr float kGa = 1.59543567f, kGb = 7.35965107e-02f, kGc = -6.31613752e-04f, kNegLog2e = -1.4426950408889634f;
+__device__ __forceinline__ float fast_cdf(float z, float& z2) {
+  const float zc = fminf(fmaxf(z, -8.f), 8.f);
+  z2 = zc * zc;
+  const float t = zc * fmaf(z2, fmaf(z2, kGc * kNegLog2e, kGb * kNegLog2e), kGa * kNegLog2e);   // -log2(e) t(z)
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
+__device__ __forceinline__ float gelu_fast(float z) {
+  float z2;
+  return z * fast_cdf(z, z2);
+}
+__device__ __forceinline__ float gelu_grad_fast(float z) {
+  float z2;
+  const float cdf = fast_cdf(z, z2);
+  const float tp = fmaf(z2, fmaf(z2, 5.f * kGc, 3.f * kGb), kGa);      // t'(z); cdf (1 - cdf) = 0 in the clamped range
+  return fmaf(z * cdf * (1.f - cdf), tp, cdf);
+}
+template <typename T> struct FastAct { static constexpr bool value = false; };
+template <> struct FastAct<__nv_bfloat16> { static constexpr bool value = true; };
+
+template <int ACT, bool FAST = false> __device__ __forceinline__ float act_f(float z) {
+  if (ACT == ACT_GELU) return FAST ? gelu_fast(z) : gelu_f(z);
   if (ACT == ACT_RELU) return fmaxf(z, 0.f);
   return z;
 }
-template <int ACT> __device__ __forceinline__ float act_grad_f(float z) {
-  if (ACT == ACT_GELU) return gelu_grad_f(z);
+template <int ACT, bool FAST = false> __device__ __forceinline__ float act_grad_f(float z) {
+  if (ACT == ACT_GELU) return FAST ? gelu_grad_fast(z) : gelu_grad_f(z);
   if (ACT == ACT_RELU) return z > 0.f ? 1.f : 0.f;
   return 1.f;
 }
@@ -192,7 +220,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
     for (int e = 0; e < VEC; ++e) {
       float z = fmaf(av[e], v[e], bv[e]);
       if (RES) z += rv[e];
-      v[e] = act_f<ACT>(z);
+      v[e] = act_f<ACT, FastAct<T>::value>(z);
     }
     Vec<T, VEC>::store(y + off, v);
   }
@@ -226,7 +254,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
         if (ACT != ACT_NONE) {
           float z = fmaf(av[e], v[e], bv[e]);
           if (RES) z += rv[e];
-          dz *= act_grad_f<ACT>(z);
+          dz *= act_grad_f<ACT, FastAct<T>::value>(z);
         }
         s1[e] += dz;
         s2[e] = fmaf(dz, (v[e] - mv[e]) * rsv[e], s2[e]);
@@ -266,7 +294,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
       if (ACT != ACT_NONE) {
         float z = fmaf(av[e], v[e], bv[e]);
         if (RES) z += rv[e];
-        dz *= act_grad_f<ACT>(z);
+        dz *= act_grad_f<ACT, FastAct<T>::value>(z);
       }
       g[e] = dz;
       const float xhat = (v[e] - mv[e]) * rsv[e];
