@@ -16,6 +16,10 @@ namespace mu {
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 constexpr int kBnThreads = 256;
+// 8 CTAs of 256 threads = full occupancy (32 registers per thread).  The streaming kernels track occupancy: the forward
+// GELU apply at 40 registers (6 CTAs / SM) ran at 0.76 of the bandwidth of the 32-register variants, and capping it
+// gives +19 % (4.27 -> 5.07 TB/s); the backward kernels need their registers (capped, they fell from 3.6 to 2.5 TB/s).
+constexpr int kBnMinBlocks = 8;
 
 // Exact-erf GELU (nn.GELU() default) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32
 // round-off level): 2 MUFU (ex2, rcp) + ~12 FMA instead of libdevice erff's branchy ~25 instructions, which made
@@ -200,7 +204,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* 
 
 // ------------------------------------------------------------------ forward: apply
 template <typename T, int VEC, int ACT, bool RES>
-__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ r,
+__global__ void __launch_bounds__(kBnThreads, (ACT == ACT_GELU && VEC == 8 && !RES) ? kBnMinBlocks : 1) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ r,
                                                               const float* __restrict__ a, const float* __restrict__ b,
                                                               T* __restrict__ y, long M, int C, int Cper) {
   const RowMap m(C, VEC);
