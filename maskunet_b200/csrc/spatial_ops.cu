@@ -97,18 +97,34 @@ __device__ __forceinline__ void src_index(int dst, float ratio, int in_size, int
   l0 = 1.f - l1;
 }
 
-template <typename T>
+// P2: channel-group count, width and height are powers of two (every U-Net shape) -- the index split is shifts and
+// masks; the generic path's 64-bit divisions cost several hundred instructions per 16-byte vector and made these
+// kernels instruction-bound (2.4 TB/s).
+__device__ __forceinline__ int ilog2_u(unsigned v) { return 31 - __clz(v); }
+
+template <typename T, bool P2>
 __global__ void __launch_bounds__(256) upcat_fwd_kernel(const T* __restrict__ skip, const T* __restrict__ x,
                                                         T* __restrict__ out, int B, int H, int W, int Cs, int Cx) {
   const int H2 = 2 * H, W2 = 2 * W, Ct = Cs + Cx, G = Ct / 8, Gs = Cs / 8;
   const float rh = H2 > 1 ? (float)(H - 1) / (H2 - 1) : 0.f, rw = W2 > 1 ? (float)(W - 1) / (W2 - 1) : 0.f;
   const long total = (long)B * H2 * W2 * G;
+  const int lg = ilog2_u(G), lw = ilog2_u(W2), lh = ilog2_u(H2);
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % G);
-    long p = idx / G;
-    const int w2 = (int)(p % W2);
-    p /= W2;
-    const int h2 = (int)(p % H2), b = (int)(p / H2);
+    int g, w2, h2, b;
+    if (P2) {
+      const unsigned u = (unsigned)idx;      // total < 2^32 is checked by the launcher
+      g = u & (G - 1);
+      w2 = (u >> lg) & (W2 - 1);
+      h2 = (u >> (lg + lw)) & (H2 - 1);
+      b = u >> (lg + lw + lh);
+    } else {
+      g = (int)(idx % G);
+      long p = idx / G;
+      w2 = (int)(p % W2);
+      p /= W2;
+      h2 = (int)(p % H2);
+      b = (int)(p / H2);
+    }
     float o[8];
     if (g < Gs) {
       V8<T>::load(skip + (((long)b * H2 + h2) * W2 + w2) * Cs + g * 8, o);
@@ -131,28 +147,46 @@ __global__ void __launch_bounds__(256) upcat_fwd_kernel(const T* __restrict__ sk
 }
 
 // backward: dskip = dout[..., :Cs];  dx[b, h, w, :] = sum over the <= 4x4 output pixels whose stencil touches (h, w)
-template <typename T>
+template <typename T, bool P2>
 __global__ void __launch_bounds__(256) upcat_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dskip,
                                                         T* __restrict__ dx, int B, int H, int W, int Cs, int Cx) {
   const int H2 = 2 * H, W2 = 2 * W, Ct = Cs + Cx, Gs = Cs / 8, Gx = Cx / 8;
   const float rh = H2 > 1 ? (float)(H - 1) / (H2 - 1) : 0.f, rw = W2 > 1 ? (float)(W - 1) / (W2 - 1) : 0.f;
   const long n_skip = (long)B * H2 * W2 * Gs, n_x = (long)B * H * W * Gx;
+  const int lgs = ilog2_u(Gs), lgx = ilog2_u(Gx), lw = ilog2_u(W), lh = ilog2_u(H);
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n_skip + n_x;
        idx += (long)gridDim.x * blockDim.x) {
     float v[8];
     if (idx < n_skip) {
-      const int g = (int)(idx % Gs);
-      const long pix = idx / Gs;
+      int g;
+      long pix;
+      if (P2) {
+        g = (unsigned)idx & (Gs - 1);
+        pix = (unsigned)idx >> lgs;
+      } else {
+        g = (int)(idx % Gs);
+        pix = idx / Gs;
+      }
       V8<T>::load(dout + pix * Ct + g * 8, v);
       V8<T>::store(dskip + pix * Cs + g * 8, v);
       continue;
     }
-    long p = idx - n_skip;
-    const int g = (int)(p % Gx);
-    p /= Gx;
-    const int w = (int)(p % W);
-    p /= W;
-    const int h = (int)(p % H), b = (int)(p / H);
+    int g, w, h, b;
+    if (P2) {
+      const unsigned u = (unsigned)(idx - n_skip);
+      g = u & (Gx - 1);
+      w = (u >> lgx) & (W - 1);
+      h = (u >> (lgx + lw)) & (H - 1);
+      b = u >> (lgx + lw + lh);
+    } else {
+      long p = idx - n_skip;
+      g = (int)(p % Gx);
+      p /= Gx;
+      w = (int)(p % W);
+      p /= W;
+      h = (int)(p % H);
+      b = (int)(p / H);
+    }
     float acc[8] = {};
     // candidate output rows: those with source row h (weight h0l) or h - 1 (weight h1l, when its hp == 1)
     const int h2_lo = max(0, 2 * h - 2), h2_hi = min(H2 - 1, 2 * h + 2);
@@ -387,47 +421,63 @@ __global__ void __launch_bounds__(256) ce_fused_vec_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ valid_count, long ignore_index,
                                                            __nv_bfloat16* __restrict__ dlogits,
                                                            float* __restrict__ loss_sum, long M, int C, int pitch) {
+  constexpr int U = 4;                       // independent rows per warp trip: four vector loads in flight per lane
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const float inv = 1.f / fmaxf(valid_count[0], 1.f);
   const bool in_row = lane * 8 < pitch;
   float local = 0.f;
-  for (long row = (long)blockIdx.x * 8 + wib; row < M; row += (long)gridDim.x * 8) {
-    const long lab = labels[row];
-    uint4 u = make_uint4(0u, 0u, 0u, 0u);
-    if (in_row && lab != ignore_index) u = *reinterpret_cast<const uint4*>(logits + row * pitch + lane * 8);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    float v[8];
-    float mx = -INFINITY;
+  const long stride = (long)gridDim.x * 8;
+  for (long row0 = (long)blockIdx.x * 8 + wib; row0 < M; row0 += stride * U) {
+    uint4 u[U];
+    long lab[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float f = __uint_as_float((e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16));
-      v[e] = (lane * 8 + e < C) ? f : -INFINITY;
-      mx = fmaxf(mx, v[e]);
+    for (int k = 0; k < U; ++k) {
+      const long row = row0 + k * stride;
+      u[k] = make_uint4(0u, 0u, 0u, 0u);
+      lab[k] = ignore_index;
+      if (row < M) {
+        lab[k] = labels[row];
+        if (in_row && lab[k] != ignore_index) u[k] = *reinterpret_cast<const uint4*>(logits + row * pitch + lane * 8);
+      }
     }
-    mx = warp_max(mx);
-    float se = 0.f;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      v[e] = __expf(v[e] - mx);
-      se += v[e];
-    }
-    se = warp_sum(se);
-    const float inv_se = 1.f / se;
-    float picked = 0.f, o[8];
+    for (int k = 0; k < U; ++k) {
+      const long row = row0 + k * stride;          // warp-uniform
+      if (row >= M) continue;
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      float v[8];
+      float mx = -INFINITY;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = lane * 8 + e;
-      const float p = v[e] * inv_se;                       // 0 for the pad classes
-      if (c == lab) picked = p;
-      o[e] = (lab == ignore_index || c >= C) ? 0.f : (p - (c == lab ? 1.f : 0.f)) * inv;
+      for (int e = 0; e < 8; ++e) {
+        const float f = __uint_as_float((e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16));
+        v[e] = (lane * 8 + e < C) ? f : -INFINITY;
+        mx = fmaxf(mx, v[e]);
+      }
+      mx = warp_max(mx);
+      float se = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[e] = __expf(v[e] - mx);
+        se += v[e];
+      }
+      se = warp_sum(se);
+      const float inv_se = 1.f / se;
+      float picked = 0.f, o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = lane * 8 + e;
+        const float p = v[e] * inv_se;                       // 0 for the pad classes
+        if (c == lab[k]) picked = p;
+        o[e] = (lab[k] == ignore_index || c >= C) ? 0.f : (p - (c == lab[k] ? 1.f : 0.f)) * inv;
+      }
+      if (in_row) {
+        uint4 r;
+        r.x = pack2(o[0], o[1]); r.y = pack2(o[2], o[3]); r.z = pack2(o[4], o[5]); r.w = pack2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(dlogits + row * pitch + lane * 8) = r;
+      }
+      picked = warp_sum(picked);
+      if (lane == 0 && lab[k] != ignore_index) local += -__logf(fmaxf(picked, 1e-38f));
     }
-    if (in_row) {
-      uint4 r;
-      r.x = pack2(o[0], o[1]); r.y = pack2(o[2], o[3]); r.z = pack2(o[4], o[5]); r.w = pack2(o[6], o[7]);
-      *reinterpret_cast<uint4*>(dlogits + row * pitch + lane * 8) = r;
-    }
-    picked = warp_sum(picked);
-    if (lane == 0 && lab != ignore_index) local += -__logf(fmaxf(picked, 1e-38f));
   }
   __shared__ float red[8];
   if (lane == 0) red[wib] = local;
@@ -556,10 +606,19 @@ int launch_upcat_fwd(const void* skip, const void* x, void* out, int B, int H, i
     set_error("upsample_concat: channel counts must be multiples of 8 (Cs=%d Cx=%d)", Cs, Cx);
     return MU_ERR_BAD_SHAPE;
   }
-  const int grid = grid_for((long)B * 4 * H * W * ((Cs + Cx) / 8));
-  MU_T(dtype, (upcat_fwd_kernel<float><<<grid, 256, 0, s>>>((const float*)skip, (const float*)x, (float*)out, B, H, W, Cs, Cx)),
-       (upcat_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)skip, (const __nv_bfloat16*)x,
-                                                             (__nv_bfloat16*)out, B, H, W, Cs, Cx)));
+  const long total = (long)B * 4 * H * W * ((Cs + Cx) / 8);
+  const int grid = grid_for(total);
+  auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  const bool p2 = pow2((Cs + Cx) / 8) && pow2(Cs / 8) && pow2(Cx / 8) && pow2(H) && pow2(W) && total < (1L << 32);
+  if (p2) {
+    MU_T(dtype, (upcat_fwd_kernel<float, true><<<grid, 256, 0, s>>>((const float*)skip, (const float*)x, (float*)out, B, H, W, Cs, Cx)),
+         (upcat_fwd_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)skip, (const __nv_bfloat16*)x,
+                                                                     (__nv_bfloat16*)out, B, H, W, Cs, Cx)));
+  } else {
+    MU_T(dtype, (upcat_fwd_kernel<float, false><<<grid, 256, 0, s>>>((const float*)skip, (const float*)x, (float*)out, B, H, W, Cs, Cx)),
+         (upcat_fwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)skip, (const __nv_bfloat16*)x,
+                                                                      (__nv_bfloat16*)out, B, H, W, Cs, Cx)));
+  }
   return check_launch("upsample_concat_fwd");
 }
 
@@ -569,10 +628,19 @@ int launch_upcat_bwd(const void* dout, void* dskip, void* dx, int B, int H, int 
     set_error("upsample_concat: channel counts must be multiples of 8 (Cs=%d Cx=%d)", Cs, Cx);
     return MU_ERR_BAD_SHAPE;
   }
-  const int grid = grid_for((long)B * 4 * H * W * (Cs / 8) + (long)B * H * W * (Cx / 8));
-  MU_T(dtype, (upcat_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)dout, (float*)dskip, (float*)dx, B, H, W, Cs, Cx)),
-       (upcat_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dskip,
-                                                             (__nv_bfloat16*)dx, B, H, W, Cs, Cx)));
+  const long total = (long)B * 4 * H * W * (Cs / 8) + (long)B * H * W * (Cx / 8);
+  const int grid = grid_for(total);
+  auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  const bool p2 = pow2(Cs / 8) && pow2(Cx / 8) && pow2(H) && pow2(W) && total < (1L << 32);
+  if (p2) {
+    MU_T(dtype, (upcat_bwd_kernel<float, true><<<grid, 256, 0, s>>>((const float*)dout, (float*)dskip, (float*)dx, B, H, W, Cs, Cx)),
+         (upcat_bwd_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dskip,
+                                                                     (__nv_bfloat16*)dx, B, H, W, Cs, Cx)));
+  } else {
+    MU_T(dtype, (upcat_bwd_kernel<float, false><<<grid, 256, 0, s>>>((const float*)dout, (float*)dskip, (float*)dx, B, H, W, Cs, Cx)),
+         (upcat_bwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dskip,
+                                                                      (__nv_bfloat16*)dx, B, H, W, Cs, Cx)));
+  }
   return check_launch("upsample_concat_bwd");
 }
 
