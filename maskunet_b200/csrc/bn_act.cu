@@ -309,6 +309,184 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
   }
 }
 
+// ------------------------------------------------------------------ backward, bulk-staged (bf16, 8-channel vectors)
+// The register-resident backward kernels above sit at 40-48 registers, i.e. 5-6 CTAs per SM with one 16-byte load per
+// stream in flight per thread: ~3.6 TB/s.  Here the input rows stream through a shared-memory ring filled by
+// cp.async.bulk (the TMA unit, 1-D: whole rows are contiguous), so the bytes in flight are the ring (3 stages x 2-3
+// streams x 16 KB per SM) and no longer depend on registers or occupancy; 512 threads read their 16-byte vectors from
+// shared memory (conflict-free: consecutive threads, consecutive vectors) and write dx / dr straight to HBM.
+constexpr int kBulkThreads = 512;
+constexpr int kBulkStages = 3;
+constexpr int kBulkChunkBytes = 16384;      // per stream per stage
+
+__device__ __forceinline__ uint32_t bn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(bn_smem_u32(dst)), "l"(src), "r"(bytes), "r"(bn_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bn_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bn_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+                 : "=r"(ok) : "r"(bn_smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void unpack8_bf16(const uint4 u, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = __uint_as_float(w[e] << 16);
+    v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+}
+
+// MODE 0: reduce (sums[c] += sum dz, sums[Cper + c] += sum dz * xhat);  MODE 1: apply (dx, dr)
+template <int ACT, bool RES, int MODE>
+__global__ void __launch_bounds__(kBulkThreads, 1)
+bn_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                   const __nv_bfloat16* __restrict__ r, const float* __restrict__ a, const float* __restrict__ b,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ sums,
+                   __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dr, long M, int C, int Cper,
+                   int rows_per_chunk) {
+  constexpr int NS = RES ? 3 : 2;                       // streams: dy, x [, r]
+  extern __shared__ __align__(128) uint8_t bulk_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(bulk_smem);                   // [kBulkStages]
+  float* red = reinterpret_cast<float*>(bulk_smem + 64);                    // [2][C] block partial sums (MODE 0)
+  uint8_t* ring = bulk_smem + 64 + ((2 * C * 4 + 127) / 128) * 128;
+  const int G = C / 8, RL = kBulkThreads / G;
+  const int g = threadIdx.x % G, rl = threadIdx.x / G;
+  const bool active = rl < RL;
+  const long n_chunks = (M + rows_per_chunk - 1) / rows_per_chunk;
+  const uint32_t row_bytes = (uint32_t)C * 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBulkStages; ++i) bar_init(full + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (MODE == 0) for (int i = threadIdx.x; i < 2 * C; i += kBulkThreads) red[i] = 0.f;
+  __syncthreads();
+
+  auto issue = [&](long chunk, int stage) {            // thread 0 only
+    const long r0 = chunk * rows_per_chunk;
+    const long nrows = min((long)rows_per_chunk, M - r0);
+    const uint32_t bytes = (uint32_t)nrows * row_bytes;
+    uint8_t* dst = ring + (size_t)stage * NS * kBulkChunkBytes;
+    bar_expect(full + stage, bytes * NS);
+    bulk_load(dst, dy + r0 * C, bytes, full + stage);
+    bulk_load(dst + kBulkChunkBytes, x + r0 * C, bytes, full + stage);
+    if (RES) bulk_load(dst + 2 * kBulkChunkBytes, r + r0 * C, bytes, full + stage);
+  };
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kBulkStages; ++i) {
+      const long chunk = blockIdx.x + (long)i * gridDim.x;
+      if (chunk < n_chunks) issue(chunk, i);
+    }
+
+  float av[8], bv[8], mv[8], rsv[8], c1[8], c2[8], s1[8], s2[8];
+  const float invM = 1.f / ((float)M * (float)(C / Cper));
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = active ? (g * 8 + e) % Cper : 0;
+    av[e] = a[c]; bv[e] = b[c]; mv[e] = mean[c]; rsv[e] = rstd[c];
+    s1[e] = s2[e] = 0.f;
+    if (MODE == 1) { c1[e] = sums[c] * invM; c2[e] = sums[Cper + c] * invM; }
+  }
+
+  int it = 0;
+  for (long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
+    const int stage = it % kBulkStages;
+    bar_wait(full + stage, (it / kBulkStages) & 1);
+    const long r0 = chunk * rows_per_chunk;
+    const int nrows = (int)min((long)rows_per_chunk, M - r0);
+    const uint8_t* src = ring + (size_t)stage * NS * kBulkChunkBytes;
+    if (active) {
+      for (int row = rl; row < nrows; row += RL) {
+        const size_t off = (size_t)row * row_bytes + g * 16;
+        float gy[8], v[8], rv[8];
+        unpack8_bf16(*reinterpret_cast<const uint4*>(src + off), gy);
+        unpack8_bf16(*reinterpret_cast<const uint4*>(src + kBulkChunkBytes + off), v);
+        if (RES) unpack8_bf16(*reinterpret_cast<const uint4*>(src + 2 * kBulkChunkBytes + off), rv);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float dz = gy[e];
+          if (ACT != ACT_NONE) {
+            float z = fmaf(av[e], v[e], bv[e]);
+            if (RES) z += rv[e];
+            dz *= act_grad_f<ACT, true>(z);
+          }
+          const float xhat = (v[e] - mv[e]) * rsv[e];
+          if (MODE == 0) {
+            s1[e] += dz;
+            s2[e] = fmaf(dz, xhat, s2[e]);
+          } else {
+            gy[e] = dz;
+            o[e] = av[e] * (dz - c1[e] - xhat * c2[e]);
+          }
+        }
+        if (MODE == 1) {
+          const size_t goff = (size_t)(r0 + row) * C + g * 8;
+          Vec<__nv_bfloat16, 8>::store(dx + goff, o);
+          if (RES) Vec<__nv_bfloat16, 8>::store(dr + goff, gy);
+        }
+      }
+    }
+    __syncthreads();                                   // everyone is done reading this stage
+    const long next = chunk + (long)kBulkStages * gridDim.x;
+    if (threadIdx.x == 0 && next < n_chunks) issue(next, stage);
+  }
+  if (MODE == 0) {
+    if (active) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(red + g * 8 + e, s1[e]);
+        atomicAdd(red + C + g * 8 + e, s2[e]);
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kBulkThreads) {
+      atomicAdd(sums + (c % Cper), red[c]);
+      atomicAdd(sums + Cper + (c % Cper), red[C + c]);
+    }
+  }
+}
+
+static bool bn_bulk_ok(long M, int C) {      // C = folded channel count (multiple of 8)
+  return C % 8 == 0 && C / 8 <= kBulkThreads && (long)C * 2 <= kBulkChunkBytes && M >= 4096;
+}
+
+template <int MODE>
+static int bn_bwd_bulk(const void* dy, const void* x, const void* r, const float* a, const float* b, const float* mean,
+                       const float* rstd, float* sums, void* dx, void* dr, long M, int C, int Cper, int act,
+                       cudaStream_t s) {
+  const int rows_per_chunk = kBulkChunkBytes / (C * 2);
+  const long n_chunks = (M + rows_per_chunk - 1) / rows_per_chunk;
+  const int grid = (int)(n_chunks < 148 ? n_chunks : 148);
+  const bool res = r != nullptr;
+  const size_t smem = 64 + ((2 * (size_t)C * 4 + 127) / 128) * 128 + (size_t)kBulkStages * (res ? 3 : 2) * kBulkChunkBytes;
+#define MU_BULK(ACTC, RESC)                                                                                          \
+  {                                                                                                                  \
+    auto kern = bn_bwd_bulk_kernel<ACTC, RESC, MODE>;                                                                \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                              \
+    kern<<<grid, kBulkThreads, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)r, \
+                                          a, b, mean, rstd, sums, (__nv_bfloat16*)dx, (__nv_bfloat16*)dr, M, C, Cper, \
+                                          rows_per_chunk);                                                           \
+  }
+  if (res) {
+    if (act == ACT_GELU) MU_BULK(ACT_GELU, true) else if (act == ACT_RELU) MU_BULK(ACT_RELU, true) else MU_BULK(ACT_NONE, true)
+  } else {
+    if (act == ACT_GELU) MU_BULK(ACT_GELU, false) else if (act == ACT_RELU) MU_BULK(ACT_RELU, false) else MU_BULK(ACT_NONE, false)
+  }
+#undef MU_BULK
+  return check_launch(MODE == 0 ? "bn_bwd_reduce_bulk" : "bn_bwd_apply_bulk");
+}
+
 // ------------------------------------------------------------------ dispatch
 static int pick_vec(int C) { return (C % 8 == 0) ? 8 : (C % 2 == 0 ? 2 : 1); }
 // Channel counts that are not a multiple of 8 (the 150-class head) would fall back to 2- or 4-byte accesses.  Instead
@@ -472,6 +650,16 @@ int launch_bn_backward(const void* dy, const void* x, const void* r, const float
     return MU_ERR_BAD_SHAPE;
   }
   cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), s);
+  if (dtype == MU_BF16) {
+    const int fold = pick_fold(M, C);
+    const long Mf = M / fold;
+    const int Cf = C * fold;
+    if (bn_bulk_ok(Mf, Cf)) {
+      int rc = bn_bwd_bulk<0>(dy, x, r, a, b, mean, rstd, sums, dx, dr, Mf, Cf, C, act, s);
+      if (rc) return rc;
+      return bn_bwd_bulk<1>(dy, x, r, a, b, mean, rstd, sums, dx, dr, Mf, Cf, C, act, s);
+    }
+  }
   return dtype == MU_F32 ? bn_bwd_t<float>(dy, x, r, a, b, mean, rstd, sums, dx, dr, M, C, act, s)
                          : bn_bwd_t<__nv_bfloat16>(dy, x, r, a, b, mean, rstd, sums, dx, dr, M, C, act, s);
 }
