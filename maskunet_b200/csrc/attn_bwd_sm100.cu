@@ -21,6 +21,9 @@ namespace mu {
 constexpr int kBK = 128;            // keys per CTA
 constexpr int kBwdThreads = 512;    // warps 0-3: TMA, MMA, 2 idle; 4-11: softmax (2 warpgroups); 12-15: dQ reduction
 constexpr float kLog2eB = 1.4426950408889634f;
+#ifndef MU_BWD_PROBE
+#define MU_BWD_PROBE 0      // 1 / 2: performance probes that skip work (wrong results), see DESIGN.md
+#endif
 
 template <int D, int BM, int DH, int STAGES, int PB>
 struct BwdCfg {
@@ -188,7 +191,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
         for (int kk = 0; kk < BM / 16; ++kk) {   // dK += dS^T Q_i
           const uint32_t offa = ((kk >> 2) * (kBK * 128) + (kk & 3) * 32) >> 4;
-          if (elect_one())
+          if (MU_BWD_PROBE != 3 && elect_one())
             umma_ss_lo(tmem_base + Cfg::kTmDK, ds_lo + offa, (qa + kk * 128) | kLboQ, hi, idesc_acc, kk > 0 ? 1u : acc);
         }
         if (i > 0) {
@@ -205,7 +208,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             a = (ds_lo + kk * 128) | kLboK;
             bd = (k_lo + kk * 128) | kLboK;
           }
-          if (elect_one()) umma_ss_lo(tmem_base + Cfg::kTmDQ, a, bd, hi, idesc_dq, kk > 0 ? 1u : 0u);
+          if (MU_BWD_PROBE != 3 && MU_BWD_PROBE != 4 && elect_one())
+            umma_ss_lo(tmem_base + Cfg::kTmDQ, a, bd, hi, idesc_dq, kk > 0 ? 1u : 0u);
         }
         if (elect_one()) {
           umma_commit(qdo_empty + st);
@@ -313,6 +317,9 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const uint32_t chunk = (((c & 1) * 4 + ch) ^ (r & 7)) * 16;
+#if MU_BWD_PROBE == 2
+          if (scale == 12345.f)
+#endif
           st_shared_v4(ds_addr + row_off + chunk, dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
         }
         tmem_st16(lane_base + Cfg::kTmP + c * 16, pk);   // 32 queries = 16 packed columns of the TMEM P^T tile
@@ -424,6 +431,9 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             mbar_arrive(dq_free);
           }
           const uint32_t row = stage + c * (BM * 128) + r * 128;   // sub-tile c = channels [32c, 32c+32)
+#if MU_BWD_PROBE == 1
+          if (scale == 12345.f)      // never true: the staging stores and the reduce are compiled but skipped
+#endif
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             const uint32_t chunk = ((uint32_t)(ch ^ (r & 7))) * 16;
@@ -435,6 +445,9 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
+#if MU_BWD_PROBE == 1
+        if (scale == 12345.f)
+#endif
         if (issuer) {
 #pragma unroll
           for (int c = 0; c < DH / 32; ++c) tma_reduce_add_3d(&tmap_dq, stage + c * (BM * 128), c * 32, i * BM, b);
