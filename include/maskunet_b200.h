@@ -246,6 +246,26 @@ int mu_column_sums(const void* x, float* sums, int64_t M, int32_t C, int32_t dty
 int mu_argmax_iou(const void* logits, const int64_t* labels, int64_t* pred, int32_t* hist, float* miou, int64_t M,
                   int32_t C, int32_t pitch, float smooth, int32_t dtype, mu_stream_t stream);
 
+/* InstanceContrastiveLoss (coco/coco_panoptic.py:482-521; cityscapes/city_instance.py:279-307).
+ * The caller groups the pixels by instance id (stable sort) and draws the negative ranks from the CPU generator as
+ * :510 does; the device selects anchor / positive (first two pixels of the instance) and the k-th non-member pixel
+ * as the negative, gathers the three logit columns sem[:, :, i0, i1] -- (i0, i1) = (batch index, row index) of the
+ * pixel, the reference's own indexing at :502-503 -- and accumulates the mean TripletMarginLoss(margin, p=2, eps).
+ *   sem     [B, C, H, W] with ELEMENT strides sem_strides[4], a HOST array (any layout, e.g. the class-padded
+ *           channels-last view the 1x1 head returns)
+ *   order   int64 [M = B*H*W]  pixel positions grouped by instance id, ascending inside a group
+ *   meta    int64 [3, K]       per instance: group offset in order, pixel count (>= 2), negative rank k in [0, M - count)
+ *   sel     int32 [K, 6] out   (h, w) of anchor, positive, negative; -1 where the reference would raise IndexError
+ *   dist    f32 [K, 2] out     (d(a,p), d(a,n));   loss f32 [1] out: mean over the K instances (NaN if any -1)
+ * Backward ACCUMULATES  scale * dloss[0] * dloss/dsem  into dsem (strides dsem_strides[4], same dtype as sem); dloss
+ * may be NULL (= 1). */
+int mu_instance_triplet_fwd(const void* sem, const int64_t* sem_strides, int32_t B, int32_t C, int32_t H, int32_t W,
+                            const int64_t* order, const int64_t* meta, int32_t K, float margin, float eps, int32_t* sel,
+                            float* dist, float* loss, int32_t dtype, mu_stream_t stream);
+int mu_instance_triplet_bwd(const void* sem, const int64_t* sem_strides, int32_t B, int32_t C, const int32_t* sel,
+                            int32_t K, float margin, float eps, const float* dist, const float* dloss, float scale,
+                            void* dsem, const int64_t* dsem_strides, int32_t dtype, mu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -372,4 +372,32 @@ int mu_bn_act_fwd_stats(const void* x, const void* r, const float* gamma, const 
                                  (cudaStream_t)stream);
 }
 
+int mu_instance_triplet_fwd(const void* sem, const int64_t* sem_strides, int32_t B, int32_t C, int32_t H, int32_t W,
+                            const int64_t* order, const int64_t* meta, int32_t K, float margin, float eps, int32_t* sel,
+                            float* dist, float* loss, int32_t dtype, mu_stream_t stream) {
+  MU_DTYPE_OK("mu_instance_triplet_fwd");
+  MU_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && K >= 0, MU_ERR_BAD_SHAPE,
+             "mu_instance_triplet_fwd: bad shape (B=%d C=%d H=%d W=%d K=%d)", B, C, H, W, K);
+  MU_REQUIRE(sem != nullptr && sem_strides != nullptr && loss != nullptr, MU_ERR_NULL, "mu_instance_triplet_fwd: null pointer");
+  MU_REQUIRE(K == 0 || (order != nullptr && meta != nullptr && sel != nullptr && dist != nullptr), MU_ERR_NULL,
+             "mu_instance_triplet_fwd: null pointer (order / meta / sel / dist)");
+  const long st[4] = {(long)sem_strides[0], (long)sem_strides[1], (long)sem_strides[2], (long)sem_strides[3]};
+  return launch_instance_triplet_fwd(sem, st, B, C, H, W, order, meta, K, margin, eps, sel, dist, loss, dtype,
+                                     (cudaStream_t)stream);
+}
+
+int mu_instance_triplet_bwd(const void* sem, const int64_t* sem_strides, int32_t B, int32_t C, const int32_t* sel,
+                            int32_t K, float margin, float eps, const float* dist, const float* dloss, float scale,
+                            void* dsem, const int64_t* dsem_strides, int32_t dtype, mu_stream_t stream) {
+  MU_DTYPE_OK("mu_instance_triplet_bwd");
+  MU_REQUIRE(B > 0 && C > 0 && K >= 0, MU_ERR_BAD_SHAPE, "mu_instance_triplet_bwd: bad shape (B=%d C=%d K=%d)", B, C, K);
+  MU_REQUIRE(sem != nullptr && sem_strides != nullptr && dsem != nullptr && dsem_strides != nullptr, MU_ERR_NULL,
+             "mu_instance_triplet_bwd: null pointer");
+  MU_REQUIRE(K == 0 || (sel != nullptr && dist != nullptr), MU_ERR_NULL, "mu_instance_triplet_bwd: null pointer (sel / dist)");
+  const long st[4] = {(long)sem_strides[0], (long)sem_strides[1], (long)sem_strides[2], (long)sem_strides[3]};
+  const long gst[4] = {(long)dsem_strides[0], (long)dsem_strides[1], (long)dsem_strides[2], (long)dsem_strides[3]};
+  return launch_instance_triplet_bwd(sem, st, B, C, sel, K, margin, eps, dist, dloss, scale, dsem, gst, dtype,
+                                     (cudaStream_t)stream);
+}
+
 }  // extern "C"

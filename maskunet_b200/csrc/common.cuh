@@ -116,6 +116,12 @@ int launch_conv1x1_prep(const float* w, const float* bias, void* wf, void* wd, f
 int launch_column_sums(const void* x, float* sums, long M, int C, int dtype, cudaStream_t s);
 int launch_argmax_iou(const void* logits, const int64_t* labels, int64_t* pred, int32_t* hist, float* miou, long M, int C,
                       int pitch, float smooth, int dtype, cudaStream_t s);
+int launch_instance_triplet_fwd(const void* sem, const long* st, int B, int C, int H, int W, const int64_t* order,
+                                const int64_t* meta, int K, float margin, float eps, int32_t* sel, float* dist,
+                                float* loss, int dtype, cudaStream_t s);
+int launch_instance_triplet_bwd(const void* sem, const long* st, int B, int C, const int32_t* sel, int K, float margin,
+                                float eps, const float* dist, const float* dloss, float scale, void* dsem,
+                                const long* gst, int dtype, cudaStream_t s);
 int launch_transpose(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t s);
 
 }  // namespace mu

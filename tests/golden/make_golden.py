@@ -135,10 +135,56 @@ def make_postproc():
         print(name, float(miou))
 
 
+INSTANCE_LOSS_CASES = [  # name, script, ignore_value, B, C, H, W, seed
+    ("instance_loss_coco", "coco_panoptic", None, 4, 13, 16, 16, 11),
+    ("instance_loss_city", "city_instance", 255, 3, 19, 8, 24, 12),
+    ("instance_loss_blobs", "coco_panoptic", None, 8, 7, 16, 32, 13),
+]
+
+
+def instance_mask_case(B, H, W, gen, blobs):
+    """Ids as the datasets produce them: 0 background, large panoptic segment ids, 255, a one-pixel instance."""
+    if blobs:                                    # rectangles: the first two pixels of an instance are neighbours
+        im = torch.zeros(B, H, W, dtype=torch.int64)
+        for b in range(B):
+            for j in range(3):
+                h0, w0 = int(torch.randint(0, H - 4, (1,), generator=gen)), int(torch.randint(0, W - 6, (1,), generator=gen))
+                im[b, h0:h0 + 4, w0:w0 + 6] = 1_000_003 * (b + 1) + j
+    else:
+        im = torch.randint(0, 7, (B, H, W), generator=gen) * 4099
+        im[im == 2 * 4099] = 0
+    im[0, 0, :3] = 255
+    im[B - 1, H - 1, W - 1] = 77_777_777         # fewer than two pixels: skipped (:498)
+    return im
+
+
+def make_instance_loss():
+    """InstanceContrastiveLoss of the reference's own classes (coco_panoptic.py:482-521, city_instance.py:279-307):
+    loss, gradient and the state of the CPU generator after the call (it draws one randint per instance, :510)."""
+    for name, script, ignore, B, C, H, W, seed in INSTANCE_LOSS_CASES:
+        Ref = load_reference_classes(script, ("InstanceContrastiveLoss",)).InstanceContrastiveLoss
+        gen = torch.Generator().manual_seed(seed)
+        amp = 0.0625 if "blobs" in name else 1.0                  # small logits: the hinge stays active with d(a, p) ~ 0
+        sem = (amp * torch.relu(torch.randn(B, C, H, W, generator=gen))).to(torch.bfloat16).float().requires_grad_()
+        im = instance_mask_case(B, H, W, gen, "blobs" in name)
+        torch.manual_seed(1000 + seed)
+        loss = Ref()(sem, im)
+        next_draw = int(torch.randint(0, 2 ** 31, (1,)))          # fingerprint of the generator state after the call
+        loss.backward()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), sem=np32(sem), instance_mask=im.numpy(),
+                            loss=np.array([float(loss)], dtype=np.float64), grad=np32(sem.grad),
+                            meta=np.array([1000 + seed, -1 if ignore is None else ignore, next_draw], dtype=np.int64))
+        print(name, float(loss), "grad.abs.sum", float(sem.grad.abs().sum()))
+
+
 def main():
     if "--postproc-only" in sys.argv:
         make_postproc()
         return
+    if "--instance-loss-only" in sys.argv:
+        make_instance_loss()
+        return
+    make_instance_loss()
     make_postproc()
     ref = load_reference_classes("ade_semantic")
     make_attention(ref)

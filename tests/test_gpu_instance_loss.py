@@ -1,0 +1,124 @@
+"""GPU parity of InstanceContrastiveLoss on the device against the golden outputs of the
+reference's own classes (coco_panoptic.py:482-521, city_instance.py:279-307) and against the CPU oracle.
+
+Tolerances: fp32 loss 1e-6 absolute, gradient 1e-5 (norm-wise relative); bf16 logits: the goldens' logits are
+bf16-representable, so the loss is still fp32-exact (1e-6) and the bf16 gradient holds 2e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+from oracle import instance_loss_oracle as ilo
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+CASES = ["instance_loss_coco", "instance_loss_city", "instance_loss_blobs"]
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    seed, ignore, next_draw = (int(v) for v in z["meta"])
+    return z, seed, (None if ignore < 0 else ignore), next_draw
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("layout", ["fp32_nchw", "fp32_channels_last", "bf16_padded_view"])
+def test_loss_and_gradient_match_reference_golden(name, layout):
+    from maskunet_b200 import InstanceContrastiveLoss, ops
+    z, seed, ignore, next_draw = _load(name)
+    sem = torch.from_numpy(z["sem"]).to(DEV)
+    im = torch.from_numpy(z["instance_mask"]).to(DEV)
+    B, C, H, W = sem.shape
+    if layout == "fp32_channels_last":
+        sem = sem.contiguous(memory_format=torch.channels_last)
+    elif layout == "bf16_padded_view":          # what the 1x1 head returns: first C channels of a class-padded buffer
+        buf = torch.zeros(B, ops.pad_channels(C), H, W, device=DEV, dtype=torch.bfloat16).contiguous(
+            memory_format=torch.channels_last)
+        buf[:, :C] = sem.to(torch.bfloat16)
+        sem = buf[:, :C]
+    sem = sem.detach().requires_grad_()
+    crit = InstanceContrastiveLoss(margin=1.0, ignore_value=ignore)
+    torch.manual_seed(seed)
+    loss = crit(sem, im)
+    assert int(torch.randint(0, 2 ** 31, (1,))) == next_draw          # CPU generator consumed exactly as the reference
+    assert abs(float(loss) - float(z["loss"][0])) < 1e-6
+    loss.backward()
+    tol = 2e-2 if sem.dtype == torch.bfloat16 else 1e-5
+    assert rel_err(sem.grad.float(), torch.from_numpy(z["grad"])) < tol
+
+
+def test_accumulate_into_existing_gradient_buffer():
+    """The trainer's path: d(CE) already sits in the class-padded buffer, the triplet gradient is added in place."""
+    from maskunet_b200 import losses, ops
+    z, seed, ignore, _ = _load("instance_loss_coco")
+    sem = torch.from_numpy(z["sem"]).to(DEV)
+    im = torch.from_numpy(z["instance_mask"]).to(DEV)
+    B, C, H, W = sem.shape
+    P = ops.pad_channels(C)
+    base = torch.randn(B, P, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
+    dpad = base.clone()
+    torch.manual_seed(seed)
+    order, meta, K = losses.plan_instances(im, ignore)
+    l, sel, dist = losses.instance_triplet(sem, order, meta, 1.0)
+    losses.accumulate_grad(sem, sel, dist, 1.0, dpad[:, :C], scale=0.1)
+    assert torch.equal(dpad[:, C:], base[:, C:])                      # pad channels untouched
+    assert rel_err((dpad - base)[:, :C], 0.1 * torch.from_numpy(z["grad"])) < 1e-5
+    assert abs(float(l) - float(z["loss"][0])) < 1e-6
+
+
+def test_selection_at_training_size_against_oracle():
+    """128 x 128 labels, batch 64, a few hundred instances with large ids: every selected pixel, loss and gradient
+    against the CPU oracle; properties: anchors are the first two pixels, negatives never belong to the instance."""
+    from maskunet_b200 import InstanceContrastiveLoss, losses
+    g = torch.Generator().manual_seed(21)
+    B, C, H, W = 64, 19, 128, 128
+    im = torch.zeros(B, H, W, dtype=torch.int64)
+    for b in range(B):
+        for j in range(4):
+            h0, w0 = int(torch.randint(0, H - 20, (1,), generator=g)), int(torch.randint(0, W - 30, (1,), generator=g))
+            im[b, h0:h0 + 20, w0:w0 + 30] = 1_000_003 * (b + 1) + j
+    im[3, :2] = 255
+    sem_cpu = (0.05 * torch.randn(B, C, H, W, generator=g)).to(torch.bfloat16).float()
+    torch.manual_seed(5)
+    sem_o = sem_cpu.clone().requires_grad_()
+    lo, sel_o = ilo.instance_contrastive_loss(sem_o, im, 1.0, 255)
+    lo.backward()
+    sem = sem_cpu.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_()
+    imd = im.to(DEV)
+    torch.manual_seed(5)
+    order, meta, K = losses.plan_instances(imd, 255)
+    assert K == len(sel_o)
+    loss, sel, dist = losses.instance_triplet(sem, order, meta, 1.0)
+    pos = torch.tensor([[a, p, n] for _, a, p, n in sel_o])
+    want = torch.stack([pos // (H * W), (pos // W) % H], dim=-1).reshape(K, 6).to(torch.int32)
+    assert torch.equal(sel.cpu(), want)                               # identical pixels, instance by instance
+    flat = im.reshape(-1)
+    for (i, a, p, n) in sel_o[:50]:
+        assert flat[a] == i and flat[p] == i and flat[n] != i and a < p
+    assert abs(float(loss) - float(lo)) < 1e-5
+    loss.backward()
+    assert rel_err(sem.grad, sem_o.grad) < 1e-5
+    torch.manual_seed(5)
+    assert abs(float(InstanceContrastiveLoss(ignore_value=255)(sem.detach(), imd)) - float(lo)) < 1e-5
+
+
+def test_edge_cases():
+    from maskunet_b200 import InstanceContrastiveLoss
+    crit = InstanceContrastiveLoss()
+    sem = torch.randn(2, 4, 8, 8, device=DEV)
+    state = torch.get_rng_state()
+    assert float(crit(sem, torch.zeros(2, 8, 8, dtype=torch.int64, device=DEV))) == 0.0     # background only (:521)
+    one = torch.zeros(2, 8, 8, dtype=torch.int64, device=DEV)
+    one[0, 0, 0] = 9                                                                       # a one-pixel instance (:498)
+    assert float(crit(sem, one)) == 0.0
+    full = torch.full((2, 8, 8), 5, dtype=torch.int64, device=DEV)                         # no negatives exist (:507)
+    assert float(crit(sem, full)) == 0.0
+    assert torch.equal(state, torch.get_rng_state())                                       # none of them drew a number
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        crit(sem.cpu(), one.cpu())
+    # batch index used as a row index (:502): B > H is an IndexError in the reference, NaN here
+    tall = torch.zeros(6, 4, 4, dtype=torch.int64, device=DEV)
+    tall[5, 0, :2] = 3
+    assert torch.isnan(crit(torch.randn(6, 2, 4, 4, device=DEV), tall))

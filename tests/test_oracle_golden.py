@@ -104,3 +104,24 @@ def test_metrics_oracle_matches_reference_golden(name, C):
     logits, labels = torch.from_numpy(z["logits"]), torch.from_numpy(z["labels"])
     assert torch.equal(mo.class_map(logits), torch.from_numpy(z["pred"].astype(np.int64)))   # bit-exact class map
     assert abs(float(mo.mean_iou(logits, labels, C)) - float(z["miou"][0])) < 1e-6
+
+
+INSTANCE_LOSS_CASES = ["instance_loss_coco", "instance_loss_city", "instance_loss_blobs"]
+
+
+@pytest.mark.parametrize("name", INSTANCE_LOSS_CASES)
+def test_instance_contrastive_loss_matches_reference_golden(name):
+    """oracle/instance_loss_oracle.py against the reference's own InstanceContrastiveLoss (coco_panoptic.py:482-521,
+    city_instance.py:279-307): loss, gradient, and the same number of draws from the CPU generator."""
+    from oracle import instance_loss_oracle as ilo
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    seed, ignore, next_draw = (int(v) for v in z["meta"])
+    sem = torch.from_numpy(z["sem"]).requires_grad_()
+    torch.manual_seed(seed)
+    loss, sel = ilo.instance_contrastive_loss(sem, torch.from_numpy(z["instance_mask"]), 1.0,
+                                              None if ignore < 0 else ignore)
+    assert int(torch.randint(0, 2 ** 31, (1,))) == next_draw       # generator left in the reference's state
+    assert abs(float(loss) - float(z["loss"][0])) < 1e-6
+    loss.backward()
+    assert rel_err(sem.grad, torch.from_numpy(z["grad"])) < 1e-5
+    assert len(sel) >= 3

@@ -73,3 +73,30 @@ def test_mean_iou_live():
         labels = torch.randint(0, C, (2, 12, 12), generator=g)
         assert abs(float(fn(logits, labels, C)) - float(mo.mean_iou(logits, labels, C))) < 1e-6
         assert torch.equal(torch.argmax(torch.softmax(logits / 0.5, dim=1), dim=1), mo.class_map(logits))
+
+
+@pytest.mark.parametrize("script,ignore", [("coco_panoptic", None), ("city_instance", 255), ("ade_panoptic", None),
+                                           ("city_panoptic", None)])
+def test_instance_contrastive_loss_live(script, ignore):
+    """The restated InstanceContrastiveLoss against every copy of the reference's class, same CPU generator stream."""
+    from oracle import instance_loss_oracle as ilo
+    paths = {"ade_panoptic": "code/ade20k/ade_panoptic.py", "city_panoptic": "code/cityscapes/city_panoptic.py"}
+    Ref = load_reference_classes(paths.get(script, script), ("InstanceContrastiveLoss",)).InstanceContrastiveLoss
+    g = torch.Generator().manual_seed(5)
+    for B, C, H, W in ((2, 5, 8, 8), (4, 19, 16, 16), (3, 7, 8, 12)):
+        sem = torch.randn(B, C, H, W, generator=g).requires_grad_()
+        im = torch.randint(0, 6, (B, H, W), generator=g) * 37
+        im[0, 0, :3] = 255
+        im[1, 2, 3] = 99999
+        torch.manual_seed(77)
+        ref = Ref()(sem, im)
+        ref.backward()
+        gref, sem.grad = sem.grad.clone(), None
+        state = torch.get_rng_state()
+        torch.manual_seed(77)
+        ours, _ = ilo.instance_contrastive_loss(sem, im, 1.0, ignore)
+        ours.backward()
+        assert torch.equal(state, torch.get_rng_state())
+        assert abs(float(ref) - float(ours)) < 1e-6 and rel_err(sem.grad, gref) < 1e-5
+    # nothing qualifies: background only
+    assert float(ilo.instance_contrastive_loss(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4, dtype=torch.int64))[0]) == 0.0
