@@ -266,6 +266,34 @@ int mu_instance_triplet_bwd(const void* sem, const int64_t* sem_strides, int32_t
                             int32_t K, float margin, float eps, const float* dist, const float* dloss, float scale,
                             void* dsem, const int64_t* dsem_strides, int32_t dtype, mu_stream_t stream);
 
+/* ---- Generalised mode of the kernel sweep (BASELINE.json configs[4]) -------------------------
+ * The north star names a per-query mask-logit einsum and a sigmoid > 0.5 binarisation; the reference has neither (its
+ * bias is torch.randint, :177-181).  These entry points implement that generalisation for the
+ * sweep; their oracle is builder-written (oracle/query_attention_oracle.py): "parity unpinned by reference".
+ *
+ * K13. bits = sigmoid(einsum('bqc,bnc->bqn', qe, feat)) > 0.5 on tcgen05 (bf16 in, fp32 accumulate), logits never stored.
+ *   qe [B, Q, C] bf16, feat [B, N, C] bf16, C = 256;  NKP = roundup(N, 128), QP = roundup(Q, 128)
+ *   bits   uint32 [B, Q, NKP/32]   bit n%32 of word n/32 set <=> query q may attend key n (bias 0.0, else -inf)
+ *   bits_t uint32 [B, NKP, QP/32]  the same relation transposed (what the backward kernel reads)
+ *   row_count int32 [B, Q]         kept keys per query BEFORE the rule below
+ *   logits f32 [B, Q, N] or NULL   test hook
+ * Binarisation is bit-exact to torch.sigmoid(x) > 0.5 in fp32 (x > 1.5 * 2^-24, not x > 0).  A query that kept no key
+ * attends every key (Mask2Former's rule; a fully masked row is NaN otherwise). */
+int mu_query_mask_bits(const void* qe, const void* feat, int32_t B, int32_t Q, int32_t N, int32_t C, uint32_t* bits,
+                       uint32_t* bits_t, int32_t* row_count, float* logits, int32_t dtype, mu_stream_t stream);
+/* Masked multi-head cross attention of Q queries over N keys, (sample, head) pairs as the batch BH = B * heads:
+ *   q, o, d_o, dq [BH, Q, D]; k, v [BH, NKP, D] (rows >= N zero); dk, dv [BH, N, D]; lse, delta f32 [BH, Q]
+ *   o = softmax(q k^T * scale + bias(bits[bh / heads])) v;  D = 64 (pad 32-wide heads with zeros and pass their scale).
+ * tcgen05 kernels of K3 / K5 with the bias applied in registers; bf16 only. */
+int mu_query_attn_fwd(const void* q, const void* k, const void* v, const uint32_t* bits, void* o, float* lse, int32_t BH,
+                      int32_t heads, int32_t Q, int32_t N, int32_t NKP, int32_t D, float scale, int32_t dtype,
+                      mu_stream_t stream);
+size_t mu_query_attn_bwd_workspace_bytes(int32_t BH, int32_t Q, int32_t D);
+int mu_query_attn_bwd(const void* q, const void* k, const void* v, const uint32_t* bits_t, const void* d_o,
+                      const float* lse, const float* delta, void* dq, void* dk, void* dv, void* workspace,
+                      size_t workspace_bytes, int32_t BH, int32_t heads, int32_t Q, int32_t N, int32_t NKP, int32_t D,
+                      float scale, int32_t dtype, mu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,9 @@ SIGNATURES = {
     "mu_bn_update_running": [_P, _P, _P, _P, _F, _F, ctypes.c_int64, _I, _P],
     "mu_instance_triplet_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _I, _F, _F, _P, _P, _P, _I, _P],
     "mu_instance_triplet_bwd": [_P, _P, _I, _I, _P, _I, _F, _F, _P, _P, _F, _P, _P, _I, _P],
+    "mu_query_mask_bits": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P],
+    "mu_query_attn_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "mu_query_attn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "mu_bn_act_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
 }
 
@@ -78,6 +81,8 @@ def load() -> ctypes.CDLL:
     lib.mu_conv3x3_workspace_bytes.argtypes = [_I, _I]
     lib.mu_conv1x1_workspace_bytes.restype = ctypes.c_size_t
     lib.mu_conv1x1_workspace_bytes.argtypes = [_I, _I]
+    lib.mu_query_attn_bwd_workspace_bytes.restype = ctypes.c_size_t
+    lib.mu_query_attn_bwd_workspace_bytes.argtypes = [_I, _I, _I]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int32

@@ -51,14 +51,18 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int D, int BM, int DH, int STAGES, int PB>
+// QM = true: generalised mode of the kernel sweep (see attn_fwd_sm100.cu): a per-(query, key) bias as transposed bits
+// (bits_t [B / heads, NKP keys, wpq words over queries], K13), every key kept (no compaction: n_keep == nk_all and key
+// row r of tile j is token k0 + r), N queries against NT key tokens.
+template <int D, int BM, int DH, int STAGES, int PB, bool QM>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                       const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                       const __grid_constant__ CUtensorMap tmap_dq, const int32_t* __restrict__ n_keep,
                       const int32_t* __restrict__ keep_idx,
                       const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
-                      __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int N, int NKP, float scale) {
+                      __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int N, int NKP, float scale,
+                      int NT, const uint32_t* __restrict__ bits_t, int heads, int wpq, int nk_all) {
   using Cfg = BwdCfg<D, BM, DH, STAGES, PB>;
   constexpr bool DQT = Cfg::kDQT;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -89,7 +93,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int b = blockIdx.y, k0 = blockIdx.x * kBK, half = blockIdx.z;
-  const int nk = n_keep[b];
+  const int nk = QM ? nk_all : n_keep[b];
   if (k0 >= nk) return;                      // whole CTA: nothing kept in this tile
   const int T = (N + BM - 1) / BM;           // query tiles
 
@@ -288,6 +292,16 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
           for (int e = 0; e < 32; ++e) s[cc][e] = 0xff800000u;
       }
+      if (QM) {                                          // per-(query, key) bias: p = exp2(-inf) = 0 where the bit is clear
+        const uint32_t* kb = bits_t + ((size_t)(b / heads) * NKP + k0 + r) * wpq + i * (BM / 32) + hcol * kChunksPerThread;
+#pragma unroll
+        for (int cc = 0; cc < kChunksPerThread; ++cc) {
+          const uint32_t w = kb[cc];
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (!((w >> e) & 1u)) s[cc][e] = 0xff800000u;
+        }
+      }
       // the MMAs that last read this P^T / dS^T buffer (tile i - PB) must have completed
       if (i >= PB) mbar_wait(pds_free + (i % PB), ((i / PB) - 1) & 1);
       if (i > 0) mbar_wait(p_free, (i - 1) & 1);         // dV MMAs of tile i-1 are done with P^T
@@ -333,8 +347,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     mbar_wait(pds_free + ((T - 1) % PB), ((T - 1) / PB) & 1);   // last tile's MMAs (and all before) are done
     tc_fence_after();
     // dense token-space outputs: key row r of this tile goes back to token keep_idx[k0 + r]
-    const int tok = key_ok ? keep_idx[(size_t)b * N + k0 + r] : 0;
-    const size_t row_off = ((size_t)b * N + tok) * D + half * DH;
+    const int tok = key_ok ? (QM ? k0 + r : keep_idx[(size_t)b * NT + k0 + r]) : 0;
+    const size_t row_off = ((size_t)b * NT + tok) * D + half * DH;
     {
       const int which = hcol;
       __nv_bfloat16* dst = (which == 0 ? dv : dk) + row_off;
@@ -478,10 +492,12 @@ __global__ void dq_convert_kernel(const float4* __restrict__ acc, uint2* __restr
   }
 }
 
-template <int D, int BM, int DH, int STAGES, int PB>
+template <int D, int BM, int DH, int STAGES, int PB, bool QM = false>
 static int run(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const int32_t* keep_idx,
                const void* d_o, const float* lse, const float* delta, void* dq, void* dkc, void* dvc, float* dq_acc,
-               int B, int N, int NKP, cudaStream_t s) {
+               int B, int N, int NKP, cudaStream_t s, int NT = 0, float scale_in = 0.f, const uint32_t* bits_t = nullptr,
+               int heads = 1, int nk_all = 0) {
+  if (NT == 0) NT = N;                     // self-attention: as many key tokens as queries
   using Cfg = BwdCfg<D, BM, DH, STAGES, PB>;
   CUtensorMap tq, tdo, tk, tv, tdq;
   int rc;
@@ -490,20 +506,21 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
   if ((rc = make_tmap_bf16_3d(&tdo, d_o, D, N, B, BM))) return rc;
   if ((rc = make_tmap_bf16_3d(&tk, kc, D, NKP, B, kBK))) return rc;
   if ((rc = make_tmap_bf16_3d(&tv, vc, D, NKP, B, kBK))) return rc;
-  auto kern = attn_bwd_sm100_kernel<D, BM, DH, STAGES, PB>;
+  auto kern = attn_bwd_sm100_kernel<D, BM, DH, STAGES, PB, QM>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("attn_bwd_sm100: cudaFuncSetAttribute(%d bytes): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
     return (int)e;
   }
-  const size_t n = (size_t)B * N * D;
+  const size_t n = (size_t)B * N * D, nt = (size_t)B * NT * D;
   cudaMemsetAsync(dq_acc, 0, n * sizeof(float), s);
-  cudaMemsetAsync(dkc, 0, n * 2, s);   // rows of masked keys stay zero
-  cudaMemsetAsync(dvc, 0, n * 2, s);
+  cudaMemsetAsync(dkc, 0, nt * 2, s);   // rows of masked keys stay zero
+  cudaMemsetAsync(dvc, 0, nt * 2, s);
   dim3 grid(NKP / kBK, B, D / DH);
-  const float scale = 1.f / sqrtf((float)D);
+  const float scale = scale_in > 0.f ? scale_in : 1.f / sqrtf((float)D);
   kern<<<grid, kBwdThreads, Cfg::kSmemBytes, s>>>(tq, tdo, tk, tv, tdq, n_keep, keep_idx, lse, delta, dq_acc, (__nv_bfloat16*)dkc,
-                                                  (__nv_bfloat16*)dvc, N, NKP, scale);
+                                                  (__nv_bfloat16*)dvc, N, NKP, scale, NT, bits_t, heads,
+                                                  round_up(N, 128) / 32, nk_all);
   if ((rc = check_launch("attn_bwd_sm100"))) return rc;
   const size_t n4 = n / 4;
   const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
@@ -532,6 +549,20 @@ int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const i
       set_error("attn_bwd_sm100: channels must be 64, 128 or 256 (got %d)", C);
       return MU_ERR_BAD_SHAPE;
   }
+}
+
+// Generalised mode: q, d_o [BH, Q, 64], k / v [BH, NKP, 64], bits_t [BH / heads, NKP, roundup(Q, 128) / 32];
+// dq [BH, Q, 64], dk / dv [BH, N, 64]; workspace = fp32 dQ accumulator.
+int launch_query_attn_bwd_sm100(const void* q, const void* k, const void* v, const uint32_t* bits_t, const void* d_o,
+                                const float* lse, const float* delta, void* dq, void* dk, void* dv, void* workspace,
+                                size_t workspace_bytes, int BH, int heads, int Q, int N, int NKP, int D, float scale,
+                                cudaStream_t s) {
+  MU_REQUIRE(D == 64, MU_ERR_BAD_SHAPE, "mu_query_attn_bwd: head dim must be 64 (pad 32 to 64), got %d", D);
+  MU_REQUIRE(workspace != nullptr && workspace_bytes >= attn_bwd_sm100_workspace(BH, Q, D), MU_ERR_WORKSPACE,
+             "mu_query_attn_bwd: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
+             attn_bwd_sm100_workspace(BH, Q, D));
+  return run<64, 128, 64, 2, 2, true>(q, k, v, nullptr, nullptr, d_o, lse, delta, dq, dk, dv, (float*)workspace, BH, Q,
+                                      NKP, s, N, scale, bits_t, heads, N);
 }
 
 }  // namespace mu

@@ -46,11 +46,16 @@ struct FwdCfg {
   static_assert(kTmemUsed <= 512, "TMEM overflow");
 };
 
-template <int D, int BN, int SBUFS, int SLOTS, int MINB>
+// QM = true is the generalised mode of the kernel sweep (no counterpart in the reference):
+// a per-(query, key) bias given as bits (K13, mask_logits_sm100.cu: qbits [B / heads, N queries, wpr words], bit set
+// <=> may attend) applied in registers before the row maximum, and every key of the tile list is "kept"
+// (n_keep == number of keys).  The batch index counts (sample, head) pairs; heads of one sample share the mask.
+template <int D, int BN, int SBUFS, int SLOTS, int MINB, bool QM>
 __global__ void __launch_bounds__(kFwdThreads, MINB)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                       const __grid_constant__ CUtensorMap tmap_v, const int32_t* __restrict__ n_keep,
-                      __nv_bfloat16* __restrict__ o, float* __restrict__ lse, int N, float scale_log2) {
+                      __nv_bfloat16* __restrict__ o, float* __restrict__ lse, int N, float scale_log2,
+                      const uint32_t* __restrict__ qbits, int heads, int wpr, int nk_all) {
   using Cfg = FwdCfg<D, BN, SBUFS, SLOTS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -68,7 +73,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int b = blockIdx.y, q0 = blockIdx.x * kBM;
-  const int nk = n_keep[b];
+  const int nk = QM ? nk_all : n_keep[b];
   const int T = (nk + BN - 1) / BN;  // key tiles
 
   if (threadIdx.x == 0) {
@@ -202,6 +207,16 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             for (int i = 0; i < 32; ++i)
               if (c * 32 + i >= limit) v[c][i] = 0xff800000u;   // -inf
         }
+        if (QM) {                                   // per-(query, key) bias: -inf where the bit is clear
+          const uint32_t* rb = qbits + ((size_t)(b / heads) * N + (row_ok ? q0 + r : 0)) * wpr + j * (BN / 32);
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) {
+            const uint32_t w = row_ok ? rb[c] : 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!((w >> i) & 1u)) v[c][i] = 0xff800000u;
+          }
+        }
         // ---- row max: independent FMNMX3 chains
         float mx[BN / 32];
 #pragma unroll
@@ -221,7 +236,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         float alpha = 1.f;
         const bool grow = (m_new - m) * scale_log2 > kLazyLog2;       // true on the first tile (m = -inf)
         if (__any_sync(0xffffffffu, grow)) {
-          alpha = fast_exp2((m - m_new) * scale_log2);
+          alpha = (QM && m_new == -INFINITY) ? 1.f : fast_exp2((m - m_new) * scale_log2);   // row masked so far
           m = m_new;
           if (j > 0) {
             mbar_wait(o_done, (j - 1) & 1);                            // the previous PV has landed in TMEM
@@ -239,7 +254,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           }
         }
         // ---- p = exp2((s - m) * scale * log2e), bf16 P tile into shared memory
-        const float mb = m * scale_log2;
+        const float mb = (QM && m == -INFINITY) ? 0.f : m * scale_log2;   // all -inf so far: p = exp2(-inf) = 0
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
@@ -296,25 +311,34 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
-template <int D, int BN, int SBUFS, int SLOTS, int MINB>
+template <int D, int BN, int SBUFS, int SLOTS, int MINB, bool QM = false>
 static int run(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse, int B, int N,
-               int NKP, cudaStream_t s) {
+               int NKP, cudaStream_t s, float scale = 0.f, const uint32_t* qbits = nullptr, int heads = 1,
+               int nk_all = 0) {
   using Cfg = FwdCfg<D, BN, SBUFS, SLOTS>;
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_tmap_bf16_3d(&tq, q, D, N, B, kBM))) return rc;
   if ((rc = make_tmap_bf16_3d(&tk, kc, D, NKP, B, BN))) return rc;
   if ((rc = make_tmap_bf16_3d(&tv, vc, D, NKP, B, BN))) return rc;
-  auto kern = attn_fwd_sm100_kernel<D, BN, SBUFS, SLOTS, MINB>;
+  auto kern = attn_fwd_sm100_kernel<D, BN, SBUFS, SLOTS, MINB, QM>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("attn_fwd_sm100: cudaFuncSetAttribute(%d bytes): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
     return (int)e;
   }
   dim3 grid((N + kBM - 1) / kBM, B);
-  const float scale_log2 = kLog2eF / sqrtf((float)D);
-  kern<<<grid, kFwdThreads, Cfg::kSmemBytes, s>>>(tq, tk, tv, n_keep, (__nv_bfloat16*)o, lse, N, scale_log2);
+  const float scale_log2 = kLog2eF * (scale > 0.f ? scale : 1.f / sqrtf((float)D));
+  kern<<<grid, kFwdThreads, Cfg::kSmemBytes, s>>>(tq, tk, tv, n_keep, (__nv_bfloat16*)o, lse, N, scale_log2, qbits, heads,
+                                                  NKP / 32, nk_all);
   return check_launch("attn_fwd_sm100");
+}
+
+// Generalised mode: q [BH, Q, 64], k / v [BH, NKP, 64] (rows >= N zero), qbits [BH / heads, Q, NKP / 32]
+int launch_query_attn_fwd_sm100(const void* q, const void* k, const void* v, const uint32_t* qbits, void* o, float* lse,
+                                int BH, int heads, int Q, int N, int NKP, int D, float scale, cudaStream_t s) {
+  MU_REQUIRE(D == 64, MU_ERR_BAD_SHAPE, "mu_query_attn_fwd: head dim must be 64 (pad 32 to 64), got %d", D);
+  return run<64, 128, 1, 3, 2, true>(q, k, v, nullptr, o, lse, BH, Q, NKP, s, scale, qbits, heads, N);
 }
 
 int launch_attn_fwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep, void* o, float* lse,

@@ -213,7 +213,7 @@ int mu_bn_act_bwd(const void* dy, const void* x, const void* r, const float* a, 
 }
 
 #define MU_BF16_ONLY(fn) \
-  MU_REQUIRE(dtype == MU_BF16, MU_ERR_BAD_DTYPE, fn ": tensor-core convolution takes MU_BF16 activations (got %d)", dtype)
+  MU_REQUIRE(dtype == MU_BF16, MU_ERR_BAD_DTYPE, fn ": this tcgen05 entry point takes MU_BF16 activations (got %d)", dtype)
 #define MU_SM100_ONLY(fn) \
   MU_REQUIRE(device_cc_major() == 10, MU_ERR_ARCH, fn ": needs an sm_100 device (tcgen05 / TMEM)")
 
@@ -398,6 +398,45 @@ int mu_instance_triplet_bwd(const void* sem, const int64_t* sem_strides, int32_t
   const long gst[4] = {(long)dsem_strides[0], (long)dsem_strides[1], (long)dsem_strides[2], (long)dsem_strides[3]};
   return launch_instance_triplet_bwd(sem, st, B, C, sel, K, margin, eps, dist, dloss, scale, dsem, gst, dtype,
                                      (cudaStream_t)stream);
+}
+
+int mu_query_mask_bits(const void* qe, const void* feat, int32_t B, int32_t Q, int32_t N, int32_t C, uint32_t* bits,
+                       uint32_t* bits_t, int32_t* row_count, float* logits, int32_t dtype, mu_stream_t stream) {
+  MU_BF16_ONLY("mu_query_mask_bits");
+  MU_REQUIRE(B > 0 && Q > 0 && N > 0, MU_ERR_BAD_SHAPE, "mu_query_mask_bits: bad shape (B=%d Q=%d N=%d)", B, Q, N);
+  MU_PTRS("mu_query_mask_bits", qe, feat, bits, bits_t, row_count);
+  MU_SM100_ONLY("mu_query_mask_bits");
+  return launch_query_mask_bits_sm100(qe, feat, B, Q, N, C, bits, bits_t, row_count, logits, (cudaStream_t)stream);
+}
+
+static int check_query_attn(const char* fn, int BH, int heads, int Q, int N, int NKP) {
+  MU_REQUIRE(BH > 0 && heads > 0 && BH % heads == 0 && Q > 0 && N > 0, MU_ERR_BAD_SHAPE,
+             "%s: bad shape (BH=%d heads=%d Q=%d N=%d)", fn, BH, heads, Q, N);
+  return check_nkp(fn, N, NKP);
+}
+
+int mu_query_attn_fwd(const void* q, const void* k, const void* v, const uint32_t* bits, void* o, float* lse, int32_t BH,
+                      int32_t heads, int32_t Q, int32_t N, int32_t NKP, int32_t D, float scale, int32_t dtype,
+                      mu_stream_t stream) {
+  MU_BF16_ONLY("mu_query_attn_fwd");
+  if (int rc = check_query_attn("mu_query_attn_fwd", BH, heads, Q, N, NKP)) return rc;
+  MU_PTRS("mu_query_attn_fwd", q, k, v, bits, o, lse);
+  MU_SM100_ONLY("mu_query_attn_fwd");
+  return launch_query_attn_fwd_sm100(q, k, v, bits, o, lse, BH, heads, Q, N, NKP, D, scale, (cudaStream_t)stream);
+}
+
+size_t mu_query_attn_bwd_workspace_bytes(int32_t BH, int32_t Q, int32_t D) { return attn_bwd_sm100_workspace(BH, Q, D); }
+
+int mu_query_attn_bwd(const void* q, const void* k, const void* v, const uint32_t* bits_t, const void* d_o,
+                      const float* lse, const float* delta, void* dq, void* dk, void* dv, void* workspace,
+                      size_t workspace_bytes, int32_t BH, int32_t heads, int32_t Q, int32_t N, int32_t NKP, int32_t D,
+                      float scale, int32_t dtype, mu_stream_t stream) {
+  MU_BF16_ONLY("mu_query_attn_bwd");
+  if (int rc = check_query_attn("mu_query_attn_bwd", BH, heads, Q, N, NKP)) return rc;
+  MU_PTRS("mu_query_attn_bwd", q, k, v, bits_t, d_o, lse, delta, dq, dk, dv, workspace);
+  MU_SM100_ONLY("mu_query_attn_bwd");
+  return launch_query_attn_bwd_sm100(q, k, v, bits_t, d_o, lse, delta, dq, dk, dv, workspace, workspace_bytes, BH, heads,
+                                     Q, N, NKP, D, scale, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -122,6 +122,14 @@ int launch_instance_triplet_fwd(const void* sem, const long* st, int B, int C, i
 int launch_instance_triplet_bwd(const void* sem, const long* st, int B, int C, const int32_t* sel, int K, float margin,
                                 float eps, const float* dist, const float* dloss, float scale, void* dsem,
                                 const long* gst, int dtype, cudaStream_t s);
+int launch_query_mask_bits_sm100(const void* qe, const void* feat, int B, int Q, int N, int C, uint32_t* bits,
+                                 uint32_t* bits_t, int32_t* row_count, float* logits, cudaStream_t s);
+int launch_query_attn_fwd_sm100(const void* q, const void* k, const void* v, const uint32_t* qbits, void* o, float* lse,
+                                int BH, int heads, int Q, int N, int NKP, int D, float scale, cudaStream_t s);
+int launch_query_attn_bwd_sm100(const void* q, const void* k, const void* v, const uint32_t* bits_t, const void* d_o,
+                                const float* lse, const float* delta, void* dq, void* dk, void* dv, void* workspace,
+                                size_t workspace_bytes, int BH, int heads, int Q, int N, int NKP, int D, float scale,
+                                cudaStream_t s);
 int launch_transpose(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t s);
 
 }  // namespace mu
