@@ -67,6 +67,66 @@ def run(B, N, C, bwd, peak):
     return rec
 
 
+def run_generalised(B, Q, N, heads, peak, C=256):
+    """Generalised mode: K13 bits + masked multi-head cross attention, fwd and bwd.
+    FLOPs: executed = every (query, key) pair of the tiles; useful = pairs whose bit is set."""
+    from maskunet_b200 import query_attention as qa
+    g = torch.Generator(device=DEV).manual_seed(0)
+    mk = lambda *s, amp=1.0: (amp * torch.randn(*s, device=DEV, generator=g)).bfloat16()
+    qe, feat = mk(B, Q, C, amp=0.25), mk(B, N, C, amp=0.25)
+    q, k, v = mk(B, Q, C), mk(B, N, C), mk(B, N, C)
+    d = C // heads
+    ms_bits = time_fn(lambda: qa.query_mask_bits(qe, feat))
+    bits, bits_t, row_count = qa.query_mask_bits(qe, feat)
+    kept = float(row_count.sum())
+    NKP = ops.nkp_of(N)
+    qh, kh, vh = qa._to_heads(q, heads, Q), qa._to_heads(k, heads, NKP), qa._to_heads(v, heads, NKP)
+    scale = d ** -0.5
+    ms_f = time_fn(lambda: qa.query_attn_fwd(qh, kh, vh, bits, heads, N, scale))
+    o, lse = qa.query_attn_fwd(qh, kh, vh, bits, heads, N, scale)
+    d_o = torch.randn_like(o)
+    delta = (d_o.float() * o.float()).sum(-1)
+    ms_b = time_fn(lambda: qa.query_attn_bwd(qh, kh, vh, bits_t, d_o, lse, delta, heads, N, scale), iters=5, warm=2)
+    pairs = B * Q * N
+    rec = {"mode": "generalised", "B": B, "Q": Q, "N": N, "heads": heads, "head_dim": d, "kept_frac": round(kept / pairs, 3),
+           "bits_ms": round(ms_bits, 4), "bits_tflops": round(2 * pairs * C / ms_bits / 1e9, 1),
+           "fwd_ms": round(ms_f, 4), "fwd_tflops_useful": round(4 * kept * heads * d / ms_f / 1e9, 1),
+           "fwd_tflops_executed": round(4 * pairs * heads * 64 / ms_f / 1e9, 1),
+           "bwd_ms": round(ms_b, 4), "bwd_tflops_useful": round(8 * kept * heads * d / ms_b / 1e9, 1),
+           "bwd_tflops_executed": round(10 * pairs * heads * 64 / ms_b / 1e9, 1), "peak_tflops": peak}
+    print(json.dumps(rec), flush=True)
+    return rec
+
+
+def run_eager(B, N, C, dtype, peak):
+    """Secondary baseline of SURVEY 8(d): the reference module's attention arithmetic (ade_semantic.py:174-186) as eager
+    PyTorch on this GPU -- scores, division, additive 0 / -inf mask, softmax, PV, all materialised -- fwd + bwd."""
+    g = torch.Generator(device=DEV).manual_seed(0)
+    q, k, v = (torch.randn(B, N, C, device=DEV, generator=g, dtype=dtype).requires_grad_() for _ in range(3))
+    bias = torch.where(torch.randint(0, 2, (B, N), device=DEV, generator=g) > 0.5, 0.0, float("-inf")).to(dtype)
+    mask = bias.unsqueeze(1).expand(-1, N, -1)
+    nk = float((bias == 0).sum())
+
+    def fwd():
+        s = torch.matmul(q, k.transpose(-2, -1)) / (C ** 0.5)
+        return torch.matmul(torch.softmax(s + mask, dim=-1), v)
+
+    def fwd_bwd():
+        out = fwd()
+        out.backward(torch.ones_like(out))
+        q.grad = k.grad = v.grad = None
+
+    with torch.no_grad():
+        ms_f = time_fn(fwd, iters=5, warm=2)
+    ms_fb = time_fn(fwd_bwd, iters=5, warm=2)
+    rec = {"mode": "eager reference arithmetic", "dtype": str(dtype).replace("torch.", ""), "B": B, "N": N, "C": C,
+           "fwd_ms": round(ms_f, 3), "fwd_tflops_useful": round(4 * N * nk * C / ms_f / 1e9, 1),
+           "fwd_bwd_ms": round(ms_fb, 3), "fwd_bwd_tflops_useful": round(12 * N * nk * C / ms_fb / 1e9, 1),
+           "peak_tflops": peak}
+    print(json.dumps(rec), flush=True)
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sweep", action="store_true")
@@ -74,12 +134,28 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--out", default=None)
     ap.add_argument("--site", type=int, default=None, help="run only this entry of the site list (for ncu)")
+    ap.add_argument("--generalised", action="store_true", help="only the generalised-mode sweep (heads, queries)")
+    ap.add_argument("--eager", action="store_true", help="only the eager-PyTorch reference arithmetic on this GPU")
     args = ap.parse_args()
     peak = 1601.0
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.isfile(pk):
         peak = json.load(open(pk))["bf16_tflops"]
     recs = []
+    if args.generalised or args.eager:
+        if args.generalised:
+            for heads in (4, 8):
+                for Q in (50, 100, 200):
+                    for N in (1024, 4096):
+                        recs.append(run_generalised(64, Q, N, heads, peak))
+            recs.append(run_generalised(16, 200, 16384, 4, peak))
+        if args.eager:
+            for N, C, B in ((16384, 64, 4), (4096, 128, 32), (1024, 256, 128)):
+                for dt in (torch.float32, torch.bfloat16):
+                    recs.append(run_eager(B, N, C, dt, peak))
+        if args.out:
+            json.dump({"peak_tflops_burst": peak, "records": recs}, open(args.out, "w"), indent=1)
+        return
     sites = [(16384, 64), (4096, 64), (4096, 128), (1024, 128), (1024, 256), (256, 256)]
     if args.site is not None:
         sites = [sites[args.site]]
