@@ -21,8 +21,36 @@ namespace mu {
 constexpr int kBK = 128;            // keys per CTA
 constexpr int kBwdThreads = 512;    // warps 0-3: TMA, MMA, 2 idle; 4-11: softmax (2 warpgroups); 12-15: dQ reduction
 constexpr float kLog2eB = 1.4426950408889634f;
+// Q_i / dO_i ring depth.  With 2 stages the loads of tile i+2 can only be issued when every MMA of tile i has
+// completed, and the ~1250-cycle TMA round trip sat on the critical path of every tile (timeline of one CTA:
+// tools/bwd_trace.py, profiles/r01_attn_bwd_timeline.txt): 3 stages = 686 -> 742 TFLOP/s at N = 16384, d = 64.
+// 3 stages still fit: 231,680 (d = 64) and 230,656 (d = 128) of 232,448 bytes.
+#ifndef MU_BWD_STAGES_64
+#define MU_BWD_STAGES_64 3
+#endif
+#ifndef MU_BWD_STAGES_128
+#define MU_BWD_STAGES_128 3
+#endif
 #ifndef MU_BWD_PROBE
 #define MU_BWD_PROBE 0      // 1 / 2: performance probes that skip work (wrong results), see DESIGN.md
+#endif
+
+// -DMU_BWD_TRACE=1: CTA (0, 0, 0) records clock64() at its pipeline events for query tiles [8, 40) into a global
+// array read back by tools/bwd_trace.py (a timeline of one CTA; not part of the product build).
+#ifndef MU_BWD_TRACE
+#define MU_BWD_TRACE 0
+#endif
+#if MU_BWD_TRACE
+constexpr int kTraceTiles = 32, kTraceFirst = 8, kTraceEvents = 24;
+__device__ long long g_bwd_trace[kTraceTiles * kTraceEvents];
+#define MU_TRACE(ev, i)                                                                                 \
+  do {                                                                                                  \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0 &&             \
+        (i) >= kTraceFirst && (i) < kTraceFirst + kTraceTiles)                                          \
+      g_bwd_trace[((i) - kTraceFirst) * kTraceEvents + (ev)] = clock64();                               \
+  } while (0)
+#else
+#define MU_TRACE(ev, i) do { } while (0)
 #endif
 
 template <int D, int BM, int DH, int STAGES, int PB>
@@ -143,6 +171,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       for (int i = 0; i < T; ++i) {
         const int st = i % STAGES, use = i / STAGES;
         if (use > 0) mbar_wait(qdo_empty + st, (use - 1) & 1);
+        MU_TRACE(0, i);                          // TMA: stage free, loads of tile i issued
         mbar_expect_tx(qdo_full + st, 2 * Cfg::kQBytes);
         for (int blk = 0; blk < D / 64; ++blk) {
           tma_load_3d(sQ + st * Cfg::kQBytes + blk * (BM * 128), &tmap_q, qdo_full + st, blk * 64, i * BM, b);
@@ -166,6 +195,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       auto issue_s_dp = [&](int i) {
         const int st = i % STAGES;
         mbar_wait(qdo_full + st, (i / STAGES) & 1);
+        MU_TRACE(1, i);                          // MMA: Q_i / dO_i landed
         tc_fence_after();
         const uint32_t qa = q_lo0 + st * (Cfg::kQBytes >> 4), da = do_lo0 + st * (Cfg::kQBytes >> 4);
 #pragma unroll
@@ -198,10 +228,12 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           if (MU_BWD_PROBE != 3 && elect_one())
             umma_ss_lo(tmem_base + Cfg::kTmDK, ds_lo + offa, (qa + kk * 128) | kLboQ, hi, idesc_acc, kk > 0 ? 1u : acc);
         }
+        MU_TRACE(4, i);                          // MMA: dV / dK issued
         if (i > 0) {
           mbar_wait(dq_free, (i - 1) & 1);
           tc_fence_after();
         }
+        MU_TRACE(5, i);                          // MMA: dQ accumulator free
 #pragma unroll
         for (int kk = 0; kk < kBK / 16; ++kk) {  // dQ tile: contraction over the 128 keys of this CTA
           uint32_t a, bd;
@@ -226,11 +258,14 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       for (int i = 0; i < T; ++i) {
         if (STAGES >= 2) {
           mbar_wait(sdp_free, i & 1);        // S^T / dP^T of tile i drained into registers
+          MU_TRACE(2, i);                    // MMA: sdp_free(i) seen
           tc_fence_after();
           if (i + 1 < T) issue_s_dp(i + 1);  // runs underneath the softmax arithmetic of tile i
           mbar_wait(pds_full, i & 1);        // P^T / dS^T of tile i are in shared memory
+          MU_TRACE(3, i);                    // MMA: pds_full(i) seen
           tc_fence_after();
           issue_acc(i);
+          MU_TRACE(6, i);                    // MMA: acc(i) issued
         } else {                             // single Q/dO stage: tile i+1 can only load after acc(i) released it
           mbar_wait(pds_full, i & 1);
           tc_fence_after();
@@ -275,7 +310,10 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       }
       if (i + 1 < T) fetch(i + 1, nl2, ndl);
       named_bar_sync(1, 256);
+      if (warp == 4) MU_TRACE(7, i);                     // softmax: waiting for S^T / dP^T
       mbar_wait(s_full, i & 1);
+      if (warp == 4) MU_TRACE(8, i);                     // softmax: s_full(i)
+      if (warp == 8) MU_TRACE(19, i);                    // second warpgroup: s_full(i)
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < kChunksPerThread; ++cc) {
@@ -286,6 +324,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(sdp_free);
+      if (warp == 4) MU_TRACE(9, i);                     // softmax: tile in registers
       if (tile_partial && !key_ok) {                     // rows past n_keep in the last key tile: p = exp2(-inf) = 0
 #pragma unroll
         for (int cc = 0; cc < kChunksPerThread; ++cc)
@@ -305,6 +344,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       // the MMAs that last read this P^T / dS^T buffer (tile i - PB) must have completed
       if (i >= PB) mbar_wait(pds_free + (i % PB), ((i / PB) - 1) & 1);
       if (i > 0) mbar_wait(p_free, (i - 1) & 1);         // dV MMAs of tile i-1 are done with P^T
+      if (warp == 4) MU_TRACE(10, i);                    // softmax: output buffers free
+      if (warp == 8) MU_TRACE(20, i);                    // second warpgroup: output buffers free
       const uint32_t ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
 #pragma unroll
       for (int cc = 0; cc < kChunksPerThread; ++cc) {
@@ -312,8 +353,12 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         uint32_t pk[16], dk[16];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
+#if MU_BWD_PROBE == 5    // no per-column statistics loads (wrong results): what do the broadcast LDS.128 cost?
+          const float4 l2 = make_float4(scale, scale, scale, scale), dl = l2;
+#else
           const float4 l2 = ld_shared_v4f(my_lse + (c * 32 + 4 * e) * 4);
           const float4 dl = ld_shared_v4f(my_delta + (c * 32 + 4 * e) * 4);
+#endif
           const float p0 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 0]), scale_log2, -l2.x));
           const float p1 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 1]), scale_log2, -l2.y));
           const float p2 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 2]), scale_log2, -l2.z));
@@ -337,11 +382,16 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           st_shared_v4(ds_addr + row_off + chunk, dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
         }
         tmem_st16(lane_base + Cfg::kTmP + c * 16, pk);   // 32 queries = 16 packed columns of the TMEM P^T tile
+        if (warp == 4) MU_TRACE(15 + cc, i);             // softmax: chunk cc computed and stored
       }
       tmem_wait_st();
+      if (warp == 4) MU_TRACE(17, i);                    // softmax: tcgen05.wait::st
       tc_fence_before();
       fence_proxy_async_smem();
+      if (warp == 4) MU_TRACE(18, i);                    // softmax: proxy fence
       mbar_arrive(pds_full);
+      if (warp == 4) MU_TRACE(11, i);                    // softmax: P^T / dS^T published
+      if (warp == 8) MU_TRACE(21, i);                    // second warpgroup: published
     }
     // ---- epilogue: dV_j (first warpgroup) and dK_j (second) out of TMEM, rows of kept keys only
     mbar_wait(pds_free + ((T - 1) % PB), ((T - 1) / PB) & 1);   // last tile's MMAs (and all before) are done
@@ -381,6 +431,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     uint32_t v[32];
     for (int i = 0; i < T; ++i) {
       mbar_wait(dq_full, i & 1);
+      if (warp == 12) MU_TRACE(12, i);                   // dQ warps: dq_full(i)
       tc_fence_after();
       if (DQT && Cfg::kDQTma) {
         // dQ^T tile: lanes = channels, columns = queries.  Staged transposed ([query][channel], 128-byte rows,
@@ -436,6 +487,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         const bool issuer = (threadIdx.x == kBwdThreads - 128);
         if (issuer) tma_store_wait_read<0>();          // the previous tile's reduce has finished reading the stage
         named_bar_sync(2, 128);
+        if (warp == 12) MU_TRACE(13, i);                 // dQ warps: staging buffer free
 #pragma unroll
         for (int c = 0; c < DH / 32; ++c) {
           tmem_ld32(lane_base + Cfg::kTmDQ + c * 32, v);
@@ -467,6 +519,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           for (int c = 0; c < DH / 32; ++c) tma_reduce_add_3d(&tmap_dq, stage + c * (BM * 128), c * 32, i * BM, b);
           tma_store_commit();
         }
+        if (warp == 12) MU_TRACE(14, i);                 // dQ warps: reduce issued
       }
     }
     if (Cfg::kDQTma && threadIdx.x == kBwdThreads - 128) tma_store_wait<0>();   // all reduce-adds landed before exit
@@ -528,6 +581,12 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
   return check_launch("dq_convert");
 }
 
+#if MU_BWD_TRACE
+extern "C" int mu_debug_bwd_trace(long long* host, int n) {   // tools/bwd_trace.py only (trace builds)
+  return (int)cudaMemcpyFromSymbol(host, g_bwd_trace, sizeof(long long) * (n < kTraceTiles * kTraceEvents ? n : kTraceTiles * kTraceEvents));
+}
+#endif
+
 size_t attn_bwd_sm100_workspace(int B, int N, int C) { return (size_t)B * N * C * sizeof(float); }
 
 int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep,
@@ -540,9 +599,9 @@ int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const i
   float* acc = (float*)workspace;
   switch (C) {
     case 64:
-      return run<64, 128, 64, 2, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+      return run<64, 128, 64, MU_BWD_STAGES_64, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
     case 128:
-      return run<128, 64, 128, 2, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+      return run<128, 64, 128, MU_BWD_STAGES_128, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
     case 256:
       return run<256, 64, 128, 1, 1>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
     default:
@@ -561,7 +620,7 @@ int launch_query_attn_bwd_sm100(const void* q, const void* k, const void* v, con
   MU_REQUIRE(workspace != nullptr && workspace_bytes >= attn_bwd_sm100_workspace(BH, Q, D), MU_ERR_WORKSPACE,
              "mu_query_attn_bwd: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
              attn_bwd_sm100_workspace(BH, Q, D));
-  return run<64, 128, 64, 2, 2, true>(q, k, v, nullptr, nullptr, d_o, lse, delta, dq, dk, dv, (float*)workspace, BH, Q,
+  return run<64, 128, 64, MU_BWD_STAGES_64, 2, true>(q, k, v, nullptr, nullptr, d_o, lse, delta, dq, dk, dv, (float*)workspace, BH, Q,
                                       NKP, s, N, scale, bits_t, heads, N);
 }
 
