@@ -343,7 +343,6 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       }
       // the MMAs that last read this P^T / dS^T buffer (tile i - PB) must have completed
       if (i >= PB) mbar_wait(pds_free + (i % PB), ((i / PB) - 1) & 1);
-      if (i > 0) mbar_wait(p_free, (i - 1) & 1);         // dV MMAs of tile i-1 are done with P^T
       if (warp == 4) MU_TRACE(10, i);                    // softmax: output buffers free
       if (warp == 8) MU_TRACE(20, i);                    // second warpgroup: output buffers free
       const uint32_t ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
@@ -380,6 +379,13 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           if (scale == 12345.f)
 #endif
           st_shared_v4(ds_addr + row_off + chunk, dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
+        }
+        // P^T is single-buffered in TMEM: the dV MMAs of tile i-1 must be done with it.  They run right after S^T /
+        // dP^T of this tile on the tensor pipe, so waiting here -- after the first chunk's arithmetic -- instead of
+        // before it takes ~400 cycles of stall off the critical chain of every tile (tools/bwd_trace.py).
+        if (cc == 0 && i > 0) {
+          mbar_wait(p_free, (i - 1) & 1);
+          tc_fence_after();
         }
         tmem_st16(lane_base + Cfg::kTmP + c * 16, pk);   // 32 queries = 16 packed columns of the TMEM P^T tile
         if (warp == 4) MU_TRACE(15 + cc, i);             // softmax: chunk cc computed and stored

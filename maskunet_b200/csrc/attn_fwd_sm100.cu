@@ -29,6 +29,26 @@ constexpr float kLog2eF = 1.4426950408889634f;
 constexpr int kPolyEvery = MU_FWD_POLY_EVERY;   // 0: all exponentials on MUFU; k: one in k on the FMA pipe
 constexpr float kLazyLog2 = 8.f;         // rescale O only when the row maximum grew by more than 2^8
 
+// -DMU_FWD_TRACE=1: CTA (0, 0) records clock64() at its pipeline events for key tiles [8, 40) (tools/fwd_trace.py).
+#ifndef MU_FWD_TRACE
+#define MU_FWD_TRACE 0
+#endif
+#if MU_FWD_TRACE
+constexpr int kFTraceTiles = 32, kFTraceFirst = 8, kFTraceEvents = 16;
+__device__ long long g_fwd_trace[kFTraceTiles * kFTraceEvents];
+#define MU_FTRACE(ev, j)                                                                                   \
+  do {                                                                                                     \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (j) >= kFTraceFirst &&            \
+        (j) < kFTraceFirst + kFTraceTiles)                                                                 \
+      g_fwd_trace[((j) - kFTraceFirst) * kFTraceEvents + (ev)] = clock64();                                \
+  } while (0)
+extern "C" int mu_debug_fwd_trace(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, g_fwd_trace, sizeof(long long) * (n < kFTraceTiles * kFTraceEvents ? n : kFTraceTiles * kFTraceEvents));
+}
+#else
+#define MU_FTRACE(ev, j) do { } while (0)
+#endif
+
 template <int D, int BN, int SBUFS, int SLOTS>
 struct FwdCfg {
   static constexpr int kDBlocks = D / 64;                   // 64-column (128-byte) blocks per row
@@ -116,6 +136,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       for (int t = 0; t < 2 * T; ++t) {  // t = 2j: K_j, t = 2j+1: V_j
         const int slot = t % SLOTS, use = t / SLOTS;
         if (use > 0) mbar_wait(kv_empty + slot, (use - 1) & 1);
+        MU_FTRACE(11 + (t & 1), t >> 1);           // TMA: K_j (11) / V_j (12) issued
         mbar_expect_tx(kv_full + slot, Cfg::kKVBytes);
         const CUtensorMap* tm = (t & 1) ? &tmap_v : &tmap_k;
         uint8_t* dst = sKV + slot * Cfg::kKVBytes;
@@ -134,6 +155,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       auto issue_s = [&](int j) {
         const int t = 2 * j, slot = t % SLOTS, buf = j % SBUFS;
         mbar_wait(kv_full + slot, (t / SLOTS) & 1);
+        MU_FTRACE(0, j);                           // MMA: K_j landed
         tc_fence_after();
         const uint32_t k_lo = kv_lo + slot * (Cfg::kKVBytes >> 4);
 #pragma unroll
@@ -147,6 +169,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           umma_commit(kv_empty + slot);
           umma_commit(s_full + buf);
         }
+        MU_FTRACE(1, j);                           // MMA: S_j issued
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -158,7 +181,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
         const int t = 2 * j + 1, slot = t % SLOTS;
         mbar_wait(kv_full + slot, (t / SLOTS) & 1);
+        MU_FTRACE(13, j);                          // MMA: V_j landed
         mbar_wait(p_full, j & 1);
+        MU_FTRACE(2, j);                           // MMA: p_full(j)
         tc_fence_after();
         const uint32_t v_lo = desc_lo_lbo(smem_u32(sKV) + slot * Cfg::kKVBytes, BN * 128);
 #pragma unroll
@@ -170,6 +195,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           umma_commit(kv_empty + slot);
           umma_commit(o_done);
         }
+        MU_FTRACE(3, j);                           // MMA: PV_j issued
       }
     }
   }
@@ -193,13 +219,16 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         const int buf = j % SBUFS;
         const uint32_t s_addr = lane_base + Cfg::kTmemS + buf * BN;
         const int limit = nk - j * BN;              // valid key columns in this tile (>= 1)
+        if (warp == 4) MU_FTRACE(4, j);             // softmax: waiting for S_j
         mbar_wait(s_full + buf, (j / SBUFS) & 1);
+        if (warp == 4) MU_FTRACE(5, j);             // softmax: s_full(j)
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) tmem_ld32(s_addr + c * 32, v[c]);
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(s_free + buf);                  // S lives in registers now: the next QK^T may overwrite TMEM
+        if (warp == 4) MU_FTRACE(6, j);             // softmax: S_j in registers
         if (limit < BN) {                           // tail of the last key tile
 #pragma unroll
           for (int c = 0; c < BN / 32; ++c)
@@ -254,8 +283,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           }
         }
         // ---- p = exp2((s - m) * scale * log2e), bf16 P tile into shared memory
+        if (warp == 4) MU_FTRACE(7, j);             // softmax: row maximum (and rescale) done
         const float mb = (QM && m == -INFINITY) ? 0.f : m * scale_log2;   // all -inf so far: p = exp2(-inf) = 0
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk_prev[16];                       // chunk c is stored while chunk c+1 is computed (see below)
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t pk[16];
@@ -271,15 +302,29 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           }
           // P never touches shared memory: 32 keys = 16 packed columns of the TMEM P tile.  The previous PV must
           // have consumed the tile first (normally long done: it was issued a whole exp phase ago).
-          if (c == 0 && j > 0) {
+          // The P tile is single-buffered in TMEM and PV_{j-1} (issued when P_{j-1} was published, one exp phase
+          // ago, on a tensor pipe shared with the other CTA of this SM) still reads it ~1400 cycles into this tile
+          // (tools/fwd_trace.py).  Stores trail the arithmetic by one 32-key chunk so that the wait comes after 64
+          // exponentials instead of 32 and is normally already satisfied.
+          if (c == 1 && j > 0) {
+            if (warp == 4) MU_FTRACE(8, j);         // softmax: first 64 exponentials done
             mbar_wait(o_done, (j - 1) & 1);
+            if (warp == 4) MU_FTRACE(9, j);         // softmax: PV_{j-1} done, P tile free
             tc_fence_after();
           }
-          tmem_st16(lane_base + Cfg::kTmemP + c * 16, pk);
+          if (c > 0) tmem_st16(lane_base + Cfg::kTmemP + (c - 1) * 16, pk_prev);
+          if (c + 1 < BN / 32) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk_prev[i] = pk[i];
+          } else {
+            tmem_st16(lane_base + Cfg::kTmemP + c * 16, pk);
+          }
         }
+        if (warp == 4) MU_FTRACE(10, j);            // softmax: all exponentials done
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(p_full);
+        if (warp == 4) MU_FTRACE(14, j);            // softmax: P_j published
         l = l * alpha + ((sum[0] + sum[1]) + (sum[2] + sum[3]));
       }
       // ---- epilogue: O / l, LSE
