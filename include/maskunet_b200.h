@@ -294,6 +294,13 @@ int mu_query_attn_bwd(const void* q, const void* k, const void* v, const uint32_
                       size_t workspace_bytes, int32_t BH, int32_t heads, int32_t Q, int32_t N, int32_t NKP, int32_t D,
                       float scale, int32_t dtype, mu_stream_t stream);
 
+/* SURVEY 8(f) rank 3, device half of the input pipeline: torchvision ToTensor() (:56-79, :97) on a uint8 batch.
+ *   img uint8 [B, H, W, Cin] (HWC as cv2 / PIL deliver it);  out = img / 255 (IEEE division, bit-exact with ToTensor)
+ *   channels_last = 0: out [B, Cin, H, W] (the reference's layout; Cpad ignored)
+ *   channels_last = 1: out [B, H, W, Cpad], channels >= Cin zero (Cpad = 8 feeds the tcgen05 stem convolution) */
+int mu_to_tensor_u8(const uint8_t* img, void* out, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cpad,
+                    int32_t channels_last, int32_t dtype, mu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,7 @@ SIGNATURES = {
     "mu_query_mask_bits": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P],
     "mu_query_attn_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "mu_query_attn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    "mu_to_tensor_u8": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "mu_bn_act_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
 }
 

@@ -439,4 +439,13 @@ int mu_query_attn_bwd(const void* q, const void* k, const void* v, const uint32_
                                      Q, N, NKP, D, scale, (cudaStream_t)stream);
 }
 
+int mu_to_tensor_u8(const uint8_t* img, void* out, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cpad,
+                    int32_t channels_last, int32_t dtype, mu_stream_t stream) {
+  MU_DTYPE_OK("mu_to_tensor_u8");
+  MU_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && (!channels_last || Cpad >= Cin), MU_ERR_BAD_SHAPE,
+             "mu_to_tensor_u8: bad shape (B=%d H=%d W=%d Cin=%d Cpad=%d)", B, H, W, Cin, Cpad);
+  MU_REQUIRE(img != nullptr && out != nullptr, MU_ERR_NULL, "mu_to_tensor_u8: null pointer");
+  return launch_to_tensor_u8(img, out, B, H, W, Cin, Cpad, channels_last, dtype, (cudaStream_t)stream);
+}
+
 }  // extern "C"

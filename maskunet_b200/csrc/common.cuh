@@ -130,6 +130,8 @@ int launch_query_attn_bwd_sm100(const void* q, const void* k, const void* v, con
                                 const float* lse, const float* delta, void* dq, void* dk, void* dv, void* workspace,
                                 size_t workspace_bytes, int BH, int heads, int Q, int N, int NKP, int D, float scale,
                                 cudaStream_t s);
+int launch_to_tensor_u8(const uint8_t* img, void* out, int B, int H, int W, int Cin, int Cpad, int channels_last,
+                        int dtype, cudaStream_t s);
 int launch_transpose(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t s);
 
 }  // namespace mu

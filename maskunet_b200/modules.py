@@ -202,9 +202,12 @@ def conv_bn_act(conv: nn.Conv2d, bn: nn.BatchNorm2d, x: torch.Tensor, act: int,
             and conv.kernel_size == (3, 3) and x.is_contiguous(memory_format=torch.channels_last)):
         # the 3-channel stem: zero-pad image and weight to 8 input channels (16-byte pixels, TMA-addressable);
         # autograd slices the weight gradient back
+        # (maskunet_b200.data.to_tensor(..., pad_to=8) delivers the image already padded)
         extra = 8 - conv.in_channels
-        x = F.pad(x, (0, 0, 0, 0, 0, extra)).contiguous(memory_format=torch.channels_last)
-        weight = F.pad(weight, (0, 0, 0, 0, 0, extra))
+        if x.shape[1] == conv.in_channels:
+            x = F.pad(x, (0, 0, 0, 0, 0, extra)).contiguous(memory_format=torch.channels_last)
+        if x.shape[1] == 8:
+            weight = F.pad(weight, (0, 0, 0, 0, 0, extra))
     if _own_conv3x3(conv, x, weight):
         y, sums, _ = ops.conv3x3(x, weight, bn.training)
         return fused_bn_act(y, bn, act, residual, sums=sums if bn.training else None)

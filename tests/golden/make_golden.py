@@ -177,7 +177,22 @@ def make_instance_loss():
         print(name, float(loss), "grad.abs.sum", float(sem.grad.abs().sum()))
 
 
+def make_to_tensor():
+    """torchvision's own ToTensor (the reference's transform, ade_semantic.py:9,85) on every uint8 value and on a
+    random RGB image."""
+    from torchvision.transforms import ToTensor
+    ramp = np.arange(256, dtype=np.uint8).reshape(16, 16, 1).repeat(3, axis=2)
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, size=(12, 20, 3), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "to_tensor.npz"), ramp=ramp, ramp_out=ToTensor()(ramp).numpy(),
+                        img=img, img_out=ToTensor()(img).numpy())
+    print("to_tensor", float(ToTensor()(img).sum()))
+
+
 def main():
+    if "--to-tensor-only" in sys.argv:
+        make_to_tensor()
+        return
     if "--postproc-only" in sys.argv:
         make_postproc()
         return
@@ -185,6 +200,7 @@ def main():
         make_instance_loss()
         return
     make_instance_loss()
+    make_to_tensor()
     make_postproc()
     ref = load_reference_classes("ade_semantic")
     make_attention(ref)

@@ -1,0 +1,56 @@
+"""GPU parity of the device ToTensor against torchvision's own output (goldens) and the oracle:
+bit-exact in fp32; bf16 = the fp32 value rounded once; the padded channels-last image feeds the U-Net unchanged."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import input_oracle as io_
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+def test_to_tensor_bit_exact_against_torchvision_golden():
+    from maskunet_b200 import data
+    z = np.load(os.path.join(GOLDEN, "to_tensor.npz"))
+    for k in ("ramp", "img"):
+        u8 = torch.from_numpy(z[k])[None].to(DEV)
+        want = torch.from_numpy(z[k + "_out"])[None]
+        got = data.to_tensor(u8)
+        assert got.dtype == torch.float32 and got.is_contiguous() and torch.equal(got.cpu(), want)
+        cl = data.to_tensor(u8, torch.float32, channels_last=True)
+        assert cl.is_contiguous(memory_format=torch.channels_last) and torch.equal(cl.cpu(), want)
+        bf = data.to_tensor(u8, torch.bfloat16, channels_last=True, pad_to=8)
+        assert bf.shape[1] == 8 and bf.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(bf[:, :3].float().cpu(), want.to(torch.bfloat16).float())
+        assert float(bf[:, 3:].abs().max()) == 0.0
+
+
+def test_full_size_batch_and_errors():
+    from maskunet_b200 import data
+    g = torch.Generator().manual_seed(0)
+    u8 = torch.randint(0, 256, (64, 128, 128, 3), dtype=torch.uint8, generator=g)
+    got = data.to_tensor(u8.to(DEV))
+    assert torch.equal(got.cpu(), torch.from_numpy(io_.to_tensor(u8.numpy())))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        data.to_tensor(u8)
+    with pytest.raises(ValueError):
+        data.to_tensor(u8.to(DEV), pad_to=8)
+
+
+def test_padded_image_feeds_the_unet_unchanged_and_prefetcher_order():
+    import maskunet_b200
+    from maskunet_b200 import data
+    torch.manual_seed(0)
+    net = maskunet_b200.UNet(3, 19, compute_dtype=torch.bfloat16, channels_last=True).to(DEV).eval()
+    g = torch.Generator().manual_seed(1)
+    batches = [(torch.randint(0, 256, (2, 128, 128, 3), dtype=torch.uint8, generator=g),
+                torch.randint(0, 19, (2, 128, 128), generator=g)) for _ in range(3)]
+    with torch.no_grad():
+        for (u8, lab), (x, y) in zip(batches, data.DevicePrefetcher(batches, DEV)):
+            assert x.shape == (2, 8, 128, 128) and x.dtype == torch.bfloat16 and torch.equal(y.cpu(), lab)
+            ref_in = torch.from_numpy(io_.to_tensor(u8.numpy())).to(DEV)          # what the reference would feed
+            assert torch.equal(net(x), net(ref_in))

@@ -125,3 +125,13 @@ def test_instance_contrastive_loss_matches_reference_golden(name):
     loss.backward()
     assert rel_err(sem.grad, torch.from_numpy(z["grad"])) < 1e-5
     assert len(sel) >= 3
+
+
+def test_to_tensor_matches_torchvision_golden():
+    """oracle/input_oracle.py against torchvision's own ToTensor (the reference's transform, ade_semantic.py:9,85):
+    all 256 byte values and a random RGB image, bit for bit."""
+    from oracle import input_oracle as io_
+    z = np.load(os.path.join(GOLDEN, "to_tensor.npz"))
+    for k in ("ramp", "img"):
+        got = io_.to_tensor(z[k][None])[0]
+        assert got.dtype == np.float32 and np.array_equal(got, z[k + "_out"])
