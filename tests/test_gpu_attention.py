@@ -294,3 +294,49 @@ def test_resample_mode_draws_new_mask_each_forward():
     a = m.mask[:, 0, :].clone()
     m(x)
     assert not torch.equal(a, m.mask[:, 0, :])
+
+
+def test_full_size_properties_of_the_attention_kernels():
+    """BASELINE size of the dominant site (N = 16384 tokens, C = 64, ~50 % keys kept; batch 16 so that the grid is
+    several waves deep): size-independent identities instead of an oracle the CPU cannot finish.
+      * rows of P sum to 1:   V = const  =>  O = const
+      * linearity in V:       attn(a v1 + b v2) = a attn(v1) + b attn(v2)
+      * sum over kept keys of dV = sum over queries of dO            (columns of P^T dO, rows of P sum to 1)
+      * sum over kept keys of dK = 0                                 (rows of dS sum to 0: the key bias has no gradient)
+      * rows of masked keys in dK / dV (token space) are exactly zero; dO = 0  =>  all gradients exactly zero"""
+    from maskunet_b200 import ops
+    dev = _dev()
+    B, N, C = 16, 16384, 64
+    g = torch.Generator(device=dev).manual_seed(7)
+    bits = (torch.rand(B, N, device=dev, generator=g) < 0.5).to(torch.int64)
+    _, n_keep, keep_idx, keep_rank = ops.mask_binarize(bits)
+    NKP = ops.nkp_of(N)
+    q = torch.randn(B, N, C, device=dev, generator=g).bfloat16()
+
+    def compact(t):                                            # [B, N, C] token space -> compacted kept rows
+        out = torch.zeros(B, NKP, C, device=dev, dtype=t.dtype)
+        for b in range(B):
+            out[b, :int(n_keep[b])] = t[b, bits[b] > 0]
+        return out
+
+    k_tok, v1_tok, v2_tok = (torch.randn(B, N, C, device=dev, generator=g).bfloat16() for _ in range(3))
+    kc, v1, v2 = compact(k_tok), compact(v1_tok), compact(v2_tok)
+    ones = compact(torch.full((B, N, C), 0.75, device=dev, dtype=torch.bfloat16))
+    o_const, _ = ops.attn_fwd(q, kc, ones, n_keep)
+    assert float((o_const.float() - 0.75).abs().max()) < 1e-2
+    o1, lse = ops.attn_fwd(q, kc, v1, n_keep)
+    o2, _ = ops.attn_fwd(q, kc, v2, n_keep)
+    mix = (0.5 * v1.float() - 0.25 * v2.float()).bfloat16()    # exact in bf16 up to one rounding
+    om, _ = ops.attn_fwd(q, kc, mix, n_keep)
+    assert rel_err(om, 0.5 * o1.float() - 0.25 * o2.float()) < 2e-2
+    d_o = torch.randn(B, N, C, device=dev, generator=g).bfloat16()
+    delta = (d_o.float() * o1.float()).sum(-1)
+    dq, dk, dv = ops.attn_bwd(q, kc, v1, n_keep, keep_idx, d_o, lse, delta)
+    masked = bits == 0
+    assert float(dk[masked].abs().max()) == 0.0 and float(dv[masked].abs().max()) == 0.0
+    sum_do = d_o.float().sum(1)
+    assert rel_err(dv.float().sum(1), sum_do) < 2e-2
+    scale_dk = float(dk.float().abs().sum(1).mean())           # sum of |dK| over keys: the scale the zero is judged on
+    assert float(dk.float().sum(1).abs().max()) < 2e-2 * scale_dk
+    zq, zk, zv = ops.attn_bwd(q, kc, v1, n_keep, keep_idx, torch.zeros_like(d_o), lse, torch.zeros_like(delta))
+    assert float(zq.abs().max()) == 0.0 and float(zk.abs().max()) == 0.0 and float(zv.abs().max()) == 0.0
