@@ -31,6 +31,12 @@ constexpr float kLog2eB = 1.4426950408889634f;
 #ifndef MU_BWD_STAGES_128
 #define MU_BWD_STAGES_128 3
 #endif
+// 1: K_j / V_j as TMEM-resident A operands of the S^T / dP^T MMAs (d = 64).  Measured on B200 at N = 16384:
+// 715 TFLOP/s against 741 with shared-memory A operands (parity-green either way), so it stays off: the TS-mode MMAs
+// and the extra dq_free dependency of the shared P^T / dQ columns cost more than 32 KB per tile of operand reads save.
+#ifndef MU_BWD_KV_TMEM
+#define MU_BWD_KV_TMEM 0
+#endif
 #ifndef MU_BWD_PROBE
 #define MU_BWD_PROBE 0      // 1 / 2: performance probes that skip work (wrong results), see DESIGN.md
 #endif
@@ -60,10 +66,17 @@ struct BwdCfg {
   static constexpr int kKBytes = kBK * D * 2;            // K_j or V_j
   static constexpr int kQBytes = BM * D * 2;             // Q_i or dO_i
   static constexpr int kPBytes = kBK * BM * 2;           // P^T or dS^T
-  static constexpr int kTmS = 0, kTmDP = BM, kTmDV = 2 * BM, kTmDK = 2 * BM + DH, kTmDQ = 2 * BM + 2 * DH;
+  // Optional (MU_BWD_KV_TMEM, off: measured slower), d = 64: K_j and V_j, the A operands of the S^T / dP^T MMAs of
+  // EVERY query tile, live in TMEM for the whole CTA (32 KB less shared-memory operand traffic per tile).  The columns
+  // come from letting the dQ accumulator share the P^T tile's columns: the tensor pipe runs dV_i (last reader of
+  // P^T_i) before dQ_i, and the softmax warps wait for dq_free(i) before they store P^T_{i+1}.
+  static constexpr bool kKVT = (MU_BWD_KV_TMEM != 0) && (D == 64) && !kDQT;
+  static constexpr int kTmS = 0, kTmDP = BM, kTmDV = 2 * BM, kTmDK = 2 * BM + DH;
   static constexpr int kDQCols = kDQT ? BM : DH;
-  static constexpr int kTmP = kTmDQ + kDQCols;           // bf16 P^T tile, two queries per 32-bit column (A of the dV MMA)
-  static constexpr int kTmemUsed = kTmP + BM / 2;
+  static constexpr int kTmK = 2 * BM + 2 * DH, kTmV = kTmK + D / 2;          // packed bf16: two channels per column
+  static constexpr int kTmDQ = kKVT ? kTmV + D / 2 : 2 * BM + 2 * DH;
+  static constexpr int kTmP = kKVT ? kTmDQ : kTmDQ + kDQCols;   // bf16 P^T tile, two queries per 32-bit column (A of the dV MMA)
+  static constexpr int kTmemUsed = kTmP + (kKVT ? (BM / 2 > kDQCols ? BM / 2 : kDQCols) : BM / 2);
   static_assert(kTmemUsed <= 512, "TMEM overflow");
   static constexpr int kStatBytes = 2 * 2 * BM * 4;       // lse2, delta, double-buffered over tiles
   // PB = 2 double-buffers the P^T / dS^T tiles so that the exp / dS work of query tile i+1 overlaps the
@@ -117,7 +130,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   uint64_t* dq_free = dq_full + 1;          // 1 (128 arrivals)
   uint64_t* sdp_free = dq_free + 1;         // 1 (256 arrivals): S^T / dP^T of this tile are in registers
   uint64_t* p_free = sdp_free + 1;          // 1: the dV MMAs have consumed P^T
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 1);
+  uint64_t* kv_tm = p_free + 1;             // 1 (256 arrivals): K_j / V_j copied into TMEM (kKVT)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_tm + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int b = blockIdx.y, k0 = blockIdx.x * kBK, half = blockIdx.z;
@@ -138,6 +152,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     mbar_init(dq_free, 128);
     mbar_init(sdp_free, 256);
     mbar_init(p_free, 1);
+    mbar_init(kv_tm, 256);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -201,12 +216,20 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t offa = ((kk >> 2) * (kBK * 128) + (kk & 3) * 32) >> 4, offb = ((kk >> 2) * (BM * 128) + (kk & 3) * 32) >> 4;
-          if (elect_one()) umma_ss_lo(tmem_base + Cfg::kTmS, k_lo + offa, qa + offb, hi, idesc_s, kk > 0 ? 1u : 0u);
+          if (Cfg::kKVT) {
+            if (elect_one()) umma_ts_lo(tmem_base + Cfg::kTmS, tmem_base + Cfg::kTmK + kk * 8, qa + offb, hi, idesc_s, kk > 0 ? 1u : 0u);
+          } else {
+            if (elect_one()) umma_ss_lo(tmem_base + Cfg::kTmS, k_lo + offa, qa + offb, hi, idesc_s, kk > 0 ? 1u : 0u);
+          }
         }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t offa = ((kk >> 2) * (kBK * 128) + (kk & 3) * 32) >> 4, offb = ((kk >> 2) * (BM * 128) + (kk & 3) * 32) >> 4;
-          if (elect_one()) umma_ss_lo(tmem_base + Cfg::kTmDP, v_lo + offa, da + offb, hi, idesc_s, kk > 0 ? 1u : 0u);
+          if (Cfg::kKVT) {
+            if (elect_one()) umma_ts_lo(tmem_base + Cfg::kTmDP, tmem_base + Cfg::kTmV + kk * 8, da + offb, hi, idesc_s, kk > 0 ? 1u : 0u);
+          } else {
+            if (elect_one()) umma_ss_lo(tmem_base + Cfg::kTmDP, v_lo + offa, da + offb, hi, idesc_s, kk > 0 ? 1u : 0u);
+          }
         }
         if (elect_one()) umma_commit(s_full);
       };
@@ -254,6 +277,10 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
       };
       mbar_wait(kv_full, 0);
+      if (Cfg::kKVT) {
+        mbar_wait(kv_tm, 0);                 // the softmax warps have copied K_j / V_j into TMEM
+        tc_fence_after();
+      }
       issue_s_dp(0);
       for (int i = 0; i < T; ++i) {
         if (STAGES >= 2) {
@@ -299,6 +326,25 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     };
     float nl2, ndl;
     fetch(0, nl2, ndl);
+    if (Cfg::kKVT) {
+      // thread <-> key row r: its 64 channels (128 bytes, 8 swizzled 16-byte chunks) become 32 packed TMEM columns;
+      // the first warpgroup copies K_j, the second V_j
+      mbar_wait(kv_full, 0);
+      const uint32_t src = smem_u32(hcol == 0 ? sK : sV) + r * 128;
+      uint32_t w[32];
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const float4 f = ld_shared_v4f(src + ((uint32_t)(ch ^ (r & 7))) * 16);
+        w[4 * ch] = __float_as_uint(f.x);
+        w[4 * ch + 1] = __float_as_uint(f.y);
+        w[4 * ch + 2] = __float_as_uint(f.z);
+        w[4 * ch + 3] = __float_as_uint(f.w);
+      }
+      tmem_st32(lane_base + (hcol == 0 ? Cfg::kTmK : Cfg::kTmV), w);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(kv_tm);
+    }
     constexpr int kChunksPerThread = BM / 64;            // 32-column chunks per thread
     uint32_t s[kChunksPerThread][32], dp[kChunksPerThread][32];
     const bool tile_partial = k0 + kBK > nk;
@@ -385,6 +431,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         // before it takes ~400 cycles of stall off the critical chain of every tile (tools/bwd_trace.py).
         if (cc == 0 && i > 0) {
           mbar_wait(p_free, (i - 1) & 1);
+          if (Cfg::kKVT) mbar_wait(dq_free, (i - 1) & 1);   // dQ_{i-1} shares these columns and has been read out
           tc_fence_after();
         }
         tmem_st16(lane_base + Cfg::kTmP + c * 16, pk);   // 32 queries = 16 packed columns of the TMEM P^T tile
