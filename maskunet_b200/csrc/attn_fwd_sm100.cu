@@ -27,6 +27,10 @@ constexpr float kLog2eF = 1.4426950408889634f;
 #define MU_FWD_POLY_EVERY 0
 #endif
 constexpr int kPolyEvery = MU_FWD_POLY_EVERY;   // 0: all exponentials on MUFU; k: one in k on the FMA pipe
+#ifndef MU_FWD_SPECULATE
+#define MU_FWD_SPECULATE 1
+#endif
+constexpr bool kSpeculate = MU_FWD_SPECULATE != 0;   // exponentials before the tile maximum is known (see the softmax loop)
 constexpr float kLazyLog2 = 8.f;         // rescale O only when the row maximum grew by more than 2^8
 
 // -DMU_FWD_TRACE=1: CTA (0, 0) records clock64() at its pipeline events for key tiles [8, 40) (tools/fwd_trace.py).
@@ -246,86 +250,112 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
               if (!((w >> i) & 1u)) v[c][i] = 0xff800000u;
           }
         }
-        // ---- row max: independent FMNMX3 chains
-        float mx[BN / 32];
+        // ---- row maximum: independent FMNMX3 chains (ALU pipe)
+        auto row_max = [&]() -> float {
+          float mx[BN / 32];
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-          mx[c] = max3(__uint_as_float(v[c][0]), __uint_as_float(v[c][1]), __uint_as_float(v[c][2]));
+          for (int c = 0; c < BN / 32; ++c) {
+            mx[c] = max3(__uint_as_float(v[c][0]), __uint_as_float(v[c][1]), __uint_as_float(v[c][2]));
 #pragma unroll
-          for (int i = 3; i + 1 < 32; i += 2)
-            mx[c] = max3(mx[c], __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
-          mx[c] = fmaxf(mx[c], __uint_as_float(v[c][31]));
-        }
-        float m_new = m;
+            for (int i = 3; i + 1 < 32; i += 2)
+              mx[c] = max3(mx[c], __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
+            mx[c] = fmaxf(mx[c], __uint_as_float(v[c][31]));
+          }
+          float r_ = mx[0];
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) m_new = fmaxf(m_new, mx[c]);
+          for (int c = 1; c < BN / 32; ++c) r_ = fmaxf(r_, mx[c]);
+          return r_;
+        };
+        // ---- O *= alpha in TMEM (only when the exponent offset moves)
+        auto rescale_o = [&](float a) {
+          mbar_wait(o_done, (j - 1) & 1);                              // the previous PV has landed in TMEM
+          tc_fence_after();
+          uint32_t ov[32];
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) {
+            tmem_ld32(lane_base + Cfg::kTmemO + c * 32, ov);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * a);
+            tmem_st32(lane_base + Cfg::kTmemO + c * 32, ov);
+          }
+          tmem_wait_st();
+        };
+        // ---- p = exp2((s - m) * scale * log2e) -> bf16 P tile in TMEM (it never touches shared memory: 32 keys = 16
+        // packed columns); returns the row sum.  The P tile is single-buffered and PV_{j-1} (issued when P_{j-1} was
+        // published, one exp phase ago, on a tensor pipe shared with the other CTA of this SM) still reads it ~1400
+        // cycles into this tile (tools/fwd_trace.py): stores trail the arithmetic by one 32-key chunk so that the wait
+        // comes after 64 exponentials and is normally already satisfied.
+        auto exp_pass = [&](float m_off) -> float {
+          const float mb = (QM && m_off == -INFINITY) ? 0.f : m_off * scale_log2;   // all -inf so far: p = exp2(-inf) = 0
+          float sum[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t pk_prev[16];
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i]), scale_log2, -mb));
+              const float x1 = fmaf(__uint_as_float(v[c][2 * i + 1]), scale_log2, -mb);
+              // every kPolyEvery-th exponential goes to the FMA pipe (MUFU.EX2 is the forward pass's busiest pipe)
+              const float p1 = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? poly_exp2(x1)
+                                                                                                    : fast_exp2(x1);
+              sum[i & 3] += p0 + p1;
+              pk[i] = pack_bf16(p0, p1);
+            }
+            if (c == 1 && j > 0) {
+              if (warp == 4) MU_FTRACE(8, j);         // softmax: first 64 exponentials done
+              mbar_wait(o_done, (j - 1) & 1);
+              if (warp == 4) MU_FTRACE(9, j);         // softmax: PV_{j-1} done, P tile free
+              tc_fence_after();
+            }
+            if (c > 0) tmem_st16(lane_base + Cfg::kTmemP + (c - 1) * 16, pk_prev);
+            if (c + 1 < BN / 32) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk_prev[i] = pk[i];
+            } else {
+              tmem_st16(lane_base + Cfg::kTmemP + c * 16, pk);
+            }
+          }
+          return (sum[0] + sum[1]) + (sum[2] + sum[3]);
+        };
         // ---- lazy rescale: the exponent offset m only follows the running maximum when it has moved by more than
         // 2^kLazyLog2 (P then stays below 2^kLazyLog2, harmless in bf16 / fp32), so after the first tiles the
         // softmax warps neither wait for the previous PV nor touch O in TMEM.  O / l and the LSE use the same m.
-        float alpha = 1.f;
-        const bool grow = (m_new - m) * scale_log2 > kLazyLog2;       // true on the first tile (m = -inf)
-        if (__any_sync(0xffffffffu, grow)) {
-          alpha = (QM && m_new == -INFINITY) ? 1.f : fast_exp2((m - m_new) * scale_log2);   // row masked so far
-          m = m_new;
-          if (j > 0) {
-            mbar_wait(o_done, (j - 1) & 1);                            // the previous PV has landed in TMEM
-            tc_fence_after();
-            uint32_t ov[32];
-#pragma unroll
-            for (int c = 0; c < D / 32; ++c) {
-              tmem_ld32(lane_base + Cfg::kTmemO + c * 32, ov);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-              tmem_st32(lane_base + Cfg::kTmemO + c * 32, ov);
-            }
+        float alpha = 1.f, tile_sum;
+        if (kSpeculate && j > 0) {
+          // Speculative order (MU_FWD_SPECULATE): the offset almost never moves after the first tiles, so the
+          // exponentials start at once with the current m while the tile maximum is reduced on the ALU pipe beside
+          // them -- the 400-cycle max phase leaves the serial chain of the tile (tools/fwd_trace.py).  If some row
+          // did outgrow m by more than 2^kLazyLog2 the tile is redone with the new offset (its first pass may have
+          // overflowed: every P value and the row sum are rewritten).
+          tile_sum = exp_pass(m);
+          const float m_new = fmaxf(m, row_max());
+          const bool grow = (m_new - m) * scale_log2 > kLazyLog2;
+          if (__any_sync(0xffffffffu, grow)) {
+            alpha = (QM && m_new == -INFINITY) ? 1.f : fast_exp2((m - m_new) * scale_log2);
+            m = m_new;
             tmem_wait_st();
+            rescale_o(alpha);
+            tile_sum = exp_pass(m);
           }
-        }
-        // ---- p = exp2((s - m) * scale * log2e), bf16 P tile into shared memory
-        if (warp == 4) MU_FTRACE(7, j);             // softmax: row maximum (and rescale) done
-        const float mb = (QM && m == -INFINITY) ? 0.f : m * scale_log2;   // all -inf so far: p = exp2(-inf) = 0
-        float sum[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t pk_prev[16];                       // chunk c is stored while chunk c+1 is computed (see below)
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i]), scale_log2, -mb));
-            const float x1 = fmaf(__uint_as_float(v[c][2 * i + 1]), scale_log2, -mb);
-            // every kPolyEvery-th exponential goes to the FMA pipe (MUFU.EX2 is the forward pass's busiest pipe)
-            const float p1 = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? poly_exp2(x1)
-                                                                                                  : fast_exp2(x1);
-            sum[i & 3] += p0 + p1;
-            pk[i] = pack_bf16(p0, p1);
+        } else {
+          const float m_new = fmaxf(m, row_max());
+          const bool grow = (m_new - m) * scale_log2 > kLazyLog2;       // true on the first tile (m = -inf)
+          if (__any_sync(0xffffffffu, grow)) {
+            alpha = (QM && m_new == -INFINITY) ? 1.f : fast_exp2((m - m_new) * scale_log2);   // row masked so far
+            m = m_new;
+            if (j > 0) rescale_o(alpha);
           }
-          // P never touches shared memory: 32 keys = 16 packed columns of the TMEM P tile.  The previous PV must
-          // have consumed the tile first (normally long done: it was issued a whole exp phase ago).
-          // The P tile is single-buffered in TMEM and PV_{j-1} (issued when P_{j-1} was published, one exp phase
-          // ago, on a tensor pipe shared with the other CTA of this SM) still reads it ~1400 cycles into this tile
-          // (tools/fwd_trace.py).  Stores trail the arithmetic by one 32-key chunk so that the wait comes after 64
-          // exponentials instead of 32 and is normally already satisfied.
-          if (c == 1 && j > 0) {
-            if (warp == 4) MU_FTRACE(8, j);         // softmax: first 64 exponentials done
-            mbar_wait(o_done, (j - 1) & 1);
-            if (warp == 4) MU_FTRACE(9, j);         // softmax: PV_{j-1} done, P tile free
-            tc_fence_after();
-          }
-          if (c > 0) tmem_st16(lane_base + Cfg::kTmemP + (c - 1) * 16, pk_prev);
-          if (c + 1 < BN / 32) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk_prev[i] = pk[i];
-          } else {
-            tmem_st16(lane_base + Cfg::kTmemP + c * 16, pk);
-          }
+          if (warp == 4) MU_FTRACE(7, j);             // softmax: row maximum (and rescale) done
+          tile_sum = exp_pass(m);
         }
         if (warp == 4) MU_FTRACE(10, j);            // softmax: all exponentials done
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(p_full);
         if (warp == 4) MU_FTRACE(14, j);            // softmax: P_j published
-        l = l * alpha + ((sum[0] + sum[1]) + (sum[2] + sum[3]));
+        l = l * alpha + tile_sum;
       }
       // ---- epilogue: O / l, LSE
       mbar_wait(o_done, (T - 1) & 1);
