@@ -185,7 +185,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       }
       for (int i = 0; i < T; ++i) {
         const int st = i % STAGES, use = i / STAGES;
-        if (use > 0) mbar_wait(qdo_empty + st, (use - 1) & 1);
+        if (use > 0) mbar_wait_relaxed(qdo_empty + st, (use - 1) & 1);
         MU_TRACE(0, i);                          // TMA: stage free, loads of tile i issued
         mbar_expect_tx(qdo_full + st, 2 * Cfg::kQBytes);
         for (int blk = 0; blk < D / 64; ++blk) {
@@ -483,7 +483,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t v[32];
     for (int i = 0; i < T; ++i) {
-      mbar_wait(dq_full, i & 1);
+      mbar_wait_relaxed(dq_full, i & 1);
       if (warp == 12) MU_TRACE(12, i);                   // dQ warps: dq_full(i)
       tc_fence_after();
       if (DQT && Cfg::kDQTma) {

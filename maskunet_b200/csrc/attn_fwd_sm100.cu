@@ -139,7 +139,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       for (int blk = 0; blk < Cfg::kDBlocks; ++blk) tma_load_3d(sQ + blk * (kBM * 128), &tmap_q, q_full, blk * 64, q0, b);
       for (int t = 0; t < 2 * T; ++t) {  // t = 2j: K_j, t = 2j+1: V_j
         const int slot = t % SLOTS, use = t / SLOTS;
-        if (use > 0) mbar_wait(kv_empty + slot, (use - 1) & 1);
+        if (use > 0) mbar_wait_relaxed(kv_empty + slot, (use - 1) & 1);
         MU_FTRACE(11 + (t & 1), t >> 1);           // TMA: K_j (11) / V_j (12) issued
         mbar_expect_tx(kv_full + slot, Cfg::kKVBytes);
         const CUtensorMap* tm = (t & 1) ? &tmap_v : &tmap_k;

@@ -125,7 +125,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         for (int ch = 0; ch < kchunks; ++ch) {
 #pragma unroll
           for (int g = 0; g < GROUPS; ++g) {
-            mbar_wait(a_empty + sa, pa ^ 1);
+            mbar_wait_relaxed(a_empty + sa, pa ^ 1);
             mbar_expect_tx(a_full + sa, a_bytes);
             const int cx = MODE == CONV_W128 ? -1 : (MODE == CONV_ROWS ? g - 1 : 0);
             const int cy = MODE == CONV_1X1 ? y0 : y0 - 1;
@@ -134,7 +134,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) {
               const int tap = MODE == CONV_ROWS ? j * 3 + g : j;
-              mbar_wait(b_empty + sb, pb ^ 1);
+              mbar_wait_relaxed(b_empty + sb, pb ^ 1);
               mbar_expect_tx(b_full + sb, kBBytes);
               tma_load_3d(sB + sb * kBBytes, &tmap_w, b_full + sb, ch * 64, n0, tap);
               if (++sb == SB) { sb = 0; pb ^= 1; }
@@ -383,7 +383,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     if (lane_id() == 0) {
       for (int j = 0; j < nchunks; ++j) {
         const int st = j % p.S, use = j / p.S;
-        if (use > 0) mbar_wait(empty + st, (use - 1) & 1);
+        if (use > 0) mbar_wait_relaxed(empty + st, (use - 1) & 1);
         const int mt = c_begin + j;
         const int b = mt / p.tiles_y, y0 = (mt - b * p.tiles_y) * p.TH;
         uint8_t* sX = smem + st * stage_bytes;

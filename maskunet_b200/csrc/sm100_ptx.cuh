@@ -70,6 +70,30 @@ MU_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// Waits with slack (TMA producers waiting for a free ring slot, read-out warps waiting for an accumulator): sleep
+// between polls instead of spinning -- a spinning warp issues instructions, and the training step is power-capped.
+#ifndef MU_RELAXED_SLEEP_NS
+#define MU_RELAXED_SLEEP_NS 64
+#endif
+MU_DEVICE void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+#if MU_RELAXED_SLEEP_NS > 0
+  if (mbar_try_wait(bar, parity)) return;
+  const long long start = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(MU_RELAXED_SLEEP_NS);
+#if MU_SPIN_CYCLES > 0
+    if (clock64() - start > MU_SPIN_CYCLES) {
+      printf("mbar_wait_relaxed timeout: block (%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+#endif
+  }
+#else
+  mbar_wait(bar, parity);
+#endif
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 MU_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
