@@ -14,9 +14,10 @@ from .modules import (ConvBlock, DownSample, InstanceUNet, Mask2FormerAttention,
 
 from . import checkpoint  # noqa: E402
 from . import data  # noqa: E402  (device ToTensor + prefetcher, ade_semantic.py:56-97)
+from . import query_attention  # noqa: E402  (generalised mode of the kernel sweep)
 from .losses import InstanceContrastiveLoss  # noqa: E402  (device version of coco_panoptic.py:482-521)
 from .ops import mean_iou, segmentation_argmax  # noqa: E402  (device versions of ade_semantic.py:128-146)
 
 __all__ = ["Mask2FormerAttention", "ConvBlock", "DownSample", "UpSample", "UNet", "InstanceUNet", "ops",
-           "mean_iou", "segmentation_argmax", "checkpoint", "InstanceContrastiveLoss", "data"]
+           "mean_iou", "segmentation_argmax", "checkpoint", "InstanceContrastiveLoss", "data", "query_attention"]
 __version__ = "0.1.0"

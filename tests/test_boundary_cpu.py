@@ -66,3 +66,34 @@ def test_module_surface_matches_reference_contract():
         assert set(digest) == set(meta["param_digest"])           # same state_dict keys (incl. dead emb_layer.*)
         same_rng = all(abs(digest[k] - v) <= 1e-6 * max(1.0, abs(v)) for k, v in meta["param_digest"].items())
         assert same_rng, "initialisation does not reproduce the reference's RNG order"
+
+
+def test_widened_ops_are_registered_with_fake_shapes():
+    """The ops of the rows widened after the hot path exist, infer shapes without a device and have no
+    CPU kernel."""
+    import maskunet_b200  # noqa: F401
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    for name in ("instance_triplet", "instance_triplet_bwd", "argmax_iou", "to_tensor_u8", "query_mask_bits",
+                 "query_attn_fwd", "query_attn_bwd"):
+        assert hasattr(torch.ops.maskunet, name), name
+    with FakeTensorMode():
+        bf = dict(device="cuda", dtype=torch.bfloat16)
+        qe, feat = torch.empty(2, 100, 256, **bf), torch.empty(2, 1000, 256, **bf)
+        bits, bits_t, cnt, logits = torch.ops.maskunet.query_mask_bits(qe, feat, False)
+        assert bits.shape == (2, 100, 32) and bits_t.shape == (2, 1024, 4) and cnt.shape == (2, 100) and logits.numel() == 0
+        qh, kh = torch.empty(8, 100, 64, **bf), torch.empty(8, 1024, 64, **bf)
+        o, lse = torch.ops.maskunet.query_attn_fwd(qh, kh, kh, bits, 4, 1000, 0.125)
+        assert o.shape == qh.shape and lse.shape == (8, 100) and lse.dtype == torch.float32
+        u8 = torch.empty(4, 128, 128, 3, device="cuda", dtype=torch.uint8)
+        x = torch.ops.maskunet.to_tensor_u8(u8, True, True, 8)
+        assert x.shape == (4, 8, 128, 128) and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+        sem = torch.empty(2, 19, 16, 16, device="cuda")
+        loss, sel, dist = torch.ops.maskunet.instance_triplet(sem, torch.empty(512, device="cuda", dtype=torch.int64),
+                                                              torch.empty(3, 5, device="cuda", dtype=torch.int64), 1.0)
+        assert loss.shape == (1,) and sel.shape == (5, 6) and dist.shape == (5, 2)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.maskunet.to_tensor_u8(torch.zeros(1, 4, 4, 3, dtype=torch.uint8), False, False, 0)
+    crit = maskunet_b200.InstanceContrastiveLoss(margin=1.0, ignore_value=255)
+    assert crit.margin == 1.0 and crit.ignore_value == 255 and len(list(crit.parameters())) == 0
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        crit(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4, dtype=torch.int64))
