@@ -42,8 +42,8 @@ def to_tensor_u8(images: Tensor, bf16: bool, channels_last: bool, pad_to: int) -
 def _(images, bf16, channels_last, pad_to):
     B, H, W, C = images.shape
     cpad = max(C, pad_to) if channels_last else C
-    return images.new_empty((B, cpad, H, W), dtype=torch.bfloat16 if bf16 else torch.float32,
-                            memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    return torch.empty((B, cpad, H, W), dtype=torch.bfloat16 if bf16 else torch.float32, device=images.device,
+                       memory_format=torch.channels_last if channels_last else torch.contiguous_format)
 
 
 def to_tensor(images: Tensor, dtype: torch.dtype = torch.float32, channels_last: bool = False, pad_to: int = 0) -> Tensor:
