@@ -37,6 +37,9 @@ constexpr float kLog2eB = 1.4426950408889634f;
 #ifndef MU_BWD_KV_TMEM
 #define MU_BWD_KV_TMEM 0
 #endif
+#ifndef MU_BWD_DQ_RED
+#define MU_BWD_DQ_RED 0     // 1: dQ tiles leave through red.global.add.v4.f32 from registers instead of the TMA reduce-add
+#endif
 #ifndef MU_BWD_PROBE
 #define MU_BWD_PROBE 0      // 1 / 2: performance probes that skip work (wrong results), see DESIGN.md
 #endif
@@ -531,6 +534,26 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
           for (int e = 0; e < 32; ++e)
             if (i * BM + c * 32 + e < N) atomicAdd(base + (size_t)(c * 32 + e) * D, __uint_as_float(v[e]) * scale);
+        }
+      } else if (MU_BWD_DQ_RED) {
+        // A/B option: lanes = query row, 16-byte vector reductions straight from registers (no shared-memory staging:
+        // 64 KB less port traffic per tile, but 64 RED.128 warp instructions through the LSU instead)
+        const int qrow = i * BM + r;
+        float* dst = dq_acc + ((size_t)b * N + qrow) * D;
+#pragma unroll
+        for (int c = 0; c < DH / 32; ++c) {
+          tmem_ld32(lane_base + Cfg::kTmDQ + c * 32, v);
+          tmem_wait_ld();
+          if (c == DH / 32 - 1) {
+            tc_fence_before();
+            mbar_arrive(dq_free);
+          }
+          if (qrow < N) {
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4)
+              red_add_v4(dst + c * 32 + 4 * g4, __uint_as_float(v[4 * g4]) * scale, __uint_as_float(v[4 * g4 + 1]) * scale,
+                         __uint_as_float(v[4 * g4 + 2]) * scale, __uint_as_float(v[4 * g4 + 3]) * scale);
+          }
         }
       } else {
         // lanes = query row, columns = channels.  The fp32 tile is staged in shared memory (128-byte rows,
