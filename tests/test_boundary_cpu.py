@@ -97,3 +97,42 @@ def test_widened_ops_are_registered_with_fake_shapes():
     assert crit.margin == 1.0 and crit.ignore_value == 255 and len(list(crit.parameters())) == 0
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         crit(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4, dtype=torch.int64))
+
+
+def test_c_abi_error_convention_without_a_device():
+    """SURVEY 8(b) error convention: 0 on success, a negative mu_status for argument errors (checked before anything
+    touches the device), text behind mu_last_error(); a tcgen05 entry point on a machine without an sm_100 device
+    answers MU_ERR_ARCH instead of crashing."""
+    import ctypes
+    from maskunet_b200 import _lib
+    lib = _lib.load()
+    MU_ERR_BAD_SHAPE, MU_ERR_BAD_DTYPE, MU_ERR_MISALIGNED, MU_ERR_ARCH, MU_ERR_NULL = -1, -2, -3, -4, -5
+    buf = ctypes.create_string_buffer(4096)
+    base = (ctypes.addressof(buf) + 15) & ~15            # a 16-byte aligned (host) address: never dereferenced here
+    P = ctypes.c_void_p
+    err = lambda: lib.mu_last_error().decode()
+    # channels must be 64 / 128 / 256
+    rc = lib.mu_attn_fwd(P(base), P(base), P(base), P(base), P(base), P(base), 1, 128, 128, 65, _lib.MU_BF16, P(0))
+    assert rc == MU_ERR_BAD_SHAPE and "channels must be 64, 128 or 256" in err()
+    # NKP must be a multiple of 128 and >= N
+    rc = lib.mu_attn_fwd(P(base), P(base), P(base), P(base), P(base), P(base), 1, 200, 128, 64, _lib.MU_BF16, P(0))
+    assert rc == MU_ERR_BAD_SHAPE and "NKP" in err()
+    rc = lib.mu_attn_fwd(P(base), P(base), P(base), P(base), P(base), P(base), 1, 128, 128, 64, 7, P(0))
+    assert rc == MU_ERR_BAD_DTYPE and "dtype" in err()
+    rc = lib.mu_attn_fwd(P(0), P(base), P(base), P(base), P(base), P(base), 1, 128, 128, 64, _lib.MU_BF16, P(0))
+    assert rc == MU_ERR_NULL and "null pointer" in err()
+    rc = lib.mu_attn_fwd(P(base + 4), P(base), P(base), P(base), P(base), P(base), 1, 128, 128, 64, _lib.MU_BF16, P(0))
+    assert rc == MU_ERR_MISALIGNED and "16-byte" in err()
+    rc = lib.mu_attn_bwd(*([P(base)] * 11), P(base), 0, 1, 128, 128, 64, _lib.MU_BF16, P(0))
+    assert rc != 0                                        # workspace too small (or no device): never a crash
+    assert lib.mu_attn_bwd_workspace_bytes(2, 400, 64, _lib.MU_BF16) == 2 * 400 * 64 * 4     # fp32 dQ accumulator
+    assert lib.mu_query_attn_bwd_workspace_bytes(8, 100, 64) == 8 * 100 * 64 * 4
+    rc = lib.mu_query_mask_bits(P(base), P(base), 1, 100, 1000, 256, P(base), P(base), P(base), P(0), _lib.MU_F32, P(0))
+    assert rc == MU_ERR_BAD_DTYPE
+    rc = lib.mu_instance_triplet_fwd(P(base), P(0), 1, 2, 4, 4, P(base), P(base), 1, 1.0, 1e-6, P(base), P(base), P(base),
+                                     _lib.MU_F32, P(0))
+    assert rc == MU_ERR_NULL
+    if not torch.cuda.is_available():                     # build container: the tcgen05 path refuses to run
+        assert lib.mu_device_supported() == 0
+        rc = lib.mu_attn_fwd(P(base), P(base), P(base), P(base), P(base), P(base), 1, 128, 128, 64, _lib.MU_BF16, P(0))
+        assert rc == MU_ERR_ARCH and "sm_100" in err()
