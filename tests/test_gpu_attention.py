@@ -340,3 +340,39 @@ def test_full_size_properties_of_the_attention_kernels():
     assert float(dk.float().sum(1).abs().max()) < 2e-2 * scale_dk
     zq, zk, zv = ops.attn_bwd(q, kc, v1, n_keep, keep_idx, torch.zeros_like(d_o), lse, torch.zeros_like(delta))
     assert float(zq.abs().max()) == 0.0 and float(zk.abs().max()) == 0.0 and float(zv.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("C,N", [(64, 2048), (128, 1024), (256, 512), (64, 1000)])
+def test_forward_rescale_paths_with_growing_scores(C, N):
+    """The lazy rescale and the speculative-exponential redo only trigger when a row's maximum outgrows the running
+    offset by more than 2^8 AFTER the first key tile -- never with i.i.d. inputs.  Keys whose magnitude grows tile by
+    tile (and queries of mixed magnitude, so that only some rows of a warp grow) drive both paths on every tile;
+    checked against the fp32-math CUDA-core kernel, forward and backward."""
+    from maskunet_b200 import ops
+    dev = _dev()
+    B = 2
+    gen = torch.Generator(device=dev).manual_seed(11 + C)
+    NKP = ops.nkp_of(N)
+    rows = torch.arange(N, device=dev)
+    q = torch.randn(B, N, C, device=dev, generator=gen) * (1 + (rows % 3).float()).view(1, N, 1)
+    ramp = 1 + 4.0 * (torch.arange(NKP, device=dev) // 64).float()            # x5 after 64 keys, x9 after 128, ...
+    kc = torch.randn(B, NKP, C, device=dev, generator=gen) * ramp.view(1, NKP, 1)
+    vc = torch.randn(B, NKP, C, device=dev, generator=gen)
+    q, kc, vc = q.bfloat16(), kc.bfloat16(), vc.bfloat16()
+    n_keep = torch.tensor([N, N - 37], dtype=torch.int32, device=dev)
+    keep_idx = torch.arange(N, dtype=torch.int32, device=dev).repeat(B, 1)
+    for b in range(B):
+        kc[b, int(n_keep[b]):] = 0
+        vc[b, int(n_keep[b]):] = 0
+    o_ref, lse_ref = ops.attn_fwd_cudacore(q, kc, vc, n_keep)
+    o, lse = ops.attn_fwd(q, kc, vc, n_keep)
+    assert bool(torch.isfinite(o.float()).all()) and bool(torch.isfinite(lse).all())
+    assert float(lse_ref.max()) > 200.0                                       # the offsets really moved by hundreds
+    assert rel_err(o, o_ref) < 2e-2
+    assert float(((lse - lse_ref).abs() / lse_ref.abs().clamp_min(1.0)).max()) < 1e-3
+    d_o = torch.randn(B, N, C, device=dev, generator=gen).bfloat16()
+    delta = (d_o.float() * o_ref.float()).sum(-1)
+    ref = ops.attn_bwd_cudacore(q, kc, vc, n_keep, keep_idx, d_o, lse_ref, delta)
+    got = ops.attn_bwd(q, kc, vc, n_keep, keep_idx, d_o, lse_ref, delta)
+    for a, b_, name in zip(got, ref, ("dq", "dk", "dv")):
+        assert rel_err(a, b_) < 2e-2, name
