@@ -53,21 +53,29 @@ class Trainer:
                     + w_inst * crit(logits, inst))
             loss.backward()
             return loss
-        # both gradients land in ONE buffer: the fused cross-entropy writes d(CE)/d(logits) into the class-padded
-        # buffer, the triplet kernel adds its three columns per instance, backward starts from the sum
-        c_out = logits.shape[1]
+        loss, dpad = self.fused_panoptic_loss(padded, logits.shape[1], labels, inst)
+        padded.backward(dpad)
+        return loss
+
+    def fused_panoptic_loss(self, padded, c_out, labels, inst):
+        """(w_sem * CE + w_inst * InstanceContrastiveLoss, its gradient w.r.t. the class-padded logit buffer).  Both
+        gradients land in ONE buffer: the fused cross-entropy writes d(CE)/d(logits) into it, the triplet kernel adds
+        its three logit columns per instance; backward then starts from the sum."""
+        from . import losses
+        w_sem, w_inst = self.loss_weights
+        crit = self.instance_loss
         with torch.no_grad():
-            loss, dpad = ops.cross_entropy_fused(padded.detach(), labels, self.ignore_index, c_out)
+            padded = padded.detach()
+            loss, dpad = ops.cross_entropy_fused(padded, labels, self.ignore_index, c_out)
             dpad.mul_(w_sem)
             loss = w_sem * loss.squeeze(0)
             order, meta, K = losses.plan_instances(inst, crit.ignore_value)
             if K:
-                view = logits.detach()
+                view = padded[:, :c_out]
                 l_inst, sel, dist = losses.instance_triplet(view, order, meta, float(crit.margin))
                 losses.accumulate_grad(view, sel, dist, float(crit.margin), dpad[:, :c_out], scale=w_inst)
                 loss = loss + w_inst * l_inst.squeeze(0)
-        padded.backward(dpad)
-        return loss
+        return loss, dpad
 
     def step(self, images: torch.Tensor, labels: torch.Tensor,
              instance_labels: Optional[torch.Tensor] = None) -> torch.Tensor:
