@@ -135,3 +135,31 @@ def test_to_tensor_matches_torchvision_golden():
     for k in ("ramp", "img"):
         got = io_.to_tensor(z[k][None])[0]
         assert got.dtype == np.float32 and np.array_equal(got, z[k + "_out"])
+
+
+def test_generalised_mode_oracle_agrees_with_torch_sdpa():
+    """oracle/query_attention_oracle.py is builder-written (parity unpinned by reference: the reference has no such
+    stage).  It is at least held to PyTorch's own masked attention and to the sigmoid rule it states."""
+    import torch.nn.functional as F
+    from oracle import query_attention_oracle as qo
+    g = torch.Generator().manual_seed(2)
+    B, Q, N, C, heads = 2, 37, 200, 64, 4
+    qe, feat = torch.randn(B, Q, C, generator=g), torch.randn(B, N, C, generator=g)
+    qe[0, 3] = 0                                                     # all-zero logits: keeps nothing -> attends everything
+    logits = qo.mask_logits(qe, feat)
+    keep, count = qo.keep_from_logits(logits)
+    assert int(count[0, 3]) == 0 and bool(keep[0, 3].all())
+    raw = torch.sigmoid(logits) > 0.5
+    assert torch.equal(keep[count > 0], raw[count > 0])
+    # the fp32 boundary the kernel implements: sigmoid(x) > 0.5  <=>  x > 1.5 * 2^-24
+    t = torch.tensor([0.0, 1.5 * 2.0 ** -24, float(np.nextafter(np.float32(1.5 * 2.0 ** -24), np.float32(1))), 2.0 ** -23])
+    assert (torch.sigmoid(t) > 0.5).tolist() == [False, False, True, True]
+    assert torch.equal(torch.sigmoid(t) > 0.5, t > 1.5 * 2.0 ** -24)
+    q, k, v = (torch.randn(B, n, C, generator=g) for n in (Q, N, N))
+    out = qo.attention(q, k, v, keep, heads)
+    d = C // heads
+    split = lambda x: x.view(B, -1, heads, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(split(q), split(k), split(v), attn_mask=keep.unsqueeze(1))
+    assert rel_err(out, ref.transpose(1, 2).reshape(B, Q, C)) < 1e-5
+    words = (N + 127) // 128 * 4
+    assert torch.equal(qo.unpack_bits(qo.pack_bits(keep, words), N), keep)
