@@ -13,6 +13,16 @@
 #include "sm100_ptx.cuh"
 #include "tma_host.cuh"
 
+// Measured at B = 256, N = 16384, C = 64 (tools/bench_qkv.py): one accumulator buffer (64 TMEM columns, more of these
+// short latency-bound CTAs resident) 0.572 ms against 0.597 ms with two.
+#ifndef MU_P1_ACC_BUFS_64
+#define MU_P1_ACC_BUFS_64 1
+#endif
+#ifndef MU_P1_NC_128
+#define MU_P1_NC_128 64     // output columns per chunk at C = 128: 64-column chunks (smaller weight tiles, 3 CTAs per SM
+                            // instead of 2) 0.378 ms against 0.503 ms with 128-column chunks at B = 256, N = 4096
+#endif
+
 namespace mu {
 
 constexpr int kGemmThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
@@ -20,11 +30,14 @@ constexpr int kGemmThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 // ============================================================================ P1: forward projection
 template <int C>
 struct P1Cfg {
-  static constexpr int NC = (C == 64) ? 64 : 128;       // output columns per chunk
+  static constexpr int NC = (C == 64) ? 64 : (C == 128 ? MU_P1_NC_128 : 128);   // output columns per chunk
   static constexpr int kChunks = 3 * C / NC;
   static constexpr int kXBytes = 128 * C * 2;
   static constexpr int kWBytes = NC * C * 2;
-  static constexpr int kTmemCols = 2 * NC;              // 128 or 256 (power of two)
+  // accumulator buffers in TMEM: 2 lets the MMA of chunk j+1 run under the epilogue of chunk j; 1 halves the TMEM
+  // columns per CTA (64 at C = 64), so that twice as many of these short, latency-bound CTAs are resident
+  static constexpr int kAcc = (C == 64) ? MU_P1_ACC_BUFS_64 : 2;
+  static constexpr int kTmemCols = kAcc * NC;           // 64, 128 or 256 (power of two)
   static constexpr int kSmemBytes = 1024 + kXBytes + 2 * kWBytes + 256;
 };
 
@@ -89,18 +102,19 @@ qkv_project_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       mbar_wait(x_full, 0);
       for (int j = 0; j < Cfg::kChunks; ++j) {
         const int st = j & 1, use = j >> 1;
+        const int ast = Cfg::kAcc == 2 ? st : 0, ause = Cfg::kAcc == 2 ? use : j;   // accumulator buffer / its use count
         mbar_wait(w_full + st, use & 1);
-        if (use > 0) mbar_wait(acc_free + st, (use - 1) & 1);
+        if (ause > 0) mbar_wait(acc_free + ast, (ause - 1) & 1);
         tc_fence_after();
         const uint32_t w_lo = w_lo0 + st * (Cfg::kWBytes >> 4);
 #pragma unroll
         for (int kk = 0; kk < C / 16; ++kk)
           if (elect_one())
-            umma_ss_lo(tmem_base + st * NC, x_lo + (((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+            umma_ss_lo(tmem_base + ast * NC, x_lo + (((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
                        w_lo + (((kk >> 2) * (NC * 128) + (kk & 3) * 32) >> 4), hi, idesc, kk > 0 ? 1u : 0u);
         if (elect_one()) {
           umma_commit(w_empty + st);
-          umma_commit(acc_full + st);
+          umma_commit(acc_full + ast);
         }
       }
     }
@@ -117,7 +131,7 @@ qkv_project_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     }
     uint32_t v[32];
     for (int j = 0; j < Cfg::kChunks; ++j) {
-      const int st = j & 1, use = j >> 1;
+      const int st = Cfg::kAcc == 2 ? (j & 1) : 0, use = Cfg::kAcc == 2 ? (j >> 1) : j;
       const int which = (j * NC) / C, col0 = j * NC - which * C;
       __nv_bfloat16* dst = nullptr;
       if (tok_ok) {
