@@ -18,6 +18,15 @@
 #ifndef MU_P1_ACC_BUFS_64
 #define MU_P1_ACC_BUFS_64 1
 #endif
+// C = 256: the 64 KB token tile dominates shared memory; 64-column chunks in a 1-deep weight ring fit two CTAs per SM
+// instead of one: 0.362 -> 0.259 ms at B = 256, N = 1024 (128-column chunks, 2-deep ring: MU_P1_NC_256=128
+// MU_P1_WSTAGES_256=2).
+#ifndef MU_P1_NC_256
+#define MU_P1_NC_256 64
+#endif
+#ifndef MU_P1_WSTAGES_256
+#define MU_P1_WSTAGES_256 1
+#endif
 #ifndef MU_P1_NC_128
 #define MU_P1_NC_128 64     // output columns per chunk at C = 128: 64-column chunks (smaller weight tiles, 3 CTAs per SM
                             // instead of 2) 0.378 ms against 0.503 ms with 128-column chunks at B = 256, N = 4096
@@ -30,7 +39,8 @@ constexpr int kGemmThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 // ============================================================================ P1: forward projection
 template <int C>
 struct P1Cfg {
-  static constexpr int NC = (C == 64) ? 64 : (C == 128 ? MU_P1_NC_128 : 128);   // output columns per chunk
+  static constexpr int NC = (C == 64) ? 64 : (C == 128 ? MU_P1_NC_128 : MU_P1_NC_256);   // output columns per chunk
+  static constexpr int kWStages = (C == 256) ? MU_P1_WSTAGES_256 : 2;                  // weight-chunk ring depth
   static constexpr int kChunks = 3 * C / NC;
   static constexpr int kXBytes = 128 * C * 2;
   static constexpr int kWBytes = NC * C * 2;
@@ -38,7 +48,7 @@ struct P1Cfg {
   // columns per CTA (64 at C = 64), so that twice as many of these short, latency-bound CTAs are resident
   static constexpr int kAcc = (C == 64) ? MU_P1_ACC_BUFS_64 : 2;
   static constexpr int kTmemCols = kAcc * NC;           // 64, 128 or 256 (power of two)
-  static constexpr int kSmemBytes = 1024 + kXBytes + 2 * kWBytes + 256;
+  static constexpr int kSmemBytes = 1024 + kXBytes + kWStages * kWBytes + 256;
 };
 
 template <int C>
@@ -53,7 +63,7 @@ qkv_project_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sX = smem;
   uint8_t* sW = sX + Cfg::kXBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 2 * Cfg::kWBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + Cfg::kWStages * Cfg::kWBytes);
   uint64_t* x_full = bars;
   uint64_t* w_full = bars + 1;      // 2
   uint64_t* w_empty = bars + 3;     // 2
@@ -87,7 +97,7 @@ qkv_project_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       mbar_expect_tx(x_full, Cfg::kXBytes);
       for (int blk = 0; blk < C / 64; ++blk) tma_load_3d(sX + blk * 16384, &tmap_x, x_full, blk * 64, t0, 0);
       for (int j = 0; j < Cfg::kChunks; ++j) {
-        const int st = j & 1, use = j >> 1;
+        const int st = j % Cfg::kWStages, use = j / Cfg::kWStages;
         if (use > 0) mbar_wait(w_empty + st, (use - 1) & 1);
         mbar_expect_tx(w_full + st, Cfg::kWBytes);
         for (int blk = 0; blk < C / 64; ++blk)
@@ -101,8 +111,8 @@ qkv_project_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       const uint32_t x_lo = desc_lo(smem_u32(sX)), w_lo0 = desc_lo(smem_u32(sW));
       mbar_wait(x_full, 0);
       for (int j = 0; j < Cfg::kChunks; ++j) {
-        const int st = j & 1, use = j >> 1;
-        const int ast = Cfg::kAcc == 2 ? st : 0, ause = Cfg::kAcc == 2 ? use : j;   // accumulator buffer / its use count
+        const int st = j % Cfg::kWStages, use = j / Cfg::kWStages;                  // weight ring slot / its use count
+        const int ast = Cfg::kAcc == 2 ? (j & 1) : 0, ause = Cfg::kAcc == 2 ? (j >> 1) : j;   // accumulator buffer / use count
         mbar_wait(w_full + st, use & 1);
         if (ause > 0) mbar_wait(acc_free + ast, (ause - 1) & 1);
         tc_fence_after();

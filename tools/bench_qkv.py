@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from maskunet_b200 import ops  # noqa: E402
 from tools.bench_kernels import time_fn  # noqa: E402
 dev = torch.device("cuda", 0)
-for B, N, C in ((256, 16384, 64), (256, 4096, 64), (256, 4096, 128)):
+for B, N, C in ((256, 16384, 64), (256, 4096, 64), (256, 4096, 128), (256, 1024, 256), (256, 256, 256)):
     g = torch.Generator(device=dev).manual_seed(0)
     x = torch.randn(B, N, C, device=dev, generator=g).bfloat16()
     w = torch.randn(3 * C, C, device=dev, generator=g) * 0.1
