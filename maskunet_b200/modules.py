@@ -126,6 +126,15 @@ def _fast_layout(x: torch.Tensor, channel_multiple: int = 8) -> bool:
 _NBT_PENDING: Optional[list] = None
 
 
+def _bn_eval_affine(x: torch.Tensor, bn: nn.BatchNorm2d, n_pad: int) -> torch.Tensor:
+    """Eval-mode BatchNorm2d as y = a x + b on a tensor whose trailing ``n_pad`` channels are zero padding
+    (differentiable w.r.t. x, weight and bias; the pad channels get a = b = 0)."""
+    a = bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+    b = bn.bias.float() - bn.running_mean.float() * a
+    a, b = F.pad(a, (0, n_pad)), F.pad(b, (0, n_pad))
+    return x * a.to(x.dtype).view(1, -1, 1, 1) + b.to(x.dtype).view(1, -1, 1, 1)
+
+
 def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Optional[torch.Tensor] = None,
                  sums: Optional[torch.Tensor] = None):
     """act(BatchNorm2d(x) [+ residual]) -- the BN / GELU / ReLU / residual chains of ade_semantic.py:198-210,
@@ -141,7 +150,13 @@ def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Option
              and x.is_contiguous(memory_format=torch.channels_last) and bn.affine
              and (bn.training or not torch.is_grad_enabled()))
     if not fused:
-        y = bn(x)
+        n_pad = x.shape[1] - bn.num_features
+        if n_pad > 0 and not bn.training and bn.track_running_stats and bn.affine:
+            # class-padded head output in eval() with autograd on (frozen-BN fine-tuning, gradient checks): the
+            # inference affine form in plain torch ops, pad channels stay zero (a = b = 0, act(0) = 0)
+            y = _bn_eval_affine(x, bn, n_pad)
+        else:
+            y = bn(x)
         if residual is not None:
             y = residual + y
         if act == ops.ACT_GELU:

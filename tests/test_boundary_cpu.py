@@ -136,3 +136,23 @@ def test_c_abi_error_convention_without_a_device():
         assert lib.mu_device_supported() == 0
         rc = lib.mu_attn_fwd(P(base), P(base), P(base), P(base), P(base), P(base), 1, 128, 128, 64, _lib.MU_BF16, P(0))
         assert rc == MU_ERR_ARCH and "sm_100" in err()
+
+
+def test_eval_mode_affine_batchnorm_on_a_class_padded_tensor():
+    """The plain-torch path used for the class-padded head output in eval() with autograd on: equals
+    nn.BatchNorm2d.eval() on the real channels, keeps the pad channels zero, and is differentiable."""
+    from maskunet_b200.modules import _bn_eval_affine
+    g = torch.Generator().manual_seed(0)
+    bn = torch.nn.BatchNorm2d(19).eval()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(19, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(19, generator=g))
+        bn.running_mean.copy_(torch.randn(19, generator=g))
+        bn.running_var.copy_(torch.rand(19, generator=g) + 0.1)
+    x = torch.zeros(2, 32, 5, 7)
+    x[:, :19] = torch.randn(2, 19, 5, 7, generator=g)
+    x = x.contiguous(memory_format=torch.channels_last).requires_grad_()
+    y = _bn_eval_affine(x, bn, 13)
+    assert torch.allclose(y[:, :19], bn(x[:, :19]), atol=1e-6) and float(y[:, 19:].abs().max()) == 0.0
+    y.square().sum().backward()
+    assert x.grad is not None and bn.weight.grad is not None and float(x.grad[:, 19:].abs().max()) == 0.0

@@ -248,3 +248,22 @@ def test_cross_entropy_fused_matches_torch(C, dtype, tol):
     (ref * 2.0).backward()
     assert float((logits.grad.float() - lr.grad).norm() / lr.grad.norm()) < tol
     assert (logits.grad[0, :, :4] == 0).all()
+
+
+def test_unet_eval_mode_with_autograd_on_class_padded_head():
+    """eval() with autograd enabled (frozen-BatchNorm fine-tuning, gradient checks): the class-padded head output takes
+    the plain-torch affine BatchNorm path.  Logits equal the no_grad (fused inference kernels) forward within bf16
+    tolerance and backward reaches every live parameter."""
+    import maskunet_b200
+    torch.manual_seed(0)
+    net = maskunet_b200.UNet(3, 19, compute_dtype=torch.bfloat16, channels_last=True).to(DEV)
+    net = net.to(memory_format=torch.channels_last).eval()
+    x = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(1)).to(DEV)
+    with torch.no_grad():
+        ref = net(x).float()
+    out = net(x)
+    assert out.requires_grad and out.shape == (2, 19, 128, 128)
+    assert float((out.float() - ref).norm() / ref.norm()) < 2e-2
+    out.float().square().mean().backward()
+    grads = [p.grad for n, p in net.named_parameters() if "emb_layer" not in n]
+    assert all(g is not None and bool(torch.isfinite(g).all()) for g in grads)
