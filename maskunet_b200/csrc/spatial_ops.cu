@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(256) ce_fused_kernel(const T* __restrict__ log
   // pitch >= C: row stride in elements (class-padded logits of the 1x1 head); gradient pad columns are zeroed
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const float inv = 1.f / fmaxf(valid_count[0], 1.f);
-  float local = 0.f;
+  // every row ignored: torch's mean over zero rows is NaN (0 / 0) with zero gradients
+  float local = (valid_count[0] == 0.f && blockIdx.x == 0 && threadIdx.x == 0) ? NAN : 0.f;
   for (long row = (long)blockIdx.x * 8 + wib; row < M; row += (long)gridDim.x * 8) {
     const T* lr = logits + row * pitch;
     T* dr = dlogits + row * pitch;
@@ -366,6 +367,14 @@ __global__ void __launch_bounds__(256) ce_fused_kernel(const T* __restrict__ log
     for (int c = C + lane; c < pitch; c += 32) st_f(dr + c, 0.f);
     if (lab == ignore_index) {
       for (int c = lane; c < C; c += 32) st_f(dr + c, 0.f);
+      continue;
+    }
+    if (lab < 0 || lab >= C) {
+      // a label outside [0, C) that is not ignore_index: nn.CrossEntropyLoss raises a device assert for it.  Kernels
+      // cannot raise, so the loss and this row's gradient are poisoned with NaN -- a wrong ignore_index (e.g. 255-void
+      // Cityscapes labels under the default -100) cannot train silently on garbage.
+      for (int c = lane; c < C; c += 32) st_f(dr + c, NAN);
+      if (lane == 0) local += NAN;
       continue;
     }
     float v[8];  // C <= 256
@@ -425,7 +434,7 @@ __global__ void __launch_bounds__(256) ce_fused_vec_kernel(const __nv_bfloat16* 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const float inv = 1.f / fmaxf(valid_count[0], 1.f);
   const bool in_row = lane * 8 < pitch;
-  float local = 0.f;
+  float local = (valid_count[0] == 0.f && blockIdx.x == 0 && threadIdx.x == 0) ? NAN : 0.f;
   const long stride = (long)gridDim.x * 8;
   for (long row0 = (long)blockIdx.x * 8 + wib; row0 < M; row0 += stride * U) {
     uint4 u[U];
@@ -445,6 +454,7 @@ __global__ void __launch_bounds__(256) ce_fused_vec_kernel(const __nv_bfloat16* 
       const long row = row0 + k * stride;          // warp-uniform
       if (row >= M) continue;
       const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      const bool bad = lab[k] != ignore_index && (lab[k] < 0 || lab[k] >= C);
       float v[8];
       float mx = -INFINITY;
 #pragma unroll
@@ -469,6 +479,7 @@ __global__ void __launch_bounds__(256) ce_fused_vec_kernel(const __nv_bfloat16* 
         const float p = v[e] * inv_se;                       // 0 for the pad classes
         if (c == lab[k]) picked = p;
         o[e] = (lab[k] == ignore_index || c >= C) ? 0.f : (p - (c == lab[k] ? 1.f : 0.f)) * inv;
+        if (bad && c < C) o[e] = NAN;                        // label outside [0, C): poisoned like the scalar kernel
       }
       if (in_row) {
         uint4 r;
@@ -476,7 +487,7 @@ __global__ void __launch_bounds__(256) ce_fused_vec_kernel(const __nv_bfloat16* 
         *reinterpret_cast<uint4*>(dlogits + row * pitch + lane * 8) = r;
       }
       picked = warp_sum(picked);
-      if (lane == 0 && lab[k] != ignore_index) local += -__logf(fmaxf(picked, 1e-38f));
+      if (lane == 0 && lab[k] != ignore_index) local += bad ? NAN : -__logf(fmaxf(picked, 1e-38f));
     }
   }
   __shared__ float red[8];

@@ -14,6 +14,7 @@ to the reference's behaviour.
 """
 from __future__ import annotations
 
+import threading
 from typing import Optional
 
 import torch
@@ -121,41 +122,75 @@ def _fast_layout(x: torch.Tensor, channel_multiple: int = 8) -> bool:
             and x.shape[1] % channel_multiple == 0 and x.is_contiguous(memory_format=torch.channels_last))
 
 
-# BatchNorm `num_batches_tracked += 1` is one tiny kernel per layer; UNet.forward collects the counters here and
-# bumps them with a single multi-tensor add.  None outside a UNet forward (each layer then updates its own).
-_NBT_PENDING: Optional[list] = None
+# BatchNorm `num_batches_tracked += 1` is one tiny kernel per layer; UNet.forward collects the counters of its own
+# forward in a per-thread list and bumps them with a single multi-tensor add.  Thread-local and saved / restored around
+# the forward, so nn.DataParallel replicas (threads) and nested or re-entrant UNets never see each other's list; outside
+# a UNet forward there is no list and each layer updates its own counter.
+_TLS = threading.local()
 
 
-def _bn_eval_affine(x: torch.Tensor, bn: nn.BatchNorm2d, n_pad: int) -> torch.Tensor:
+def _nbt_list() -> Optional[list]:
+    return getattr(_TLS, "nbt", None)
+
+
+def _bn_eval_affine(x: torch.Tensor, bn: nn.BatchNorm2d, n_pad: int,
+                    pre_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Eval-mode BatchNorm2d as y = a x + b on a tensor whose trailing ``n_pad`` channels are zero padding
-    (differentiable w.r.t. x, weight and bias; the pad channels get a = b = 0)."""
+    (differentiable w.r.t. x, weight, bias and ``pre_bias``; the pad channels get a = b = 0).  The affine is
+    evaluated in fp32 and rounded once, as torch's own eval BatchNorm does.  ``pre_bias``: a per-channel bias the
+    producing convolution left out (BN(x + pre_bias))."""
     a = bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
-    b = bn.bias.float() - bn.running_mean.float() * a
+    shift = bn.running_mean.float() if pre_bias is None else bn.running_mean.float() - pre_bias.float()
+    b = bn.bias.float() - shift * a
     a, b = F.pad(a, (0, n_pad)), F.pad(b, (0, n_pad))
-    return x * a.to(x.dtype).view(1, -1, 1, 1) + b.to(x.dtype).view(1, -1, 1, 1)
+    return (x.float() * a.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)).to(x.dtype)
+
+
+class _AttachZeroGrad(torch.autograd.Function):
+    """y unchanged; ``param`` receives an all-zero gradient.  A convolution bias in front of a training-mode BatchNorm
+    cancels in the forward and has an exactly-zero gradient: the kernels skip it, and this node still hands the
+    optimiser the zero gradient the reference's autograd produces (AdamW decays a parameter whose gradient is zero,
+    and skips one whose gradient is None)."""
+
+    @staticmethod
+    def forward(ctx, y, param):
+        ctx.shape, ctx.dtype, ctx.device = param.shape, param.dtype, param.device
+        return y.view_as(y)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, torch.zeros(ctx.shape, dtype=ctx.dtype, device=ctx.device)
 
 
 def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Optional[torch.Tensor] = None,
-                 sums: Optional[torch.Tensor] = None):
+                 sums: Optional[torch.Tensor] = None, pre_bias: Optional[torch.Tensor] = None):
     """act(BatchNorm2d(x) [+ residual]) -- the BN / GELU / ReLU / residual chains of ade_semantic.py:198-210,
     :219, :240 and :283-287.  ``sums`` = per-channel (sum, sum of squares) of x already reduced by the producer
-    (the epilogue of our convolution kernel), which removes the statistics pass.
+    (the epilogue of our convolution kernel), which removes the statistics pass.  ``pre_bias``: the bias of the
+    producing convolution when the kernel left it out -- the result is act(BN(x + pre_bias) [+ residual]): under batch
+    statistics the bias cancels (only the running mean sees it), in eval mode it folds into the affine.
 
     Channels-last CUDA activations (the bf16 production layout) run on our fused sm_100a kernels
     (csrc/bn_act.cu: one statistics pass, one apply pass; backward one reduce + one apply pass).  Any other
     layout (the NCHW fp32 validation configuration) is evaluated with the stock torch CUDA ops in the
     reference's own order.
     """
+    batch_stats = bn.training or not bn.track_running_stats      # nn.BatchNorm2d: no running statistics -> batch ones
     fused = (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16)
              and x.is_contiguous(memory_format=torch.channels_last) and bn.affine
-             and (bn.training or not torch.is_grad_enabled()))
+             and (batch_stats or not torch.is_grad_enabled()))
     if not fused:
         n_pad = x.shape[1] - bn.num_features
-        if n_pad > 0 and not bn.training and bn.track_running_stats and bn.affine:
+        if (n_pad > 0 or pre_bias is not None) and not batch_stats and bn.affine:
             # class-padded head output in eval() with autograd on (frozen-BN fine-tuning, gradient checks): the
             # inference affine form in plain torch ops, pad channels stay zero (a = b = 0, act(0) = 0)
-            y = _bn_eval_affine(x, bn, n_pad)
+            y = _bn_eval_affine(x, bn, n_pad, pre_bias)
         else:
+            if n_pad > 0:
+                raise RuntimeError("fused_bn_act: a class-padded activation needs an affine BatchNorm2d "
+                                   f"({x.shape[1]} channels against {bn.num_features} features)")
+            if pre_bias is not None:
+                x = x + pre_bias.to(x.dtype).view(1, -1, 1, 1)
             y = bn(x)
         if residual is not None:
             y = residual + y
@@ -170,26 +205,32 @@ def fused_bn_act(x: torch.Tensor, bn: nn.BatchNorm2d, act: int, residual: Option
     n_feat, n_pad = bn.num_features, x.shape[1] - bn.num_features
     if n_pad > 0:       # class-padded output of our 1x1 head: the pad channels are zero and stay zero (gamma = beta = 0)
         gamma, beta = F.pad(gamma, (0, n_pad)), F.pad(beta, (0, n_pad))
-    if bn.training:
+    if batch_stats:
         if sums is not None and sums.numel() == 2 * x.shape[1]:
             y, mean, rstd, _, _ = ops.bn_act_fwd_stats(x, residual, gamma, beta, sums, bn.eps, act)
         else:
             y, mean, rstd, _, _ = ops.bn_act_fwd(x, residual, gamma, beta, bn.eps, act)
-        if bn.track_running_stats:      # nn.BatchNorm2d's running-statistics update (:200), one small kernel
+        if bn.training and bn.track_running_stats:   # nn.BatchNorm2d's running-statistics update (:200), one small kernel
             with torch.no_grad():
-                if _NBT_PENDING is not None and bn.momentum is not None:
-                    _NBT_PENDING.append(bn.num_batches_tracked)
+                nbt_pending = _nbt_list()
+                if nbt_pending is not None and bn.momentum is not None:
+                    nbt_pending.append(bn.num_batches_tracked)
                 else:
                     bn.num_batches_tracked += 1
                 momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
                 if n_pad > 0:
                     mean, rstd = mean[:n_feat].contiguous(), rstd[:n_feat].contiguous()
+                if pre_bias is not None:
+                    mean = mean + pre_bias.float()
                 ops.bn_update_running(bn.running_mean, bn.running_var, mean, rstd, momentum, bn.eps,
                                       x.shape[0] * x.shape[2] * x.shape[3])
+        if pre_bias is not None and pre_bias.requires_grad and torch.is_grad_enabled():
+            y = _AttachZeroGrad.apply(y, pre_bias)
         return y
     with torch.no_grad():
         a = gamma[:n_feat] * torch.rsqrt(bn.running_var.float() + bn.eps)
-        b = beta[:n_feat] - bn.running_mean.float() * a
+        shift = bn.running_mean.float() if pre_bias is None else bn.running_mean.float() - pre_bias.float()
+        b = beta[:n_feat] - shift * a
         if n_pad > 0:
             a, b = F.pad(a, (0, n_pad)), F.pad(b, (0, n_pad))
         return ops.bn_act_apply(x, residual, a, b, act)
@@ -366,13 +407,13 @@ class UNet(nn.Module):
                 and conv.groups == 1 and conv.weight.dtype == torch.float32
                 and ops.conv1x1_shape_ok(conv.in_channels, conv.out_channels, h.shape[2], h.shape[3]))
 
-    def _conv_bn_relu(self, seq, h, keep_padded=False):
+    def _conv_bn_relu(self, seq, h, keep_padded=False, min_pad=0):
         """ReLU(BN(conv(h))) of the output heads (ade_semantic.py:283-287).  On the production layout the 1x1
         convolution writes a class-padded buffer ([B, 160, H, W] for 150 classes, pad channels zero); the result is
         the first c_out channels of it, as a view."""
         conv, bn = seq[0], seq[1]
         if self._own_conv1x1(conv, h):
-            n_pad = ops.pad_channels(conv.out_channels)
+            n_pad = ops.pad_channels(max(conv.out_channels, min_pad))
             bias = conv.bias.float() if conv.bias is not None else None
             y_pad = ops.conv1x1(h, conv.weight, bias, n_pad)[0]
             out_pad = fused_bn_act(y_pad, bn, ops.ACT_RELU)
@@ -381,30 +422,57 @@ class UNet(nn.Module):
             return out_pad[:, :conv.out_channels] if n_pad > conv.out_channels else out_pad
         return fused_bn_act(conv(h), bn, ops.ACT_RELU)
 
+    def _boundary(self, semantic):
+        """boundary_head (city_instance.py:242-247, :275): conv3x3(c_out -> 32, bias) -> BN -> ReLU -> conv1x1(32 -> 1).
+        On the production layout both convolutions run on our tcgen05 kernels: the semantic head left its logits in a
+        64-channel class-padded buffer (pad channels exactly zero), so the 3x3 is K7's plain 64 -> 64 shape with the
+        weight zero-padded (autograd slices the gradient back); its bias cancels under batch statistics and folds into
+        the affine in eval mode (fused_bn_act's ``pre_bias``); the 1x1 is K12 on the 64-channel activation."""
+        conv3, bn, _, conv1 = self.boundary_head
+        pad = self._padded_logits
+        own = (pad is not None and pad.shape[1] == 64 and pad.data_ptr() == semantic.data_ptr()
+               and conv3.out_channels <= 64 and conv3.in_channels <= 64 and conv3.kernel_size == (3, 3)
+               and conv3.padding == (1, 1) and conv3.weight.dtype == torch.float32
+               and conv1.kernel_size == (1, 1) and conv1.weight.dtype == torch.float32
+               and ops.conv3x3_shape_ok(pad.shape[0], 64, 64, pad.shape[2], pad.shape[3])
+               and ops.conv1x1_shape_ok(64, conv1.out_channels, pad.shape[2], pad.shape[3]))
+        if not own:
+            return conv1(fused_bn_act(conv3(semantic), bn, ops.ACT_RELU))
+        w3 = F.pad(conv3.weight, (0, 0, 0, 0, 0, 64 - conv3.in_channels, 0, 64 - conv3.out_channels))
+        y, sums, _ = ops.conv3x3(pad, w3, bn.training)
+        hid = fused_bn_act(y, bn, ops.ACT_RELU, sums=sums if bn.training else None, pre_bias=conv3.bias)
+        w1 = F.pad(conv1.weight, (0, 0, 0, 0, 0, 64 - conv1.in_channels))
+        n_pad = ops.pad_channels(conv1.out_channels)
+        bias = conv1.bias.float() if conv1.bias is not None else None
+        out = ops.conv1x1(hid, w1, bias, n_pad)[0]
+        return out[:, :conv1.out_channels]
+
     def _heads(self, h):
         self._padded_logits = None
         if not self.instance_variant:
             return self._conv_bn_relu(self.final_layer, h, keep_padded=True)
         embeddings = self._conv_bn_relu(self.embedding_head, h)          # city_instance.py:273-276 order
-        semantic = self._conv_bn_relu(self.final_layer, h, keep_padded=True)
-        boundary = self.boundary_head[3](self._conv_bn_relu(self.boundary_head, semantic))
+        # 64-channel class padding (instead of 32 for 19 classes): the boundary head's 3x3 then is a 64 -> 64 conv
+        semantic = self._conv_bn_relu(self.final_layer, h, keep_padded=True,
+                                      min_pad=64 if self.final_layer[0].out_channels <= 64 else 0)
+        boundary = self._boundary(semantic)
         return semantic, boundary, embeddings
 
     def forward(self, x):
-        global _NBT_PENDING
         if self.channels_last:
             x = x.contiguous(memory_format=torch.channels_last)
-        _NBT_PENDING = [] if self.training else None
+        outer = _nbt_list()
+        _TLS.nbt = pending = [] if self.training else None
         try:
             if self.compute_dtype == torch.bfloat16:
                 with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
                     out = self._heads(self._trunk(x.to(torch.bfloat16)))
             else:
                 out = self._heads(self._trunk(x))
-            if _NBT_PENDING:
-                torch._foreach_add_(_NBT_PENDING, 1)
+            if pending:
+                torch._foreach_add_(pending, 1)
         finally:
-            _NBT_PENDING = None
+            _TLS.nbt = outer
         return out
 
 

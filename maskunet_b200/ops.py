@@ -866,17 +866,27 @@ sample_layernorm.register_autograd(_sln_backward, setup_context=_sln_setup)
 
 # ------------------------------------------------------------------ A14: fused cross-entropy (mean) + gradient
 @torch.library.custom_op("maskunet::cross_entropy_fused", mutates_args=(), device_types="cuda")
-def cross_entropy_fused(logits: Tensor, labels: Tensor, ignore_index: int, n_classes: int = -1) -> Tuple[Tensor, Tensor]:
+def cross_entropy_fused(logits: Tensor, labels: Tensor, ignore_index: int, n_classes: int = -1,
+                        valid_count: Tensor | None = None) -> Tuple[Tensor, Tensor]:
     """logits channels-last [B, P, H, W], labels int64 [B, H, W] -> (mean loss [1] f32, dlogits like logits).
     n_classes > 0: only the first n_classes of the P channels are classes (the class-padded output of the 1x1
-    head); the pad channels of dlogits are zero."""
+    head); the pad channels of dlogits are zero.
+    valid_count f32 [1]: the normaliser of the loss sum when it is not this call's own valid-pixel count (micro-batches
+    and data-parallel ranks normalise by the count of the whole global batch, see train.py).
+    A label outside [0, C) that is not ``ignore_index`` (nn.CrossEntropyLoss: device assert) makes the loss and that
+    row's gradient NaN; with every row ignored the loss is NaN and the gradient zero, as in torch."""
     B, P, H, W = _nhwc(logits)
     C = n_classes if n_classes > 0 else P
     _cuda(labels)
     assert labels.dtype == torch.int64 and labels.shape == (B, H, W) and C <= P
     dlogits = torch.empty_like(logits)
     loss = torch.empty((1,), dtype=torch.float32, device=logits.device)
-    count = (labels != ignore_index).sum().to(torch.float32).reshape(1)
+    if valid_count is None:
+        count = (labels != ignore_index).sum().to(torch.float32).reshape(1)
+    else:
+        _cuda(valid_count)
+        assert valid_count.dtype == torch.float32 and valid_count.numel() == 1
+        count = valid_count
     with torch.cuda.device(logits.device):
         _count(1)
         check(_L.mu_cross_entropy_fused(_p(logits), _p(labels), _p(count), ignore_index, _p(dlogits), _p(loss),
@@ -885,7 +895,7 @@ def cross_entropy_fused(logits: Tensor, labels: Tensor, ignore_index: int, n_cla
 
 
 @cross_entropy_fused.register_fake
-def _(logits, labels, ignore_index, n_classes=-1):
+def _(logits, labels, ignore_index, n_classes=-1, valid_count=None):
     return logits.new_empty((1,), dtype=torch.float32), torch.empty_like(logits)
 
 
@@ -896,7 +906,7 @@ def _ce_setup(ctx, inputs, output):
 
 def _ce_backward(ctx, dloss, *unused):
     (dlogits,) = ctx.saved_tensors
-    return dlogits * dloss.to(dlogits.dtype), None, None, None
+    return dlogits * dloss.to(dlogits.dtype), None, None, None, None
 
 
 cross_entropy_fused.register_autograd(_ce_backward, setup_context=_ce_setup)

@@ -10,12 +10,20 @@ Under data parallelism the gradient all-reduce (ddp.GradReducer) sits between ba
 The panoptic scripts add the instance term (coco/coco_panoptic.py:544-553):
     loss = 0.9 * semantic_loss_fn(logits, semantic_labels) + 0.1 * instance_loss_fn(logits, instance_labels)
 -- pass ``instance_loss=InstanceContrastiveLoss()`` and give ``step`` the instance labels.
+
+Loss normalisation.  The reference computes ONE mean over the whole (global) batch: ``nn.DataParallel`` gathers the
+outputs on GPU 0 before the criterion (:373, :399).  Here every rank -- and, with ``micro_batch``, every slice of a
+rank's batch -- normalises its cross-entropy sum by the number of valid pixels of the WHOLE global batch divided by the
+world size, so that the all-reduce(mean) of the gradients is exactly the gradient of that global mean even when
+``ignore_index`` pixels are spread unevenly.  ``step`` returns the rank-local share of the loss (device tensor, no
+host sync); its mean over ranks is the global loss.
 """
 from __future__ import annotations
 
 from typing import Optional
 
 import torch
+import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import ops
@@ -38,7 +46,49 @@ class Trainer:
             self.reducer = GradReducer(params, bucket_bytes=bucket_bytes)
             self.reducer.broadcast_parameters(model)
 
-    def _step_with_instance_term(self, logits, labels, inst):
+    # ------------------------------------------------------------------------------------------ loss pieces
+    def _valid_count(self, labels: torch.Tensor, sliced: bool) -> Optional[torch.Tensor]:
+        """f32 [1] normaliser of the cross-entropy sum: valid pixels of the global batch / world size.  None when one
+        pass over this rank's batch with its own count is already that (the fused kernel then counts itself)."""
+        world = self.reducer.world if self.reducer is not None else 1
+        uneven = world > 1 and self.ignore_index >= 0          # ranks may hold different numbers of valid pixels
+        if not (sliced or uneven):
+            return None
+        count = (labels != self.ignore_index).sum().to(torch.float32).reshape(1)
+        if uneven:
+            dist.all_reduce(count, group=self.reducer.group)   # 4 bytes
+            count = count / world
+        return count
+
+    def _ce_backward(self, logits, labels, count):
+        """Cross-entropy of one (micro-)batch, normalised by ``count``; starts backward; returns the loss share."""
+        fused_ok = logits.is_cuda and logits.shape[1] <= 256 and logits.dtype in (torch.float32, torch.bfloat16)
+        padded = getattr(self.model, "_padded_logits", None)
+        if (fused_ok and padded is not None and padded.requires_grad and padded.data_ptr() == logits.data_ptr()
+                and padded.is_contiguous(memory_format=torch.channels_last)):
+            # logits are the first c_out channels of the head's class-padded buffer: run the fused loss on the
+            # buffer itself and start backward there (no narrow / pad passes, no loss node)
+            with torch.no_grad():
+                loss, dpad = ops.cross_entropy_fused(padded.detach(), labels, self.ignore_index, logits.shape[1], count)
+            padded.backward(dpad)
+            return loss.squeeze(0)
+        if fused_ok and logits.is_contiguous(memory_format=torch.channels_last):
+            # fused CrossEntropyLoss(mean) forward + gradient on channels-last logits (one read, one write), and
+            # backward starts from d(loss)/d(logits) directly: the loss node and its `dlogits * dloss` pass are skipped
+            with torch.no_grad():
+                loss, dlogits = ops.cross_entropy_fused(logits.detach(), labels, self.ignore_index, -1, count)
+            logits.backward(dlogits)
+            return loss.squeeze(0)
+        loss = self._ce_torch(logits, labels, count)
+        loss.backward()
+        return loss.detach()
+
+    def _ce_torch(self, logits, labels, count):
+        if count is None:
+            return F.cross_entropy(logits.float(), labels, ignore_index=self.ignore_index)
+        return F.cross_entropy(logits.float(), labels, ignore_index=self.ignore_index, reduction="sum") / count[0]
+
+    def _panoptic_backward(self, logits, labels, inst, count, inst_scale):
         from . import losses
         w_sem, w_inst = self.loss_weights
         crit = self.instance_loss
@@ -49,71 +99,73 @@ class Trainer:
                  and padded.requires_grad and padded.data_ptr() == logits.data_ptr()
                  and padded.is_contiguous(memory_format=torch.channels_last) and logits.shape[1] <= 256)
         if not fused:
-            loss = (w_sem * F.cross_entropy(logits.float(), labels, ignore_index=self.ignore_index)
-                    + w_inst * crit(logits, inst))
+            loss = w_sem * self._ce_torch(logits, labels, count) + (w_inst * inst_scale) * crit(logits, inst)
             loss.backward()
-            return loss
-        loss, dpad = self.fused_panoptic_loss(padded, logits.shape[1], labels, inst)
+            return loss.detach()
+        loss, dpad = self.fused_panoptic_loss(padded, logits.shape[1], labels, inst, count, inst_scale)
         padded.backward(dpad)
         return loss
 
-    def fused_panoptic_loss(self, padded, c_out, labels, inst):
-        """(w_sem * CE + w_inst * InstanceContrastiveLoss, its gradient w.r.t. the class-padded logit buffer).  Both
-        gradients land in ONE buffer: the fused cross-entropy writes d(CE)/d(logits) into it, the triplet kernel adds
-        its three logit columns per instance; backward then starts from the sum."""
+    def fused_panoptic_loss(self, padded, c_out, labels, inst, count=None, inst_scale: float = 1.0):
+        """(w_sem * CE + w_inst * inst_scale * InstanceContrastiveLoss, its gradient w.r.t. the class-padded logit
+        buffer).  Both gradients land in ONE buffer: the fused cross-entropy writes d(CE)/d(logits) into it, the
+        triplet kernel adds its three logit columns per instance; backward then starts from the sum."""
         from . import losses
         w_sem, w_inst = self.loss_weights
+        w_inst = w_inst * inst_scale
         crit = self.instance_loss
         with torch.no_grad():
             padded = padded.detach()
-            loss, dpad = ops.cross_entropy_fused(padded, labels, self.ignore_index, c_out)
+            loss, dpad = ops.cross_entropy_fused(padded, labels, self.ignore_index, c_out, count)
             dpad.mul_(w_sem)
             loss = w_sem * loss.squeeze(0)
             order, meta, K = losses.plan_instances(inst, crit.ignore_value)
             if K:
                 view = padded[:, :c_out]
-                l_inst, sel, dist = losses.instance_triplet(view, order, meta, float(crit.margin))
-                losses.accumulate_grad(view, sel, dist, float(crit.margin), dpad[:, :c_out], scale=w_inst)
+                l_inst, sel, dist_ = losses.instance_triplet(view, order, meta, float(crit.margin))
+                losses.accumulate_grad(view, sel, dist_, float(crit.margin), dpad[:, :c_out], scale=w_inst)
                 loss = loss + w_inst * l_inst.squeeze(0)
         return loss, dpad
 
-    def step(self, images: torch.Tensor, labels: torch.Tensor,
-             instance_labels: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """One training step; ``images``/``labels`` may live in (pinned) host memory.  Returns the loss (device)."""
+    # ------------------------------------------------------------------------------------------ the step
+    def forward_backward(self, images: torch.Tensor, labels: torch.Tensor,
+                         instance_labels: Optional[torch.Tensor] = None,
+                         micro_batch: Optional[int] = None) -> torch.Tensor:
+        """Forward + loss + backward (gradients ACCUMULATE into ``.grad``; no zero_grad, no optimiser).  With
+        ``micro_batch`` the batch is processed in slices of that many samples -- the same gradient as one pass for the
+        cross-entropy term (every slice is normalised by the valid-pixel count of the whole batch); BatchNorm batch
+        statistics and the instance term are per slice, as they are per replica under the reference's DataParallel.
+        Returns the loss (device tensor)."""
         if images.device != self.device:
             images = images.to(self.device, non_blocking=True)
         if labels.device != self.device:
             labels = labels.to(self.device, non_blocking=True)
-        self.optimizer.zero_grad(set_to_none=True)
-        out = self.model(images)
-        logits = out[0] if isinstance(out, tuple) else out
-        if self.instance_loss is not None and instance_labels is not None:
-            loss = self._step_with_instance_term(logits, labels, instance_labels)
+        B = images.shape[0]
+        mb = B if not micro_batch or micro_batch >= B else int(micro_batch)
+        n_slices = (B + mb - 1) // mb
+        count = self._valid_count(labels, n_slices > 1)
+        total = None
+        for i in range(n_slices):
+            sl = slice(i * mb, min(B, (i + 1) * mb))
             if self.reducer is not None:
-                self.reducer.finish()
-            self.optimizer.step()
-            return loss.detach()
-        fused_ok = logits.is_cuda and logits.shape[1] <= 256 and logits.dtype in (torch.float32, torch.bfloat16)
-        padded = getattr(self.model, "_padded_logits", None)
-        if (fused_ok and padded is not None and padded.requires_grad and padded.data_ptr() == logits.data_ptr()
-                and padded.is_contiguous(memory_format=torch.channels_last)):
-            # logits are the first c_out channels of the head's class-padded buffer: run the fused loss on the
-            # buffer itself and start backward there (no narrow / pad passes, no loss node)
-            with torch.no_grad():
-                loss, dpad = ops.cross_entropy_fused(padded.detach(), labels, self.ignore_index, logits.shape[1])
-            loss = loss.squeeze(0)
-            padded.backward(dpad)
-        elif fused_ok and logits.is_contiguous(memory_format=torch.channels_last):
-            # fused CrossEntropyLoss(mean) forward + gradient on channels-last logits (one read, one write), and
-            # backward starts from d(loss)/d(logits) directly: the loss node and its `dlogits * dloss` pass are skipped
-            with torch.no_grad():
-                loss, dlogits = ops.cross_entropy_fused(logits.detach(), labels, self.ignore_index)
-            loss = loss.squeeze(0)
-            logits.backward(dlogits)
-        else:
-            loss = F.cross_entropy(logits.float(), labels, ignore_index=self.ignore_index)
-            loss.backward()
+                self.reducer.accumulate(i < n_slices - 1)      # the all-reduce rides on the last slice's backward
+            out = self.model(images[sl])
+            logits = out[0] if isinstance(out, tuple) else out
+            if self.instance_loss is not None and instance_labels is not None:
+                # the instance term is a mean over instances per slice, averaged over the slices
+                loss = self._panoptic_backward(logits, labels[sl], instance_labels[sl], count, 1.0 / n_slices)
+            else:
+                loss = self._ce_backward(logits, labels[sl], count)
+            total = loss if total is None else total + loss
+        return total.detach()
+
+    def step(self, images: torch.Tensor, labels: torch.Tensor, instance_labels: Optional[torch.Tensor] = None,
+             micro_batch: Optional[int] = None) -> torch.Tensor:
+        """One training step; ``images``/``labels`` may live in (pinned) host memory.  Returns this rank's share of
+        the loss (device tensor; mean over ranks = the global loss)."""
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.forward_backward(images, labels, instance_labels, micro_batch)
         if self.reducer is not None:
             self.reducer.finish()
         self.optimizer.step()
-        return loss.detach()
+        return loss

@@ -150,6 +150,29 @@ def mask_attention(x, sd, prefix, keep):
     return mao.module_output(out["y"], C, H, W)
 
 
+def mask_attention_reference_ops(x, sd, prefix, keep):
+    """ade_semantic.py:163-190 in the reference's OWN op sequence -- ``nn.Linear`` (F.linear), ``matmul``, true
+    division by ``C ** 0.5``, ``+`` the cached expanded 0 / -inf mask, ``F.softmax``, ``matmul``, residual,
+    ``nn.LayerNorm`` (F.layer_norm), ``.view`` -- under autograd.  This is what the CPU baseline times: the explicit
+    restatement above (max / exp / sum / div as separate N x N tensors, hand-derived backward) is an independent
+    statement of the maths for parity and costs ~1.7x the reference's own sequence on the same cores."""
+    B, C, H, W = x.shape
+    N = H * W
+    xt = x.view(B, C, N).permute(0, 2, 1)                                           # :168
+    q = F.linear(xt, sd[f"{prefix}.query.weight"], sd[f"{prefix}.query.bias"])      # :170
+    k = F.linear(xt, sd[f"{prefix}.key.weight"], sd[f"{prefix}.key.bias"])          # :171
+    v = F.linear(xt, sd[f"{prefix}.value.weight"], sd[f"{prefix}.value.bias"])      # :172
+    scores = torch.matmul(q, k.transpose(-2, -1))                                   # :174
+    scores = scores / (C ** 0.5)                                                    # :175
+    mask = mao.expand_bias(mao.additive_bias(keep), N)                              # :179-181 (cached by the module)
+    scores = scores + mask                                                          # :183
+    w = F.softmax(scores, dim=-1)                                                   # :185
+    out = torch.matmul(w, v)                                                        # :186
+    out = out + xt                                                                  # :187
+    out = F.layer_norm(out, [C], sd[f"{prefix}.norm.weight"], sd[f"{prefix}.norm.bias"], 1e-5)   # :188
+    return out.view(B, C, H, W)                                                     # :190
+
+
 def draw_keeps(batch: int, image_hw: Tuple[int, int] = (128, 128)) -> Dict[str, torch.Tensor]:
     """Per-site keep masks drawn in forward order with the reference's randint call (:178)."""
     keeps = {}
@@ -164,14 +187,31 @@ def draw_keeps(batch: int, image_hw: Tuple[int, int] = (128, 128)) -> Dict[str, 
     return keeps
 
 
+class LazyKeeps(dict):
+    """Keep masks drawn on first use, i.e. in forward order between the dropout draws -- exactly where the
+    reference's modules call ``torch.randint`` (ade_semantic.py:177-178) -- and cached afterwards."""
+
+    def __init__(self, batch: int, image_hw: Tuple[int, int] = (128, 128)):
+        super().__init__()
+        self.batch, self.image_hw = batch, image_hw
+
+    def __missing__(self, name):
+        side = dict((n, s) for n, _, s in ATTN_SITES)[name]
+        h, w = int(side * self.image_hw[0] / 128.0), int(side * self.image_hw[1] / 128.0)
+        self[name] = mao.binarize_mask(mao.draw_mask_bits(self.batch, h, w))
+        return self[name]
+
+
 def unet_forward(sd, x, keeps: Dict[str, torch.Tensor], training: bool = False,
-                 dropout_p: float = 0.0, update_stats: bool = False, variant: str = "semantic"):
+                 dropout_p: float = 0.0, update_stats: bool = False, variant: str = "semantic",
+                 attention=None):
     """ade_semantic.py:289-314 (semantic) / city_instance.py:253-276 (instance, 3 outputs).
 
     ``dropout_p`` defaults to 0 (parity runs); pass 0.3 with ``training=True`` for the
     timed CPU baseline, where it consumes the torch RNG as nn.Dropout does (:273,304,307).
     """
     t, u = training, update_stats
+    mask_attention = attention or globals()["mask_attention"]      # explicit restatement unless told otherwise
     x1 = conv_block(x, sd, "initial_conv", False, t, u)
     x2 = mask_attention(down_sample(x1, sd, "downsample1", t, u), sd, "self_attention1", keeps["self_attention1"])
     x3 = mask_attention(down_sample(x2, sd, "downsample2", t, u), sd, "self_attention2", keeps["self_attention2"])
@@ -208,7 +248,11 @@ class OracleTrainer:
     """The reference's timed loop body (ade_semantic.py:394-401) on the restated network:
     zero_grad -> forward -> CrossEntropyLoss -> backward -> AdamW(lr 5e-5, wd 1e-1)."""
 
-    def __init__(self, c_in=3, c_out=150, lr=5e-5, weight_decay=1e-1, seed=42, dropout_p=0.3):
+    def __init__(self, c_in=3, c_out=150, lr=5e-5, weight_decay=1e-1, seed=42, dropout_p=0.3,
+                 reference_ops: bool = False):
+        """reference_ops=True: the attention sites run the reference's own op sequence
+        (mask_attention_reference_ops) -- the CPU baseline that bench.py times; False: the explicit restatement."""
+        self.attention = mask_attention_reference_ops if reference_ops else None
         torch.manual_seed(seed)
         self.sd = init_state(c_in, c_out)
         self.params = [self.sd[k].requires_grad_(True) for k in trainable_keys(self.sd)]
@@ -217,11 +261,11 @@ class OracleTrainer:
         self.dropout_p = dropout_p
 
     def step(self, images: torch.Tensor, labels: torch.Tensor) -> float:
-        if self.keeps is None:  # cached on first forward, as self.mask is (:177)
-            self.keeps = draw_keeps(images.shape[0], tuple(images.shape[-2:]))
+        if self.keeps is None:  # cached on first forward, as self.mask is (:177); drawn in forward order
+            self.keeps = LazyKeeps(images.shape[0], tuple(images.shape[-2:]))
         self.opt.zero_grad(set_to_none=True)
         logits = unet_forward(self.sd, images, self.keeps, training=True,
-                              dropout_p=self.dropout_p, update_stats=True)
+                              dropout_p=self.dropout_p, update_stats=True, attention=self.attention)
         loss = F.cross_entropy(logits, labels)
         loss.backward()
         self.opt.step()

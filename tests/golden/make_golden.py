@@ -96,26 +96,96 @@ def make_unet(script, variant, c_out, fname, batch=2):
     for n, k in keeps.items():
         store[f"keep.{n}"] = np.packbits(k.numpy().astype(np.uint8), axis=1)
 
-    # one train-mode step with dropout disabled: loss + per-parameter grad norms
-    model.train()
-    model.dropout.p = 0.0
+    # ---- gradient goldens.  Every phase starts from the initial state (fresh BatchNorm running statistics), with the
+    # masks drawn above, dropout disabled, labels from seed 1.
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
     labels = torch.randint(0, c_out, (batch, 128, 128), generator=torch.Generator().manual_seed(1))
-    outs_t = model(x)
-    sem = outs_t[0] if isinstance(outs_t, tuple) else outs_t
-    loss = torch.nn.functional.cross_entropy(sem, labels)
-    loss.backward()
-    names, norms = [], []
-    for k, p in model.named_parameters():
-        names.append(k)
-        norms.append(float(p.grad.double().norm()) if p.grad is not None else -1.0)
-    store["train.loss"] = np.array([loss.item()], dtype=np.float64)
-    store["train.grad_norms"] = np.array(norms, dtype=np.float64)
-    store["train.logits_stats"] = np.array([sem.double().sum().item(), sem.abs().max().item()], dtype=np.float64)
+
+    def step(mode, rounded=False, autocast=False):
+        """loss, logits, {name: grad} of one forward + backward of the reference's own classes.
+        mode 'train': batch-statistics BatchNorm (the benchmarked step); 'evalgrad': model.eval() with autograd on
+        (frozen BatchNorm).  rounded: parameters and input rounded to bf16, arithmetic still fp32 -- the perturbation
+        ANY bf16 implementation applies before it computes anything.  autocast: the reference under
+        torch.autocast('cpu', bfloat16), i.e. the reference's own bf16 arithmetic."""
+        model.load_state_dict(sd0)
+        model.zero_grad(set_to_none=True)
+        model.train(mode == "train")
+        model.dropout.p = 0.0
+        xi = x
+        if rounded:
+            xi = x.bfloat16().float()
+            with torch.no_grad():
+                for p in model.parameters():
+                    p.copy_(p.bfloat16().float())
+        if autocast:
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                o = model(xi)
+        else:
+            o = model(xi)
+        o = tuple(t.float() for t in o) if isinstance(o, tuple) else (o.float(),)
+        loss = torch.nn.functional.cross_entropy(o[0], labels)
+        if len(o) == 3:     # instance variant: every head gets a gradient
+            loss = loss + 0.5 * o[1].square().mean() + 0.5 * o[2].square().mean()
+        loss.backward()
+        grads = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in model.named_parameters()}
+        return float(loss), o[0].detach(), grads
+
+    def vec_err(ga, gb):
+        ks = [k for k in ga if ga[k] is not None]
+        num = torch.cat([(ga[k] - gb[k]).flatten() for k in ks]).double().norm()
+        return float(num / torch.cat([ga[k].flatten() for k in ks]).double().norm())
+
+    def norm_errs(ga, gb):
+        out = []
+        for k in ga:
+            if ga[k] is None or k.endswith("key.bias"):
+                continue
+            na, nb = float(ga[k].double().norm()), float(gb[k].double().norm())
+            if na > 1e-7:
+                out.append(abs(nb - na) / na)
+        return np.array(out)
+
+    sgen = torch.Generator().manual_seed(7)
+    names = [k for k, _ in model.named_parameters()]
+    for mode in ("train", "evalgrad"):
+        loss, logits, grads = step(mode)
+        norms = [float(grads[k].double().norm()) if grads[k] is not None else -1.0 for k in names]
+        store[f"{mode}.loss"] = np.array([loss], dtype=np.float64)
+        store[f"{mode}.grad_norms"] = np.array(norms, dtype=np.float64)
+        store[f"{mode}.logits_stats"] = np.array([logits.double().sum().item(), logits.abs().max().item()], dtype=np.float64)
+        flat = logits.reshape(-1)
+        lidx = torch.randint(0, flat.numel(), (8192,), generator=sgen)
+        store[f"{mode}.logits_sample_idx"] = lidx.numpy()
+        store[f"{mode}.logits_sample"] = np32(flat[lidx])
+        # a fixed 256-element sample of every parameter gradient (enough for a whole-vector error estimate)
+        idx_of = {}
+        for k in names:
+            if grads[k] is None:
+                continue
+            n = grads[k].numel()
+            idx_of[k] = torch.randint(0, n, (256,), generator=sgen) if n > 256 else torch.arange(n)
+
+        def sample(g):
+            return torch.cat([g[k].reshape(-1)[i] for k, i in idx_of.items()])
+
+        store[f"{mode}.grad_sample_idx"] = np.concatenate([i.numpy().astype(np.int64) for i in idx_of.values()])
+        store[f"{mode}.grad_sample"] = np32(sample(grads))
+        # the reference's OWN sensitivity to bf16: what a bf16 implementation can be held to at network level
+        for tag, kw in (("rounded", dict(rounded=True)), ("autocast", dict(autocast=True))):
+            l2, lg2, g2 = step(mode, **kw)
+            ne = norm_errs(grads, g2)
+            sv = float((sample(g2) - sample(grads)).double().norm() / sample(grads).double().norm())
+            store[f"{mode}.sens.{tag}"] = np.array([
+                abs(l2 - loss) / abs(loss), float((lg2 - logits).norm() / logits.norm()), vec_err(grads, g2),
+                float(np.median(ne)), float(np.quantile(ne, 0.9)), float(ne.max()), sv], dtype=np.float64)
+            print(fname, mode, tag, "loss/logits/gradvec/norm-median/norm-p90/norm-max/sample-vec", store[f"{mode}.sens.{tag}"])
+    model.load_state_dict(sd0)
+    loss = store["train.loss"][0]
     np.savez_compressed(os.path.join(HERE, fname + ".npz"), **store)
     with open(os.path.join(HERE, fname + ".json"), "w") as fh:
         json.dump({"script": script, "variant": variant, "c_out": c_out, "seed": 1234, "batch": batch,
                    "torch": torch.__version__, "param_digest": digest, "grad_names": names}, fh, indent=0)
-    print(fname, "out0 stats", store["out0.stats"], "loss", loss.item())
+    print(fname, "out0 stats", store["out0.stats"], "loss", float(loss))
 
 
 def make_postproc():
@@ -198,6 +268,10 @@ def main():
         return
     if "--instance-loss-only" in sys.argv:
         make_instance_loss()
+        return
+    if "--unet-only" in sys.argv:
+        make_unet("ade_semantic", "semantic", 150, "unet_semantic")
+        make_unet("city_instance", "instance", 19, "unet_instance")
         return
     make_instance_loss()
     make_to_tensor()

@@ -52,6 +52,23 @@ def _worker(rank, world, port, tmp):
             assert torch.allclose(p.grad, q.grad, atol=1e-6), f"rank {rank} step {step}"
         assert all(p.grad is None for p in dead.parameters())
     assert len(red.buckets) >= 2 and red.launched == 3 * len(red.buckets)
+    # after finish() every gradient is a slice of its bucket's persistent flat buffer (no copy back)
+    for b in red.buckets:
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(b.params, b.views))
+    # gradient accumulation: two half-batches per rank, the exchange rides on the last backward only
+    launched = red.launched
+    for p in params:
+        p.grad = None
+    xs, ys = x_all[0].chunk(world)[rank], y_all[0].chunk(world)[rank]
+    for i, (xm, ym) in enumerate(zip(xs.chunk(2), ys.chunk(2))):
+        red.accumulate(i == 0)
+        (torch.nn.functional.mse_loss(net(xm), ym) / 2).backward()
+    red.finish()
+    ref.zero_grad()
+    torch.nn.functional.mse_loss(ref(x_all[0]), y_all[0]).backward()
+    for p, q in zip(net.parameters(), ref.parameters()):
+        assert torch.allclose(p.grad, q.grad, atol=1e-6), f"rank {rank} accumulation"
+    assert red.launched == launched + len(red.buckets)
     torch.save(torch.tensor(1), os.path.join(tmp, f"ok{rank}"))
     dist.destroy_process_group()
 
@@ -59,4 +76,39 @@ def _worker(rank, world, port, tmp):
 def test_grad_reducer_world2_gloo(tmp_path):
     port = 29600 + os.getpid() % 300
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def _worker_shared(rank, world, port, tmp):
+    """A parameter used twice in the forward fires its hook once per backward: one bucket slot, not two."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ddp = _load_ddp()
+    torch.manual_seed(1)
+    lin = torch.nn.Linear(8, 8)
+    red = ddp.GradReducer(list(lin.parameters()), bucket_bytes=1 << 20)
+    try:
+        red.finish()                                   # before any backward: refuse, do not finalise an empty discovery
+        raise AssertionError("finish() before backward must raise")
+    except RuntimeError:
+        pass
+    x = torch.randn(4, 8, generator=torch.Generator().manual_seed(5))
+    for _ in range(2):
+        for p in lin.parameters():
+            p.grad = None
+        lin(lin(x[rank * 2:rank * 2 + 2])).square().mean().backward()
+        red.finish()
+    assert sum(len(b.params) for b in red.buckets) == 2
+    ref = torch.nn.Linear(8, 8)
+    ref.load_state_dict(lin.state_dict())
+    ref(ref(x)).square().mean().backward()
+    for p, q in zip(lin.parameters(), ref.parameters()):
+        assert torch.allclose(p.grad, q.grad, atol=1e-6)
+    torch.save(torch.tensor(1), os.path.join(tmp, f"ok{rank}"))
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_shared_parameter_and_empty_finish(tmp_path):
+    port = 29300 + os.getpid() % 300
+    mp.spawn(_worker_shared, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")

@@ -1,10 +1,11 @@
 """SURVEY 8(e) equivalence test on real GPUs: gradients of the data-parallel path (one process per GPU, per-rank shard,
 bucketed NCCL all-reduce of maskunet_b200.ddp.GradReducer) == gradients of ONE GPU on the concatenated batch, with
 BatchNorm in eval() (batch statistics are per replica by design, as under the reference's DataParallel) and identical
-per-sample masks injected into the six attention modules.  Needs >= 2 GPUs AND an explicit opt-in (it spawns its own
-NCCL processes): `MASKUNET_MULTI_GPU_TESTS=1 gpurun --gpus 2 -- python -m pytest tests/test_gpu_ddp_equivalence.py -m gpu`.
-Status: written at the end of round 1; its first run exposed a real bug (eval() with autograd on crashed on the
-class-padded head, fixed in modules.fused_bn_act) and the GPU budget ended before the re-run -- NOT YET GREEN ON GPUS."""
+per-sample masks injected into the six attention modules.  Needs >= 2 GPUs (it spawns its own NCCL processes):
+`gpurun --gpus 2 -- python -m pytest tests/test_gpu_ddp_equivalence.py -m gpu`; on a 1-GPU box it reports a skip.
+Part 2 runs the same comparison through `Trainer` with ignore_index=255 and void pixels on ONE rank only: the loss
+must be the mean over the valid pixels of the global batch (what the reference's DataParallel computes on the gathered
+outputs, ade_semantic.py:373,399), not the mean of per-rank means."""
 import os
 
 import pytest
@@ -77,11 +78,39 @@ def _worker(rank, port, tmp):
         mean_loss = torch.tensor([losses[-1]], device=dev)
         dist.all_reduce(mean_loss)
     dist.barrier()
+
+    # ---- part 2: Trainer, ignore_index = 255, void pixels on rank 0's shard only
+    from maskunet_b200.train import Trainer
+    yv = y.clone()
+    yv[0, :96] = 255                                                  # 75 % of sample 0 is void; every other sample is full
+    net2 = build()
+    tr = Trainer(net2, ignore_index=255, data_parallel=True, bucket_bytes=4 * 1024 * 1024)
+    _inject_masks(net2, keep, lo, hi, dev)
+    for _ in range(2):
+        tr.optimizer.zero_grad(set_to_none=True)
+        loss2 = tr.forward_backward(x[lo:hi].to(dev), yv[lo:hi].to(dev))
+        tr.reducer.finish()
+    got2 = {n: p.grad.detach().float().clone() for n, p in net2.named_parameters() if p.grad is not None}
+    share = loss2.detach().reshape(1).clone()
+    dist.all_reduce(share)
+    if rank == 0:
+        ref2 = build()
+        _inject_masks(ref2, keep, 0, B, dev)
+        tr1 = Trainer(ref2, ignore_index=255)
+        tr1.optimizer.zero_grad(set_to_none=True)
+        ref_loss2 = float(tr1.forward_backward(x.to(dev), yv.to(dev)))
+        want2 = {n: p.grad.detach().float() for n, p in ref2.named_parameters() if p.grad is not None}
+        flat = lambda d: torch.cat([d[n].reshape(-1) for n in sorted(d)]).double()
+        err2 = float((flat(got2) - flat(want2)).norm() / flat(want2).norm())
+        # what the naive "mean of per-rank means" would have produced, for the record
+        res = torch.load(os.path.join(tmp, "result.pt"))
+        res.update({"err_ignore": err2, "loss_dp_ignore": float(share) / WORLD, "loss_1gpu_ignore": ref_loss2})
+        torch.save(res, os.path.join(tmp, "result.pt"))
+    dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < WORLD or os.environ.get("MASKUNET_MULTI_GPU_TESTS") != "1",
-                    reason="needs 2 GPUs and MASKUNET_MULTI_GPU_TESTS=1")
+@pytest.mark.skipif(torch.cuda.device_count() < WORLD, reason="needs 2 GPUs (gpurun --gpus 2)")
 def test_two_gpu_gradients_equal_one_gpu_on_the_concatenated_batch(tmp_path):
     port = 29700 + os.getpid() % 200
     mp.spawn(_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
@@ -89,3 +118,10 @@ def test_two_gpu_gradients_equal_one_gpu_on_the_concatenated_batch(tmp_path):
     print("ddp equivalence:", r)
     assert abs(r["loss_dp"] - r["loss_1gpu"]) < 1e-3 * abs(r["loss_1gpu"])
     assert r["err"] < 2e-2, r                                         # bf16 tolerance of the north star
+    assert abs(r["loss_dp_ignore"] - r["loss_1gpu_ignore"]) < 1e-3 * abs(r["loss_1gpu_ignore"]), r
+    assert r["err_ignore"] < 2e-2, r
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        import json
+        with open(os.path.join(out, "ddp_equivalence.json"), "w") as fh:
+            json.dump(r, fh)

@@ -50,7 +50,7 @@ def time_fn(fn, iters=10, warm=3):
     return ts[len(ts) // 2]
 
 
-def run(B, N, C, bwd, peak):
+def run(B, N, C, bwd, peak, verbose=True):
     q, kc, vc, n_keep, keep_idx = make(B, N, C)
     nk = float(n_keep.sum())
     ms = time_fn(lambda: ops.attn_fwd(q, kc, vc, n_keep))
@@ -63,11 +63,12 @@ def run(B, N, C, bwd, peak):
         ms = time_fn(lambda: ops.attn_bwd(q, kc, vc, n_keep, keep_idx, d_o, lse, delta), iters=5, warm=2)
         tf = 8 * N * nk * C / (ms * 1e-3) / 1e12
         rec.update({"bwd_ms": round(ms, 4), "bwd_tflops": round(tf, 1), "bwd_frac": round(tf / peak, 3)})
-    print(json.dumps(rec), flush=True)
+    if verbose:
+        print(json.dumps(rec), flush=True)
     return rec
 
 
-def run_generalised(B, Q, N, heads, peak, C=256):
+def run_generalised(B, Q, N, heads, peak, C=256, verbose=True):
     """Generalised mode: K13 bits + masked multi-head cross attention, fwd and bwd.
     FLOPs: executed = every (query, key) pair of the tiles; useful = pairs whose bit is set."""
     from maskunet_b200 import query_attention as qa
@@ -94,7 +95,8 @@ def run_generalised(B, Q, N, heads, peak, C=256):
            "fwd_tflops_executed": round(4 * pairs * heads * 64 / ms_f / 1e9, 1),
            "bwd_ms": round(ms_b, 4), "bwd_tflops_useful": round(8 * kept * heads * d / ms_b / 1e9, 1),
            "bwd_tflops_executed": round(10 * pairs * heads * 64 / ms_b / 1e9, 1), "peak_tflops": peak}
-    print(json.dumps(rec), flush=True)
+    if verbose:
+        print(json.dumps(rec), flush=True)
     return rec
 
 
