@@ -56,6 +56,10 @@ int mu_version(void);
 const char* mu_last_error(void);
 /* 1 when the current device is compute capability 10.x; tcgen05 entry points refuse to run otherwise. */
 int mu_device_supported(void);
+/* TMA descriptor cache: tensor maps are kept per (base pointer, shape, box) -- a pure function of the
+ * key, so a hit is never stale -- behind a mutex; bounded (cleared when 4096 entries are reached).  Counters since load. */
+void mu_tmap_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* entries);
+void mu_tmap_cache_clear(void);
 
 /* K2. Mask binarisation (:179-180  `binary_mask > 0.5` -> 0 / -inf bias, per key).
  *   bits      int64 [B, N]   the torch.randint(0, 2, ...) draw of :178 (stays a torch call)
@@ -300,6 +304,21 @@ int mu_query_attn_bwd(const void* q, const void* k, const void* v, const uint32_
  *   channels_last = 1: out [B, H, W, Cpad], channels >= Cin zero (Cpad = 8 feeds the tcgen05 stem convolution) */
 int mu_to_tensor_u8(const uint8_t* img, void* out, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cpad,
                     int32_t channels_last, int32_t dtype, mu_stream_t stream);
+
+/* SURVEY 8(f) rank 3, the resize of the dataset classes (ade_semantic.py:72-73), bit-exact with OpenCV's uint8
+ * arithmetic (opencv-python, third party: restated in oracle/resize_oracle.py, pinned against cv2 4.13 itself):
+ *   mu_resize_linear_to_tensor_u8: cv2.resize(img, (out_w, out_h), INTER_LINEAR) of ONE uint8 image [src_h, src_w, Cin]
+ *     followed by ToTensor when normalise = 1 (/ 255; normalise = 0 keeps the resized bytes as numbers 0..255);
+ *     out is one image slot of the network input: [Cin, out_h, out_w] (channels_last = 0) or [out_h, out_w, Cpad]
+ *     with channels >= Cin zero (channels_last = 1), dtype f32 / bf16.  Call once per image of a batch with the slot's
+ *     pointer: source sizes differ per image.
+ *   mu_resize_nearest_u8_i64: cv2.resize(mask, (out_w, out_h), INTER_NEAREST) of one uint8 label map, written as the
+ *     int64 labels the loss takes (`torch.from_numpy(mask).long()`, :78). */
+int mu_resize_linear_to_tensor_u8(const uint8_t* img, void* out, int32_t src_h, int32_t src_w, int32_t Cin, int32_t out_h,
+                                  int32_t out_w, int32_t Cpad, int32_t channels_last, int32_t normalise, int32_t dtype,
+                                  mu_stream_t stream);
+int mu_resize_nearest_u8_i64(const uint8_t* mask, int64_t* out, int32_t src_h, int32_t src_w, int32_t out_h,
+                             int32_t out_w, mu_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,8 @@ SIGNATURES = {
     "mu_query_attn_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "mu_query_attn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "mu_to_tensor_u8": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "mu_resize_linear_to_tensor_u8": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "mu_resize_nearest_u8_i64": [_P, _P, _I, _I, _I, _I, _P],
     "mu_bn_act_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
 }
 
@@ -84,12 +86,24 @@ def load() -> ctypes.CDLL:
     lib.mu_conv1x1_workspace_bytes.argtypes = [_I, _I]
     lib.mu_query_attn_bwd_workspace_bytes.restype = ctypes.c_size_t
     lib.mu_query_attn_bwd_workspace_bytes.argtypes = [_I, _I, _I]
+    _u64p = ctypes.POINTER(ctypes.c_uint64)
+    lib.mu_tmap_cache_stats.restype = None
+    lib.mu_tmap_cache_stats.argtypes = [_u64p, _u64p, _u64p]
+    lib.mu_tmap_cache_clear.restype = None
+    lib.mu_tmap_cache_clear.argtypes = []
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int32
         fn.argtypes = argtypes
     _lib = lib
     return lib
+
+
+def tmap_cache_stats() -> dict:
+    """Counters of the library's TMA descriptor cache: {'hits', 'misses', 'entries'}."""
+    h, m, e = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+    load().mu_tmap_cache_stats(ctypes.byref(h), ctypes.byref(m), ctypes.byref(e))
+    return {"hits": h.value, "misses": m.value, "entries": e.value}
 
 
 def check(rc: int, what: str) -> None:

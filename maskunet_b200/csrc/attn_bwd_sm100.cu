@@ -636,7 +636,7 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
   if ((rc = make_tmap_bf16_3d(&tk, kc, D, NKP, B, kBK))) return rc;
   if ((rc = make_tmap_bf16_3d(&tv, vc, D, NKP, B, kBK))) return rc;
   auto kern = attn_bwd_sm100_kernel<D, BM, DH, STAGES, PB, QM>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  cudaError_t e = set_max_dynamic_smem_once(kern, Cfg::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("attn_bwd_sm100: cudaFuncSetAttribute(%d bytes): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
     return (int)e;

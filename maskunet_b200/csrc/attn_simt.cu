@@ -262,7 +262,7 @@ static int run_fwd(const void* q, const void* kc, const void* vc, const int32_t*
   constexpr int KT = (D <= 128) ? 64 : 32;
   const size_t smem = sizeof(float) * (kQ * (D + 1) + KT * (D + 1) + KT * D + kQ * (KT + 1));
   auto kern = attn_fwd_simt_kernel<T, D, KT>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  set_max_dynamic_smem_once(kern, (int)smem);
   dim3 grid((N + kQ - 1) / kQ, B);
   const float scale_log2 = kLog2e / sqrtf((float)D);
   kern<<<grid, kThreadsA, smem, s>>>((const T*)q, (const T*)kc, (const T*)vc, n_keep, (T*)o, lse, N, NKP, scale_log2);
@@ -279,7 +279,7 @@ static int run_bwd(const void* q, const void* kc, const void* vc, const int32_t*
   {
     const size_t smem = sizeof(float) * (4 * 32 * (D + 1) + 32 * 33);
     auto kern = attn_bwd_dq_simt_kernel<T, D>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    set_max_dynamic_smem_once(kern, (int)smem);
     dim3 grid((N + kQ - 1) / kQ, B);
     kern<<<grid, kThreadsA, smem, s>>>((const T*)q, (const T*)kc, (const T*)vc, n_keep, (const T*)d_o, lse, delta,
                                        (T*)dq, N, NKP, scale);
@@ -287,7 +287,7 @@ static int run_bwd(const void* q, const void* kc, const void* vc, const int32_t*
   {
     const size_t smem = sizeof(float) * (4 * 32 * (D + 1) + 2 * 32 * 33);
     auto kern = attn_bwd_dkv_simt_kernel<T, D>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    set_max_dynamic_smem_once(kern, (int)smem);
     dim3 grid((N + 31) / 32, B);
     kern<<<grid, kThreadsA, smem, s>>>((const T*)q, (const T*)kc, (const T*)vc, n_keep, (const T*)d_o, lse, delta,
                                        keep_idx, (T*)dkc, (T*)dvc, N, NKP, scale);

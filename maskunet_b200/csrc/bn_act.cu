@@ -473,7 +473,7 @@ static int bn_bwd_bulk(const void* dy, const void* x, const void* r, const float
 #define MU_BULK(ACTC, RESC)                                                                                          \
   {                                                                                                                  \
     auto kern = bn_bwd_bulk_kernel<ACTC, RESC, MODE>;                                                                \
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                              \
+    set_max_dynamic_smem_once(kern, (int)smem);                              \
     kern<<<grid, kBulkThreads, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)r, \
                                           a, b, mean, rstd, sums, (__nv_bfloat16*)dx, (__nv_bfloat16*)dr, M, C, Cper, \
                                           rows_per_chunk);                                                           \

@@ -3,10 +3,16 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "tma_host.cuh"
 
 namespace mu {
 
 static thread_local char g_err[512] = "";
+
+TmapCache& tmap_cache() {
+  static TmapCache cache;
+  return cache;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -62,6 +68,20 @@ int mu_version(void) { return 100; }  // 0.1.0
 const char* mu_last_error(void) { return g_err; }
 
 int mu_device_supported(void) { return device_cc_major() == 10 ? 1 : 0; }
+
+void mu_tmap_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* entries) {
+  TmapCache& c = tmap_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (hits) *hits = c.hits;
+  if (misses) *misses = c.misses;
+  if (entries) *entries = c.map.size();
+}
+
+void mu_tmap_cache_clear(void) {
+  TmapCache& c = tmap_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  c.map.clear();
+}
 
 int mu_mask_binarize(const int64_t* bits, int32_t B, int32_t N, uint32_t* keep_bits, int32_t* n_keep,
                      int32_t* keep_idx, int32_t* keep_rank, mu_stream_t stream) {
@@ -446,6 +466,26 @@ int mu_to_tensor_u8(const uint8_t* img, void* out, int32_t B, int32_t H, int32_t
              "mu_to_tensor_u8: bad shape (B=%d H=%d W=%d Cin=%d Cpad=%d)", B, H, W, Cin, Cpad);
   MU_REQUIRE(img != nullptr && out != nullptr, MU_ERR_NULL, "mu_to_tensor_u8: null pointer");
   return launch_to_tensor_u8(img, out, B, H, W, Cin, Cpad, channels_last, dtype, (cudaStream_t)stream);
+}
+
+int mu_resize_linear_to_tensor_u8(const uint8_t* img, void* out, int32_t src_h, int32_t src_w, int32_t Cin, int32_t out_h,
+                                  int32_t out_w, int32_t Cpad, int32_t channels_last, int32_t normalise, int32_t dtype,
+                                  mu_stream_t stream) {
+  MU_DTYPE_OK("mu_resize_linear_to_tensor_u8");
+  MU_REQUIRE(src_h > 0 && src_w > 0 && out_h > 0 && out_w > 0 && Cin > 0 && Cin <= 4 && Cpad >= Cin, MU_ERR_BAD_SHAPE,
+             "mu_resize_linear_to_tensor_u8: bad shape (src %dx%d out %dx%d Cin=%d Cpad=%d)", src_h, src_w, out_h, out_w,
+             Cin, Cpad);
+  MU_REQUIRE(img != nullptr && out != nullptr, MU_ERR_NULL, "mu_resize_linear_to_tensor_u8: null pointer");
+  return launch_resize_linear_to_tensor(img, out, src_h, src_w, Cin, out_h, out_w, Cpad, channels_last, normalise, dtype,
+                                        (cudaStream_t)stream);
+}
+
+int mu_resize_nearest_u8_i64(const uint8_t* mask, int64_t* out, int32_t src_h, int32_t src_w, int32_t out_h,
+                             int32_t out_w, mu_stream_t stream) {
+  MU_REQUIRE(src_h > 0 && src_w > 0 && out_h > 0 && out_w > 0, MU_ERR_BAD_SHAPE,
+             "mu_resize_nearest_u8_i64: bad shape (src %dx%d out %dx%d)", src_h, src_w, out_h, out_w);
+  MU_REQUIRE(mask != nullptr && out != nullptr, MU_ERR_NULL, "mu_resize_nearest_u8_i64: null pointer");
+  return launch_resize_nearest_u8_i64(mask, out, src_h, src_w, out_h, out_w, (cudaStream_t)stream);
 }
 
 }  // extern "C"

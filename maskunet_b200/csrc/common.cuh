@@ -6,6 +6,9 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "../../include/maskunet_b200.h"
 
 namespace mu {
@@ -21,6 +24,28 @@ int check_launch(const char* what);  // returns 0 or the positive cudaError_t of
       return (code);                 \
     }                                \
   } while (0)
+
+// One-time cudaFuncSetAttribute(MaxDynamicSharedMemorySize) per (kernel, device): the attribute is sticky, and the call
+// takes a driver lock on every launch otherwise.  Idempotent, so a race between two first callers is harmless.
+template <typename Kern>
+inline cudaError_t set_max_dynamic_smem_once(Kern kern, int bytes) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, int> done;      // (kernel pointer ^ device) -> bytes set
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(reinterpret_cast<const void*>(kern)) ^ ((uint64_t)dev << 56);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return cudaSuccess;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> lock(mu);
+    done[key] = bytes;
+  }
+  return e;
+}
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -132,6 +157,9 @@ int launch_query_attn_bwd_sm100(const void* q, const void* k, const void* v, con
                                 cudaStream_t s);
 int launch_to_tensor_u8(const uint8_t* img, void* out, int B, int H, int W, int Cin, int Cpad, int channels_last,
                         int dtype, cudaStream_t s);
+int launch_resize_linear_to_tensor(const uint8_t* img, void* out, int sh, int sw, int cin, int oh, int ow, int cpad,
+                                   int channels_last, int normalise, int dtype, cudaStream_t s);
+int launch_resize_nearest_u8_i64(const uint8_t* mask, int64_t* out, int sh, int sw, int oh, int ow, cudaStream_t s);
 int launch_transpose(const void* in, void* out, int batch, int rows, int cols, int elem_bytes, cudaStream_t s);
 
 }  // namespace mu

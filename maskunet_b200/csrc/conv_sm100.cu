@@ -574,7 +574,7 @@ static int run_fprop(const void* x, const void* wt, void* y, float* stats, const
   if ((rc = make_tmap_bf16_3d(&tw, wt, round_up(K, 64), N, taps, NT))) return rc;   // weight rows are padded to 64 K
   if ((rc = make_tmap_bf16_nhwc(&ty, y, N, W, H, B, W, p.TH))) return rc;
   auto kern = conv_fprop_sm100_kernel<NT, MT, MODE>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  set_max_dynamic_smem_once(kern, smem);
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
   kern<<<grid, kConvThreads, smem, s>>>(tx, tw, ty, stats, bias, p);
@@ -687,7 +687,7 @@ static int run_wgrad(const void* x, const void* dy, float* ws, int B, int H, int
   if ((rc = make_tmap_bf16_nhwc(&tx, x, Cin, W, H, B, box_w, box_h))) return rc;
   if ((rc = make_tmap_bf16_nhwc(&td, dy, Cout, W, H, B, W, p.TH))) return rc;
   auto kern = conv_wgrad_sm100_kernel<NB>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  set_max_dynamic_smem_once(kern, smem);
   kern<<<dim3(combos, splits), kConvThreads, smem, s>>>(tx, td, ws, p);
   return check_launch("conv_wgrad_sm100");
 }

@@ -159,7 +159,7 @@ int launch_query_mask_bits_sm100(const void* qe, const void* feat, int B, int Q,
   if ((rc = make_tmap_bf16_3d(&tq, qe, C, Q, B, kMLTile))) return rc;
   if ((rc = make_tmap_bf16_3d(&tf, feat, C, N, B, kMLTile))) return rc;
   auto kern = mask_logits_sm100_kernel<256>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  cudaError_t e = set_max_dynamic_smem_once(kern, Cfg::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("mask_logits_sm100: cudaFuncSetAttribute(%d bytes): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
     return (int)e;

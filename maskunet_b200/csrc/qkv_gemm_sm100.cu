@@ -467,7 +467,7 @@ static int run_p1(const void* xt, const void* w_bf16, const float* bias, const i
   if ((rc = make_tmap_bf16_3d(&tx, xt, C, Mtot, 1, 128))) return rc;
   if ((rc = make_tmap_bf16_3d(&tw, w_bf16, C, 3 * C, 1, Cfg::NC))) return rc;
   auto kern = qkv_project_sm100_kernel<C>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  set_max_dynamic_smem_once(kern, Cfg::kSmemBytes);
   kern<<<(Mtot + 127) / 128, kGemmThreads, Cfg::kSmemBytes, s>>>(tx, tw, bias, rank, (__nv_bfloat16*)q,
                                                                 (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, Mtot, N, NKP);
   return check_launch("qkv_project_sm100");
@@ -487,7 +487,7 @@ static int run_bwd(const void* xt, const void* dz, const void* dq, const void* d
   {
     using Cfg = P2Cfg<C>;
     auto kern = qkv_dx_sm100_kernel<C>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    set_max_dynamic_smem_once(kern, Cfg::kSmemBytes);
     kern<<<(Mtot + 127) / 128, kGemmThreads, Cfg::kSmemBytes, s>>>(tdq, tdk, tdv, tw, (const __nv_bfloat16*)dz,
                                                                   (__nv_bfloat16*)dxt, Mtot);
     if ((rc = check_launch("qkv_dx_sm100"))) return rc;
@@ -495,7 +495,7 @@ static int run_bwd(const void* xt, const void* dz, const void* dq, const void* d
   {
     using Cfg = P3Cfg<C>;
     auto kern = qkv_dw_sm100_kernel<C>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    set_max_dynamic_smem_once(kern, Cfg::kSmemBytes);
     const int total_chunks = (Mtot + 127) / 128;
     int per = (total_chunks + 147) / 148;          // about one wave of CTAs per M tile
     if (per < 8) per = 8;

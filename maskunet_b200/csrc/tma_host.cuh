@@ -5,6 +5,11 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <array>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace mu {
@@ -27,9 +32,63 @@ inline PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+// ---- descriptor cache: a training step re-uses the same (pointer, shape) pairs every iteration --
+// parameters, the caching allocator's recycled activation blocks -- so an encoded CUtensorMap is kept per key instead
+// of re-encoding on every launch.  A tensor map is a pure function of its key (base pointer, dims, box, kind): a hit
+// can never be stale, whatever the buffer holds now.  Mutex-guarded, process-wide (the device is part of the key only
+// through the pointer: unified addressing makes device pointers unique per process), bounded: it is cleared when full.
+struct TmapKey {
+  std::array<uint64_t, 8> v;
+  bool operator==(const TmapKey& o) const { return v == o.v; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint64_t x : k.v) {
+      h ^= x;
+      h *= 0x100000001b3ull;
+      h ^= h >> 29;
+    }
+    return (size_t)h;
+  }
+};
+struct TmapCache {
+  std::mutex mu;
+  std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> map;
+  uint64_t hits = 0, misses = 0;
+};
+TmapCache& tmap_cache();          // one instance for the library (capi.cu)
+constexpr size_t kTmapCacheMax = 4096;
+
+// look up / fill: returns true on a hit (map filled); on a miss the caller encodes and calls tmap_cache_put
+inline bool tmap_cache_get(const TmapKey& key, CUtensorMap* out) {
+  TmapCache& c = tmap_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto it = c.map.find(key);
+  if (it == c.map.end()) {
+    ++c.misses;
+    return false;
+  }
+  ++c.hits;
+  std::memcpy(out, &it->second, sizeof(CUtensorMap));
+  return true;
+}
+inline void tmap_cache_put(const TmapKey& key, const CUtensorMap* m) {
+  TmapCache& c = tmap_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (c.map.size() >= kTmapCacheMax) c.map.clear();
+  std::memcpy(&c.map[key], m, sizeof(CUtensorMap));
+}
+inline TmapKey tmap_key(int kind, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t b0,
+                        uint64_t b1) {
+  return TmapKey{{(uint64_t)kind, (uint64_t)reinterpret_cast<uintptr_t>(base), d0, d1, d2, d3, b0, b1}};
+}
+
 // bf16 tensor [batch][rows][cols] (cols contiguous); box = [1][box_rows][64 cols], 128-byte swizzle.
 // Out-of-bounds rows are zero-filled on load and dropped on store.
 inline int make_tmap_bf16_3d(CUtensorMap* map, const void* base, int cols, int rows, int batch, int box_rows) {
+  const TmapKey key = tmap_key(1, base, cols, rows, batch, 0, box_rows, 0);
+  if (tmap_cache_get(key, map)) return 0;
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return MU_ERR_DRIVER;
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
@@ -44,12 +103,15 @@ inline int make_tmap_bf16_3d(CUtensorMap* map, const void* base, int cols, int r
               batch, box_rows);
     return MU_ERR_DRIVER;
   }
+  tmap_cache_put(key, map);
   return 0;
 }
 
 // fp32 tensor [batch][rows][cols]; box = [1][box_rows][32 cols] (128-byte rows), 128-byte swizzle.
 // Used as the destination of TMA reduce-add stores (rows past `rows` are dropped).
 inline int make_tmap_f32_3d(CUtensorMap* map, const void* base, int cols, int rows, int batch, int box_rows) {
+  const TmapKey key = tmap_key(2, base, cols, rows, batch, 0, box_rows, 0);
+  if (tmap_cache_get(key, map)) return 0;
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return MU_ERR_DRIVER;
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
@@ -64,6 +126,7 @@ inline int make_tmap_f32_3d(CUtensorMap* map, const void* base, int cols, int ro
               rows, batch, box_rows);
     return MU_ERR_DRIVER;
   }
+  tmap_cache_put(key, map);
   return 0;
 }
 
@@ -71,6 +134,8 @@ inline int make_tmap_f32_3d(CUtensorMap* map, const void* base, int cols, int ro
 // 128-byte swizzle.  Coordinates may be negative / past the edge: those elements are zero-filled on load (the
 // zero padding of a 3x3 convolution) and dropped on store.
 inline int make_tmap_bf16_nhwc(CUtensorMap* map, const void* base, int C, int W, int H, int B, int box_w, int box_h) {
+  const TmapKey key = tmap_key(3, base, C, W, H, B, box_w, box_h);
+  if (tmap_cache_get(key, map)) return 0;
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return MU_ERR_DRIVER;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -85,6 +150,7 @@ inline int make_tmap_bf16_nhwc(CUtensorMap* map, const void* base, int C, int W,
               box_w, box_h);
     return MU_ERR_DRIVER;
   }
+  tmap_cache_put(key, map);
   return 0;
 }
 

@@ -33,7 +33,11 @@ class _Bucket:
         self.flat = torch.zeros(sum(p.numel() for p in params), dtype=dtype, device=device)
         self.views, off = [], 0
         for p in params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            # the slice carries the parameter's own strides (channels-last convolution weights are dense but permuted):
+            # the fused optimiser insists on gradients with the parameter's layout
+            dense = p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last)
+            self.views.append(self.flat.as_strided(p.size(), p.stride(), off) if dense
+                              else self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
         self.work = None
         self.seen = set()

@@ -88,12 +88,10 @@ class Trainer:
             return F.cross_entropy(logits.float(), labels, ignore_index=self.ignore_index)
         return F.cross_entropy(logits.float(), labels, ignore_index=self.ignore_index, reduction="sum") / count[0]
 
-    def _panoptic_backward(self, logits, labels, inst, count, inst_scale):
+    def _panoptic_backward(self, logits, labels, inst, count, inst_scale, plan=None):
         from . import losses
         w_sem, w_inst = self.loss_weights
         crit = self.instance_loss
-        if inst.device != self.device:
-            inst = inst.to(self.device, non_blocking=True)
         padded = getattr(self.model, "_padded_logits", None)
         fused = (logits.is_cuda and isinstance(crit, losses.InstanceContrastiveLoss) and padded is not None
                  and padded.requires_grad and padded.data_ptr() == logits.data_ptr()
@@ -102,11 +100,11 @@ class Trainer:
             loss = w_sem * self._ce_torch(logits, labels, count) + (w_inst * inst_scale) * crit(logits, inst)
             loss.backward()
             return loss.detach()
-        loss, dpad = self.fused_panoptic_loss(padded, logits.shape[1], labels, inst, count, inst_scale)
+        loss, dpad = self.fused_panoptic_loss(padded, logits.shape[1], labels, inst, count, inst_scale, plan)
         padded.backward(dpad)
         return loss
 
-    def fused_panoptic_loss(self, padded, c_out, labels, inst, count=None, inst_scale: float = 1.0):
+    def fused_panoptic_loss(self, padded, c_out, labels, inst, count=None, inst_scale: float = 1.0, plan=None):
         """(w_sem * CE + w_inst * inst_scale * InstanceContrastiveLoss, its gradient w.r.t. the class-padded logit
         buffer).  Both gradients land in ONE buffer: the fused cross-entropy writes d(CE)/d(logits) into it, the
         triplet kernel adds its three logit columns per instance; backward then starts from the sum."""
@@ -119,7 +117,7 @@ class Trainer:
             loss, dpad = ops.cross_entropy_fused(padded, labels, self.ignore_index, c_out, count)
             dpad.mul_(w_sem)
             loss = w_sem * loss.squeeze(0)
-            order, meta, K = losses.plan_instances(inst, crit.ignore_value)
+            order, meta, K = plan if plan is not None else losses.plan_instances(inst, crit.ignore_value)
             if K:
                 view = padded[:, :c_out]
                 l_inst, sel, dist_ = losses.instance_triplet(view, order, meta, float(crit.margin))
@@ -144,6 +142,19 @@ class Trainer:
         mb = B if not micro_batch or micro_batch >= B else int(micro_batch)
         n_slices = (B + mb - 1) // mb
         count = self._valid_count(labels, n_slices > 1)
+        panoptic = self.instance_loss is not None and instance_labels is not None
+        plans = None
+        if panoptic:
+            from . import losses
+            if instance_labels.device != self.device:
+                instance_labels = instance_labels.to(self.device, non_blocking=True)
+            if isinstance(self.instance_loss, losses.InstanceContrastiveLoss):
+                # the grouping of the instance ids (one sort + ONE device->host copy per slice, the bounds of the
+                # reference's randint draws, coco_panoptic.py:510) depends on the labels only: done for every slice
+                # BEFORE the first forward is enqueued, so no host sync sits between a forward and its backward.
+                # The CPU generator is consumed in the reference's order (slice by slice, ascending instance id).
+                plans = [losses.plan_instances(instance_labels[i * mb:min(B, (i + 1) * mb)],
+                                               self.instance_loss.ignore_value) for i in range(n_slices)]
         total = None
         for i in range(n_slices):
             sl = slice(i * mb, min(B, (i + 1) * mb))
@@ -151,9 +162,10 @@ class Trainer:
                 self.reducer.accumulate(i < n_slices - 1)      # the all-reduce rides on the last slice's backward
             out = self.model(images[sl])
             logits = out[0] if isinstance(out, tuple) else out
-            if self.instance_loss is not None and instance_labels is not None:
+            if panoptic:
                 # the instance term is a mean over instances per slice, averaged over the slices
-                loss = self._panoptic_backward(logits, labels[sl], instance_labels[sl], count, 1.0 / n_slices)
+                loss = self._panoptic_backward(logits, labels[sl], instance_labels[sl], count, 1.0 / n_slices,
+                                               plans[i] if plans is not None else None)
             else:
                 loss = self._ce_backward(logits, labels[sl], count)
             total = loss if total is None else total + loss

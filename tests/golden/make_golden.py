@@ -259,7 +259,35 @@ def make_to_tensor():
     print("to_tensor", float(ToTensor()(img).sum()))
 
 
+RESIZE_CASES = [  # name, source (H, W), output (H, W): down-scaling, the exact-2x INTER_AREA route, enlarging, mixed
+    ("ade_like", (150, 233), (128, 128)), ("exact_2x", (256, 256), (128, 128)), ("enlarge", (37, 50), (128, 128)),
+    ("wide", (96, 512), (128, 128)), ("tall_to_rect", (75, 100), (64, 96)),
+]
+
+
+def make_resize():
+    """cv2's OWN outputs for the two resize calls of the dataset classes (ade_semantic.py:72-73) and ToTensor on the
+    resized image (:75-76): INTER_LINEAR on an RGB uint8 image, INTER_NEAREST on a uint8 label map."""
+    import cv2
+    from torchvision.transforms import ToTensor
+    rng = np.random.default_rng(21)
+    store = {"cv2_version": np.array([int(v) for v in cv2.__version__.split(".")[:3]], dtype=np.int64)}
+    for name, (sh, sw), (oh, ow) in RESIZE_CASES:
+        img = rng.integers(0, 256, size=(sh, sw, 3), dtype=np.uint8)
+        img[: sh // 2] = (np.linspace(0, 255, sw)[None, :, None] * np.ones((sh // 2, 1, 3))).astype(np.uint8)   # ramps too
+        mask = rng.integers(0, 151, size=(sh, sw), dtype=np.uint8)
+        lin = cv2.resize(img, (ow, oh), interpolation=cv2.INTER_LINEAR)
+        near = cv2.resize(mask, (ow, oh), interpolation=cv2.INTER_NEAREST)
+        store.update({f"{name}.img": img, f"{name}.mask": mask, f"{name}.linear": lin, f"{name}.nearest": near,
+                      f"{name}.tensor": ToTensor()(lin).numpy()})
+        print("resize", name, img.shape, "->", lin.shape, int(lin.sum()), int(near.sum()))
+    np.savez_compressed(os.path.join(HERE, "resize.npz"), **store)
+
+
 def main():
+    if "--resize-only" in sys.argv:
+        make_resize()
+        return
     if "--to-tensor-only" in sys.argv:
         make_to_tensor()
         return
@@ -275,6 +303,7 @@ def main():
         return
     make_instance_loss()
     make_to_tensor()
+    make_resize()
     make_postproc()
     ref = load_reference_classes("ade_semantic")
     make_attention(ref)

@@ -86,6 +86,21 @@ def _worker_shared(rank, world, port, tmp):
     ddp = _load_ddp()
     torch.manual_seed(1)
     lin = torch.nn.Linear(8, 8)
+    # a channels-last convolution weight (model.to(memory_format=channels_last)): its gradient slice must carry the
+    # parameter's strides, or torch's fused AdamW refuses the step ("same dtype, device, and layout")
+    conv = torch.nn.Conv2d(4, 6, 3).to(memory_format=torch.channels_last)
+    red_c = ddp.GradReducer(list(conv.parameters()), bucket_bytes=1 << 20)
+    opt = torch.optim.AdamW(conv.parameters(), lr=1e-3)
+    xc = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(3 + rank))
+    for _ in range(2):
+        opt.zero_grad(set_to_none=True)
+        conv(xc).square().mean().backward()
+        red_c.finish()
+        assert conv.weight.grad.stride() == conv.weight.stride() and conv.weight.grad.shape == conv.weight.shape
+        opt.step()
+    gathered = [torch.zeros_like(conv.weight.grad.contiguous()) for _ in range(world)]
+    dist.all_gather(gathered, conv.weight.grad.contiguous())
+    assert torch.equal(gathered[0], gathered[1])       # both ranks hold the same mean gradient
     red = ddp.GradReducer(list(lin.parameters()), bucket_bytes=1 << 20)
     try:
         red.finish()                                   # before any backward: refuse, do not finalise an empty discovery

@@ -164,3 +164,16 @@ def test_generalised_mode_oracle_agrees_with_torch_sdpa():
     assert rel_err(out, ref.transpose(1, 2).reshape(B, Q, C)) < 1e-5
     words = (N + 127) // 128 * 4
     assert torch.equal(qo.unpack_bits(qo.pack_bits(keep, words), N), keep)
+
+
+@pytest.mark.parametrize("name", ["ade_like", "exact_2x", "enlarge", "wide", "tall_to_rect"])
+def test_resize_oracle_matches_cv2_golden(name):
+    """oracle/resize_oracle.py against cv2's own INTER_LINEAR / INTER_NEAREST outputs (ade_semantic.py:72-73)."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from oracle import resize_oracle as ro
+    z = np.load(os.path.join(GOLDEN, "resize.npz"))
+    size = z[name + ".linear"].shape[:2]
+    assert np.array_equal(ro.resize_linear_u8(z[name + ".img"], size), z[name + ".linear"])
+    assert np.array_equal(ro.resize_nearest_u8(z[name + ".mask"], size), z[name + ".nearest"])

@@ -140,3 +140,24 @@ def test_cpu_baseline_step_is_the_reference_step_value_and_speed():
     ratio = min(t_port) / min(t_ref)
     print(f"CPU baseline port / reference step time: {ratio:.3f} ({min(t_port):.2f} s vs {min(t_ref):.2f} s, batch {B})")
     assert 0.8 < ratio < 1.15, (t_port, t_ref)
+
+
+def test_resize_oracle_fuzz_against_cv2():
+    """oracle/resize_oracle.py against the third-party library the reference calls (cv2.resize, ade_semantic.py:72-73),
+    live: random source sizes, down- and up-scaling, 1 and 3 channels, three output sizes -- every byte equal."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    from oracle import resize_oracle as ro
+    rng = np.random.default_rng(0)
+    shapes = [(512, 683), (1024, 2048), (480, 640), (256, 256), (128, 128), (100, 37), (1, 5), (2000, 3)]
+    shapes += [tuple(int(v) for v in rng.integers(1, 700, 2)) for _ in range(25)]
+    for sh in shapes:
+        for oh, ow in ((128, 128), (64, 96), (200, 150)):
+            img = rng.integers(0, 256, size=(sh[0], sh[1], 3), dtype=np.uint8)
+            assert np.array_equal(cv2.resize(img, (ow, oh), interpolation=cv2.INTER_LINEAR),
+                                  ro.resize_linear_u8(img, (oh, ow))), (sh, oh, ow)
+            m = img[:, :, 0]
+            assert np.array_equal(cv2.resize(m, (ow, oh), interpolation=cv2.INTER_NEAREST),
+                                  ro.resize_nearest_u8(m, (oh, ow))), (sh, oh, ow)
+            assert np.array_equal(cv2.resize(m, (ow, oh), interpolation=cv2.INTER_LINEAR),
+                                  ro.resize_linear_u8(m, (oh, ow))), (sh, oh, ow)
