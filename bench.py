@@ -262,7 +262,10 @@ def run_ours(args):
     else:
         crit = maskunet_b200.InstanceContrastiveLoss() if wl == "coco_panoptic" else None
         trainer = Trainer(model, lr=5e-5, weight_decay=1e-1, data_parallel=world > 1 and not args.no_ddp,
-                          instance_loss=crit)
+                          instance_loss=crit, bucket_bytes=int(args.bucket_mb * 1024 * 1024),
+                          cuda_graph=args.cuda_graph)
+        if trainer.reducer is not None and args.ddp_dryrun:
+            trainer.reducer.dry_run = True
     torch.manual_seed(42 + rank)                            # masks / dropout differ per rank
     img_host = torch.rand(B, 3, 128, 128, generator=torch.Generator().manual_seed(rank)).pin_memory()
     lab_host = torch.randint(0, c_out, (B, 128, 128), generator=torch.Generator().manual_seed(1000 + rank)).pin_memory()
@@ -278,14 +281,39 @@ def run_ours(args):
                 return model(img_dev)
         return trainer.step(img_dev, lab_dev, inst_dev, micro_batch=micro)
 
+    # end to end: every step copies ITS batch host -> device from pinned memory and reads its result back.  The copy of
+    # batch k + 1 is issued on a copy stream before step k is enqueued (double buffering, what maskunet_b200.data.
+    # DevicePrefetcher does for a real loader), so it overlaps step k's kernels; the first copy and every result
+    # read-back are exposed.  K steps = K copies + K read-backs inside the timed region.
+    copy_stream = torch.cuda.Stream(dev)
+    host_batch = [img_host] if infer else [t for t in (img_host, lab_host, inst_host) if t is not None]
+
+    def stage():
+        with torch.cuda.stream(copy_stream):
+            tensors = [t.to(dev, non_blocking=True) for t in host_batch]
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return tensors, ev
+
+    staged = []
+
     def step_e2e():
+        if not staged:
+            staged.append(stage())
+        tensors, ev = staged.pop()
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ev)
+        for t in tensors:
+            t.record_stream(cur)
+        staged.append(stage())                  # batch k + 1 travels while step k computes
         if infer:        # host images in, class map (city_instance.py:461-462: argmax of the semantic logits) out
             with torch.no_grad():
-                sem = model(img_host.to(dev, non_blocking=True))[0]
+                sem = model(tensors[0])[0]
                 result_host.copy_(maskunet_b200.segmentation_argmax(sem), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            cur.synchronize()
             return None
-        return trainer.step(img_host, lab_host, inst_host, micro_batch=micro).item()
+        inst = tensors[2] if len(tensors) > 2 else None
+        return trainer.step(tensors[0], tensors[1], inst, micro_batch=micro).item()
 
     def barrier():
         if world > 1:
@@ -320,12 +348,15 @@ def run_ours(args):
     launches0 = ops.LAUNCHES["count"]
     ms_dev, ms_mine = timed(step_dev, args.steps)
     launches = ops.LAUNCHES["count"] - launches0
+    if trainer is not None and trainer._graph is not None:
+        launches += trainer.graph_launches * args.steps        # replays launch the captured kernels; Python does not see them
     ops.KERNEL_TIMING["enabled"] = False
     clocks = sampler.stop()
 
     # end to end: host buffers in, result out, every step
     results = []
     ms_e2e, _ = timed(lambda: results.append(step_e2e()), args.steps)
+    staged.clear()
 
     # roofline of the dominant kernel of ours: attention at the 16384-token site
     roof = None
@@ -387,13 +418,22 @@ def run_ours(args):
            "parallelism": f"dp{world}",
            "l2": "per-step working set (tens of GB of activations) exceeds the 126 MB L2; no flush needed",
            "precision": "bf16 activations, fp32 master parameters / statistics / accumulation",
-           "layout": "channels_last" if cl else "nchw"}
+           "layout": "channels_last" if cl else "nchw",
+           "e2e_input": "pinned host batch per step; batch k+1 is copied on a side stream while step k runs "
+                        "(K steps = K + 1 copies issued, K consumed), result read back every step"}
     if not infer:
         cfg["optimizer"] = "AdamW(lr=5e-5, wd=1e-1)"
     if micro:
         cfg["micro_batch"] = micro
+    if args.cuda_graph:
+        cfg["cuda_graph"] = trainer is not None and trainer._graph is not None
     if args.no_ddp and world > 1:
         cfg["note"] = "--no-ddp: independent replicas, no gradient exchange (scaling attribution run)"
+    if world > 1 and not args.no_ddp:
+        cfg["grad_buckets"] = len(trainer.reducer.buckets) if trainer is not None and trainer.reducer else None
+        cfg["bucket_mb"] = args.bucket_mb
+        if args.ddp_dryrun:
+            cfg["note"] = "--ddp-dryrun: hooks + bucket packing without the collective (scaling attribution run)"
     line = {
         "metric": w["metric"], "value": gb / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": w["scaling"],
@@ -426,6 +466,9 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=0, help="override the workload's per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ddp", action="store_true", help="N independent replicas without the gradient exchange")
+    ap.add_argument("--cuda-graph", action="store_true", help="capture the train step in a CUDA graph after warm-up")
+    ap.add_argument("--ddp-dryrun", action="store_true", help="hooks and bucket packing, but no collective")
+    ap.add_argument("--bucket-mb", type=float, default=25.0, help="gradient bucket size of the data-parallel exchange")
     ap.add_argument("--full-sweep", action="store_true", help="kernel_sweep: add the token-grid and generalised sweeps")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

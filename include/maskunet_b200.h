@@ -60,6 +60,17 @@ int mu_device_supported(void);
  * key, so a hit is never stale -- behind a mutex; bounded (cleared when 4096 entries are reached).  Counters since load. */
 void mu_tmap_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* entries);
 void mu_tmap_cache_clear(void);
+/* Deterministic mode (process-wide switch, default off).  On: every kernel that sums partial results across CTAs does it
+ * in a fixed order -- mu_attn_bwd adds the per-key-tile dQ partials through per-query-tile order semaphores in its
+ * workspace -- so that two runs on the same inputs return the same bits. */
+void mu_set_deterministic(int32_t on);
+int32_t mu_get_deterministic(void);
+/* Scratch of deterministic mode for the CURRENT device: caller-owned device memory (the library never allocates), at
+ * least 1 MiB -- 128 MiB covers every shape of the U-Net -- whose first 1 KiB must be zero when it is registered (the
+ * kernels keep it zero).  The reductions that free-running mode does with float atomics (BatchNorm statistics and
+ * gradients, LayerNorm / projection / convolution weight gradients, the loss) store one partial per CTA here and add
+ * them in CTA order.  One compute stream per device: the kernels of a stream share the scratch.  NULL unregisters. */
+int mu_set_deterministic_scratch(void* scratch, size_t bytes);
 
 /* K2. Mask binarisation (:179-180  `binary_mask > 0.5` -> 0 / -inf bias, per key).
  *   bits      int64 [B, N]   the torch.randint(0, 2, ...) draw of :178 (stays a torch call)

@@ -17,7 +17,9 @@ from . import data  # noqa: E402  (device ToTensor + prefetcher, ade_semantic.py
 from . import query_attention  # noqa: E402  (generalised mode of the kernel sweep)
 from .losses import InstanceContrastiveLoss  # noqa: E402  (device version of coco_panoptic.py:482-521)
 from .ops import mean_iou, segmentation_argmax  # noqa: E402  (device versions of ade_semantic.py:128-146)
+from ._lib import is_deterministic, set_deterministic  # noqa: E402  (fixed-order accumulation across CTAs)
 
 __all__ = ["Mask2FormerAttention", "ConvBlock", "DownSample", "UpSample", "UNet", "InstanceUNet", "ops",
-           "mean_iou", "segmentation_argmax", "checkpoint", "InstanceContrastiveLoss", "data", "query_attention"]
+           "mean_iou", "segmentation_argmax", "checkpoint", "InstanceContrastiveLoss", "data", "query_attention",
+           "set_deterministic", "is_deterministic"]
 __version__ = "0.1.0"

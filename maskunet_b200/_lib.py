@@ -91,6 +91,12 @@ def load() -> ctypes.CDLL:
     lib.mu_tmap_cache_stats.argtypes = [_u64p, _u64p, _u64p]
     lib.mu_tmap_cache_clear.restype = None
     lib.mu_tmap_cache_clear.argtypes = []
+    lib.mu_set_deterministic.restype = None
+    lib.mu_set_deterministic.argtypes = [c_int32]
+    lib.mu_get_deterministic.restype = c_int32
+    lib.mu_get_deterministic.argtypes = []
+    lib.mu_set_deterministic_scratch.restype = c_int32
+    lib.mu_set_deterministic_scratch.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int32
@@ -104,6 +110,35 @@ def tmap_cache_stats() -> dict:
     h, m, e = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
     load().mu_tmap_cache_stats(ctypes.byref(h), ctypes.byref(m), ctypes.byref(e))
     return {"hits": h.value, "misses": m.value, "entries": e.value}
+
+
+_det_scratch = {}      # device index -> the registered scratch tensor (kept alive here)
+DET_SCRATCH_BYTES = 128 << 20
+
+
+def set_deterministic(on: bool, device=None) -> None:
+    """Process-wide switch: fixed-order accumulation in every kernel that sums across CTAs, so that two runs on the
+    same inputs return the same bits (free-running mode uses float atomics: last-bit differences that 39 batch-statistics
+    BatchNorms amplify).  Turning it on registers a zeroed 128 MiB scratch tensor for ``device`` (default: the current
+    CUDA device); call it once per device / process after ``torch.cuda.set_device``.  One compute stream per device.
+    Costs: the attention backward adds its dQ partials through order semaphores; everything else is a
+    few microseconds per kernel."""
+    lib = load()
+    if on:
+        import torch
+        if torch.cuda.is_available():
+            idx = torch.cuda.current_device() if device is None else torch.device(device).index
+            if idx not in _det_scratch:
+                with torch.cuda.device(idx):
+                    buf = torch.zeros(DET_SCRATCH_BYTES, dtype=torch.uint8, device=f"cuda:{idx}")
+                    check(lib.mu_set_deterministic_scratch(ctypes.c_void_p(buf.data_ptr()), DET_SCRATCH_BYTES),
+                          "mu_set_deterministic_scratch")
+                _det_scratch[idx] = buf
+    lib.mu_set_deterministic(1 if on else 0)
+
+
+def is_deterministic() -> bool:
+    return bool(load().mu_get_deterministic())
 
 
 def check(rc: int, what: str) -> None:

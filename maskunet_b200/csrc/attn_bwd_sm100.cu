@@ -12,6 +12,8 @@
 //         read back by a second warpgroup and added into an fp32 dQ accumulator with red.global.add
 // D = 256 splits the accumulator width over blockIdx.z (DH = 128 channels each) because dK + dV alone
 // would need 512 TMEM columns.  The 1/sqrt(C) factor of dS is applied when dK / dQ leave the chip.
+#include <atomic>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "tma_host.cuh"
@@ -39,6 +41,22 @@ constexpr float kLog2eB = 1.4426950408889634f;
 #endif
 #ifndef MU_BWD_DQ_RED
 #define MU_BWD_DQ_RED 0     // 1: dQ tiles leave through red.global.add.v4.f32 from registers instead of the TMA reduce-add
+#endif
+// 1: the key-tile CTAs of a sample start their walk over the query tiles at staggered offsets (CTA j of J starts at
+// tile floor(j T / J) and wraps), so that at any moment they reduce-add into DIFFERENT dQ tiles instead of all hitting
+// the same 32 KB of the accumulator at once.  Measured on B200 (N = 16384, d = 64, 128 samples): 14.30 ms against
+// 12.10 ms with every CTA of a sample on the same query tile (profiles/r02_attn_bwd_stagger_det_ab.log) -- the shared
+// Q_i / dO_i tile is what the L2 serves best -- so the walk stays in lock step in free-running mode.  Deterministic
+// mode (fixed accumulation order, below) turns the stagger on at run time: in lock step the ordered adds of a tile form a
+// chain of J completions, staggered the CTA that is next in the order passed the tile two periods earlier.
+#ifndef MU_BWD_STAGGER
+#define MU_BWD_STAGGER 0
+#endif
+// Deterministic mode: 1 = publish a tile's semaphore one step late (after the NEXT reduce-add was issued), 0 = wait
+// for the reduce-add to land and publish at once.  The successor in a tile's order arrives two tile periods after its
+// predecessor, so the hand-over has to fit in that: publishing at once keeps the slack.
+#ifndef MU_BWD_DET_LAG
+#define MU_BWD_DET_LAG 0
 #endif
 #ifndef MU_BWD_PROBE
 #define MU_BWD_PROBE 0      // 1 / 2: performance probes that skip work (wrong results), see DESIGN.md
@@ -95,6 +113,29 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Ordered accumulation (deterministic mode): sem counts the partial tiles already added into one dQ tile.
+__device__ __forceinline__ void sem_wait_turn(const int32_t* sem, int turn) {
+  const long long start = clock64();
+  int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(sem) : "memory");
+    if (v == turn) break;
+    __nanosleep(32);
+#if MU_SPIN_CYCLES > 0
+    if (clock64() - start > MU_SPIN_CYCLES) {
+      printf("attn_bwd_sm100: dQ order semaphore timeout: block (%d,%d,%d) sees %d, waits for %d\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, v, turn);
+      __trap();
+    }
+#endif
+  } while (true);
+  asm volatile("fence.proxy.async.global;" ::: "memory");   // the acquire above orders the TMA reduce-add issued next
+}
+__device__ __forceinline__ void sem_publish(int32_t* sem) {
+  __threadfence();
+  asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(sem) : "memory");
+}
+
 // QM = true: generalised mode of the kernel sweep (see attn_fwd_sm100.cu): a per-(query, key) bias as transposed bits
 // (bits_t [B / heads, NKP keys, wpq words over queries], K13), every key kept (no compaction: n_keep == nk_all and key
 // row r of tile j is token k0 + r), N queries against NT key tokens.
@@ -106,7 +147,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                       const int32_t* __restrict__ keep_idx,
                       const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
                       __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int N, int NKP, float scale,
-                      int NT, const uint32_t* __restrict__ bits_t, int heads, int wpq, int nk_all) {
+                      int NT, const uint32_t* __restrict__ bits_t, int heads, int wpq, int nk_all,
+                      int32_t* __restrict__ sem) {
   using Cfg = BwdCfg<D, BM, DH, STAGES, PB>;
   constexpr bool DQT = Cfg::kDQT;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -139,8 +181,40 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int b = blockIdx.y, k0 = blockIdx.x * kBK, half = blockIdx.z;
   const int nk = QM ? nk_all : n_keep[b];
+  if (!QM && nk == 0) {
+    // no key kept in this sample (probability 2^-N for the reference's masks, but masks can be injected): nobody
+    // scatters a row, so the first CTA clears this sample's dk / dv rows (its half of the channels)
+    if (blockIdx.x == 0) {
+      const int vec_per_row = DH / 8;
+      for (long idx = threadIdx.x; idx < (long)NT * vec_per_row; idx += kBwdThreads) {
+        const long row = idx / vec_per_row;
+        const int v = (int)(idx % vec_per_row);
+        const size_t off = ((size_t)b * NT + row) * D + half * DH + v * 8;
+        *reinterpret_cast<uint4*>(dk + off) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dv + off) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    return;
+  }
   if (k0 >= nk) return;                      // whole CTA: nothing kept in this tile
   const int T = (N + BM - 1) / BM;           // query tiles
+  // Walk order over the query tiles.  J = key tiles of this sample that hold kept keys (this CTA is tile j < J).
+  const int J = QM ? (nk + kBK - 1) / kBK : (nk + kBK - 1) / kBK;
+  const bool stagger = ((MU_BWD_STAGGER != 0) || sem != nullptr) && !QM && J <= T;
+  const int i0 = stagger ? (int)(((long)blockIdx.x * T) / J) : 0;
+  auto tile_of = [&](int step) {             // query tile processed at `step` (0 <= step < T)
+    const int t = step + i0;
+    return t >= T ? t - T : t;
+  };
+  // Deterministic mode (sem != nullptr): the J partial dQ tiles of query tile qt are added in a FIXED order -- the
+  // order in which the staggered walks reach qt: CTA j is number turn_of(qt) in it.  sem[b][qt] counts finished adds.
+  auto turn_of = [&](int qt) {
+    if (!stagger) return (int)blockIdx.x;
+    int c = (int)((((long)qt + 1) * J + T - 1) / T);           // CTAs whose start tile is <= qt
+    if (c > J) c = J;
+    int t = c - 1 - (int)blockIdx.x;
+    return t < 0 ? t + J : t;
+  };
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
@@ -192,8 +266,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         MU_TRACE(0, i);                          // TMA: stage free, loads of tile i issued
         mbar_expect_tx(qdo_full + st, 2 * Cfg::kQBytes);
         for (int blk = 0; blk < D / 64; ++blk) {
-          tma_load_3d(sQ + st * Cfg::kQBytes + blk * (BM * 128), &tmap_q, qdo_full + st, blk * 64, i * BM, b);
-          tma_load_3d(sDO + st * Cfg::kQBytes + blk * (BM * 128), &tmap_do, qdo_full + st, blk * 64, i * BM, b);
+          tma_load_3d(sQ + st * Cfg::kQBytes + blk * (BM * 128), &tmap_q, qdo_full + st, blk * 64, tile_of(i) * BM, b);
+          tma_load_3d(sDO + st * Cfg::kQBytes + blk * (BM * 128), &tmap_do, qdo_full + st, blk * 64, tile_of(i) * BM, b);
         }
       }
     }
@@ -322,7 +396,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const uint32_t lse_addr = smem_u32(sLse), delta_addr = smem_u32(sDelta);
     const uint32_t ds_base = smem_u32(sDS);
     auto fetch = [&](int i, float& l2, float& dl) {
-      const int qi = i * BM + t;
+      const int qi = tile_of(i) * BM + t;
       const bool ok = (t < BM) && (qi < N);
       l2 = ok ? lse_b[qi] : INFINITY;                    // +inf -> p = 0 for rows past N (scaled by log2e when staged)
       dl = ok ? delta_b[qi] : 0.f;
@@ -381,7 +455,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           for (int e = 0; e < 32; ++e) s[cc][e] = 0xff800000u;
       }
       if (QM) {                                          // per-(query, key) bias: p = exp2(-inf) = 0 where the bit is clear
-        const uint32_t* kb = bits_t + ((size_t)(b / heads) * NKP + k0 + r) * wpq + i * (BM / 32) + hcol * kChunksPerThread;
+        const uint32_t* kb = bits_t + ((size_t)(b / heads) * NKP + k0 + r) * wpq + tile_of(i) * (BM / 32) + hcol * kChunksPerThread;
 #pragma unroll
         for (int cc = 0; cc < kChunksPerThread; ++cc) {
           const uint32_t w = kb[cc];
@@ -457,6 +531,20 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const size_t row_off = ((size_t)b * NT + tok) * D + half * DH;
     {
       const int which = hcol;
+      if (!QM && key_ok) {
+        // Rows of masked keys must read zero (token-space outputs).  Instead of clearing the whole tensor first (two
+        // 0.5 GiB memsets per launch at the 16384-token site), the thread that owns kept key k also clears the masked
+        // tokens between the previous kept key and its own -- and, for the last kept key, the tail of the sample.
+        __nv_bfloat16* base = (which == 0 ? dv : dk) + (size_t)b * NT * D + half * DH;
+        const int prev = (k0 + r == 0) ? -1 : keep_idx[(size_t)b * NT + k0 + r - 1];
+        for (int z = prev + 1; z < tok; ++z)
+#pragma unroll
+          for (int g = 0; g < DH / 8; ++g) *reinterpret_cast<uint4*>(base + (size_t)z * D + g * 8) = make_uint4(0u, 0u, 0u, 0u);
+        if (k0 + r == nk - 1)
+          for (int z = tok + 1; z < NT; ++z)
+#pragma unroll
+            for (int g = 0; g < DH / 8; ++g) *reinterpret_cast<uint4*>(base + (size_t)z * D + g * 8) = make_uint4(0u, 0u, 0u, 0u);
+      }
       __nv_bfloat16* dst = (which == 0 ? dv : dk) + row_off;
       const float mul = which == 0 ? 1.f : scale;
       const int col0 = which == 0 ? Cfg::kTmDV : Cfg::kTmDK;
@@ -485,7 +573,10 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const int r = quad * 32 + (int)lane_id();
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t v[32];
+    int32_t* sem_b = sem != nullptr ? sem + ((size_t)(b * (int)gridDim.z + half)) * T : nullptr;
+    int prev_qt = -1;                                    // tile whose reduce-add is still in flight (TMA paths)
     for (int i = 0; i < T; ++i) {
+      const int qt = tile_of(i);                         // query tile of this step
       mbar_wait_relaxed(dq_full, i & 1);
       if (warp == 12) MU_TRACE(12, i);                   // dQ warps: dq_full(i)
       tc_fence_after();
@@ -515,14 +606,31 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (issuer) {
+          if (sem_b != nullptr) sem_wait_turn(sem_b + qt, turn_of(qt));
 #pragma unroll
           for (int c = 0; c < DH / 32; ++c)
-            tma_reduce_add_3d(&tmap_dq, stage + c * (BM * 128), half * DH + c * 32, i * BM, b);
+            tma_reduce_add_3d(&tmap_dq, stage + c * (BM * 128), half * DH + c * 32, qt * BM, b);
           tma_store_commit();
+          if (sem_b != nullptr) {
+#if MU_BWD_DET_LAG
+            if (prev_qt >= 0) {                          // the PREVIOUS tile's adds have landed: let its next CTA in
+              tma_store_wait<1>();
+              sem_publish(sem_b + prev_qt);
+            }
+            prev_qt = qt;
+#else
+            tma_store_wait<0>();                         // this tile's adds have landed: let the next CTA of its order in
+            sem_publish(sem_b + qt);
+#endif
+          }
         }
       } else if (DQT) {
         // lanes = channel (half * 128 + r), columns = queries of tile i: coalesced scalar reductions
-        float* base = dq_acc + ((size_t)b * N + (size_t)i * BM) * D + half * DH + r;
+        float* base = dq_acc + ((size_t)b * N + (size_t)qt * BM) * D + half * DH + r;
+        if (sem_b != nullptr) {                          // ordered: nobody adds before this CTA's turn
+          if (threadIdx.x == kBwdThreads - 128) sem_wait_turn(sem_b + qt, turn_of(qt));
+          named_bar_sync(2, 128);
+        }
 #pragma unroll
         for (int c = 0; c < BM / 32; ++c) {
           tmem_ld32(lane_base + Cfg::kTmDQ + c * 32, v);
@@ -533,12 +641,17 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           }
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if (i * BM + c * 32 + e < N) atomicAdd(base + (size_t)(c * 32 + e) * D, __uint_as_float(v[e]) * scale);
+            if (qt * BM + c * 32 + e < N) atomicAdd(base + (size_t)(c * 32 + e) * D, __uint_as_float(v[e]) * scale);
+        }
+        if (sem_b != nullptr) {
+          __threadfence();
+          named_bar_sync(2, 128);
+          if (threadIdx.x == kBwdThreads - 128) sem_publish(sem_b + qt);
         }
       } else if (MU_BWD_DQ_RED) {
         // A/B option: lanes = query row, 16-byte vector reductions straight from registers (no shared-memory staging:
         // 64 KB less port traffic per tile, but 64 RED.128 warp instructions through the LSU instead)
-        const int qrow = i * BM + r;
+        const int qrow = qt * BM + r;
         float* dst = dq_acc + ((size_t)b * N + qrow) * D;
 #pragma unroll
         for (int c = 0; c < DH / 32; ++c) {
@@ -591,14 +704,30 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         if (scale == 12345.f)
 #endif
         if (issuer) {
+          if (sem_b != nullptr) sem_wait_turn(sem_b + qt, turn_of(qt));
 #pragma unroll
-          for (int c = 0; c < DH / 32; ++c) tma_reduce_add_3d(&tmap_dq, stage + c * (BM * 128), c * 32, i * BM, b);
+          for (int c = 0; c < DH / 32; ++c) tma_reduce_add_3d(&tmap_dq, stage + c * (BM * 128), c * 32, qt * BM, b);
           tma_store_commit();
+          if (sem_b != nullptr) {
+#if MU_BWD_DET_LAG
+            if (prev_qt >= 0) {                          // the PREVIOUS tile's adds have landed: let its next CTA in
+              tma_store_wait<1>();
+              sem_publish(sem_b + prev_qt);
+            }
+            prev_qt = qt;
+#else
+            tma_store_wait<0>();                         // this tile's adds have landed: let the next CTA of its order in
+            sem_publish(sem_b + qt);
+#endif
+          }
         }
         if (warp == 12) MU_TRACE(14, i);                 // dQ warps: reduce issued
       }
     }
-    if (Cfg::kDQTma && threadIdx.x == kBwdThreads - 128) tma_store_wait<0>();   // all reduce-adds landed before exit
+    if (Cfg::kDQTma && threadIdx.x == kBwdThreads - 128) {
+      tma_store_wait<0>();                               // all reduce-adds landed before exit
+      if (sem_b != nullptr && prev_qt >= 0) sem_publish(sem_b + prev_qt);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -625,7 +754,7 @@ template <int D, int BM, int DH, int STAGES, int PB, bool QM = false>
 static int run(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const int32_t* keep_idx,
                const void* d_o, const float* lse, const float* delta, void* dq, void* dkc, void* dvc, float* dq_acc,
                int B, int N, int NKP, cudaStream_t s, int NT = 0, float scale_in = 0.f, const uint32_t* bits_t = nullptr,
-               int heads = 1, int nk_all = 0) {
+               int heads = 1, int nk_all = 0, int32_t* sem = nullptr) {
   if (NT == 0) NT = N;                     // self-attention: as many key tokens as queries
   using Cfg = BwdCfg<D, BM, DH, STAGES, PB>;
   CUtensorMap tq, tdo, tk, tv, tdq;
@@ -642,14 +771,15 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
     return (int)e;
   }
   const size_t n = (size_t)B * N * D, nt = (size_t)B * NT * D;
-  cudaMemsetAsync(dq_acc, 0, n * sizeof(float), s);
-  cudaMemsetAsync(dkc, 0, nt * 2, s);   // rows of masked keys stay zero
-  cudaMemsetAsync(dvc, 0, nt * 2, s);
+  // one memset clears the fp32 dQ accumulator and, in deterministic mode, the order semaphores right behind it
+  const size_t sem_bytes = sem != nullptr ? (size_t)B * (D / DH) * ((N + BM - 1) / BM) * sizeof(int32_t) : 0;
+  cudaMemsetAsync(dq_acc, 0, n * sizeof(float) + sem_bytes, s);
+  (void)nt;   // dk / dv need no clearing: the kernel writes every row (kept keys: gradients, masked keys: zeros)
   dim3 grid(NKP / kBK, B, D / DH);
   const float scale = scale_in > 0.f ? scale_in : 1.f / sqrtf((float)D);
   kern<<<grid, kBwdThreads, Cfg::kSmemBytes, s>>>(tq, tdo, tk, tv, tdq, n_keep, keep_idx, lse, delta, dq_acc, (__nv_bfloat16*)dkc,
                                                   (__nv_bfloat16*)dvc, N, NKP, scale, NT, bits_t, heads,
-                                                  round_up(N, 128) / 32, nk_all);
+                                                  round_up(N, 128) / 32, nk_all, sem);
   if ((rc = check_launch("attn_bwd_sm100"))) return rc;
   const size_t n4 = n / 4;
   const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
@@ -663,7 +793,15 @@ extern "C" int mu_debug_bwd_trace(long long* host, int n) {   // tools/bwd_trace
 }
 #endif
 
-size_t attn_bwd_sm100_workspace(int B, int N, int C) { return (size_t)B * N * C * sizeof(float); }
+// fp32 dQ accumulator [B, N, C] + order semaphores int32 [B, C / DH, ceil(N / 64)] (sized for the smallest query tile)
+static size_t dq_acc_bytes(int B, int N, int C) { return (size_t)B * N * C * sizeof(float); }
+size_t attn_bwd_sm100_workspace(int B, int N, int C) {
+  return dq_acc_bytes(B, N, C) + (size_t)B * 2 * ((N + 63) / 64) * sizeof(int32_t) + 16;
+}
+
+static std::atomic<int> g_deterministic{0};
+void set_deterministic(int on) { g_deterministic.store(on ? 1 : 0); }
+int get_deterministic() { return g_deterministic.load(); }
 
 int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const int32_t* n_keep,
                           const int32_t* keep_idx, const void* d_o, const float* lse, const float* delta, void* dq,
@@ -673,13 +811,18 @@ int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const i
              "mu_attn_bwd: workspace too small (%zu bytes given, %zu needed)", workspace_bytes,
              attn_bwd_sm100_workspace(B, N, C));
   float* acc = (float*)workspace;
+  // deterministic mode: semaphores live right behind the accumulator (same memset); nullptr = free-running adds
+  int32_t* sem = get_deterministic() ? reinterpret_cast<int32_t*>((char*)workspace + dq_acc_bytes(B, N, C)) : nullptr;
   switch (C) {
     case 64:
-      return run<64, 128, 64, MU_BWD_STAGES_64, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+      return run<64, 128, 64, MU_BWD_STAGES_64, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s,
+                                                   0, 0.f, nullptr, 1, 0, sem);
     case 128:
-      return run<128, 64, 128, MU_BWD_STAGES_128, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+      return run<128, 64, 128, MU_BWD_STAGES_128, 2>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s,
+                                                     0, 0.f, nullptr, 1, 0, sem);
     case 256:
-      return run<256, 64, 128, 1, 1>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s);
+      return run<256, 64, 128, 1, 1>(q, kc, vc, n_keep, keep_idx, d_o, lse, delta, dq, dkc, dvc, acc, B, N, NKP, s,
+                                     0, 0.f, nullptr, 1, 0, sem);
     default:
       set_error("attn_bwd_sm100: channels must be 64, 128 or 256 (got %d)", C);
       return MU_ERR_BAD_SHAPE;

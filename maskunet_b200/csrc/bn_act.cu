@@ -11,6 +11,7 @@
 // All HBM-bound: thread <-> fixed channel group (16-byte vectors when C % 8 == 0), rows strided over the grid,
 // per-thread fp32 partial sums, shared-memory reduction across row lanes, one atomicAdd per channel per CTA.
 #include "common.cuh"
+#include "det_reduce.cuh"
 
 namespace mu {
 
@@ -139,9 +140,11 @@ struct RowMap {
 };
 
 // block reduction of per-thread [VEC] partials over row lanes, then one atomicAdd per channel
+// (deterministic mode: `part` = this CTA's [C] slice of the scratch; the block totals are stored there and det_finish
+// adds the slices in CTA order)
 template <int VEC>
 __device__ __forceinline__ void block_reduce_add(float* red /*[kBnThreads*VEC]*/, const float (&a)[VEC], const RowMap& m,
-                                                 float* out, int C, int Cper) {
+                                                 float* out, int C, int Cper, float* part = nullptr) {
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < VEC; ++e) red[threadIdx.x * VEC + e] = m.active ? a[e] : 0.f;
@@ -150,14 +153,15 @@ __device__ __forceinline__ void block_reduce_add(float* red /*[kBnThreads*VEC]*/
     const int g = c / VEC, e = c - g * VEC;
     float s = 0.f;
     for (int rl = 0; rl < m.RL; ++rl) s += red[(rl * m.G + g) * VEC + e];
-    atomicAdd(out + (c % Cper), s);      // folded rows: column c of the wide row is channel c mod Cper
+    if (part != nullptr) part[c] = s;
+    else atomicAdd(out + (c % Cper), s);      // folded rows: column c of the wide row is channel c mod Cper
   }
 }
 
 // ------------------------------------------------------------------ forward: statistics
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restrict__ x, float* __restrict__ sums, long M,
-                                                              int C, int Cper) {
+                                                              int C, int Cper, const DetCtx det) {
   __shared__ float red[kBnThreads * VEC];
   const RowMap m(C, VEC);
   float s1[VEC], s2[VEC];
@@ -174,8 +178,10 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
       }
     }
   }
-  block_reduce_add<VEC>(red, s1, m, sums, C, Cper);
-  block_reduce_add<VEC>(red, s2, m, sums + Cper, C, Cper);
+  float* part = det.on() ? det.partial + (size_t)blockIdx.x * 2 * C : nullptr;
+  block_reduce_add<VEC>(red, s1, m, sums, C, Cper, part);
+  block_reduce_add<VEC>(red, s2, m, sums + Cper, C, Cper, det.on() ? part + C : nullptr);
+  if (det.on()) det_finish(det, gridDim.x, gridDim.x, 2, C, Cper, sums, sums + Cper, threadIdx.x, kBnThreads, SyncThreads());
 }
 
 // ------------------------------------------------------------------ forward: finalize ([C] work, one CTA)
@@ -235,7 +241,7 @@ template <typename T, int VEC, int ACT, bool RES>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
     const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ a,
     const float* __restrict__ b, const float* __restrict__ mean, const float* __restrict__ rstd,
-    float* __restrict__ sums, long M, int C, int Cper) {
+    float* __restrict__ sums, long M, int C, int Cper, const DetCtx det) {
   __shared__ float red[kBnThreads * VEC];
   const RowMap m(C, VEC);
   float s1[VEC], s2[VEC], av[VEC], bv[VEC], mv[VEC], rsv[VEC];
@@ -265,8 +271,10 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
       }
     }
   }
-  block_reduce_add<VEC>(red, s1, m, sums, C, Cper);
-  block_reduce_add<VEC>(red, s2, m, sums + Cper, C, Cper);
+  float* part = det.on() ? det.partial + (size_t)blockIdx.x * 2 * C : nullptr;
+  block_reduce_add<VEC>(red, s1, m, sums, C, Cper, part);
+  block_reduce_add<VEC>(red, s2, m, sums + Cper, C, Cper, det.on() ? part + C : nullptr);
+  if (det.on()) det_finish(det, gridDim.x, gridDim.x, 2, C, Cper, sums, sums + Cper, threadIdx.x, kBnThreads, SyncThreads());
 }
 
 // ------------------------------------------------------------------ backward: apply
@@ -353,7 +361,7 @@ bn_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
                    const __nv_bfloat16* __restrict__ r, const float* __restrict__ a, const float* __restrict__ b,
                    const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ sums,
                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dr, long M, int C, int Cper,
-                   int rows_per_chunk) {
+                   int rows_per_chunk, const DetCtx det) {
   constexpr int NS = RES ? 3 : 2;                       // streams: dy, x [, r]
   extern __shared__ __align__(128) uint8_t bulk_smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(bulk_smem);                   // [kBulkStages]
@@ -442,17 +450,35 @@ bn_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
     if (threadIdx.x == 0 && next < n_chunks) issue(next, stage);
   }
   if (MODE == 0) {
-    if (active) {
+    if (!det.on()) {
+      if (active) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        atomicAdd(red + g * 8 + e, s1[e]);
-        atomicAdd(red + C + g * 8 + e, s2[e]);
+        for (int e = 0; e < 8; ++e) {
+          atomicAdd(red + g * 8 + e, s1[e]);
+          atomicAdd(red + C + g * 8 + e, s2[e]);
+        }
       }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += kBulkThreads) {
-      atomicAdd(sums + (c % Cper), red[c]);
-      atomicAdd(sums + Cper + (c % Cper), red[C + c]);
+      __syncthreads();
+      for (int c = threadIdx.x; c < C; c += kBulkThreads) {
+        atomicAdd(sums + (c % Cper), red[c]);
+        atomicAdd(sums + Cper + (c % Cper), red[C + c]);
+      }
+    } else {
+      // deterministic mode: the row lanes add into the block totals one after the other (RL rounds), every CTA stores
+      // its totals, the last CTA adds the slices in CTA order
+      for (int round = 0; round < RL; ++round) {
+        if (active && rl == round) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            red[g * 8 + e] += s1[e];
+            red[C + g * 8 + e] += s2[e];
+          }
+        }
+        __syncthreads();
+      }
+      float* part = det.partial + (size_t)blockIdx.x * 2 * C;
+      for (int c = threadIdx.x; c < 2 * C; c += kBulkThreads) part[c] = red[c];
+      det_finish(det, gridDim.x, gridDim.x, 2, C, Cper, sums, sums + Cper, threadIdx.x, kBulkThreads, SyncThreads());
     }
   }
 }
@@ -469,6 +495,9 @@ static int bn_bwd_bulk(const void* dy, const void* x, const void* r, const float
   const long n_chunks = (M + rows_per_chunk - 1) / rows_per_chunk;
   const int grid = (int)(n_chunks < 148 ? n_chunks : 148);
   const bool res = r != nullptr;
+  DetCtx det;
+  if (!det_context(kDetSlotBn, MODE == 0 ? (size_t)grid * 2 * C : 0, &det, "bn_backward")) return MU_ERR_WORKSPACE;
+  if (MODE != 0) det.partial = nullptr;
   const size_t smem = 64 + ((2 * (size_t)C * 4 + 127) / 128) * 128 + (size_t)kBulkStages * (res ? 3 : 2) * kBulkChunkBytes;
 #define MU_BULK(ACTC, RESC)                                                                                          \
   {                                                                                                                  \
@@ -476,7 +505,7 @@ static int bn_bwd_bulk(const void* dy, const void* x, const void* r, const float
     set_max_dynamic_smem_once(kern, (int)smem);                              \
     kern<<<grid, kBulkThreads, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)r, \
                                           a, b, mean, rstd, sums, (__nv_bfloat16*)dx, (__nv_bfloat16*)dr, M, C, Cper, \
-                                          rows_per_chunk);                                                           \
+                                          rows_per_chunk, det);                                                      \
   }
   if (res) {
     if (act == ACT_GELU) MU_BULK(ACT_GELU, true) else if (act == ACT_RELU) MU_BULK(ACT_RELU, true) else MU_BULK(ACT_NONE, true)
@@ -538,7 +567,9 @@ static int bn_stats_t(const void* x, float* sums, long M, int C, cudaStream_t s)
   M /= fold;
   C *= fold;
   const int vec = pick_vec(C), grid = pick_grid(M, C, vec);
-  MU_BN_VEC(vec, (bn_stats_kernel<T, VEC><<<grid, kBnThreads, 0, s>>>((const T*)x, sums, M, C, Cper)));
+  DetCtx det;
+  if (!det_context(kDetSlotBn, (size_t)grid * 2 * C, &det, "bn_stats")) return MU_ERR_WORKSPACE;
+  MU_BN_VEC(vec, (bn_stats_kernel<T, VEC><<<grid, kBnThreads, 0, s>>>((const T*)x, sums, M, C, Cper, det)));
   return check_launch("bn_stats");
 }
 template <typename T>
@@ -561,8 +592,10 @@ static int bn_bwd_t(const void* dy, const void* x, const void* r, const float* a
   C *= fold;
   const int vec = pick_vec(C), grid = pick_grid(M, C, vec);
   const bool res = r != nullptr;
+  DetCtx det;
+  if (!det_context(kDetSlotBn, (size_t)grid * 2 * C, &det, "bn_backward")) return MU_ERR_WORKSPACE;
   MU_BN_VEC(vec, MU_BN_ACT(act, res, (bn_bwd_reduce_kernel<T, VEC, ACT, RES><<<grid, kBnThreads, 0, s>>>(
-                                         (const T*)dy, (const T*)x, (const T*)r, a, b, mean, rstd, sums, M, C, Cper))));
+                                         (const T*)dy, (const T*)x, (const T*)r, a, b, mean, rstd, sums, M, C, Cper, det))));
   int rc = check_launch("bn_bwd_reduce");
   if (rc) return rc;
   MU_BN_VEC(vec, MU_BN_ACT(act, res, (bn_bwd_apply_kernel<T, VEC, ACT, RES><<<grid, kBnThreads, 0, s>>>(

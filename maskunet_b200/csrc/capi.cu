@@ -3,9 +3,42 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "det_reduce.cuh"
 #include "tma_host.cuh"
 
 namespace mu {
+
+// ---- deterministic-mode scratch, registered per device by the caller (mu_set_deterministic_scratch)
+namespace {
+struct DetScratch { void* ptr; size_t bytes; };
+std::mutex g_det_mu;
+DetScratch g_det_scratch[64] = {};
+constexpr size_t kDetCounterBytes = 1024;     // 256 uint32 counters in front of the partial area
+}  // namespace
+
+bool det_context(int slot, size_t floats_needed, DetCtx* out, const char* who) {
+  out->partial = nullptr;
+  out->counter = nullptr;
+  out->floats = 0;
+  if (!get_deterministic()) return true;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DetScratch sc{nullptr, 0};
+  if (dev >= 0 && dev < 64) {
+    std::lock_guard<std::mutex> lock(g_det_mu);
+    sc = g_det_scratch[dev];
+  }
+  const size_t need = kDetCounterBytes + floats_needed * sizeof(float);
+  if (sc.ptr == nullptr || sc.bytes < need) {
+    set_error("%s: deterministic mode needs a scratch buffer of at least %zu bytes on device %d "
+              "(mu_set_deterministic_scratch; %zu registered)", who, need, dev, sc.bytes);
+    return false;
+  }
+  out->counter = reinterpret_cast<unsigned*>(sc.ptr) + slot;
+  out->partial = reinterpret_cast<float*>(reinterpret_cast<char*>(sc.ptr) + kDetCounterBytes);
+  out->floats = (sc.bytes - kDetCounterBytes) / sizeof(float);
+  return true;
+}
 
 static thread_local char g_err[512] = "";
 
@@ -76,6 +109,22 @@ void mu_tmap_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* entries) {
   if (misses) *misses = c.misses;
   if (entries) *entries = c.map.size();
 }
+
+void mu_set_deterministic(int32_t on) { set_deterministic(on); }
+
+int mu_set_deterministic_scratch(void* scratch, size_t bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    set_error("mu_set_deterministic_scratch: no current CUDA device");
+    return MU_ERR_DRIVER;
+  }
+  MU_REQUIRE(scratch == nullptr || (aligned16(scratch) && bytes >= (1u << 20)), MU_ERR_WORKSPACE,
+             "mu_set_deterministic_scratch: the scratch must be 16-byte aligned and at least 1 MiB (got %zu bytes)", bytes);
+  std::lock_guard<std::mutex> lock(g_det_mu);
+  g_det_scratch[dev] = DetScratch{scratch, scratch != nullptr ? bytes : 0};
+  return 0;
+}
+int32_t mu_get_deterministic(void) { return get_deterministic(); }
 
 void mu_tmap_cache_clear(void) {
   TmapCache& c = tmap_cache();

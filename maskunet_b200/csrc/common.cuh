@@ -95,6 +95,8 @@ int launch_attn_bwd_sm100(const void* q, const void* kc, const void* vc, const i
                           void* dk, void* dv, void* workspace, size_t workspace_bytes, int B, int N, int NKP, int C,
                           cudaStream_t s);
 size_t attn_bwd_sm100_workspace(int B, int N, int C);
+void set_deterministic(int on);   // fixed-order accumulation in every kernel that sums across CTAs (attn_bwd_sm100.cu)
+int get_deterministic();
 int launch_qkv_project_sm100(const void* xt, const void* w_bf16, const float* bias, const int32_t* rank, void* q,
                              void* kc, void* vc, int B, int C, int N, int NKP, cudaStream_t s);
 int launch_qkv_project_bwd_sm100(const void* xt, const void* dz, const void* dq, const void* dk, const void* dv,

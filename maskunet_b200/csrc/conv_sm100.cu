@@ -21,6 +21,7 @@
 //     with halo; 3 taps x 128 ci x 128 co accumulate in TMEM over the CTA's pixel range (split-K), then
 //     red.global.add.v4.f32 into an fp32 [9][Cin][Cout] workspace; a small kernel permutes to the parameter layout.
 #include "common.cuh"
+#include "det_reduce.cuh"
 #include "sm100_ptx.cuh"
 #include "tma_host.cuh"
 
@@ -56,7 +57,7 @@ template <int NT, int MT, int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         const __grid_constant__ CUtensorMap tmap_y, float* __restrict__ stats,
-                        const float* __restrict__ bias, const ConvArgs p) {
+                        const float* __restrict__ bias, const ConvArgs p, const DetCtx det) {
   constexpr int kBBytes = NT * 128;
   constexpr int GROUPS = MODE == CONV_ROWS ? 3 : 1;
   constexpr int TAPS = MODE == CONV_W128 ? 9 : (MODE == CONV_ROWS ? 3 : 1);
@@ -212,6 +213,24 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     int acc_nt = -1;
     auto flush_stats = [&](int nt_done) {
       if (nt_done < 0) return;
+      if (det.on()) {
+        // deterministic mode: the four row groups add into the CTA totals one after the other
+        for (int round = 0; round < 4; ++round) {
+          if (sq == round) {
+#pragma unroll
+            for (int i = 0; i < kBlocks; ++i) {
+              const int chn = nt_done * NT + i * 64 + 2 * cp;
+              s_stats[chn] += acc[i][0];
+              s_stats[chn + 1] += acc[i][1];
+              s_stats[512 + chn] += acc[i][2];
+              s_stats[512 + chn + 1] += acc[i][3];
+              acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+            }
+          }
+          named_bar_sync(1, 128);
+        }
+        return;
+      }
 #pragma unroll
       for (int i = 0; i < kBlocks; ++i) {
         const int chn = nt_done * NT + i * 64 + 2 * cp;
@@ -301,11 +320,20 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     if (stats != nullptr) {
       flush_stats(acc_nt);
       named_bar_sync(1, 128);
-      for (int i = e; i < p.N; i += 128) {
-        const float a = s_stats[i], q = s_stats[512 + i];
-        if (a != 0.f || q != 0.f) {
-          atomicAdd(stats + i, a);
-          atomicAdd(stats + p.N + i, q);
+      if (det.on()) {                        // every CTA stores its totals, the last one adds them in CTA order
+        float* part = det.partial + (size_t)blockIdx.x * 2 * p.N;
+        for (int i = e; i < p.N; i += 128) {
+          part[i] = s_stats[i];
+          part[p.N + i] = s_stats[512 + i];
+        }
+        det_finish(det, gridDim.x, gridDim.x, 2, p.N, p.N, stats, stats + p.N, e, 128, SyncNamed<1, 128>());
+      } else {
+        for (int i = e; i < p.N; i += 128) {
+          const float a = s_stats[i], q = s_stats[512 + i];
+          if (a != 0.f || q != 0.f) {
+            atomicAdd(stats + i, a);
+            atomicAdd(stats + p.N + i, q);
+          }
         }
       }
     }
@@ -327,6 +355,7 @@ struct WgradArgs {
   int ci_blocks;            // 64-channel x blocks per CTA: 2 (Cin % 128 == 0) or 1 (two taps share an M tile)
   int n_cb, n_nb;           // ci / co blocks over the grid
   int S, chunks_per_cta;
+  long slice_floats;        // deterministic mode: every pixel split (blockIdx.y) STORES into its own [taps][Cin][Cout] slice
 };
 
 template <int NB>
@@ -461,16 +490,24 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       }
       valid = valid && ci < p.Cin;                            // stem: 8 (3 + padding) of the 64 tile rows exist
       const int tap = p.mode == CONV_1X1 ? 0 : (p.mode == CONV_W128 ? g * 3 + j : j * 3 + g);
-      float* dst = ws + ((size_t)tap * p.Cin + ci) * p.Cout + nb * NB;
+      float* dst = ws + (size_t)blockIdx.y * p.slice_floats + ((size_t)tap * p.Cin + ci) * p.Cout + nb * NB;
 #pragma unroll
       for (int c = 0; c < NB / 32; ++c) {
         tmem_ld32(lane_base + m * NB + c * 32, v);
         tmem_wait_ld();
         if (valid) {
+          if (p.slice_floats != 0) {           // deterministic mode: plain stores, the finish kernel adds the slices in order
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            red_add_v4f(dst + c * 32 + q * 4, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                        __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(dst + c * 32 + q * 4) =
+                  make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                              __uint_as_float(v[4 * q + 3]));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              red_add_v4f(dst + c * 32 + q * 4, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                          __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          }
         }
       }
     }
@@ -500,14 +537,21 @@ __global__ void conv_prep_weights_kernel(const float* __restrict__ w, __nv_bfloa
   }
 }
 
-// ws f32 [taps][Cin][Cout] -> dw f32 [Cout][Cin][taps]
+// ws f32 [n_slices][taps][Cin][Cout] -> dw f32 [Cout][Cin][taps], slices added in order (free-running mode: one slice
+// that the CTAs reduced into with red.global.add; deterministic mode: one slice per pixel split)
 __global__ void conv_wgrad_finish_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cout, int Cin,
-                                         int taps) {
+                                         int taps, int n_slices) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // co fastest: coalesced reads
   if (idx >= Cout * Cin) return;
   const int ci = idx / Cout, co = idx - ci * Cout;
   float* dst = dw + ((size_t)co * Cin + ci) * taps;
-  for (int t = 0; t < taps; ++t) dst[t] = ws[((size_t)t * Cin + ci) * Cout + co];
+  const size_t slice = (size_t)taps * Cin * Cout;
+  for (int t = 0; t < taps; ++t) {
+    const float* src = ws + ((size_t)t * Cin + ci) * Cout + co;
+    float acc = src[0];
+    for (int k = 1; k < n_slices; ++k) acc += src[(size_t)k * slice];
+    dst[t] = acc;
+  }
 }
 
 // ============================================================================ launchers
@@ -577,7 +621,9 @@ static int run_fprop(const void* x, const void* wt, void* y, float* stats, const
   set_max_dynamic_smem_once(kern, smem);
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
-  kern<<<grid, kConvThreads, smem, s>>>(tx, tw, ty, stats, bias, p);
+  DetCtx det{nullptr, nullptr, 0};
+  if (stats != nullptr && !det_context(kDetSlotConvStats, (size_t)grid * 2 * N, &det, "conv_fprop_sm100")) return MU_ERR_WORKSPACE;
+  kern<<<grid, kConvThreads, smem, s>>>(tx, tw, ty, stats, bias, p, det);
   return check_launch("conv_fprop_sm100");
 }
 
@@ -643,9 +689,11 @@ int launch_conv1x1_fprop_sm100(const void* x, const void* wt, const float* bias,
   }
 }
 
+// *ws_io: in = the caller's [taps][Cin][Cout] workspace; out = where the partials are (deterministic mode: the
+// registered scratch, *n_slices of them; free-running: the caller's workspace, cleared here, one slice)
 template <int NB>
-static int run_wgrad(const void* x, const void* dy, float* ws, int B, int H, int W, int Cin, int Cout, int taps,
-                     cudaStream_t s) {
+static int run_wgrad(const void* x, const void* dy, float** ws_io, int* n_slices, int B, int H, int W, int Cin, int Cout,
+                     int taps, cudaStream_t s) {
   WgradArgs p;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.TH = 128 / W;
@@ -682,6 +730,20 @@ static int run_wgrad(const void* x, const void* dy, float* ws, int B, int H, int
   if (splits > p.m_tiles) splits = p.m_tiles;
   p.chunks_per_cta = (p.m_tiles + splits - 1) / splits;
   splits = (p.m_tiles + p.chunks_per_cta - 1) / p.chunks_per_cta;
+  const size_t slice = (size_t)taps * Cin * Cout;
+  DetCtx det;
+  if (!det_context(kDetSlotMisc, slice * splits, &det, "conv_wgrad_sm100")) return MU_ERR_WORKSPACE;
+  float* ws = *ws_io;
+  if (det.on()) {
+    ws = det.partial;
+    p.slice_floats = (long)slice;
+    *n_slices = splits;
+  } else {
+    cudaMemsetAsync(ws, 0, slice * sizeof(float), s);
+    p.slice_floats = 0;
+    *n_slices = 1;
+  }
+  *ws_io = ws;
   CUtensorMap tx, td;
   int rc;
   if ((rc = make_tmap_bf16_nhwc(&tx, x, Cin, W, H, B, box_w, box_h))) return rc;
@@ -697,12 +759,12 @@ int launch_conv_wgrad_sm100(const void* x, const void* dy, float* ws, float* dw,
                             cudaStream_t s) {
   int rc;
   if ((rc = conv_geometry_ok("conv_wgrad_sm100", B, H, W, Cin, Cout))) return rc;
-  cudaMemsetAsync(ws, 0, (size_t)9 * Cin * Cout * sizeof(float), s);
-  rc = Cout % 128 == 0 ? run_wgrad<128>(x, dy, ws, B, H, W, Cin, Cout, 9, s)
-                       : run_wgrad<64>(x, dy, ws, B, H, W, Cin, Cout, 9, s);
+  int n_slices = 1;
+  rc = Cout % 128 == 0 ? run_wgrad<128>(x, dy, &ws, &n_slices, B, H, W, Cin, Cout, 9, s)
+                       : run_wgrad<64>(x, dy, &ws, &n_slices, B, H, W, Cin, Cout, 9, s);
   if (rc) return rc;
   const int n = Cin * Cout;
-  conv_wgrad_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(ws, dw, Cout, Cin, 9);
+  conv_wgrad_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(ws, dw, Cout, Cin, 9, n_slices);
   return check_launch("conv_wgrad_finish");
 }
 
@@ -712,17 +774,17 @@ int launch_conv1x1_wgrad_sm100(const void* x, const void* dy, float* ws, float* 
   int rc;
   if ((rc = conv1x1_geometry_ok("conv1x1_wgrad_sm100", B, H, W, Cin, Np))) return rc;
   MU_REQUIRE(Cin % 64 == 0, MU_ERR_BAD_SHAPE, "conv1x1_wgrad_sm100: input channels must be a multiple of 64 (got %d)", Cin);
-  cudaMemsetAsync(ws, 0, (size_t)Cin * Np * sizeof(float), s);
+  int n_slices = 1;
   switch (Np) {
-    case 32: rc = run_wgrad<32>(x, dy, ws, B, H, W, Cin, Np, 1, s); break;
-    case 64: rc = run_wgrad<64>(x, dy, ws, B, H, W, Cin, Np, 1, s); break;
-    case 128: rc = run_wgrad<128>(x, dy, ws, B, H, W, Cin, Np, 1, s); break;
-    case 160: rc = run_wgrad<160>(x, dy, ws, B, H, W, Cin, Np, 1, s); break;
-    default: rc = run_wgrad<128>(x, dy, ws, B, H, W, Cin, Np, 1, s); break;   // 256 = two 128-channel blocks
+    case 32: rc = run_wgrad<32>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s); break;
+    case 64: rc = run_wgrad<64>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s); break;
+    case 128: rc = run_wgrad<128>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s); break;
+    case 160: rc = run_wgrad<160>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s); break;
+    default: rc = run_wgrad<128>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s); break;   // 256 = two 128-channel blocks
   }
   if (rc) return rc;
   const int n = Cin * Np;
-  conv_wgrad_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(ws, dw, Np, Cin, 1);
+  conv_wgrad_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(ws, dw, Np, Cin, 1, n_slices);
   return check_launch("conv1x1_wgrad_finish");
 }
 

@@ -10,6 +10,7 @@
 // critical path, the layout work (TMA 128B-swizzled tiles, MN-major operands for the transposed products) is
 // what removes every explicit transpose.
 #include "common.cuh"
+#include "det_reduce.cuh"
 #include "sm100_ptx.cuh"
 #include "tma_host.cuh"
 
@@ -314,7 +315,7 @@ template <int C>
 __global__ void __launch_bounds__(kGemmThreads)
 qkv_dw_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_dk,
                     const __grid_constant__ CUtensorMap tmap_dv, const __grid_constant__ CUtensorMap tmap_x,
-                    float* __restrict__ dw, int Mtot, int chunks_per_cta) {
+                    float* __restrict__ dw, int Mtot, int chunks_per_cta, float* __restrict__ det_slices) {
   using Cfg = P3Cfg<C>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -399,7 +400,10 @@ qkv_dw_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int h = r >> 6;
     const bool valid = !(C == 64 && m == 1 && h == 1);
-    float* wrow = dw + (size_t)(src[h] * C + col[h] + (r & 63)) * C;
+    // deterministic mode: every token split (blockIdx.x) stores its [3C, C] partial into its own slice, a small kernel
+    // adds the slices in order; free-running: float atomics into dw
+    float* wrow = (det_slices != nullptr ? det_slices + (size_t)blockIdx.x * 3 * C * C : dw) +
+                  (size_t)(src[h] * C + col[h] + (r & 63)) * C;
     uint32_t v[32];
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -408,8 +412,16 @@ qkv_dw_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
       tmem_ld32(lane_base + c * 32, v);
       tmem_wait_ld();
       if (valid) {
+        if (det_slices != nullptr) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) atomicAdd(wrow + c * 32 + e, __uint_as_float(v[e]));
+          for (int e = 0; e < 8; ++e)
+            *reinterpret_cast<float4*>(wrow + c * 32 + 4 * e) =
+                make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                            __uint_as_float(v[4 * e + 3]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) atomicAdd(wrow + c * 32 + e, __uint_as_float(v[e]));
+        }
       }
     }
   }
@@ -421,13 +433,22 @@ qkv_dw_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
   }
 }
 
+// deterministic mode: out[i] = slices[0][i] + slices[1][i] + ... in order
+__global__ void sum_slices_kernel(const float* __restrict__ slices, float* __restrict__ out, int n, int n_slices) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = slices[i];
+  for (int k = 1; k < n_slices; ++k) acc += slices[(size_t)k * n + i];
+  out[i] = acc;
+}
+
 // ============================================================================ db: column sums of dq | dk | dv
 // grid (row blocks, 3).  Each thread owns 8 channels (one 16-byte load per row).
 template <int C>
 __global__ void __launch_bounds__(256) qkv_db_kernel(const __nv_bfloat16* __restrict__ dq,
                                                      const __nv_bfloat16* __restrict__ dk,
                                                      const __nv_bfloat16* __restrict__ dv, float* __restrict__ db,
-                                                     int Mtot, int rows_per_block) {
+                                                     int Mtot, int rows_per_block, const DetCtx det) {
   constexpr int G = C / 8;          // column groups
   constexpr int RL = 256 / G;       // row lanes
   __shared__ float red[RL][C + 1];
@@ -452,8 +473,11 @@ __global__ void __launch_bounds__(256) qkv_db_kernel(const __nv_bfloat16* __rest
     float s = 0.f;
 #pragma unroll 4
     for (int i = 0; i < RL; ++i) s += red[i][c];
-    atomicAdd(db + blockIdx.y * C + c, s);
+    if (det.on()) det.partial[(size_t)blockIdx.x * 3 * C + blockIdx.y * C + c] = s;     // slice = row block
+    else atomicAdd(db + blockIdx.y * C + c, s);
   }
+  if (det.on())
+    det_finish(det, gridDim.x * gridDim.y, gridDim.x, 1, 3 * C, 3 * C, db, db, threadIdx.x, 256, SyncThreads());
 }
 
 // ============================================================================ launchers
@@ -500,15 +524,24 @@ static int run_bwd(const void* xt, const void* dz, const void* dq, const void* d
     int per = (total_chunks + 147) / 148;          // about one wave of CTAs per M tile
     if (per < 8) per = 8;
     dim3 grid((total_chunks + per - 1) / per, Cfg::kMTiles);
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(tdq, tdk, tdv, tx, dw, Mtot, per);
+    DetCtx det;
+    if (!det_context(kDetSlotMisc, (size_t)grid.x * 3 * C * C, &det, "qkv_project_bwd (dW)")) return MU_ERR_WORKSPACE;
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(tdq, tdk, tdv, tx, dw, Mtot, per, det.partial);
     if ((rc = check_launch("qkv_dw_sm100"))) return rc;
+    if (det.on()) {
+      const int n = 3 * C * C;
+      sum_slices_kernel<<<(n + 255) / 256, 256, 0, s>>>(det.partial, dw, n, (int)grid.x);
+      if ((rc = check_launch("qkv_dw_sum_slices"))) return rc;
+    }
   }
   {
     int rows = (Mtot + 295) / 296;
     if (rows < 256) rows = 256;
     dim3 grid((Mtot + rows - 1) / rows, 3);
+    DetCtx det;
+    if (!det_context(kDetSlotQkvDb, (size_t)grid.x * 3 * C, &det, "qkv_project_bwd")) return MU_ERR_WORKSPACE;
     qkv_db_kernel<C><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dq, (const __nv_bfloat16*)dk,
-                                          (const __nv_bfloat16*)dv, db, Mtot, rows);
+                                          (const __nv_bfloat16*)dv, db, Mtot, rows, det);
     if ((rc = check_launch("qkv_db"))) return rc;
   }
   return 0;

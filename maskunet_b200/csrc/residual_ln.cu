@@ -6,6 +6,7 @@
 // coalesced 128-byte rows, then each warp normalises tokens with shuffle reductions.
 // HBM-bound: forward moves 3*B*N*C*s bytes (o, x in; y out), backward 4*B*N*C*s (dy, o, x in; dz out).
 #include "common.cuh"
+#include "det_reduce.cuh"
 
 namespace mu {
 
@@ -78,7 +79,7 @@ template <typename T, bool TOK>
 __global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_kernel(
     const T* __restrict__ dy, const T* __restrict__ o, const T* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dz, float* __restrict__ delta,
-    float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int N) {
+    float* __restrict__ dgamma, float* __restrict__ dbeta, int C, int N, const DetCtx det) {
   extern __shared__ float xs[];  // [C][33] x tile, then reused for the dgamma/dbeta block reduction
   const int b = blockIdx.y, n0 = blockIdx.x * kLnTokens;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -141,8 +142,18 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_kernel(
       a += red[w * C + c];
       bsum += red[(8 + w) * C + c];
     }
-    atomicAdd(dgamma + c, a);
-    atomicAdd(dbeta + c, bsum);
+    if (det.on()) {                                  // deterministic mode: store the block totals, add in CTA order
+      float* part = det.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C;
+      part[c] = a;
+      part[C + c] = bsum;
+    } else {
+      atomicAdd(dgamma + c, a);
+      atomicAdd(dbeta + c, bsum);
+    }
+  }
+  if (det.on()) {
+    const int n_cta = gridDim.x * gridDim.y;
+    det_finish(det, n_cta, n_cta, 2, C, C, dgamma, dbeta, threadIdx.x, kLnThreads, SyncThreads());
   }
 }
 
@@ -236,7 +247,7 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_tok_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ x,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
     __nv_bfloat16* __restrict__ dz, float* __restrict__ delta, float* __restrict__ dgamma, float* __restrict__ dbeta,
-    long M) {
+    long M, const DetCtx det) {
   constexpr int LPT = C / 8, TPB = kLnThreads / LPT;
   __shared__ float red[2 * C];
   const int g = threadIdx.x % LPT, tl = threadIdx.x / LPT;
@@ -307,17 +318,36 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_tok_kernel(
     }
   }
   __syncthreads();
-  if ((threadIdx.x & 31) < LPT) {
+  if (!det.on()) {
+    if ((threadIdx.x & 31) < LPT) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      atomicAdd(red + g * 8 + e, dg[e]);
-      atomicAdd(red + C + g * 8 + e, db[e]);
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(red + g * 8 + e, dg[e]);
+        atomicAdd(red + C + g * 8 + e, db[e]);
+      }
     }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += kLnThreads) {
-    atomicAdd(dgamma + c, red[c]);
-    atomicAdd(dbeta + c, red[C + c]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kLnThreads) {
+      atomicAdd(dgamma + c, red[c]);
+      atomicAdd(dbeta + c, red[C + c]);
+    }
+  } else {
+    // deterministic mode: the warps add their channel-group totals one after the other (lanes < LPT of a warp own
+    // distinct channel groups, or -- when a warp holds several tokens -- the xor-reduction above already merged them),
+    // every CTA stores its totals, the last CTA adds the slices in CTA order
+    for (int w = 0; w < kLnThreads / 32; ++w) {
+      if ((int)(threadIdx.x >> 5) == w && (threadIdx.x & 31) < LPT) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          red[g * 8 + e] += dg[e];
+          red[C + g * 8 + e] += db[e];
+        }
+      }
+      __syncthreads();
+    }
+    float* part = det.partial + (size_t)blockIdx.x * 2 * C;
+    for (int c = threadIdx.x; c < 2 * C; c += kLnThreads) part[c] = red[c];
+    det_finish(det, gridDim.x, gridDim.x, 2, C, C, dgamma, dbeta, threadIdx.x, kLnThreads, SyncThreads());
   }
 }
 
@@ -347,12 +377,14 @@ static int run_bwd(const void* dy, const void* o, const void* x, const float* me
                    const float* gamma, void* dz, float* delta, float* dgamma, float* dbeta, int B, int C, int N,
                    int tok, cudaStream_t s) {
   dim3 grid((N + kLnTokens - 1) / kLnTokens, B);
+  DetCtx det;
+  if (!det_context(kDetSlotLn, (size_t)grid.x * grid.y * 2 * C, &det, "residual_ln_bwd")) return MU_ERR_WORKSPACE;
   if (tok)
     residual_ln_bwd_kernel<T, true><<<grid, kLnThreads, ln_smem(C), s>>>(
-        (const T*)dy, (const T*)o, (const T*)x, mean, rstd, gamma, (T*)dz, delta, dgamma, dbeta, C, N);
+        (const T*)dy, (const T*)o, (const T*)x, mean, rstd, gamma, (T*)dz, delta, dgamma, dbeta, C, N, det);
   else
     residual_ln_bwd_kernel<T, false><<<grid, kLnThreads, ln_smem(C), s>>>(
-        (const T*)dy, (const T*)o, (const T*)x, mean, rstd, gamma, (T*)dz, delta, dgamma, dbeta, C, N);
+        (const T*)dy, (const T*)o, (const T*)x, mean, rstd, gamma, (T*)dz, delta, dgamma, dbeta, C, N, det);
   return check_launch("residual_ln_bwd");
 }
 
@@ -377,10 +409,12 @@ int launch_residual_ln_bwd(const void* dy, const void* o, const void* x, const f
   if (dtype == MU_BF16 && tok && (C == 64 || C == 128 || C == 256)) {
     const long M = (long)B * N;
     const int grid = ln_tok_grid(M, C);
+    DetCtx det;
+    if (!det_context(kDetSlotLn, (size_t)grid * 2 * C, &det, "residual_ln_bwd")) return MU_ERR_WORKSPACE;
 #define MU_LN_BWD(CC)                                                                                               \
   residual_ln_bwd_tok_kernel<CC><<<grid, kLnThreads, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)o,        \
                                                              (const __nv_bfloat16*)x, mean, rstd, gamma,              \
-                                                             (__nv_bfloat16*)dz, delta, dgamma, dbeta, M)
+                                                             (__nv_bfloat16*)dz, delta, dgamma, dbeta, M, det)
     if (C == 64) MU_LN_BWD(64); else if (C == 128) MU_LN_BWD(128); else MU_LN_BWD(256);
 #undef MU_LN_BWD
     return check_launch("residual_ln_bwd_tok");

@@ -7,6 +7,7 @@
 // coalesced 16-byte vectors along the contiguous channel axis; reductions use fp32 partials, warp shuffles and
 // one atomicAdd per CTA.
 #include "common.cuh"
+#include "det_reduce.cuh"
 
 namespace mu {
 
@@ -220,7 +221,8 @@ __global__ void __launch_bounds__(256) upcat_bwd_kernel(const T* __restrict__ do
 // ============================================================================ K11: LayerNorm over (C, H, W) per sample
 // x, y: [B][L] with L = H*W*C in NHWC order; gamma / beta: f32 [L] in the same order.
 template <typename T>
-__global__ void __launch_bounds__(256) sample_stats_kernel(const T* __restrict__ x, float* __restrict__ sums, long L) {
+__global__ void __launch_bounds__(256) sample_stats_kernel(const T* __restrict__ x, float* __restrict__ sums, long L,
+                                                           const DetCtx det) {
   // grid (chunks, B); sums[b] = (sum, sumsq)
   __shared__ float red[2][8];
   const int b = blockIdx.y;
@@ -243,8 +245,12 @@ __global__ void __launch_bounds__(256) sample_stats_kernel(const T* __restrict__
   if (threadIdx.x < 2) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
-    atomicAdd(sums + 2 * b + threadIdx.x, t);
+    if (det.on()) det.partial[((size_t)blockIdx.x * gridDim.y + b) * 2 + threadIdx.x] = t;   // slice = blockIdx.x
+    else atomicAdd(sums + 2 * b + threadIdx.x, t);
   }
+  if (det.on())
+    det_finish(det, gridDim.x * gridDim.y, gridDim.x, 1, 2 * gridDim.y, 2 * gridDim.y, sums, sums, threadIdx.x, 256,
+               SyncThreads());
 }
 
 __global__ void sample_finalize_kernel(const float* __restrict__ sums, float* __restrict__ mean,
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(256) sample_ln_bwd_stats_kernel(const T* __res
                                                                   const float* __restrict__ gamma,
                                                                   const float* __restrict__ mean,
                                                                   const float* __restrict__ rstd,
-                                                                  float* __restrict__ sums, long L) {
+                                                                  float* __restrict__ sums, long L, const DetCtx det) {
   __shared__ float red[2][8];
   const int b = blockIdx.y;
   const float mu_ = mean[b], rs = rstd[b];
@@ -311,8 +317,12 @@ __global__ void __launch_bounds__(256) sample_ln_bwd_stats_kernel(const T* __res
   if (threadIdx.x < 2) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
-    atomicAdd(sums + 2 * b + threadIdx.x, t);
+    if (det.on()) det.partial[((size_t)blockIdx.x * gridDim.y + b) * 2 + threadIdx.x] = t;   // slice = blockIdx.x
+    else atomicAdd(sums + 2 * b + threadIdx.x, t);
   }
+  if (det.on())
+    det_finish(det, gridDim.x * gridDim.y, gridDim.x, 1, 2 * gridDim.y, 2 * gridDim.y, sums, sums, threadIdx.x, 256,
+               SyncThreads());
 }
 
 // backward pass B: dx, and dgamma / dbeta reduced over the batch by the thread that owns the position
@@ -354,7 +364,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) ce_fused_kernel(const T* __restrict__ logits, const int64_t* __restrict__ labels,
                                                        const float* __restrict__ valid_count, long ignore_index,
                                                        T* __restrict__ dlogits, float* __restrict__ loss_sum, long M,
-                                                       int C, int pitch) {
+                                                       int C, int pitch, const DetCtx det) {
   // pitch >= C: row stride in elements (class-padded logits of the 1x1 head); gradient pad columns are zeroed
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const float inv = 1.f / fmaxf(valid_count[0], 1.f);
@@ -413,8 +423,10 @@ __global__ void __launch_bounds__(256) ce_fused_kernel(const T* __restrict__ log
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += red[w];
-    atomicAdd(loss_sum, t * inv);
+    if (det.on()) det.partial[blockIdx.x] = t * inv;
+    else atomicAdd(loss_sum, t * inv);
   }
+  if (det.on()) det_finish(det, gridDim.x, gridDim.x, 1, 1, 1, loss_sum, loss_sum, threadIdx.x, 256, SyncThreads());
 }
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
@@ -429,7 +441,8 @@ __global__ void __launch_bounds__(256) ce_fused_vec_kernel(const __nv_bfloat16* 
                                                            const int64_t* __restrict__ labels,
                                                            const float* __restrict__ valid_count, long ignore_index,
                                                            __nv_bfloat16* __restrict__ dlogits,
-                                                           float* __restrict__ loss_sum, long M, int C, int pitch) {
+                                                           float* __restrict__ loss_sum, long M, int C, int pitch,
+                                                           const DetCtx det) {
   constexpr int U = 4;                       // independent rows per warp trip: four vector loads in flight per lane
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const float inv = 1.f / fmaxf(valid_count[0], 1.f);
@@ -496,8 +509,10 @@ __global__ void __launch_bounds__(256) ce_fused_vec_kernel(const __nv_bfloat16* 
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w2 = 0; w2 < 8; ++w2) t += red[w2];
-    atomicAdd(loss_sum, t * inv);
+    if (det.on()) det.partial[blockIdx.x] = t * inv;
+    else atomicAdd(loss_sum, t * inv);
   }
+  if (det.on()) det_finish(det, gridDim.x, gridDim.x, 1, 1, 1, loss_sum, loss_sum, threadIdx.x, 256, SyncThreads());
 }
 
 // ============================================================================ logit post-processing
@@ -665,8 +680,10 @@ int launch_sample_ln_fwd(const void* x, const float* gamma, const float* beta, f
   int chunks = (int)((L / 8 + 255) / 256);
   if (chunks > 64) chunks = 64;
   dim3 g1(chunks, B);
-  MU_T(dtype, (sample_stats_kernel<float><<<g1, 256, 0, s>>>((const float*)x, sums, L)),
-       (sample_stats_kernel<__nv_bfloat16><<<g1, 256, 0, s>>>((const __nv_bfloat16*)x, sums, L)));
+  DetCtx det;
+  if (!det_context(kDetSlotSampleLn, (size_t)chunks * 2 * B, &det, "sample_layernorm_fwd")) return MU_ERR_WORKSPACE;
+  MU_T(dtype, (sample_stats_kernel<float><<<g1, 256, 0, s>>>((const float*)x, sums, L, det)),
+       (sample_stats_kernel<__nv_bfloat16><<<g1, 256, 0, s>>>((const __nv_bfloat16*)x, sums, L, det)));
   sample_finalize_kernel<<<(B + 127) / 128, 128, 0, s>>>(sums, mean, rstd, B, L, eps);
   int pos_blocks = (int)((L / 8 + 255) / 256);
   int by = 1;
@@ -689,9 +706,11 @@ int launch_sample_ln_bwd(const void* dy, const void* x, const float* gamma, cons
   int chunks = (int)((L / 8 + 255) / 256);
   if (chunks > 64) chunks = 64;
   dim3 g1(chunks, B);
-  MU_T(dtype, (sample_ln_bwd_stats_kernel<float><<<g1, 256, 0, s>>>((const float*)dy, (const float*)x, gamma, mean, rstd, sums, L)),
+  DetCtx det;
+  if (!det_context(kDetSlotSampleLn, (size_t)chunks * 2 * B, &det, "sample_layernorm_bwd")) return MU_ERR_WORKSPACE;
+  MU_T(dtype, (sample_ln_bwd_stats_kernel<float><<<g1, 256, 0, s>>>((const float*)dy, (const float*)x, gamma, mean, rstd, sums, L, det)),
        (sample_ln_bwd_stats_kernel<__nv_bfloat16><<<g1, 256, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
-                                                                     gamma, mean, rstd, sums, L)));
+                                                                     gamma, mean, rstd, sums, L, det)));
   const int pos_blocks = (int)((L / 8 + 255) / 256);
   MU_T(dtype, (sample_ln_bwd_apply_kernel<float><<<pos_blocks, 256, 0, s>>>((const float*)dy, (const float*)x, gamma, mean, rstd,
                                                                          sums, (float*)dx, dgamma, dbeta, B, L)),
@@ -713,15 +732,17 @@ int launch_ce_fused(const void* logits, const int64_t* labels, const float* vali
   }
   cudaMemsetAsync(loss_sum, 0, sizeof(float), s);
   const int grid = grid_for((M + 7) / 8, 1);
+  DetCtx det;
+  if (!det_context(kDetSlotCe, (size_t)grid, &det, "cross_entropy")) return MU_ERR_WORKSPACE;
   if (dtype == MU_BF16 && pitch % 8 == 0) {
     ce_fused_vec_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)logits, labels, valid_count, ignore_index,
-                                             (__nv_bfloat16*)dlogits, loss_sum, M, C, pitch);
+                                             (__nv_bfloat16*)dlogits, loss_sum, M, C, pitch, det);
     return check_launch("cross_entropy_fused_vec");
   }
   MU_T(dtype, (ce_fused_kernel<float><<<grid, 256, 0, s>>>((const float*)logits, labels, valid_count, ignore_index,
-                                                        (float*)dlogits, loss_sum, M, C, pitch)),
+                                                        (float*)dlogits, loss_sum, M, C, pitch, det)),
        (ce_fused_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)logits, labels, valid_count,
-                                                            ignore_index, (__nv_bfloat16*)dlogits, loss_sum, M, C, pitch)));
+                                                            ignore_index, (__nv_bfloat16*)dlogits, loss_sum, M, C, pitch, det)));
   return check_launch("cross_entropy_fused");
 }
 

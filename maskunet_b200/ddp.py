@@ -66,6 +66,9 @@ class GradReducer:
         self.launched = 0                            # all-reduce launches, for reporting
         backend = dist.get_backend(process_group) if dist.is_initialized() else ""
         self._avg = backend == "nccl"                # ReduceOp.AVG exists on NCCL only (gloo: sum, then divide)
+        # measurement switch (bench.py --ddp-dryrun): hooks and bucket packing run, the collective does not -- the
+        # difference to a normal run is what the exchange itself (NCCL kernels + rank synchronisation) costs
+        self.dry_run = False
         if self.world > 1:
             for p in self.params:
                 p.register_post_accumulate_grad_hook(self._on_grad)
@@ -99,7 +102,9 @@ class GradReducer:
             torch._foreach_copy_(b.views, grads)     # one multi-tensor launch packs the bucket
         for p, v in zip(b.params, b.views):
             p.grad = v                               # frees autograd's buffer; the optimiser reads the reduced slice
-        if self._avg:
+        if self.dry_run:
+            b.work = None
+        elif self._avg:
             b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
         else:
             b.flat.div_(self.world)
@@ -142,7 +147,8 @@ class GradReducer:
             if b.pending != 0:
                 raise RuntimeError("GradReducer.finish(): a bucket is missing gradients "
                                    f"({b.pending} of {len(b.params)} parameters did not report)")
-            b.work.wait()
+            if b.work is not None:
+                b.work.wait()
             b.work, b.pending = None, len(b.params)
             b.seen.clear()
 

@@ -104,8 +104,15 @@ class Mask2FormerAttention(nn.Module):
         else:
             token_major = False
             tokens = x.contiguous().view(batch, channels, n_tok).to(dtype)
-        w_qkv = torch.cat([self.query.weight, self.key.weight, self.value.weight], dim=0).float()
-        b_qkv = torch.cat([self.query.bias, self.key.bias, self.value.bias], dim=0).float()
+        def pack():
+            return (torch.cat([self.query.weight, self.key.weight, self.value.weight], dim=0).float(),
+                    torch.cat([self.query.bias, self.key.bias, self.value.bias], dim=0).float())
+        if torch.is_grad_enabled():
+            w_qkv, b_qkv = pack()
+        else:       # inference: packed once per parameter version (see _inference_cache)
+            w_qkv, b_qkv = _inference_cache(self, "_mu_qkv_operand", (self.query.weight, self.key.weight,
+                                                                    self.value.weight, self.query.bias,
+                                                                    self.key.bias, self.value.bias), pack)
         y = ops.mask_attention(tokens, w_qkv, b_qkv, self.norm.weight.float(), self.norm.bias.float(),
                                keep_rank, keep_idx, n_keep, self.norm.eps, token_major)[0]
         if channels_last_in:
@@ -248,6 +255,27 @@ def _own_conv3x3(conv: nn.Conv2d, x: torch.Tensor, weight: Optional[torch.Tensor
             and ops.conv3x3_shape_ok(x.shape[0], x.shape[1], conv.out_channels, x.shape[2], x.shape[3]))
 
 
+def _inference_cache(module: nn.Module, slot: str, params, build):
+    """Operand copies of parameters (bf16 weight tiles, the packed [3C, C] projection matrix) are rebuilt on every
+    forward while training -- the optimiser changes the parameters every step.  Under ``torch.no_grad()`` (inference:
+    BASELINE config 4, validation loops) they are kept on the module, keyed by every parameter's (storage address,
+    version counter, shape): ``optimizer.step``, ``load_state_dict`` and ``.to()`` change the key.  Writing through
+    ``param.data`` does not bump the version counter -- call ``invalidate_operand_caches(model)`` after doing that."""
+    key = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params if p is not None)
+    hit = module.__dict__.get(slot)
+    if hit is None or hit[0] != key:
+        hit = (key, build())
+        module.__dict__[slot] = hit
+    return hit[1]
+
+
+def invalidate_operand_caches(model: nn.Module) -> None:
+    """Drop the inference-mode operand copies kept on the modules of ``model`` (see _inference_cache)."""
+    for m in model.modules():
+        for slot in ("_mu_conv_operand", "_mu_qkv_operand"):
+            m.__dict__.pop(slot, None)
+
+
 def conv_bn_act(conv: nn.Conv2d, bn: nn.BatchNorm2d, x: torch.Tensor, act: int,
                 residual: Optional[torch.Tensor] = None):
     """act(BN(conv(x)) [+ residual]): one conv3x3 -> BatchNorm2d -> activation link of ade_semantic.py:198-210.
@@ -265,7 +293,13 @@ def conv_bn_act(conv: nn.Conv2d, bn: nn.BatchNorm2d, x: torch.Tensor, act: int,
         if x.shape[1] == 8:
             weight = F.pad(weight, (0, 0, 0, 0, 0, extra))
     if _own_conv3x3(conv, x, weight):
-        y, sums, _ = ops.conv3x3(x, weight, bn.training)
+        if not torch.is_grad_enabled():
+            # inference: the bf16 weight tiles are prepared once per parameter version, not once per forward
+            wf = _inference_cache(conv, "_mu_conv_operand", (conv.weight,),
+                                  lambda: ops.conv_prep_weights(weight.detach().contiguous(), False)[0])
+            y, sums = ops.conv3x3_fwd(x, wf, bn.training)
+        else:
+            y, sums, _ = ops.conv3x3(x, weight, bn.training)
         return fused_bn_act(y, bn, act, residual, sums=sums if bn.training else None)
     return fused_bn_act(conv(x[:, :conv.in_channels]), bn, act, residual)
 

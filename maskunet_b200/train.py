@@ -17,6 +17,15 @@ rank's batch -- normalises its cross-entropy sum by the number of valid pixels o
 world size, so that the all-reduce(mean) of the gradients is exactly the gradient of that global mean even when
 ``ignore_index`` pixels are spread unevenly.  ``step`` returns the rank-local share of the loss (device tensor, no
 host sync); its mean over ranks is the global loss.
+
+CUDA graph (``Trainer(cuda_graph=True)``).  A step is ~460 kernel launches of ours plus torch's own; enqueuing them
+costs the host ~25 ms, which is hidden behind 115 ms of GPU work at 256 images per GPU but not at the small per-GPU
+batches strong scaling produces.  With the flag, the first ``graph_warmup`` steps run eagerly (masks are drawn, kernel
+attributes set, TMA descriptors cached, optimiser state created), then zero_grad + forward + fused loss + backward +
+AdamW(capturable) are captured ONCE into a CUDA graph with static input buffers; every later step is two copies into
+those buffers and one graph launch.  Shapes must not change afterwards.  The instance term needs a host round trip per
+step (the reference's ``torch.randint`` draws from the CPU generator, coco_panoptic.py:510) and micro-batching changes
+the step's structure, so both stay eager.
 """
 from __future__ import annotations
 
@@ -33,14 +42,21 @@ from .ddp import GradReducer
 class Trainer:
     def __init__(self, model: torch.nn.Module, lr: float = 5e-5, weight_decay: float = 1e-1,
                  ignore_index: int = -100, data_parallel: bool = False, bucket_bytes: int = 25 * 1024 * 1024,
-                 instance_loss: Optional[torch.nn.Module] = None, loss_weights=(0.9, 0.1)):
+                 instance_loss: Optional[torch.nn.Module] = None, loss_weights=(0.9, 0.1),
+                 cuda_graph: bool = False, graph_warmup: int = 3):
         self.model = model
         self.device = next(model.parameters()).device
         self.ignore_index = ignore_index
         self.instance_loss = instance_loss          # maskunet_b200.InstanceContrastiveLoss or None
         self.loss_weights = loss_weights            # (semantic, instance), coco_panoptic.py:552
         params = [p for p in model.parameters() if p.requires_grad]
-        self.optimizer = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, fused=self.device.type == "cuda")
+        self.cuda_graph = bool(cuda_graph) and self.device.type == "cuda"
+        self.graph_warmup = max(1, int(graph_warmup))
+        self._graph = None               # (CUDAGraph, static images, static labels, static loss)
+        self._eager_steps = 0
+        self.graph_launches = 0          # kernels of ours inside one replay (ops.LAUNCHES only sees the capture)
+        self.optimizer = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, fused=self.device.type == "cuda",
+                                           capturable=self.cuda_graph)
         self.reducer: Optional[GradReducer] = None
         if data_parallel:
             self.reducer = GradReducer(params, bucket_bytes=bucket_bytes)
@@ -60,6 +76,14 @@ class Trainer:
             count = count / world
         return count
 
+    def _drop_graph_refs(self) -> None:
+        """The model keeps the class-padded logits of its last forward (the tensor backward starts from).  After
+        backward nothing needs it, and holding it would keep that iteration's autograd graph -- including the
+        parameters' AccumulateGrad nodes, which are bound to the stream they were created on -- alive into the next
+        iteration: a CUDA-graph capture on another stream then trips over the stale nodes."""
+        if hasattr(self.model, "_padded_logits"):
+            self.model._padded_logits = None
+
     def _ce_backward(self, logits, labels, count):
         """Cross-entropy of one (micro-)batch, normalised by ``count``; starts backward; returns the loss share."""
         fused_ok = logits.is_cuda and logits.shape[1] <= 256 and logits.dtype in (torch.float32, torch.bfloat16)
@@ -71,6 +95,7 @@ class Trainer:
             with torch.no_grad():
                 loss, dpad = ops.cross_entropy_fused(padded.detach(), labels, self.ignore_index, logits.shape[1], count)
             padded.backward(dpad)
+            self._drop_graph_refs()
             return loss.squeeze(0)
         if fused_ok and logits.is_contiguous(memory_format=torch.channels_last):
             # fused CrossEntropyLoss(mean) forward + gradient on channels-last logits (one read, one write), and
@@ -102,6 +127,7 @@ class Trainer:
             return loss.detach()
         loss, dpad = self.fused_panoptic_loss(padded, logits.shape[1], labels, inst, count, inst_scale, plan)
         padded.backward(dpad)
+        self._drop_graph_refs()
         return loss
 
     def fused_panoptic_loss(self, padded, c_out, labels, inst, count=None, inst_scale: float = 1.0, plan=None):
@@ -171,10 +197,42 @@ class Trainer:
             total = loss if total is None else total + loss
         return total.detach()
 
+    def _graph_step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        if self._graph is None:
+            gx = torch.empty(images.shape, dtype=images.dtype, device=self.device)
+            gy = torch.empty(labels.shape, dtype=labels.dtype, device=self.device)
+            gx.copy_(images, non_blocking=True)
+            gy.copy_(labels, non_blocking=True)
+            self.optimizer.zero_grad(set_to_none=True)
+            torch.cuda.synchronize(self.device)
+            torch.cuda.empty_cache()             # the eager steps' activation cache goes back before the graph pool grows
+            graph = torch.cuda.CUDAGraph()
+            before = ops.LAUNCHES["count"]
+            with torch.cuda.graph(graph):
+                self.optimizer.zero_grad(set_to_none=True)
+                loss = self.forward_backward(gx, gy)
+                if self.reducer is not None:
+                    self.reducer.finish()
+                self.optimizer.step()
+            self.graph_launches = ops.LAUNCHES["count"] - before
+            self._graph = (graph, gx, gy, loss)
+        graph, gx, gy, loss = self._graph
+        if tuple(images.shape) != tuple(gx.shape) or tuple(labels.shape) != tuple(gy.shape):
+            raise RuntimeError("Trainer(cuda_graph=True): the batch shape changed after the step was captured")
+        gx.copy_(images, non_blocking=True)
+        gy.copy_(labels, non_blocking=True)
+        graph.replay()
+        return loss.clone()
+
     def step(self, images: torch.Tensor, labels: torch.Tensor, instance_labels: Optional[torch.Tensor] = None,
              micro_batch: Optional[int] = None) -> torch.Tensor:
         """One training step; ``images``/``labels`` may live in (pinned) host memory.  Returns this rank's share of
         the loss (device tensor; mean over ranks = the global loss)."""
+        if (self.cuda_graph and instance_labels is None and not (micro_batch and micro_batch < images.shape[0])
+                and self.model.training):
+            if self._eager_steps >= self.graph_warmup:
+                return self._graph_step(images, labels)
+            self._eager_steps += 1
         self.optimizer.zero_grad(set_to_none=True)
         loss = self.forward_backward(images, labels, instance_labels, micro_batch)
         if self.reducer is not None:

@@ -162,6 +162,92 @@ def test_tcgen05_backward_matches_cudacore_kernel(C, N, B):
                 assert (g[b, int(n_keep[b]):] == 0).all()      # masked keys: exactly zero gradient
 
 
+@pytest.mark.parametrize("C,N", [(64, 1024), (128, 512), (256, 384)])
+def test_tcgen05_backward_clears_masked_rows_without_a_memset(C, N):
+    """dk / dv are token-space tensors whose masked rows must read zero.  The kernel clears them itself (the thread
+    that owns a kept key clears the gap before it, the last kept key the tail; a sample with NO kept key is cleared by
+    its first CTA).  Scattered masks with long gaps, a single kept key, no kept key -- on output buffers the caching
+    allocator hands back full of NaN."""
+    from maskunet_b200 import ops
+    dev = _dev()
+    gen = torch.Generator(device=dev).manual_seed(C + N)
+    B = 5
+    keep = torch.rand(B, N, device=dev, generator=gen) < 0.5
+    keep[1] = False
+    keep[1, N // 3] = True                                  # one kept key
+    keep[2] = False                                         # nothing kept: the reference's output is NaN there
+    keep[3, : N // 2] = False                               # a long leading gap
+    keep[3, N - 200:] = False                               # and a long tail
+    keep[4, 130:700] = False                                # a gap spanning several 128-key tiles
+    _, n_keep, keep_idx, keep_rank = ops.mask_binarize(keep.to(torch.int64))
+    NKP = ops.nkp_of(N)
+    q = (0.5 * torch.randn(B, N, C, device=dev, generator=gen)).bfloat16()
+    k = torch.randn(B, N, C, device=dev, generator=gen).bfloat16()
+    v = torch.randn(B, N, C, device=dev, generator=gen).bfloat16()
+    d_o = torch.randn(B, N, C, device=dev, generator=gen).bfloat16()
+    kc = torch.zeros(B, NKP, C, device=dev, dtype=torch.bfloat16)
+    vc = torch.zeros(B, NKP, C, device=dev, dtype=torch.bfloat16)
+    for b in range(B):
+        nk = int(n_keep[b])
+        kc[b, :nk] = k[b, keep[b]]
+        vc[b, :nk] = v[b, keep[b]]
+    o, lse = ops.attn_fwd_cudacore(q, kc, vc, n_keep)
+    delta = (d_o.float() * torch.nan_to_num(o.float())).sum(-1).contiguous()
+    lse = torch.nan_to_num(lse, nan=0.0, posinf=0.0, neginf=0.0)
+    ref = ops.attn_bwd_cudacore(q, kc, vc, n_keep, keep_idx, d_o, lse, delta)
+    for _ in range(3):
+        poison = [torch.full((B, N, C), float("nan"), device=dev, dtype=torch.bfloat16) for _ in range(3)]
+        del poison                                          # the next three empty_like(q) reuse these blocks
+        got = ops.attn_bwd(q, kc, vc, n_keep, keep_idx, d_o, lse, delta)
+        for name, g, r in zip(("dk", "dv"), got[1:], ref[1:]):
+            assert bool(torch.isfinite(g.float()).all()), name
+            assert float(g[~keep].float().abs().max()) == 0.0, name          # masked rows: exactly zero
+            for b in (0, 1, 3, 4):
+                if b == 1 and name == "dk":
+                    # one kept key: p = 1 for every query, dS = p (dP - delta) = 0 analytically -- both kernels return
+                    # rounding noise there, a relative error means nothing
+                    assert float(g[b].float().abs().max()) < 0.05 * float(ref[2][b].float().abs().max())
+                    continue
+                assert rel_err(g[b], r[b]) < 2e-2, (name, b)
+        for b in (0, 3, 4):
+            assert rel_err(got[0][b], ref[0][b]) < 2e-2, ("dq", b)
+
+
+@pytest.mark.parametrize("C,N,B", [(64, 4096, 3), (128, 2048, 2), (256, 1024, 2), (64, 1000, 2)])
+def test_tcgen05_backward_deterministic_mode_is_bit_reproducible(C, N, B):
+    """maskunet_b200.set_deterministic(True): the per-key-tile dQ partials are added in a fixed order (order
+    semaphores in the workspace), so repeated launches return the same bits; the free-running mode differs from it
+    only in the last bits."""
+    import maskunet_b200
+    from maskunet_b200 import ops
+    dev = _dev()
+    gen = torch.Generator(device=dev).manual_seed(C + N)
+    keep = torch.rand(B, N, device=dev, generator=gen) < 0.5
+    _, n_keep, keep_idx, keep_rank = ops.mask_binarize(keep.to(torch.int64))
+    NKP = ops.nkp_of(N)
+    q = (0.5 * torch.randn(B, N, C, device=dev, generator=gen)).bfloat16()
+    kc = torch.randn(B, NKP, C, device=dev, generator=gen).bfloat16()
+    vc = torch.randn(B, NKP, C, device=dev, generator=gen).bfloat16()
+    for b in range(B):
+        kc[b, int(n_keep[b]):] = 0
+        vc[b, int(n_keep[b]):] = 0
+    d_o = torch.randn(B, N, C, device=dev, generator=gen).bfloat16()
+    o, lse = ops.attn_fwd(q, kc, vc, n_keep)
+    delta = (d_o.float() * o.float()).sum(-1).contiguous()
+    free = ops.attn_bwd(q, kc, vc, n_keep, keep_idx, d_o, lse, delta)
+    assert not maskunet_b200.is_deterministic()
+    maskunet_b200.set_deterministic(True)
+    try:
+        runs = [ops.attn_bwd(q, kc, vc, n_keep, keep_idx, d_o, lse, delta) for _ in range(4)]
+    finally:
+        maskunet_b200.set_deterministic(False)
+    for r in runs[1:]:
+        for a, b_ in zip(runs[0], r):
+            assert torch.equal(a, b_)
+    for a, f in zip(runs[0], free):
+        assert rel_err(a, f) < 2e-3
+
+
 def test_attention_sdpa_oracle_small():
     """attn_fwd against the kernel-level oracle (explicit softmax) including a fully kept and a 1-key sample."""
     from maskunet_b200 import ops

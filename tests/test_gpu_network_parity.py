@@ -150,8 +150,12 @@ def test_train_step_bf16_channels_last_loss_and_gradients_semantic():
     net.train()
     net.dropout.p = 0.0
     tr = Trainer(net)
+    seen = {}
+    hook = net.register_forward_hook(lambda mod, inp, out: seen.__setitem__("logits", out.detach()))
     loss = float(tr.forward_backward(x, labels))
-    _check_grads("unet_semantic.train", net, z, "train", meta["grad_names"], loss, net._padded_logits[:, :meta["c_out"]])
+    hook.remove()
+    assert net._padded_logits is None          # the Trainer drops the last forward's graph once backward has run
+    _check_grads("unet_semantic.train", net, z, "train", meta["grad_names"], loss, seen["logits"])
     # run-to-run: a second identical step (fresh BatchNorm statistics do not enter train-mode outputs)
     g1 = torch.cat([p.grad.float().reshape(-1) for p in net.parameters() if p.grad is not None])
     net.zero_grad(set_to_none=True)
@@ -197,3 +201,47 @@ def test_frozen_batchnorm_gradients_bf16_channels_last(fname, variant):
         logits = outs[0]
     loss.backward()
     _check_grads(f"{fname}.evalgrad", net, z, "evalgrad", meta["grad_names"], float(loss), logits)
+
+
+@pytest.mark.parametrize("c_out,batch", [(150, 2), (19, 6)])
+def test_deterministic_mode_train_step_is_bit_reproducible(c_out, batch):
+    """maskunet_b200.set_deterministic(True): every reduction across CTAs runs in a fixed order (BatchNorm statistics from
+    the convolution epilogue, BatchNorm / LayerNorm / projection / convolution weight gradients, the dQ partials of the
+    attention backward, the loss).  Two identical train steps -- forward, fused cross-entropy, backward, dropout ON with
+    the same seed -- then agree bit for bit in the loss and in EVERY parameter gradient; free-running mode (float
+    atomics) differs from it by the run-to-run noise the network amplifies (reported, not asserted)."""
+    import maskunet_b200
+    from maskunet_b200.train import Trainer
+    torch.manual_seed(5)
+    net = maskunet_b200.UNet(3, c_out, compute_dtype=torch.bfloat16, channels_last=True).to(DEV)
+    net = net.to(memory_format=torch.channels_last).train()
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(batch, 3, 128, 128, generator=g).to(DEV)
+    y = torch.randint(0, c_out, (batch, 128, 128), generator=g).to(DEV)
+    tr = Trainer(net)
+
+    def run():
+        torch.manual_seed(99)                       # dropout mask
+        net.zero_grad(set_to_none=True)
+        loss = tr.forward_backward(x, y)
+        grads = {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+        return loss.detach().clone(), grads
+
+    run()                                           # draws the attention masks
+    free = run()
+    maskunet_b200.set_deterministic(True)
+    try:
+        a = run()
+        b = run()
+        c = run()
+    finally:
+        maskunet_b200.set_deterministic(False)
+    differing = [n for n in a[1] if not torch.equal(a[1][n], b[1][n]) or not torch.equal(a[1][n], c[1][n])]
+    flat = lambda gr: torch.cat([gr[n].float().reshape(-1) for n in sorted(gr)])
+    REPORT[f"deterministic.c{c_out}_b{batch}"] = {
+        "loss": float(a[0]), "parameters": len(a[1]), "differing_parameters": differing[:8],
+        "free_running_vs_deterministic_gradvec_rel": float((flat(free[1]) - flat(a[1])).norm() / flat(a[1]).norm())}
+    _save_report()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[0], c[0])
+    assert not differing, differing[:8]
+    assert abs(float(free[0]) - float(a[0])) < 2e-3 * abs(float(a[0]))

@@ -299,3 +299,42 @@ def test_unet_eval_mode_with_autograd_on_class_padded_head():
     out.float().square().mean().backward()
     grads = [p.grad for n, p in net.named_parameters() if "emb_layer" not in n]
     assert all(g is not None and bool(torch.isfinite(g).all()) for g in grads)
+
+
+def test_trainer_cuda_graph_step_matches_eager_steps():
+    """Trainer(cuda_graph=True): after 3 eager steps the whole step (zero_grad, forward, fused CE, backward, AdamW) is
+    captured once and replayed.  Same seeds, same batches: the loss sequence of the graph run follows the eager run
+    (dropout disabled: eager and captured Philox offsets need not coincide), and the parameters keep moving."""
+    import maskunet_b200
+    from maskunet_b200.train import Trainer
+    g = torch.Generator().manual_seed(3)
+    xs = [torch.rand(2, 3, 128, 128, generator=g).to(DEV) for _ in range(6)]
+    ys = [torch.randint(0, 19, (2, 128, 128), generator=g).to(DEV) for _ in range(6)]
+
+    def run(graph):
+        torch.manual_seed(11)
+        net = maskunet_b200.UNet(3, 19, compute_dtype=torch.bfloat16, channels_last=True).to(DEV)
+        net = net.to(memory_format=torch.channels_last).train()
+        net.dropout.p = 0.0
+        tr = Trainer(net, lr=1e-3, weight_decay=1e-2, cuda_graph=graph)
+        losses, snaps = [], []
+        for x, y in zip(xs, ys):
+            losses.append(float(tr.step(x, y)))
+            snaps.append(net.bottom2.conv_block[0].weight.detach().float().clone())
+        return losses, tr, snaps
+
+    eager, _, snaps_e = run(False)
+    graph, tr, snaps_g = run(True)
+    assert tr._graph is not None and tr.graph_launches > 300          # steps 4-6 were replays of the captured step
+    print("eager", eager, "graph", graph)
+    for a, b in zip(eager, graph):
+        assert abs(a - b) < 5e-3 * abs(a), (eager, graph)
+    assert eager[0] != eager[-1]
+    # every replay is a real optimiser step: the parameters keep moving, by about as much as in the eager run (AdamW
+    # normalises the update, so the noisy bf16 gradients make the two trajectories drift apart -- only sizes compare)
+    for k in (3, 4, 5):
+        d_g = float((snaps_g[k] - snaps_g[k - 1]).norm())
+        d_e = float((snaps_e[k] - snaps_e[k - 1]).norm())
+        assert d_g > 0 and 0.5 < d_g / d_e < 2.0, (k, d_g, d_e)
+    with pytest.raises(RuntimeError):
+        tr.step(xs[0][:1], ys[0][:1])                                  # the captured shapes are fixed

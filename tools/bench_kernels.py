@@ -138,7 +138,11 @@ def main():
     ap.add_argument("--site", type=int, default=None, help="run only this entry of the site list (for ncu)")
     ap.add_argument("--generalised", action="store_true", help="only the generalised-mode sweep (heads, queries)")
     ap.add_argument("--eager", action="store_true", help="only the eager-PyTorch reference arithmetic on this GPU")
+    ap.add_argument("--deterministic", action="store_true", help="fixed-order dQ accumulation (maskunet_b200.set_deterministic)")
     args = ap.parse_args()
+    if args.deterministic:
+        import maskunet_b200
+        maskunet_b200.set_deterministic(True)
     peak = 1601.0
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.isfile(pk):
