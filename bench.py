@@ -238,6 +238,8 @@ def run_ours(args):
     from maskunet_b200 import ops
     from maskunet_b200.train import Trainer
 
+    if args.deterministic:
+        maskunet_b200.set_deterministic(True)
     wl = args.workload
     w = WORKLOADS[wl]
     c_out = w["c_out"]
@@ -427,6 +429,8 @@ def run_ours(args):
         cfg["micro_batch"] = micro
     if args.cuda_graph:
         cfg["cuda_graph"] = trainer is not None and trainer._graph is not None
+    if args.deterministic:
+        cfg["deterministic"] = "fixed-order reductions (maskunet_b200.set_deterministic): bit-reproducible step"
     if args.no_ddp and world > 1:
         cfg["note"] = "--no-ddp: independent replicas, no gradient exchange (scaling attribution run)"
     if world > 1 and not args.no_ddp:
@@ -466,6 +470,7 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=0, help="override the workload's per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ddp", action="store_true", help="N independent replicas without the gradient exchange")
+    ap.add_argument("--deterministic", action="store_true", help="fixed-order reductions: bit-reproducible step")
     ap.add_argument("--cuda-graph", action="store_true", help="capture the train step in a CUDA graph after warm-up")
     ap.add_argument("--ddp-dryrun", action="store_true", help="hooks and bucket packing, but no collective")
     ap.add_argument("--bucket-mb", type=float, default=25.0, help="gradient bucket size of the data-parallel exchange")

@@ -139,7 +139,10 @@ __device__ __forceinline__ void sem_publish(int32_t* sem) {
 // QM = true: generalised mode of the kernel sweep (see attn_fwd_sm100.cu): a per-(query, key) bias as transposed bits
 // (bits_t [B / heads, NKP keys, wpq words over queries], K13), every key kept (no compaction: n_keep == nk_all and key
 // row r of tile j is token k0 + r), N queries against NT key tokens.
-template <int D, int BM, int DH, int STAGES, int PB, bool QM>
+// DET = true: deterministic mode (staggered walk + order semaphores); a separate instantiation, so that the
+// free-running kernel carries none of its address arithmetic (as a run-time switch it cost the softmax warps registers:
+// 224 bytes of spill loads and 14 % of the kernel's speed).
+template <int D, int BM, int DH, int STAGES, int PB, bool QM, bool DET = false>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                       const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
@@ -200,9 +203,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   const int T = (N + BM - 1) / BM;           // query tiles
   // Walk order over the query tiles.  J = key tiles of this sample that hold kept keys (this CTA is tile j < J).
   const int J = QM ? (nk + kBK - 1) / kBK : (nk + kBK - 1) / kBK;
-  const bool stagger = ((MU_BWD_STAGGER != 0) || sem != nullptr) && !QM && J <= T;
+  constexpr bool kMayStagger = ((MU_BWD_STAGGER != 0) || DET) && !QM;
+  const bool stagger = kMayStagger && J <= T;
   const int i0 = stagger ? (int)(((long)blockIdx.x * T) / J) : 0;
   auto tile_of = [&](int step) {             // query tile processed at `step` (0 <= step < T)
+    if (!kMayStagger) return step;
     const int t = step + i0;
     return t >= T ? t - T : t;
   };
@@ -573,7 +578,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const int r = quad * 32 + (int)lane_id();
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t v[32];
-    int32_t* sem_b = sem != nullptr ? sem + ((size_t)(b * (int)gridDim.z + half)) * T : nullptr;
+    int32_t* sem_b = (DET && sem != nullptr) ? sem + ((size_t)(b * (int)gridDim.z + half)) * T : nullptr;
     int prev_qt = -1;                                    // tile whose reduce-add is still in flight (TMA paths)
     for (int i = 0; i < T; ++i) {
       const int qt = tile_of(i);                         // query tile of this step
@@ -764,7 +769,9 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
   if ((rc = make_tmap_bf16_3d(&tdo, d_o, D, N, B, BM))) return rc;
   if ((rc = make_tmap_bf16_3d(&tk, kc, D, NKP, B, kBK))) return rc;
   if ((rc = make_tmap_bf16_3d(&tv, vc, D, NKP, B, kBK))) return rc;
-  auto kern = attn_bwd_sm100_kernel<D, BM, DH, STAGES, PB, QM>;
+  auto kern = (sem != nullptr && !QM) ? attn_bwd_sm100_kernel<D, BM, DH, STAGES, PB, QM, !QM>
+                                      : attn_bwd_sm100_kernel<D, BM, DH, STAGES, PB, QM, false>;
+  if (QM) sem = nullptr;                      // generalised mode has no ordered accumulation
   cudaError_t e = set_max_dynamic_smem_once(kern, Cfg::kSmemBytes);
   if (e != cudaSuccess) {
     set_error("attn_bwd_sm100: cudaFuncSetAttribute(%d bytes): %s", Cfg::kSmemBytes, cudaGetErrorString(e));

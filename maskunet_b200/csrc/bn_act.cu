@@ -527,10 +527,12 @@ static int pick_fold(long M, int C) {
     if ((f * C) % 8 == 0 && M % f == 0 && f * C / 8 <= kBnThreads) return f;
   return 1;
 }
-static int pick_grid(long M, int C, int VEC) {
+static int pick_grid(long M, int C, int VEC, bool reduce = false) {
   const int RL = kBnThreads / (C / VEC);
   long blocks = (M + RL - 1) / RL;
-  const long cap = 148L * 8;
+  // deterministic mode: the last CTA of a reduction kernel adds one partial per CTA, so those kernels run one CTA per
+  // SM instead of eight (the loops are grid-stride)
+  const long cap = (reduce && get_deterministic()) ? 148L : 148L * 8;
   return (int)(blocks < cap ? blocks : cap);
 }
 static bool bn_shape_ok(long M, int C) {
@@ -566,7 +568,7 @@ static int bn_stats_t(const void* x, float* sums, long M, int C, cudaStream_t s)
   const int Cper = C, fold = pick_fold(M, C);
   M /= fold;
   C *= fold;
-  const int vec = pick_vec(C), grid = pick_grid(M, C, vec);
+  const int vec = pick_vec(C), grid = pick_grid(M, C, vec, true);
   DetCtx det;
   if (!det_context(kDetSlotBn, (size_t)grid * 2 * C, &det, "bn_stats")) return MU_ERR_WORKSPACE;
   MU_BN_VEC(vec, (bn_stats_kernel<T, VEC><<<grid, kBnThreads, 0, s>>>((const T*)x, sums, M, C, Cper, det)));
@@ -590,11 +592,11 @@ static int bn_bwd_t(const void* dy, const void* x, const void* r, const float* a
   const int Cper = C, fold = pick_fold(M, C);
   M /= fold;
   C *= fold;
-  const int vec = pick_vec(C), grid = pick_grid(M, C, vec);
+  const int vec = pick_vec(C), grid = pick_grid(M, C, vec), rgrid = pick_grid(M, C, vec, true);
   const bool res = r != nullptr;
   DetCtx det;
-  if (!det_context(kDetSlotBn, (size_t)grid * 2 * C, &det, "bn_backward")) return MU_ERR_WORKSPACE;
-  MU_BN_VEC(vec, MU_BN_ACT(act, res, (bn_bwd_reduce_kernel<T, VEC, ACT, RES><<<grid, kBnThreads, 0, s>>>(
+  if (!det_context(kDetSlotBn, (size_t)rgrid * 2 * C, &det, "bn_backward")) return MU_ERR_WORKSPACE;
+  MU_BN_VEC(vec, MU_BN_ACT(act, res, (bn_bwd_reduce_kernel<T, VEC, ACT, RES><<<rgrid, kBnThreads, 0, s>>>(
                                          (const T*)dy, (const T*)x, (const T*)r, a, b, mean, rstd, sums, M, C, Cper, det))));
   int rc = check_launch("bn_bwd_reduce");
   if (rc) return rc;

@@ -351,10 +351,11 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_tok_kernel(
   }
 }
 
-static int ln_tok_grid(long M, int C) {
+static int ln_tok_grid(long M, int C, bool reduce = false) {
   const long per = kLnThreads / (C / 8) * kLnUnroll;
   long blocks = (M + per - 1) / per;
-  const long cap = 148L * 8;
+  // deterministic mode: one partial per CTA is added by the last CTA, so the backward runs one CTA per SM
+  const long cap = (reduce && get_deterministic()) ? 148L : 148L * 8;
   return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
@@ -408,7 +409,7 @@ int launch_residual_ln_bwd(const void* dy, const void* o, const void* x, const f
                            int dtype, int tok, cudaStream_t s) {
   if (dtype == MU_BF16 && tok && (C == 64 || C == 128 || C == 256)) {
     const long M = (long)B * N;
-    const int grid = ln_tok_grid(M, C);
+    const int grid = ln_tok_grid(M, C, true);
     DetCtx det;
     if (!det_context(kDetSlotLn, (size_t)grid * 2 * C, &det, "residual_ln_bwd")) return MU_ERR_WORKSPACE;
 #define MU_LN_BWD(CC)                                                                                               \

@@ -6,10 +6,15 @@ COUNTS = {(64, 64, 128): 2, (128, 128, 128): 2, (128, 64, 128): 1, (64, 64, 64):
           (512, 256, 16): 1}
 for f in sys.argv[1:]:
     tot = {"fwd_ms": 0.0, "dgrad_ms": 0.0, "wgrad_ms": 0.0}
-    for line in open(f):
-        if not line.startswith("{"):
-            continue
-        d = json.loads(line)
+    text = open(f).read()
+    try:                                   # tools/with_clocks.py document ({"clocks": ..., "records": [...]})
+        doc = json.loads(text)
+        recs = doc["records"] if isinstance(doc, dict) and "records" in doc else None
+    except ValueError:
+        recs = None
+    if recs is None:                       # plain JSON lines
+        recs = [json.loads(line) for line in text.splitlines() if line.startswith("{")]
+    for d in recs:
         n = COUNTS[(d["cin"], d["cout"], d["hw"])]
         for k in tot:
             tot[k] += n * d[k]
