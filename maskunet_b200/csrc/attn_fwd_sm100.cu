@@ -53,6 +53,18 @@ extern "C" int mu_debug_fwd_trace(long long* host, int n) {
 #define MU_FTRACE(ev, j) do { } while (0)
 #endif
 
+// -DMU_FWD_CTALOG=1: every CTA records (SM id, clock64 at entry, clock64 at exit) for tools/fwd_ctalog.py (how well are the
+// SMs filled over the launch, what is the SM clock inside it?); not part of the product build.
+#ifndef MU_FWD_CTALOG
+#define MU_FWD_CTALOG 0
+#endif
+#if MU_FWD_CTALOG
+__device__ long long g_fwd_ctalog[3 * 65536];
+extern "C" int mu_debug_fwd_ctalog(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, g_fwd_ctalog, sizeof(long long) * (n < 3 * 65536 ? n : 3 * 65536));
+}
+#endif
+
 template <int D, int BN, int SBUFS, int SLOTS>
 struct FwdCfg {
   static constexpr int kDBlocks = D / 64;                   // 64-column (128-byte) blocks per row
@@ -95,6 +107,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   uint64_t* o_done = p_full + 1;            // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
+#if MU_FWD_CTALOG
+  const long long cta_t0 = clock64();
+#endif
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int b = blockIdx.y, q0 = blockIdx.x * kBM;
   const int nk = QM ? nk_all : n_keep[b];
@@ -383,6 +398,18 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+#if MU_FWD_CTALOG
+  if (threadIdx.x == 0) {
+    const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
+    if (lin < 65536u) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      g_fwd_ctalog[3 * lin] = smid;
+      g_fwd_ctalog[3 * lin + 1] = cta_t0;
+      g_fwd_ctalog[3 * lin + 2] = clock64();
+    }
+  }
+#endif
   if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
