@@ -58,6 +58,15 @@ constexpr float kLog2eB = 1.4426950408889634f;
 #ifndef MU_BWD_DET_LAG
 #define MU_BWD_DET_LAG 0
 #endif
+// 1 (d = 64): the dQ partial tiles leave as bf16 and the TMA unit adds them straight into the bf16 dq output
+// (cp.reduce.async.bulk.tensor .add on a bf16 tensor map): half the staging traffic on the shared-memory port (16 KB
+// written + 16 KB read per tile instead of 32 + 32), half the L2 reduction traffic, no 1 GiB fp32 workspace, no clear of
+// it, no convert kernel.  Cost: the up to N / 128 partial sums of a query tile are accumulated in bf16 -- a random walk
+// of ~0.6 % relative error at 64 key tiles, beside the ~0.4 % the bf16 P / dS operands already carry (bar: 2e-2).
+// 0 keeps the fp32 accumulator (and is what d >= 128 uses).
+#ifndef MU_BWD_DQ_BF16
+#define MU_BWD_DQ_BF16 1
+#endif
 #ifndef MU_BWD_PROBE
 #define MU_BWD_PROBE 0      // 1 / 2: performance probes that skip work (wrong results), see DESIGN.md
 #endif
@@ -103,7 +112,8 @@ struct BwdCfg {
   // PB = 2 double-buffers the P^T / dS^T tiles so that the exp / dS work of query tile i+1 overlaps the
   // dV / dK / dQ MMAs of tile i.  Dynamic shared memory is declared __align__(1024), no alignment slack.
   static constexpr bool kDQTma = (D <= 128);             // dQ tile leaves through a TMA reduce-add (smem permitting)
-  static constexpr int kDQStageBytes = kDQTma ? BM * DH * 4 : 0;   // fp32 dQ tile staged for the TMA reduce-add
+  static constexpr bool kDQBf16 = (MU_BWD_DQ_BF16 != 0) && (D == 64) && !kDQT && (MU_BWD_DQ_RED == 0);
+  static constexpr int kDQStageBytes = kDQTma ? BM * DH * (kDQBf16 ? 2 : 4) : 0;   // dQ tile staged for the TMA reduce-add
   static constexpr int kSmemBytes =
       2 * kKBytes + 2 * STAGES * kQBytes + PB * kPBytes + kDQStageBytes + kStatBytes + 256;
   static_assert(kSmemBytes <= 232448, "shared memory overflow");
@@ -572,7 +582,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       }
     }
   } else {
-    reg_dealloc<72>();
+    reg_dealloc<88>();
     // ===================================================== dQ reduction warps
     const int quad = warp & 3;
     const int r = quad * 32 + (int)lane_id();
@@ -690,6 +700,23 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             tc_fence_before();
             mbar_arrive(dq_free);
           }
+          if (Cfg::kDQBf16) {
+            // one [BM rows][64 channels] bf16 tile (128-byte rows, TMA swizzle); this pass fills chunks 4c .. 4c + 3
+            const uint32_t row = stage + r * 128;
+#if MU_BWD_PROBE == 1
+            if (scale == 12345.f)
+#endif
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const uint32_t chunk = ((uint32_t)((c * 4 + ch) ^ (r & 7))) * 16;
+              st_shared_v4(row + chunk,
+                           pack_bf16(__uint_as_float(v[8 * ch]) * scale, __uint_as_float(v[8 * ch + 1]) * scale),
+                           pack_bf16(__uint_as_float(v[8 * ch + 2]) * scale, __uint_as_float(v[8 * ch + 3]) * scale),
+                           pack_bf16(__uint_as_float(v[8 * ch + 4]) * scale, __uint_as_float(v[8 * ch + 5]) * scale),
+                           pack_bf16(__uint_as_float(v[8 * ch + 6]) * scale, __uint_as_float(v[8 * ch + 7]) * scale));
+            }
+            continue;
+          }
           const uint32_t row = stage + c * (BM * 128) + r * 128;   // sub-tile c = channels [32c, 32c+32)
 #if MU_BWD_PROBE == 1
           if (scale == 12345.f)      // never true: the staging stores and the reduce are compiled but skipped
@@ -710,8 +737,12 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #endif
         if (issuer) {
           if (sem_b != nullptr) sem_wait_turn(sem_b + qt, turn_of(qt));
+          if (Cfg::kDQBf16) {
+            tma_reduce_add_3d(&tmap_dq, stage, 0, qt * BM, b);
+          } else {
 #pragma unroll
-          for (int c = 0; c < DH / 32; ++c) tma_reduce_add_3d(&tmap_dq, stage + c * (BM * 128), c * 32, qt * BM, b);
+            for (int c = 0; c < DH / 32; ++c) tma_reduce_add_3d(&tmap_dq, stage + c * (BM * 128), c * 32, qt * BM, b);
+          }
           tma_store_commit();
           if (sem_b != nullptr) {
 #if MU_BWD_DET_LAG
@@ -764,7 +795,11 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
   using Cfg = BwdCfg<D, BM, DH, STAGES, PB>;
   CUtensorMap tq, tdo, tk, tv, tdq;
   int rc;
-  if ((rc = make_tmap_f32_3d(&tdq, dq_acc, D, N, B, BM))) return rc;
+  if (Cfg::kDQBf16) {
+    if ((rc = make_tmap_bf16_3d(&tdq, dq, D, N, B, BM))) return rc;      // partial tiles are added straight into dq
+  } else {
+    if ((rc = make_tmap_f32_3d(&tdq, dq_acc, D, N, B, BM))) return rc;
+  }
   if ((rc = make_tmap_bf16_3d(&tq, q, D, N, B, BM))) return rc;
   if ((rc = make_tmap_bf16_3d(&tdo, d_o, D, N, B, BM))) return rc;
   if ((rc = make_tmap_bf16_3d(&tk, kc, D, NKP, B, kBK))) return rc;
@@ -780,7 +815,12 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
   const size_t n = (size_t)B * N * D, nt = (size_t)B * NT * D;
   // one memset clears the fp32 dQ accumulator and, in deterministic mode, the order semaphores right behind it
   const size_t sem_bytes = sem != nullptr ? (size_t)B * (D / DH) * ((N + BM - 1) / BM) * sizeof(int32_t) : 0;
-  cudaMemsetAsync(dq_acc, 0, n * sizeof(float) + sem_bytes, s);
+  if (Cfg::kDQBf16) {
+    cudaMemsetAsync(dq, 0, n * sizeof(__nv_bfloat16), s);
+    if (sem_bytes) cudaMemsetAsync(sem, 0, sem_bytes, s);
+  } else {
+    cudaMemsetAsync(dq_acc, 0, n * sizeof(float) + sem_bytes, s);
+  }
   (void)nt;   // dk / dv need no clearing: the kernel writes every row (kept keys: gradients, masked keys: zeros)
   dim3 grid(NKP / kBK, B, D / DH);
   const float scale = scale_in > 0.f ? scale_in : 1.f / sqrtf((float)D);
@@ -788,6 +828,7 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
                                                   (__nv_bfloat16*)dvc, N, NKP, scale, NT, bits_t, heads,
                                                   round_up(N, 128) / 32, nk_all, sem);
   if ((rc = check_launch("attn_bwd_sm100"))) return rc;
+  if (Cfg::kDQBf16) return 0;
   const size_t n4 = n / 4;
   const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
   dq_convert_kernel<<<blocks, 256, 0, s>>>((const float4*)dq_acc, (uint2*)dq, n4);
@@ -801,7 +842,10 @@ extern "C" int mu_debug_bwd_trace(long long* host, int n) {   // tools/bwd_trace
 #endif
 
 // fp32 dQ accumulator [B, N, C] + order semaphores int32 [B, C / DH, ceil(N / 64)] (sized for the smallest query tile)
-static size_t dq_acc_bytes(int B, int N, int C) { return (size_t)B * N * C * sizeof(float); }
+static size_t dq_acc_bytes(int B, int N, int C) {
+  if (MU_BWD_DQ_BF16 != 0 && MU_BWD_DQ_RED == 0 && C == 64) return 0;     // partial tiles are added into dq itself
+  return (size_t)B * N * C * sizeof(float);
+}
 size_t attn_bwd_sm100_workspace(int B, int N, int C) {
   return dq_acc_bytes(B, N, C) + (size_t)B * 2 * ((N + 63) / 64) * sizeof(int32_t) + 16;
 }

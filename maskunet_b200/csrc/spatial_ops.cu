@@ -6,6 +6,8 @@
 // Every kernel maps a thread to an 8-channel (16-byte) group of one pixel so that loads and stores are
 // coalesced 16-byte vectors along the contiguous channel axis; reductions use fp32 partials, warp shuffles and
 // one atomicAdd per CTA.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "det_reduce.cuh"
 
@@ -429,6 +431,11 @@ __global__ void __launch_bounds__(256) ce_fused_kernel(const T* __restrict__ log
   if (det.on()) det_finish(det, gridDim.x, gridDim.x, 1, 1, 1, loss_sum, loss_sum, threadIdx.x, 256, SyncThreads());
 }
 
+__device__ __forceinline__ float fast_exp2_so(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&t);
@@ -503,6 +510,121 @@ __global__ void __launch_bounds__(256) ce_fused_vec_kernel(const __nv_bfloat16* 
       if (lane == 0 && lab[k] != ignore_index) local += bad ? NAN : -__logf(fmaxf(picked, 1e-38f));
     }
   }
+  __shared__ float red[8];
+  if (lane == 0) red[wib] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w2 = 0; w2 < 8; ++w2) t += red[w2];
+    if (det.on()) det.partial[blockIdx.x] = t * inv;
+    else atomicAdd(loss_sum, t * inv);
+  }
+  if (det.on()) det_finish(det, gridDim.x, gridDim.x, 1, 1, 1, loss_sum, loss_sum, threadIdx.x, 256, SyncThreads());
+}
+
+// bf16 rows, FOUR lanes per row (8 rows per warp trip): lane q of a row's quad owns the 16-byte vectors q, q + 4, ...
+// (VPL of them: 40 classes at the 160-class pitch).  Against one warp per row -- 20 of 32 lanes busy at pitch 160,
+// three 5-step shuffle reductions per row, ~150 warp instructions per 640 bytes: 1.5 TB/s -- the row statistics cost
+// two 2-step reductions (the loss needs none: lse - x[label], the owner of the label's class subtracts its logit), the
+// warp moves 8 rows per trip in 64-byte pieces, and the kernel is bound by HBM instead of by instruction issue.
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256, VPL >= 5 ? 2 : 3) ce_fused_quad_kernel(const __nv_bfloat16* __restrict__ logits,
+                                                            const int64_t* __restrict__ labels,
+                                                            const float* __restrict__ valid_count, long ignore_index,
+                                                            __nv_bfloat16* __restrict__ dlogits,
+                                                            float* __restrict__ loss_sum, long M, int C, int pitch,
+                                                            const DetCtx det) {
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  constexpr int RPW = 32 / LPR;                            // rows per warp trip
+  const int q = lane & (LPR - 1), rq = lane / LPR;         // position in the row's lane group, row of the warp trip
+  const int nvec = pitch >> 3;
+  const float inv = 1.f / fmaxf(valid_count[0], 1.f);
+  float local = (valid_count[0] == 0.f && blockIdx.x == 0 && threadIdx.x == 0) ? NAN : 0.f;
+  const long stride = (long)gridDim.x * (8 * RPW);         // 8 warps x RPW rows per block trip
+  for (long row = (long)blockIdx.x * (8 * RPW) + wib * RPW + rq; row < M; row += stride) {
+    const long lab = labels[row];
+    const bool ignored = lab == ignore_index;
+    const bool bad = !ignored && (lab < 0 || lab >= C);
+    const __nv_bfloat16* src = logits + row * pitch;
+    uint4 u[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vec = q + LPR * k;
+      u[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (vec < nvec && !ignored) u[k] = *reinterpret_cast<const uint4*>(src + vec * 8);
+    }
+    // (per-element work is kept to unpack, max, fma + exp2 + add, mul, pack: the class-range test runs only in the
+    // vector that straddles C, the one-hot term only in the vector that holds the label)
+    float v[VPL][8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      const int c0 = (q + LPR * k) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[k][e] = __uint_as_float((e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16));
+      if (c0 + 8 > C) {                                      // tail vector (or past the row): pad classes -> -inf
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (c0 + e >= C) v[k][e] = -INFINITY;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) mx = fmaxf(mx, v[k][e]);
+    }
+#pragma unroll
+    for (int off = 1; off < LPR; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    const float mx2 = mx * kLog2e;
+    float se = 0.f, x_lab = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int rel = (int)lab - (q + LPR * k) * 8;          // label's position in this vector (if in [0, 8))
+      if (!ignored && rel >= 0 && rel < 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (e == rel) x_lab = v[k][e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[k][e] = fast_exp2_so(fmaf(v[k][e], kLog2e, -mx2));       // exp2(-inf) = 0 for the pad classes
+        se += v[k][e];
+      }
+    }
+#pragma unroll
+    for (int off = 1; off < LPR; off <<= 1) se += __shfl_xor_sync(0xffffffffu, se, off);
+    // ignored row: zero gradient; label outside [0, C): NaN gradient for the real classes, like the scalar kernel
+    const float scale = ignored ? 0.f : (bad ? NAN : inv / se);
+    __nv_bfloat16* dst = dlogits + row * pitch;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vec = q + LPR * k, c0 = vec * 8;
+      const int rel = (int)lab - c0;
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = v[k][e] * scale;
+      if (!ignored && rel >= 0 && rel < 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (e == rel) o[e] -= inv;
+      }
+      if (c0 + 8 > C) {                                      // pad classes stay exactly zero (0 * NaN would not)
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (c0 + e >= C) o[e] = 0.f;
+      }
+      if (vec < nvec) {
+        uint4 r;
+        r.x = pack2(o[0], o[1]); r.y = pack2(o[2], o[3]); r.z = pack2(o[4], o[5]); r.w = pack2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(dst + c0) = r;
+      }
+    }
+    // loss of the row = max + ln(sum) - x[label]: lane 0 of the quad adds the first two, the label's owner subtracts
+    if (!ignored) {
+      if (bad) local += (q == 0) ? NAN : 0.f;
+      else local += ((q == 0) ? fmaf(__log2f(se), kLn2, mx) : 0.f) - x_lab;
+    }
+  }
+  local = warp_sum(local);
   __shared__ float red[8];
   if (lane == 0) red[wib] = local;
   __syncthreads();
@@ -735,9 +857,42 @@ int launch_ce_fused(const void* logits, const int64_t* labels, const float* vali
   DetCtx det;
   if (!det_context(kDetSlotCe, (size_t)grid, &det, "cross_entropy")) return MU_ERR_WORKSPACE;
   if (dtype == MU_BF16 && pitch % 8 == 0) {
-    ce_fused_vec_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)logits, labels, valid_count, ignore_index,
-                                             (__nv_bfloat16*)dlogits, loss_sum, M, C, pitch, det);
-    return check_launch("cross_entropy_fused_vec");
+    // lanes per row: 4 (eight rows per warp trip, 64-byte pieces): 0.78 ms against 0.96 ms with 8 at the 160-class
+    // pitch, 256 images (tools/bench_ce.py; MU_CE_LPR overrides for A/B runs)
+    static const int lpr_env = [] {
+      const char* e = getenv("MU_CE_LPR");
+      return e != nullptr ? atoi(e) : 0;
+    }();
+    const int nvec = pitch / 8;
+    const int lpr = lpr_env ? lpr_env : 4;
+    const int grid_q = grid_for((M + 8 * (32 / lpr) - 1) / (8 * (32 / lpr)), 1);
+    DetCtx det_q;
+    if (!det_context(kDetSlotCe, (size_t)grid_q, &det_q, "cross_entropy")) return MU_ERR_WORKSPACE;
+#define MU_CE_QUAD(L, V)                                                                                              \
+  ce_fused_quad_kernel<L, V><<<grid_q, 256, 0, s>>>((const __nv_bfloat16*)logits, labels, valid_count, ignore_index, \
+                                                    (__nv_bfloat16*)dlogits, loss_sum, M, C, pitch, det_q)
+    const int vpl = (nvec + lpr - 1) / lpr;
+    if (lpr == 8) {
+      switch (vpl) {
+        case 1: MU_CE_QUAD(8, 1); break;
+        case 2: MU_CE_QUAD(8, 2); break;
+        case 3: MU_CE_QUAD(8, 3); break;
+        default: MU_CE_QUAD(8, 4); break;
+      }
+    } else {
+      switch (vpl) {
+        case 1: MU_CE_QUAD(4, 1); break;
+        case 2: MU_CE_QUAD(4, 2); break;
+        case 3: MU_CE_QUAD(4, 3); break;
+        case 4: MU_CE_QUAD(4, 4); break;
+        case 5: MU_CE_QUAD(4, 5); break;
+        case 6: MU_CE_QUAD(4, 6); break;
+        case 7: MU_CE_QUAD(4, 7); break;
+        default: MU_CE_QUAD(4, 8); break;
+      }
+    }
+#undef MU_CE_QUAD
+    return check_launch("cross_entropy_fused_quad");
   }
   MU_T(dtype, (ce_fused_kernel<float><<<grid, 256, 0, s>>>((const float*)logits, labels, valid_count, ignore_index,
                                                         (float*)dlogits, loss_sum, M, C, pitch, det)),

@@ -182,7 +182,7 @@ def _attn_bwd_impl(tensor_core, q, kc, vc, n_keep, keep_idx, d_o, lse, delta):
             ws_bytes = int(_L.mu_attn_bwd_workspace_bytes(B, N, C, _code(q)))
             ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=q.device)
             with _timed(name, (B, N, C)):
-                _count(3 if ws_bytes else 2)
+                _count(1 if C == 64 else 2)      # d = 64 adds bf16 partial tiles straight into dq: no convert kernel
                 check(_L.mu_attn_bwd(_p(q), _p(kc), _p(vc), _p(n_keep), _p(keep_idx), _p(d_o), _p(lse), _p(delta),
                                      _p(dq), _p(dk), _p(dv), _p(ws), ws_bytes, B, N, NKP, C, _code(q), _stream(q)),
                       name)

@@ -244,8 +244,36 @@ def test_tcgen05_backward_deterministic_mode_is_bit_reproducible(C, N, B):
     for r in runs[1:]:
         for a, b_ in zip(runs[0], r):
             assert torch.equal(a, b_)
-    for a, f in zip(runs[0], free):
-        assert rel_err(a, f) < 2e-3
+    # free-running against ordered: dk / dv identical arithmetic (last bits); dQ at d = 64 adds its up to N / 128 partial
+    # tiles in bf16 (attn_bwd_sm100.cu, MU_BWD_DQ_BF16), so another order of the same terms moves it by bf16 rounding
+    for name, a, f in zip(("dq", "dk", "dv"), runs[0], free):
+        assert rel_err(a, f) < (1.2e-2 if (name == "dq" and C == 64) else 2e-3), name
+
+
+def test_tcgen05_backward_dq_bf16_accumulation_error_at_full_length():
+    """d = 64: the dQ partial tiles of the 64 key tiles of a 16384-token sample are accumulated in bf16 by the TMA
+    reduce-add.  Measured against the fp32-math CUDA-core kernel the error stays a factor ~2 under the bf16 bar."""
+    from maskunet_b200 import ops
+    dev = _dev()
+    gen = torch.Generator(device=dev).manual_seed(99)
+    B, N, C = 2, 16384, 64
+    keep = torch.rand(B, N, device=dev, generator=gen) < 0.5
+    _, n_keep, keep_idx, keep_rank = ops.mask_binarize(keep.to(torch.int64))
+    NKP = ops.nkp_of(N)
+    q = (0.5 * torch.randn(B, N, C, device=dev, generator=gen)).bfloat16()
+    kc = torch.randn(B, NKP, C, device=dev, generator=gen).bfloat16()
+    vc = torch.randn(B, NKP, C, device=dev, generator=gen).bfloat16()
+    for b in range(B):
+        kc[b, int(n_keep[b]):] = 0
+        vc[b, int(n_keep[b]):] = 0
+    d_o = torch.randn(B, N, C, device=dev, generator=gen).bfloat16()
+    o, lse = ops.attn_fwd(q, kc, vc, n_keep)
+    delta = (d_o.float() * o.float()).sum(-1).contiguous()
+    got = ops.attn_bwd(q, kc, vc, n_keep, keep_idx, d_o, lse, delta)
+    ref = ops.attn_bwd_cudacore(q, kc, vc, n_keep, keep_idx, d_o, lse, delta)
+    errs = {name: rel_err(g, r) for name, g, r in zip(("dq", "dk", "dv"), got, ref)}
+    print("attention backward, N = 16384, d = 64, relative error against the fp32-math kernel:", errs)
+    assert errs["dq"] < 1.2e-2 and errs["dk"] < 1e-2 and errs["dv"] < 1e-2, errs
 
 
 def test_attention_sdpa_oracle_small():
