@@ -356,8 +356,17 @@ def run_ours(args):
     clocks = sampler.stop()
 
     # end to end: host buffers in, result out, every step
-    results = []
-    ms_e2e, _ = timed(lambda: results.append(step_e2e()), args.steps)
+    results, e2e_wall = [], []
+
+    def e2e_once():
+        t0 = time.perf_counter()
+        results.append(step_e2e())
+        e2e_wall.append(round((time.perf_counter() - t0) * 1e3, 2))      # host wall time of the step (it ends in a sync)
+
+    sampler_e2e = ClockSampler(local)
+    sampler_e2e.start()
+    ms_e2e, _ = timed(e2e_once, args.steps)
+    clocks_e2e = sampler_e2e.stop()
     staged.clear()
 
     # roofline of the dominant kernel of ours: attention at the 16384-token site
@@ -444,7 +453,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
         "clocks": clocks,
         "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-                "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e,
+                "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e, "ms_steps_host_wall": e2e_wall,
+                "clocks": clocks_e2e,
                 "last_loss": results[-1] if results and results[-1] is not None else None},
         "gpu_launches": launches,
         "host_enqueue_ms_per_step": host_ms,   # one step into an empty queue; below ms_per_step = GPU-bound

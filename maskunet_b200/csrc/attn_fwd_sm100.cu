@@ -30,6 +30,21 @@ constexpr int kPolyEvery = MU_FWD_POLY_EVERY;   // 0: all exponentials on MUFU; 
 #ifndef MU_FWD_SPECULATE
 #define MU_FWD_SPECULATE 1
 #endif
+// 1: the TMEM loads of S_{j+1} are issued before P_j is published (their latency under the store wait / fence /
+// arrive).  Measured slower -- 764 against 813 TFLOP/s at N = 16384, d = 64: the wait for S_{j+1} delays the publish,
+// and with it PV_j and the P-tile hand-back of the next tile -- so it stays off.
+#ifndef MU_FWD_PREFETCH_S
+#define MU_FWD_PREFETCH_S 0
+#endif
+constexpr bool kPrefetchS = MU_FWD_PREFETCH_S != 0;
+#ifndef MU_FWD_EXP_PIPE
+#define MU_FWD_EXP_PIPE 1
+#endif
+// Measured (tools/bench_kernels.py, 64 samples): d = 64, N = 16384: 813 -> 830 TFLOP/s; d = 128, N = 4096: 849 -> 959
+// (groups of 4 / 8 / 16 columns: 828 / 820 / 830 and 949 / 949 / 959).
+#ifndef MU_FWD_EXP_GROUP
+#define MU_FWD_EXP_GROUP 16
+#endif
 constexpr bool kSpeculate = MU_FWD_SPECULATE != 0;   // exponentials before the tile maximum is known (see the softmax loop)
 constexpr float kLazyLog2 = 8.f;         // rescale O only when the row maximum grew by more than 2^8
 
@@ -146,7 +161,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   if (warp < 4) {
     // 2 CTAs / SM start with 128 registers per thread; the data-movement warpgroup hands most of its share to the
     // softmax warpgroup, which keeps a whole score row in registers
-    if (MINB > 1) reg_dealloc<40>();
+    if (MINB > 1) reg_dealloc<32>();
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane_id() == 0 && T > 0) {
@@ -220,7 +235,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   }
   } else {
     // ===================================================== softmax / correction / epilogue
-    if (MINB > 1) reg_alloc<208>();
+    if (MINB > 1) reg_alloc<216>();
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
     const int r = quad * 32 + (int)lane_id();       // query row within the tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -238,12 +253,14 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         const int buf = j % SBUFS;
         const uint32_t s_addr = lane_base + Cfg::kTmemS + buf * BN;
         const int limit = nk - j * BN;              // valid key columns in this tile (>= 1)
-        if (warp == 4) MU_FTRACE(4, j);             // softmax: waiting for S_j
-        mbar_wait(s_full + buf, (j / SBUFS) & 1);
-        if (warp == 4) MU_FTRACE(5, j);             // softmax: s_full(j)
-        tc_fence_after();
+        if (!kPrefetchS || j == 0) {
+          if (warp == 4) MU_FTRACE(4, j);           // softmax: waiting for S_j
+          mbar_wait(s_full + buf, (j / SBUFS) & 1);
+          if (warp == 4) MU_FTRACE(5, j);           // softmax: s_full(j)
+          tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) tmem_ld32(s_addr + c * 32, v[c]);
+          for (int c = 0; c < BN / 32; ++c) tmem_ld32(s_addr + c * 32, v[c]);
+        }
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(s_free + buf);                  // S lives in registers now: the next QK^T may overwrite TMEM
@@ -301,6 +318,55 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         // published, one exp phase ago, on a tensor pipe shared with the other CTA of this SM) still reads it ~1400
         // cycles into this tile (tools/fwd_trace.py): stores trail the arithmetic by one 32-key chunk so that the wait
         // comes after 64 exponentials and is normally already satisfied.
+#if MU_FWD_EXP_PIPE
+        // Software-pipelined in the SOURCE: the FFMA + MUFU.EX2 of group G + 1 (MU_FWD_EXP_GROUP columns) are written
+        // before the additions and bf16 packs that consume group G.  With producer and consumer adjacent in the source,
+        // ptxas kept them ~16 issue cycles apart against a MUFU latency of ~23+: a warp on its own ran at 11.4 cycles
+        // per exponential instead of the 8 the MUFU pipe allows (profiles/r02_attn_fwd_timeline_1cta_2cta.txt), so the
+        // pipe idled whenever the other CTA's warp was between tiles.
+        auto exp_pass = [&](float m_off) -> float {
+          const float mb = (QM && m_off == -INFINITY) ? 0.f : m_off * scale_log2;   // all -inf so far: p = exp2(-inf) = 0
+          constexpr int GE = MU_FWD_EXP_GROUP, NG = BN / GE, GPC = 32 / GE;
+          float sum[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t pk_prev[16], pk[16];
+          float t[2][GE];
+#pragma unroll
+          for (int e = 0; e < GE; ++e) t[0][e] = fast_exp2(fmaf(__uint_as_float(v[0][e]), scale_log2, -mb));
+#pragma unroll
+          for (int G = 0; G < NG; ++G) {
+            if (G + 1 < NG) {
+#pragma unroll
+              for (int e = 0; e < GE; ++e) {
+                const int col = (G + 1) * GE + e;
+                t[(G + 1) & 1][e] = fast_exp2(fmaf(__uint_as_float(v[col >> 5][col & 31]), scale_log2, -mb));
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < GE / 2; ++e) {
+              const float p0 = t[G & 1][2 * e], p1 = t[G & 1][2 * e + 1];
+              sum[e & 3] += p0 + p1;
+              pk[(G % GPC) * (GE / 2) + e] = pack_bf16(p0, p1);
+            }
+            if ((G % GPC) == GPC - 1) {            // a 32-column chunk of P is complete
+              const int c = G / GPC;
+              if (c == 1 && j > 0) {
+                if (warp == 4) MU_FTRACE(8, j);         // softmax: first 64 exponentials done
+                mbar_wait(o_done, (j - 1) & 1);
+                if (warp == 4) MU_FTRACE(9, j);         // softmax: PV_{j-1} done, P tile free
+                tc_fence_after();
+              }
+              if (c > 0) tmem_st16(lane_base + Cfg::kTmemP + (c - 1) * 16, pk_prev);
+              if (c + 1 < BN / 32) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk_prev[i] = pk[i];
+              } else {
+                tmem_st16(lane_base + Cfg::kTmemP + c * 16, pk);
+              }
+            }
+          }
+          return (sum[0] + sum[1]) + (sum[2] + sum[3]);
+        };
+#else
         auto exp_pass = [&](float m_off) -> float {
           const float mb = (QM && m_off == -INFINITY) ? 0.f : m_off * scale_log2;   // all -inf so far: p = exp2(-inf) = 0
           float sum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -334,6 +400,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           }
           return (sum[0] + sum[1]) + (sum[2] + sum[3]);
         };
+#endif
         // ---- lazy rescale: the exponent offset m only follows the running maximum when it has moved by more than
         // 2^kLazyLog2 (P then stays below 2^kLazyLog2, harmless in bf16 / fp32), so after the first tiles the
         // softmax warps neither wait for the previous PV nor touch O in TMEM.  O / l and the LSE use the same m.
@@ -366,6 +433,19 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           tile_sum = exp_pass(m);
         }
         if (warp == 4) MU_FTRACE(10, j);            // softmax: all exponentials done
+        if (kPrefetchS && j + 1 < T) {
+          // S_j is dead (exponentials and the maximum check are done): the TMEM loads of S_{j+1} -- computed while this
+          // tile's exponentials ran -- are issued BEFORE the publish sequence of P_j, so their latency (and the MIO queue
+          // they share with the MUFU stream) overlaps the store wait, the fence and the arrive instead of adding ~170
+          // cycles without exponentials to every tile
+          const int nbuf = (j + 1) % SBUFS;
+          if (warp == 4) MU_FTRACE(4, j + 1);
+          mbar_wait(s_full + nbuf, ((j + 1) / SBUFS) & 1);
+          if (warp == 4) MU_FTRACE(5, j + 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) tmem_ld32(lane_base + Cfg::kTmemS + nbuf * BN + c * 32, v[c]);
+        }
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(p_full);

@@ -35,6 +35,26 @@ __global__ void probe(float* out, long long* cycles, int iters) {
         v[i] = __uint_as_float(w);
       }
     }
+    if (MODE == 7) {
+      // the forward softmax's instruction mix per pair of columns: 2 FFMA, 2 MUFU.EX2, 2 FADD, 1 F2FP pack, 1 ALU op
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float a = v[2 * i], b = v[2 * i + 1];
+        asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a) : "f"(1.0001f), "f"(-0.001f));
+        asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(b) : "f"(1.0001f), "f"(-0.001f));
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a));
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(b));
+        float s2;
+        asm volatile("add.f32 %0, %1, %2;" : "=f"(s2) : "f"(a), "f"(b));
+        if (i & 1) asm volatile("add.f32 %0, %0, %1;" : "+f"(sum1) : "f"(s2));
+        else asm volatile("add.f32 %0, %0, %1;" : "+f"(sum0) : "f"(s2));
+        asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(b), "f"(a));
+        v[2 * i] = __uint_as_float((pk[i] & 0x3f800000u) ^ 0x3f000000u);       // keeps the chain loop-carried (1 ALU op)
+        v[2 * i + 1] = sum0 * 0.f + 0.5f;
+      }
+      v[1] += sum1 * 0.f;
+    }
     if (MODE == 4) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
@@ -69,6 +89,7 @@ int main() {
   run<2>("F2FP.BF16.PACK_AB", 8);
   run<3>("MUFU.EX2 + FFMA (pairs)", 16);
   run<4>("16 MUFU.EX2 + 8 F2FP", 24);
+  run<7>("softmax mix, per MUFU", 16);
   run<5>("ex2.approx.f16x2", 16);
   run<6>("ex2.approx.ftz.bf16x2", 16);
   cudaError_t e = cudaDeviceSynchronize();
