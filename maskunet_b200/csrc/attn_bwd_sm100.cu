@@ -484,60 +484,6 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       if (warp == 4) MU_TRACE(10, i);                    // softmax: output buffers free
       if (warp == 8) MU_TRACE(20, i);                    // second warpgroup: output buffers free
       const uint32_t ds_addr = ds_base + (i % PB) * Cfg::kPBytes;
-            const float4 l2 = ld_shared_v4f(my_lse + (c * 32 + ci) * 4);
-            s[cc][ci + 0] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[cc][ci + 0]), scale_log2, -l2.x)));
-            s[cc][ci + 1] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[cc][ci + 1]), scale_log2, -l2.y)));
-            s[cc][ci + 2] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[cc][ci + 2]), scale_log2, -l2.z)));
-            s[cc][ci + 3] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[cc][ci + 3]), scale_log2, -l2.w)));
-          }
-        };
-        uint32_t pk[16], dk[16];
-        exp_group(0);
-#pragma unroll
-        for (int G = 0; G < NG; ++G) {
-          if (G + 1 < NG) exp_group(G + 1);
-#pragma unroll
-          for (int e = 0; e < GE / 4; ++e) {
-            const int col = G * GE + 4 * e, cc = col >> 5, ci = col & 31;
-            const int c = hcol * kChunksPerThread + cc;
-#if MU_BWD_PROBE == 5
-            const float4 dl = make_float4(scale, scale, scale, scale);
-#else
-            const float4 dl = ld_shared_v4f(my_delta + (c * 32 + ci) * 4);
-#endif
-            const float p0 = __uint_as_float(s[cc][ci + 0]), p1 = __uint_as_float(s[cc][ci + 1]);
-            const float p2 = __uint_as_float(s[cc][ci + 2]), p3 = __uint_as_float(s[cc][ci + 3]);
-            const float d0 = p0 * (__uint_as_float(dp[cc][ci + 0]) - dl.x);
-            const float d1 = p1 * (__uint_as_float(dp[cc][ci + 1]) - dl.y);
-            const float d2 = p2 * (__uint_as_float(dp[cc][ci + 2]) - dl.z);
-            const float d3 = p3 * (__uint_as_float(dp[cc][ci + 3]) - dl.w);
-            pk[ci / 2] = pack_bf16(p0, p1);
-            pk[ci / 2 + 1] = pack_bf16(p2, p3);
-            dk[ci / 2] = pack_bf16(d0, d1);
-            dk[ci / 2 + 1] = pack_bf16(d2, d3);
-          }
-          if ((G & 1) == 1) {                              // a 32-column chunk is complete
-            const int cc = G >> 1, c = hcol * kChunksPerThread + cc;
-            const uint32_t row_off = (c >> 1) * (kBK * 128) + r * 128;
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              const uint32_t chunk = (((c & 1) * 4 + ch) ^ (r & 7)) * 16;
-#if MU_BWD_PROBE == 2
-              if (scale == 12345.f)
-#endif
-              st_shared_v4(ds_addr + row_off + chunk, dk[4 * ch], dk[4 * ch + 1], dk[4 * ch + 2], dk[4 * ch + 3]);
-            }
-            if (cc == 0 && i > 0) {                        // P^T is single-buffered in TMEM (see the note below)
-              mbar_wait(p_free, (i - 1) & 1);
-              if (Cfg::kKVT) mbar_wait(dq_free, (i - 1) & 1);
-              tc_fence_after();
-            }
-            tmem_st16(lane_base + Cfg::kTmP + c * 16, pk);
-            if (warp == 4) MU_TRACE(15 + cc, i);
-          }
-        }
-      }
-#else
 #pragma unroll
       for (int cc = 0; cc < kChunksPerThread; ++cc) {
         const int c = hcol * kChunksPerThread + cc;
@@ -586,7 +532,6 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         tmem_st16(lane_base + Cfg::kTmP + c * 16, pk);   // 32 queries = 16 packed columns of the TMEM P^T tile
         if (warp == 4) MU_TRACE(15 + cc, i);             // softmax: chunk cc computed and stored
       }
-#endif
       tmem_wait_st();
       if (warp == 4) MU_TRACE(17, i);                    // softmax: tcgen05.wait::st
       tc_fence_before();

@@ -20,6 +20,8 @@
 //     contraction over pixels: both operands MN-major (pixel rows = K), the tap again a row shift of one x tile
 //     with halo; 3 taps x 128 ci x 128 co accumulate in TMEM over the CTA's pixel range (split-K), then
 //     red.global.add.v4.f32 into an fp32 [9][Cin][Cout] workspace; a small kernel permutes to the parameter layout.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "det_reduce.cuh"
 #include "sm100_ptx.cuh"
@@ -53,12 +55,21 @@ __device__ __forceinline__ void red_add_v4f(float* p, float a, float b, float c,
 // One CTA step ("super tile") = MT vertically adjacent 128-pixel tiles of one image x NT output channels: every
 // weight tile fetched from L2 feeds MT MMAs, and the activation box with halo is shared by the MT tiles.
 //   TMEM: NBUF accumulator sets of MT * NT fp32 columns (NBUF = 2 when 2 * MT * NT <= 512).
-template <int NT, int MT, int MODE>
+// PAIR = true: CTA pairs (cta_group::2).  The two CTAs of a cluster work on two adjacent super tiles of the same output
+// channel block with ONE MMA of M = 256 per step: each CTA loads its own activation box and only HALF of every weight
+// tile (NT / 2 rows), the tensor cores read the other half from the partner's shared memory.  The forward / data
+// gradient kernels were bound by the L2 -> SM stream (6.5 TB/s, 69 % of it weights at 128 -> 128 channels:
+// profiles/r01_conv_128to128_128x128_ncu.txt) and, for NT <= 128, by the shared-memory port (A 4 KB + B 4 KB per
+// 64-cycle MMA); the pair halves the weight bytes on both.  The leader (cluster rank 0) issues the MMAs and owns the
+// full / accumulator-free barriers; TMA loads of both CTAs complete on the leader's barriers, MMA completion is
+// committed to the barriers of both.
+template <int NT, int MT, int MODE, bool PAIR = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         const __grid_constant__ CUtensorMap tmap_y, float* __restrict__ stats,
                         const float* __restrict__ bias, const ConvArgs p, const DetCtx det) {
-  constexpr int kBBytes = NT * 128;
+  constexpr int kBRows = PAIR ? NT / 2 : NT;       // weight rows of a tile in THIS CTA's shared memory
+  constexpr int kBBytes = kBRows * 128;
   constexpr int GROUPS = MODE == CONV_ROWS ? 3 : 1;
   constexpr int TAPS = MODE == CONV_W128 ? 9 : (MODE == CONV_ROWS ? 3 : 1);
   constexpr int NBUF = (2 * MT * NT <= 512) ? 2 : 1;
@@ -83,7 +94,13 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   // warp index through a shuffle: the compiler then knows the role branches are warp-uniform and keeps the MMA
   // issuer's address arithmetic on the uniform datapath (no per-MMA ELECT / R2UR.BROADCAST loops)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-  const int total = p.m_tiles * p.n_tiles;        // m_tiles counts super tiles
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  // work units: a super tile (PAIR: two adjacent super tiles, one per CTA of the pair) x an output channel block
+  const int m_units = PAIR ? p.m_tiles / 2 : p.m_tiles;   // m_tiles counts super tiles
+  const int total = m_units * p.n_tiles;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kchunks = (p.K + 63) / 64;            // a partial last chunk is zero-filled by TMA (1x1 heads)
 
   if (threadIdx.x == 0) {
@@ -95,7 +112,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(acc_full + i, 1);
-      mbar_init(acc_empty + i, 128);
+      mbar_init(acc_empty + i, PAIR ? 256 : 128);   // PAIR: the epilogue warps of both CTAs arrive on the leader's
     }
     mbar_fence_init();
     tma_prefetch_desc(&tmap_x);
@@ -103,12 +120,18 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     tma_prefetch_desc(&tmap_y);
   }
   if (warp == 1) {
-    tmem_alloc<kTmemCols>(tmem_slot);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2sm<kTmemCols>(tmem_slot);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc<kTmemCols>(tmem_slot);
+      tmem_relinquish();
+    }
   }
   for (int i = threadIdx.x; i < 1024; i += kConvThreads) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                   // the partner's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -119,25 +142,35 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     if (lane_id() == 0) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       const int SA = p.SA, SB = p.SB, a_stride = p.a_stride, a_bytes = p.a_bytes;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+      for (int unit = unit0; unit < total; unit += unit_step) {
+        const int nt = unit / m_units, mt = (unit - nt * m_units) * (PAIR ? 2 : 1) + rank;
         const int b = mt / p.tiles_y, y0 = (mt - b * p.tiles_y) * (MT * p.TH);
-        const int n0 = nt * NT;
+        const int n0 = nt * NT + rank * kBRows;          // PAIR: this CTA's half of the weight rows
         for (int ch = 0; ch < kchunks; ++ch) {
 #pragma unroll
           for (int g = 0; g < GROUPS; ++g) {
             mbar_wait_relaxed(a_empty + sa, pa ^ 1);
-            mbar_expect_tx(a_full + sa, a_bytes);
             const int cx = MODE == CONV_W128 ? -1 : (MODE == CONV_ROWS ? g - 1 : 0);
             const int cy = MODE == CONV_1X1 ? y0 : y0 - 1;
-            tma_load_4d(sA + sa * a_stride, &tmap_x, a_full + sa, ch * 64, cx, cy, b);
+            if (PAIR) {   // both loads complete on the leader's barrier, which expects the bytes of both
+              if (leader) mbar_expect_tx(a_full + sa, 2 * a_bytes);
+              tma_load_4d_2sm(sA + sa * a_stride, &tmap_x, a_full + sa, ch * 64, cx, cy, b);
+            } else {
+              mbar_expect_tx(a_full + sa, a_bytes);
+              tma_load_4d(sA + sa * a_stride, &tmap_x, a_full + sa, ch * 64, cx, cy, b);
+            }
             if (++sa == SA) { sa = 0; pa ^= 1; }
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) {
               const int tap = MODE == CONV_ROWS ? j * 3 + g : j;
               mbar_wait_relaxed(b_empty + sb, pb ^ 1);
-              mbar_expect_tx(b_full + sb, kBBytes);
-              tma_load_3d(sB + sb * kBBytes, &tmap_w, b_full + sb, ch * 64, n0, tap);
+              if (PAIR) {
+                if (leader) mbar_expect_tx(b_full + sb, 2 * kBBytes);
+                tma_load_3d_2sm(sB + sb * kBBytes, &tmap_w, b_full + sb, ch * 64, n0, tap);
+              } else {
+                mbar_expect_tx(b_full + sb, kBBytes);
+                tma_load_3d(sB + sb * kBBytes, &tmap_w, b_full + sb, ch * 64, n0, tap);
+              }
               if (++sb == SB) { sb = 0; pb ^= 1; }
             }
           }
@@ -147,8 +180,8 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp walks the loop,
     // one elected lane issues)
-    {
-      constexpr uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
+    if (!PAIR || leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, NT, 0, 0);
       constexpr uint32_t hi = desc_hi_sbo(1024);
       const uint32_t a_base = desc_lo(smem_u32(sA)), b_base = desc_lo(smem_u32(sB));
       const int SA = p.SA, SB = p.SB;
@@ -156,7 +189,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       constexpr uint32_t tile_pitch16 = (MODE == CONV_W128 ? 130 : 128) * 8;   // (bytes >> 4) between the MT tiles' rows
       const uint32_t row_w16 = p.W * 8;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int unit = unit0; unit < total; unit += unit_step) {
         mbar_wait(acc_empty + buf, pacc ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (MT * NT);
@@ -179,18 +212,26 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                 const uint32_t a_lo = a_tile + row_off + m * tile_pitch16;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                  if (kk < kk_n && elect_one())
-                    umma_ss_lo(d_tmem + m * NT, a_lo + 2 * kk, b_lo + 2 * kk, hi, idesc, kk > 0 ? 1u : accumulate);
+                  if (kk < kk_n && elect_one()) {
+                    if (PAIR) umma_ss_lo_2sm(d_tmem + m * NT, a_lo + 2 * kk, b_lo + 2 * kk, hi, idesc, kk > 0 ? 1u : accumulate);
+                    else umma_ss_lo(d_tmem + m * NT, a_lo + 2 * kk, b_lo + 2 * kk, hi, idesc, kk > 0 ? 1u : accumulate);
+                  }
               }
               accumulate = 1;
-              if (elect_one()) umma_commit(b_empty + sb);
+              if (elect_one()) {
+                if (PAIR) umma_commit_2sm(b_empty + sb, 3); else umma_commit(b_empty + sb);
+              }
               if (++sb == SB) { sb = 0; pb ^= 1; }
             }
-            if (elect_one()) umma_commit(a_empty + sa);
+            if (elect_one()) {
+              if (PAIR) umma_commit_2sm(a_empty + sa, 3); else umma_commit(a_empty + sa);
+            }
             if (++sa == SA) { sa = 0; pa ^= 1; }
           }
         }
-        if (elect_one()) umma_commit(acc_full + buf);
+        if (elect_one()) {
+          if (PAIR) umma_commit_2sm(acc_full + buf, 3); else umma_commit(acc_full + buf);
+        }
         if (++buf == NBUF) { buf = 0; pacc ^= 1; }
       }
     }
@@ -241,8 +282,8 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
       }
     };
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+    for (int unit = unit0; unit < total; unit += unit_step) {
+      const int nt = unit / m_units, mt = (unit - nt * m_units) * (PAIR ? 2 : 1) + rank;
       const int b = mt / p.tiles_y, y0 = (mt - b * p.tiles_y) * (MT * p.TH);
       mbar_wait(acc_full + buf, pacc);
       tc_fence_after();
@@ -283,7 +324,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         }
         if (blk == MT * kBlocks - 1) {                     // accumulator drained: the next tile's MMAs may start
           tc_fence_before();
-          mbar_arrive(acc_empty + buf);
+          if (PAIR) mbar_arrive_leader(acc_empty + buf); else mbar_arrive(acc_empty + buf);
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
@@ -340,9 +381,10 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                   // nobody leaves while the partner may still signal its barriers
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if (PAIR) tmem_dealloc_2sm<kTmemCols>(tmem_base); else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -578,7 +620,16 @@ static int conv_geometry_ok(const char* fn, int B, int H, int W, int K, int N) {
   return 0;
 }
 
-template <int NT, int MT, int MODE>
+// MU_CONV_PAIR (environment, A/B runs): 0 = never pair CTAs, 1 = pair whenever the geometry allows (default)
+static int conv_pair_mode() {
+  static const int mode = [] {
+    const char* e = getenv("MU_CONV_PAIR");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  return mode;
+}
+
+template <int NT, int MT, int MODE, bool PAIR = false>
 static int run_fprop(const void* x, const void* wt, void* y, float* stats, const float* bias, int B, int H, int W, int K,
                      int N, int taps, cudaStream_t s) {
   ConvArgs p;
@@ -598,32 +649,59 @@ static int run_fprop(const void* x, const void* wt, void* y, float* stats, const
   }
   p.a_bytes = box_w * box_h * 128;
   p.a_stride = round_up(p.a_bytes, 1024);
+  constexpr int kBRows = PAIR ? NT / 2 : NT;     // weight rows per tile in one CTA's shared memory
   const int fixed = 1024 + 4096 + 512;
   p.SA = 2;
   p.SO = 2;
-  p.SB = (kSmemLimit - fixed - p.SO * 16384 - p.SA * p.a_stride) / (NT * 128);
+  p.SB = (kSmemLimit - fixed - p.SO * 16384 - p.SA * p.a_stride) / (kBRows * 128);
   if (p.SB < 3) {                        // a deep enough weight ring matters more than a second staging buffer
     p.SO = 1;
-    p.SB = (kSmemLimit - fixed - p.SO * 16384 - p.SA * p.a_stride) / (NT * 128);
+    p.SB = (kSmemLimit - fixed - p.SO * 16384 - p.SA * p.a_stride) / (kBRows * 128);
   }
   if (p.SB > kMaxRing) p.SB = kMaxRing;
   if (p.SB < 2) {
     set_error("conv_fprop: shared memory budget exceeded (a_stride %d NT %d)", p.a_stride, NT);
     return MU_ERR_BAD_SHAPE;
   }
-  const int smem = fixed + p.SO * 16384 + p.SA * p.a_stride + p.SB * NT * 128;
+  const int smem = fixed + p.SO * 16384 + p.SA * p.a_stride + p.SB * kBRows * 128;
   CUtensorMap tx, tw, ty;
   int rc;
   if ((rc = make_tmap_bf16_nhwc(&tx, x, K, W, H, B, box_w, box_h))) return rc;
-  if ((rc = make_tmap_bf16_3d(&tw, wt, round_up(K, 64), N, taps, NT))) return rc;   // weight rows are padded to 64 K
+  if ((rc = make_tmap_bf16_3d(&tw, wt, round_up(K, 64), N, taps, kBRows))) return rc;   // weight rows are padded to 64 K
   if ((rc = make_tmap_bf16_nhwc(&ty, y, N, W, H, B, W, p.TH))) return rc;
-  auto kern = conv_fprop_sm100_kernel<NT, MT, MODE>;
+  auto kern = conv_fprop_sm100_kernel<NT, MT, MODE, PAIR>;
   set_max_dynamic_smem_once(kern, smem);
-  const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < sm_count() ? total : sm_count();
+  int grid;
+  if (PAIR) {
+    const int units = (p.m_tiles / 2) * p.n_tiles, pairs = sm_count() / 2;
+    grid = 2 * (units < pairs ? units : pairs);
+  } else {
+    const int total = p.m_tiles * p.n_tiles;
+    grid = total < sm_count() ? total : sm_count();
+  }
   DetCtx det{nullptr, nullptr, 0};
   if (stats != nullptr && !det_context(kDetSlotConvStats, (size_t)grid * 2 * N, &det, "conv_fprop_sm100")) return MU_ERR_WORKSPACE;
-  kern<<<grid, kConvThreads, smem, s>>>(tx, tw, ty, stats, bias, p, det);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tx, tw, ty, stats, bias, p, det);
+    if (e != cudaSuccess) {
+      set_error("conv_fprop_sm100 (CTA pairs): cudaLaunchKernelEx: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+  } else {
+    kern<<<grid, kConvThreads, smem, s>>>(tx, tw, ty, stats, bias, p, det);
+  }
   return check_launch("conv_fprop_sm100");
 }
 
@@ -631,8 +709,14 @@ template <int NT, int MT>
 static int run_fprop_mode(const void* x, const void* wt, void* y, float* stats, int B, int H, int W, int K, int N,
                           int taps, cudaStream_t s) {
   if (taps == 1) return run_fprop<NT, MT, CONV_1X1>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
-  if (W == 128) return run_fprop<NT, MT, CONV_W128>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
-  return run_fprop<NT, MT, CONV_ROWS>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
+  // CTA pairs: an even number of super tiles (adjacent ones share a pair) and enough of them to fill the pairs
+  const int m_tiles = B * (H / ((128 / W) * MT));
+  const bool pair = conv_pair_mode() != 0 && m_tiles % 2 == 0 && (m_tiles / 2) * (N / NT) >= 37;
+  if (W == 128)
+    return pair ? run_fprop<NT, MT, CONV_W128, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s)
+                : run_fprop<NT, MT, CONV_W128>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
+  return pair ? run_fprop<NT, MT, CONV_ROWS, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s)
+              : run_fprop<NT, MT, CONV_ROWS>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
 }
 
 // y [B,H,W,N] = conv(x [B,H,W,K], wt [taps][N][K]); stats (optional) f32 [2N] += (sum, sum of squares) per channel

@@ -290,6 +290,68 @@ MU_DEVICE void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ------------------------------------------------------------------ CTA pairs (cta_group::2)
+// Two CTAs of a cluster (same TPC) run one MMA of M = 256: each CTA supplies 128 rows of A and HALF of B (N / 2 rows)
+// from its own shared memory at the same offsets, and receives its 128 rows of D in its own TMEM.  The leader (cluster
+// rank 0) issues the MMAs; both CTAs issue their own TMA loads, which complete on the LEADER's mbarrier (a shared
+// window address with bit 24 cleared names the even CTA of the pair); the MMA completion is committed to the barriers
+// of both CTAs (multicast).  PTX forms as in CUTLASS's cute/arch/{copy_sm100_tma,mma_sm100_umma}.hpp.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+MU_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+MU_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+MU_DEVICE void tma_load_4d_2sm(void* smem_dst, const void* tmap, uint64_t* leader_bar, int32_t c0, int32_t c1, int32_t c2,
+                               int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0),
+        "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+MU_DEVICE void tma_load_3d_2sm(void* smem_dst, const void* tmap, uint64_t* leader_bar, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0),
+        "r"(c1), "r"(c2)
+      : "memory");
+}
+// arrive on the LEADER's copy of `bar` (either CTA of the pair may call it)
+MU_DEVICE void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+template <int kCols>
+MU_DEVICE void tmem_alloc_2sm(uint32_t* smem_result) {  // one converged warp of EACH CTA, same smem offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols)
+               : "memory");
+}
+MU_DEVICE void tmem_relinquish_2sm() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+template <int kCols>
+MU_DEVICE void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+MU_DEVICE void umma_ss_lo_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued cta_group::2 MMAs of this thread arrive on `bar` in every CTA of `cta_mask` when complete
+MU_DEVICE void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
 // ------------------------------------------------------------------ per-warpgroup register budget
 // All 4 warps of a warpgroup must execute these together.  Lets the data-movement warpgroup hand its registers
 // to the softmax warpgroup(s) so that a full score row fits in registers at 2 CTAs / SM.
