@@ -63,7 +63,11 @@ __device__ __forceinline__ void red_add_v4f(float* p, float a, float b, float c,
 // 64-cycle MMA); the pair halves the weight bytes on both.  The leader (cluster rank 0) issues the MMAs and owns the
 // full / accumulator-free barriers; TMA loads of both CTAs complete on the leader's barriers, MMA completion is
 // committed to the barriers of both.
-template <int NT, int MT, int MODE, bool PAIR = false>
+// RES = true: the weight tiles of ALL taps and channel chunks stay resident in shared memory (one output channel block,
+// 9 x ceil(K / 64) tiles of NT x 64: 72 KB for 64 -> 64 channels) instead of streaming through the ring once per super
+// tile: at 64 output channels the weights were half of the L2 -> SM bytes of a super tile and the kernel sat on that
+// stream (23.6 B/clk/SM = 6.4 TB/s, the same ceiling the 128 -> 128 capture shows).
+template <int NT, int MT, int MODE, bool PAIR = false, bool RES = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         const __grid_constant__ CUtensorMap tmap_y, float* __restrict__ stats,
@@ -142,6 +146,15 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     if (lane_id() == 0) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       const int SA = p.SA, SB = p.SB, a_stride = p.a_stride, a_bytes = p.a_bytes;
+      if (RES && unit0 < total) {                        // every weight tile once: [chunk][tap] -> slot ch * 9 + tap
+        const int ntaps = GROUPS * TAPS;
+        if (!PAIR || leader) mbar_expect_tx(b_full, (PAIR ? 2 : 1) * kchunks * ntaps * kBBytes);
+        for (int ch = 0; ch < kchunks; ++ch)
+          for (int tap = 0; tap < ntaps; ++tap) {
+            if (PAIR) tma_load_3d_2sm(sB + (ch * ntaps + tap) * kBBytes, &tmap_w, b_full, ch * 64, rank * kBRows, tap);
+            else tma_load_3d(sB + (ch * ntaps + tap) * kBBytes, &tmap_w, b_full, ch * 64, 0, tap);
+          }
+      }
       for (int unit = unit0; unit < total; unit += unit_step) {
         const int nt = unit / m_units, mt = (unit - nt * m_units) * (PAIR ? 2 : 1) + rank;
         const int b = mt / p.tiles_y, y0 = (mt - b * p.tiles_y) * (MT * p.TH);
@@ -162,6 +175,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             if (++sa == SA) { sa = 0; pa ^= 1; }
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) {
+              if (RES) continue;
               const int tap = MODE == CONV_ROWS ? j * 3 + g : j;
               mbar_wait_relaxed(b_empty + sb, pb ^ 1);
               if (PAIR) {
@@ -189,6 +203,10 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       constexpr uint32_t tile_pitch16 = (MODE == CONV_W128 ? 130 : 128) * 8;   // (bytes >> 4) between the MT tiles' rows
       const uint32_t row_w16 = p.W * 8;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, buf = 0, pacc = 0;
+      if (RES && unit0 < total) {
+        mbar_wait(b_full, 0);                            // the resident weight tiles have landed
+        tc_fence_after();
+      }
       for (int unit = unit0; unit < total; unit += unit_step) {
         mbar_wait(acc_empty + buf, pacc ^ 1);
         tc_fence_after();
@@ -199,14 +217,18 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 #pragma unroll
           for (int g = 0; g < GROUPS; ++g) {
             mbar_wait(a_full + sa, pa);
+            if (RES) tc_fence_after();
             const uint32_t a_tile = a_base + sa * a_stride16;
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) {
               const uint32_t row_off = MODE == CONV_W128 ? ((j / 3) * 130 + (j % 3)) * 8
                                                          : (MODE == CONV_ROWS ? j * row_w16 : 0);
-              mbar_wait(b_full + sb, pb);
-              tc_fence_after();
-              const uint32_t b_lo = b_base + sb * (kBBytes >> 4);
+              if (!RES) {
+                mbar_wait(b_full + sb, pb);
+                tc_fence_after();
+              }
+              const int res_tap = MODE == CONV_ROWS ? j * 3 + g : j;
+              const uint32_t b_lo = b_base + (RES ? (uint32_t)(ch * (GROUPS * TAPS) + res_tap) : sb) * (kBBytes >> 4);
 #pragma unroll
               for (int m = 0; m < MT; ++m) {
                 const uint32_t a_lo = a_tile + row_off + m * tile_pitch16;
@@ -218,10 +240,12 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                   }
               }
               accumulate = 1;
-              if (elect_one()) {
-                if (PAIR) umma_commit_2sm(b_empty + sb, 3); else umma_commit(b_empty + sb);
+              if (!RES) {
+                if (elect_one()) {
+                  if (PAIR) umma_commit_2sm(b_empty + sb, 3); else umma_commit(b_empty + sb);
+                }
+                if (++sb == SB) { sb = 0; pb ^= 1; }
               }
-              if (++sb == SB) { sb = 0; pb ^= 1; }
             }
             if (elect_one()) {
               if (PAIR) umma_commit_2sm(a_empty + sa, 3); else umma_commit(a_empty + sa);
@@ -620,7 +644,8 @@ static int conv_geometry_ok(const char* fn, int B, int H, int W, int K, int N) {
   return 0;
 }
 
-// MU_CONV_PAIR (environment, A/B runs): 0 = never pair CTAs, 1 = pair whenever the geometry allows (default)
+// MU_CONV_PAIR (environment, A/B runs): 0 = never pair CTAs, 1 = pair when the geometry allows and the problem fills
+// the pairs (default), 2 = pair whenever the geometry allows
 static int conv_pair_mode() {
   static const int mode = [] {
     const char* e = getenv("MU_CONV_PAIR");
@@ -629,7 +654,15 @@ static int conv_pair_mode() {
   return mode;
 }
 
-template <int NT, int MT, int MODE, bool PAIR = false>
+static int conv_res_mode() {           // MU_CONV_RES=0 (environment): no resident weights (A/B runs)
+  static const int mode = [] {
+    const char* e = getenv("MU_CONV_RES");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  return mode;
+}
+
+template <int NT, int MT, int MODE, bool PAIR = false, bool RES = false>
 static int run_fprop(const void* x, const void* wt, void* y, float* stats, const float* bias, int B, int H, int W, int K,
                      int N, int taps, cudaStream_t s) {
   ConvArgs p;
@@ -659,6 +692,15 @@ static int run_fprop(const void* x, const void* wt, void* y, float* stats, const
     p.SB = (kSmemLimit - fixed - p.SO * 16384 - p.SA * p.a_stride) / (kBRows * 128);
   }
   if (p.SB > kMaxRing) p.SB = kMaxRing;
+  if (RES) {                             // resident weights: one slot per (chunk, tap)
+    p.SB = 9 * ((K + 63) / 64);
+    if (fixed + 2 * 16384 + p.SA * p.a_stride + p.SB * kBRows * 128 > kSmemLimit) p.SO = 1;
+    else p.SO = 2;
+    if (fixed + p.SO * 16384 + p.SA * p.a_stride + p.SB * kBRows * 128 > kSmemLimit) {
+      set_error("conv_fprop: resident weights do not fit (K %d NT %d)", K, NT);
+      return MU_ERR_BAD_SHAPE;
+    }
+  }
   if (p.SB < 2) {
     set_error("conv_fprop: shared memory budget exceeded (a_stride %d NT %d)", p.a_stride, NT);
     return MU_ERR_BAD_SHAPE;
@@ -669,7 +711,7 @@ static int run_fprop(const void* x, const void* wt, void* y, float* stats, const
   if ((rc = make_tmap_bf16_nhwc(&tx, x, K, W, H, B, box_w, box_h))) return rc;
   if ((rc = make_tmap_bf16_3d(&tw, wt, round_up(K, 64), N, taps, kBRows))) return rc;   // weight rows are padded to 64 K
   if ((rc = make_tmap_bf16_nhwc(&ty, y, N, W, H, B, W, p.TH))) return rc;
-  auto kern = conv_fprop_sm100_kernel<NT, MT, MODE, PAIR>;
+  auto kern = conv_fprop_sm100_kernel<NT, MT, MODE, PAIR, RES>;
   set_max_dynamic_smem_once(kern, smem);
   int grid;
   if (PAIR) {
@@ -711,7 +753,23 @@ static int run_fprop_mode(const void* x, const void* wt, void* y, float* stats, 
   if (taps == 1) return run_fprop<NT, MT, CONV_1X1>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
   // CTA pairs: an even number of super tiles (adjacent ones share a pair) and enough of them to fill the pairs
   const int m_tiles = B * (H / ((128 / W) * MT));
-  const bool pair = conv_pair_mode() != 0 && m_tiles % 2 == 0 && (m_tiles / 2) * (N / NT) >= 37;
+  // (measured per layer shape at 256 images, tools/bench_conv_ours.py: pairs gain 3-13 % at widths 64 and 128, lose
+  // 5-10 % at 16 x 16, mixed at 32 x 32)
+  const bool pair = conv_pair_mode() != 0 && m_tiles % 2 == 0 &&
+                    (conv_pair_mode() == 2 || (W >= 64 && (m_tiles / 2) * (N / NT) >= 148));   // 2: force (small test shapes)
+  // resident weights: a single 64-channel output block whose 9 x K weights fit beside the activation ring
+  if (NT == 64 && N == 64 && conv_res_mode() != 0) {
+    const int TH = 128 / W, box_h = (W == 128) ? MT + 2 : TH * MT + 2, box_w = (W == 128) ? 130 : W;
+    const int a_stride = round_up(box_w * box_h * 128, 1024);
+    const int b_rows = pair ? 32 : 64;
+    if (1024 + 4096 + 512 + 16384 + 2 * a_stride + 9 * ((K + 63) / 64) * b_rows * 128 <= kSmemLimit) {
+      if (W == 128)
+        return pair ? run_fprop<64, MT, CONV_W128, true, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s)
+                    : run_fprop<64, MT, CONV_W128, false, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
+      return pair ? run_fprop<64, MT, CONV_ROWS, true, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s)
+                  : run_fprop<64, MT, CONV_ROWS, false, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
+    }
+  }
   if (W == 128)
     return pair ? run_fprop<NT, MT, CONV_W128, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s)
                 : run_fprop<NT, MT, CONV_W128>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
