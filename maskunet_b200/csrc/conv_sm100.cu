@@ -309,7 +309,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     for (int unit = unit0; unit < total; unit += unit_step) {
       const int nt = unit / m_units, mt = (unit - nt * m_units) * (PAIR ? 2 : 1) + rank;
       const int b = mt / p.tiles_y, y0 = (mt - b * p.tiles_y) * (MT * p.TH);
-      mbar_wait(acc_full + buf, pacc);
+      mbar_wait_relaxed(acc_full + buf, pacc);   // (a main loop long: sleep between polls, the step is power-capped)
       tc_fence_after();
       if (stats != nullptr && nt != acc_nt) {             // (rare: at most once per CTA) new channel range
         flush_stats(acc_nt);
@@ -541,7 +541,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     const int r = quad * 32 + (int)lane_id();
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t v[32];
-    mbar_wait(acc_full, 0);
+    mbar_wait_relaxed(acc_full, 0);      // the whole contraction long: sleep between polls
     tc_fence_after();
     for (int m = 0; m < m_tiles_cta; ++m) {
       int j, ci;

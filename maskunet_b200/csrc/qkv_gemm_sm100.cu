@@ -269,7 +269,7 @@ qkv_dx_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
     const __nv_bfloat16* zrow = dz + (size_t)tok * C;
     __nv_bfloat16* orow = dxt + (size_t)tok * C;
     uint32_t v[32];
-    mbar_wait(acc_full, 0);
+    mbar_wait_relaxed(acc_full, 0);
     tc_fence_after();
 #pragma unroll
     for (int c = 0; c < C / 32; ++c) {
@@ -405,7 +405,7 @@ qkv_dw_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
     float* wrow = (det_slices != nullptr ? det_slices + (size_t)blockIdx.x * 3 * C * C : dw) +
                   (size_t)(src[h] * C + col[h] + (r & 63)) * C;
     uint32_t v[32];
-    mbar_wait(acc_full, 0);
+    mbar_wait_relaxed(acc_full, 0);
     tc_fence_after();
 #pragma unroll
     for (int c = 0; c < C / 32; ++c) {
