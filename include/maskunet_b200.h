@@ -126,8 +126,9 @@ int mu_residual_ln_bwd(const void* dy, const void* o, const void* x, const float
 /* K5. Masked attention backward (autograd of :174-186).  Recomputes P from q, kc, lse.
  *   dq, dk, dv T [B, N, C], all in TOKEN space: the gradient of compacted key row r is scattered back to
  *   token keep_idx[b, r]; rows of masked keys are zero (the entry point clears dk / dv itself).
- *   workspace: mu_attn_bwd_workspace_bytes(...) bytes of scratch (the fp32 dQ accumulator that key tiles add
- *   into with red.global.add); 0 bytes / NULL allowed for MU_F32. */
+ *   workspace: mu_attn_bwd_workspace_bytes(...) bytes of scratch: the order semaphores of deterministic mode and,
+ *   for C >= 128, the fp32 dQ accumulator the key tiles add into (C = 64 adds bf16 partial tiles straight into dq
+ *   with the TMA reduce-add and needs no accumulator); 0 bytes / NULL allowed for MU_F32. */
 size_t mu_attn_bwd_workspace_bytes(int32_t B, int32_t N, int32_t C, int32_t dtype);
 int mu_attn_bwd(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const int32_t* keep_idx,
                 const void* d_o, const float* lse, const float* delta, void* dq, void* dk, void* dv, void* workspace,

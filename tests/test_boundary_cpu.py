@@ -125,13 +125,15 @@ def test_c_abi_error_convention_without_a_device():
     assert rc == MU_ERR_MISALIGNED and "16-byte" in err()
     rc = lib.mu_attn_bwd(*([P(base)] * 11), P(base), 0, 1, 128, 128, 64, _lib.MU_BF16, P(0))
     assert rc != 0                                        # workspace too small (or no device): never a crash
-    # fp32 dQ accumulator + the order semaphores of deterministic mode (int32 per sample, channel half, 64-query tile)
-    assert lib.mu_attn_bwd_workspace_bytes(2, 400, 64, _lib.MU_BF16) == 2 * 400 * 64 * 4 + 2 * 2 * 7 * 4 + 16
+    # the order semaphores of deterministic mode (int32 per sample, channel half, 64-query tile) and, for 128 / 256
+    # channels, the fp32 dQ accumulator (64 channels add bf16 partial tiles straight into dq)
+    assert lib.mu_attn_bwd_workspace_bytes(2, 400, 64, _lib.MU_BF16) == 2 * 2 * 7 * 4 + 16
+    assert lib.mu_attn_bwd_workspace_bytes(2, 400, 128, _lib.MU_BF16) == 2 * 400 * 128 * 4 + 2 * 2 * 7 * 4 + 16
     assert lib.mu_get_deterministic() == 0
     lib.mu_set_deterministic(1)
     assert lib.mu_get_deterministic() == 1
     lib.mu_set_deterministic(0)
-    assert lib.mu_query_attn_bwd_workspace_bytes(8, 100, 64) >= 8 * 100 * 64 * 4
+    assert lib.mu_query_attn_bwd_workspace_bytes(8, 100, 64) >= 16      # 64-wide heads: bf16 partial tiles go into dq
     rc = lib.mu_query_mask_bits(P(base), P(base), 1, 100, 1000, 256, P(base), P(base), P(base), P(0), _lib.MU_F32, P(0))
     assert rc == MU_ERR_BAD_DTYPE
     rc = lib.mu_instance_triplet_fwd(P(base), P(0), 1, 2, 4, 4, P(base), P(base), 1, 1.0, 1e-6, P(base), P(base), P(base),
