@@ -646,20 +646,14 @@ static int conv_geometry_ok(const char* fn, int B, int H, int W, int K, int N) {
 
 // MU_CONV_PAIR (environment, A/B runs): 0 = never pair CTAs, 1 = pair when the geometry allows and the problem fills
 // the pairs (default), 2 = pair whenever the geometry allows
-static int conv_pair_mode() {
-  static const int mode = [] {
-    const char* e = getenv("MU_CONV_PAIR");
-    return e != nullptr ? atoi(e) : 1;
-  }();
-  return mode;
+static int conv_pair_mode() {           // (read per call: the GPU tests switch it inside one process)
+  const char* e = getenv("MU_CONV_PAIR");
+  return e != nullptr ? atoi(e) : 1;
 }
 
-static int conv_res_mode() {           // MU_CONV_RES=0 (environment): no resident weights (A/B runs)
-  static const int mode = [] {
-    const char* e = getenv("MU_CONV_RES");
-    return e != nullptr ? atoi(e) : 1;
-  }();
-  return mode;
+static int conv_res_mode() {           // MU_CONV_RES=0 (environment): no resident weights (A/B runs, tests)
+  const char* e = getenv("MU_CONV_RES");
+  return e != nullptr ? atoi(e) : 1;
 }
 
 template <int NT, int MT, int MODE, bool PAIR = false, bool RES = false>

@@ -60,6 +60,35 @@ def test_conv3x3_forward_stats_and_gradients(case):
         assert rel_err(xq.grad.float(), xr.grad) < 6e-3
 
 
+@pytest.mark.parametrize("case", [(2, 64, 64, 128, 128), (2, 128, 128, 128, 128), (2, 128, 64, 128, 128),
+                                  (4, 64, 128, 64, 64), (4, 256, 256, 32, 32), (6, 128, 64, 8, 32), (2, 512, 256, 16, 16)],
+                         ids=lambda c: "b%d_%dto%d_%dx%d" % c)
+def test_conv3x3_cta_pairs_and_resident_weights_are_bit_identical(case, monkeypatch):
+    """The CTA-pair kernels (cta_group::2: one MMA of M = 256 over two CTAs, half of every weight tile per CTA) and the
+    resident-weight kernels (all 9 x K / 64 weight tiles of a 64-channel output block kept in shared memory) add the same
+    products in the same order as the plain kernels: forward, epilogue statistics and data gradient must agree bit for
+    bit.  The benchmark shapes select these modes by size; here MU_CONV_PAIR = 2 forces pairs on small problems."""
+    from maskunet_b200 import ops
+    B, Cin, Cout, H, W = case
+    x, w, dy = _inputs(*case, seed=7)
+    wf, wd = ops.conv_prep_weights(w, True)
+    outs = {}
+    for mode, pair, res in (("plain", "0", "0"), ("pairs", "2", "0"), ("pairs+resident", "2", "1"), ("resident", "0", "1")):
+        monkeypatch.setenv("MU_CONV_PAIR", pair)
+        monkeypatch.setenv("MU_CONV_RES", res)
+        y, sums = ops.conv3x3_fwd(x, wf, True)
+        dx = ops.conv3x3_bwd_data(dy, wd)
+        outs[mode] = (y.clone(), sums.clone(), dx.clone())
+    y0, s0, d0 = outs["plain"]
+    xr = x.float()
+    assert rel_err(y0.float(), F.conv2d(xr, w.to(torch.bfloat16).float(), padding=1)) < 6e-3
+    for mode in ("pairs", "pairs+resident", "resident"):
+        y, s_, d = outs[mode]
+        assert torch.equal(y, y0), mode
+        assert torch.equal(d, d0), mode
+        assert rel_err(s_, s0) < 1e-5, mode                   # (float atomics across CTAs: order differs)
+
+
 def test_conv3x3_border_is_zero_padding():
     """A constant image through an all-ones kernel counts the taps inside the image: 4 / 6 / 9."""
     from maskunet_b200 import ops
@@ -127,6 +156,27 @@ def test_conv1x1_head_forward_and_gradients(case):
     assert rel_err(xq.grad.float(), xr.grad) < 6e-3
     assert rel_err(wq.grad, wr.grad) < 2e-3
     assert rel_err(bq.grad, br.grad) < 2e-3
+
+
+@pytest.mark.parametrize("C,P", [(19, 32), (40, 64), (100, 128), (133, 160), (200, 256), (17, 24)])
+def test_cross_entropy_quad_kernel_every_vector_count(C, P):
+    """The bf16 kernel gives four lanes to a row and 1 .. 8 sixteen-byte vectors to a lane (pitch / 32, rounded up):
+    every instantiation against F.cross_entropy, with ignored rows, a ragged last trip (rows not a multiple of 64) and
+    zero gradient in the pad classes."""
+    from maskunet_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(C)
+    B, H, W = 3, 7, 16                                      # 336 rows: not a multiple of the 64 rows of a block trip
+    logits = (3.0 * torch.randn(B, P, H, W, generator=g)).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    labels = torch.randint(0, C, (B, H, W), generator=g).to(DEV)
+    labels[1, 2, :5] = 255
+    loss, dl = ops.cross_entropy_fused(logits, labels, 255, C)
+    ref_in = logits[:, :C].float().requires_grad_(True)
+    ref = F.cross_entropy(ref_in, labels, ignore_index=255)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 2e-3 * abs(float(ref))
+    assert rel_err(dl[:, :C].float(), ref_in.grad) < 1e-2
+    assert float(dl[:, C:].float().abs().max()) == 0.0
+    assert float(dl[1, :, 2, :5].float().abs().max()) == 0.0
 
 
 def test_cross_entropy_on_class_padded_logits():
