@@ -29,4 +29,9 @@ timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 -
 python tools/step_breakdown.py gpurun_out/v_launches.csv 30 | tee gpurun_out/v_step_breakdown.txt
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:attn_.wd_sm100 -c 12 -f -o gpurun_out/v_prof_attn python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/v_ncu_attn.log 2>&1
 tail -2 gpurun_out/v_ncu_attn.log
+# paired convolution kernels alone: 128 -> 128 and 64 -> 64 at 128 x 128, 256 -> 256 at 64 x 64 (forward + data gradient)
+for sh in "128 128 128" "64 64 128" "256 256 64"; do
+  timeout 600 ncu --set full --clock-control none -k regex:conv_fprop_sm100 -s 2 -c 2 -f -o gpurun_out/v_prof_conv_${sh// /_} python tools/run_conv_once.py $sh > gpurun_out/v_ncu_conv.log 2>&1
+done
+tail -2 gpurun_out/v_ncu_conv.log
 ls -la gpurun_out/
