@@ -13,6 +13,7 @@
 // D = 256 splits the accumulator width over blockIdx.z (DH = 128 channels each) because dK + dV alone
 // would need 512 TMEM columns.  The 1/sqrt(C) factor of dS is applied when dK / dQ leave the chip.
 #include <atomic>
+#include <cstring>
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -67,6 +68,15 @@ constexpr float kLog2eB = 1.4426950408889634f;
 #ifndef MU_BWD_DQ_BF16
 #define MU_BWD_DQ_BF16 1
 #endif
+// 1 (d = 64): the per-query statistics enter through the tensor core instead of 516 broadcast LDS.128 wavefronts per tile.
+// A 16-wide "augmentation" slab per query, aug[q] = [-lse/scale split into three bf16 | 0 .. | delta split into three,
+// negated | 0 ..], travels with Q_i / dO_i (two 2 KB TMA boxes per stage, canonical no-swizzle K-major core matrices);
+// one extra K = 16 MMA step adds  ones_S . aug^T  to S^T  (S' = S - lse / scale, so P = exp2(c S')) and one adds
+// ones_dP . aug^T  to dP^T  (dP' = dP - delta): the softmax warps load nothing from shared memory.  The shared memory
+// comes from the bf16 dQ staging (16 KB less than the fp32 tile).
+#ifndef MU_BWD_FOLD_STATS
+#define MU_BWD_FOLD_STATS 1
+#endif
 #ifndef MU_BWD_PROBE
 #define MU_BWD_PROBE 0      // 1 / 2: performance probes that skip work (wrong results), see DESIGN.md
 #endif
@@ -108,12 +118,15 @@ struct BwdCfg {
   static constexpr int kTmP = kKVT ? kTmDQ : kTmDQ + kDQCols;   // bf16 P^T tile, two queries per 32-bit column (A of the dV MMA)
   static constexpr int kTmemUsed = kTmP + (kKVT ? (BM / 2 > kDQCols ? BM / 2 : kDQCols) : BM / 2);
   static_assert(kTmemUsed <= 512, "TMEM overflow");
-  static constexpr int kStatBytes = 2 * 2 * BM * 4;       // lse2, delta, double-buffered over tiles
   // PB = 2 double-buffers the P^T / dS^T tiles so that the exp / dS work of query tile i+1 overlaps the
   // dV / dK / dQ MMAs of tile i.  Dynamic shared memory is declared __align__(1024), no alignment slack.
   static constexpr bool kDQTma = (D <= 128);             // dQ tile leaves through a TMA reduce-add (smem permitting)
   static constexpr bool kDQBf16 = (MU_BWD_DQ_BF16 != 0) && (D == 64) && !kDQT && (MU_BWD_DQ_RED == 0);
   static constexpr int kDQStageBytes = kDQTma ? BM * DH * (kDQBf16 ? 2 : 4) : 0;   // dQ tile staged for the TMA reduce-add
+  static constexpr bool kFold = (MU_BWD_FOLD_STATS != 0) && kDQBf16;     // statistics folded into the accumulators (d = 64)
+  static constexpr int kAugBytes = kFold ? BM * 16 * 2 : 0;            // per stage: [2 K-chunks][BM queries][8 bf16]
+  static constexpr int kOnesBytes = kFold ? 3 * kBK * 16 : 0;          // [zeros | ones | zeros] 16-byte chunk tiles
+  static constexpr int kStatBytes = kFold ? STAGES * kAugBytes + kOnesBytes : 2 * 2 * BM * 4;   // or lse2, delta (x2 tiles)
   static constexpr int kSmemBytes =
       2 * kKBytes + 2 * STAGES * kQBytes + PB * kPBytes + kDQStageBytes + kStatBytes + 256;
   static_assert(kSmemBytes <= 232448, "shared memory overflow");
@@ -156,7 +169,8 @@ template <int D, int BM, int DH, int STAGES, int PB, bool QM, bool DET = false>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                       const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
-                      const __grid_constant__ CUtensorMap tmap_dq, const int32_t* __restrict__ n_keep,
+                      const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_aug,
+                      const int32_t* __restrict__ n_keep,
                       const int32_t* __restrict__ keep_idx,
                       const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
                       __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int N, int NKP, float scale,
@@ -175,9 +189,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   uint8_t* sDO = sQ + STAGES * Cfg::kQBytes;             // STAGES x dO_i
   uint8_t* sDS = sDO + STAGES * Cfg::kQBytes;             // PB x dS^T (P^T lives in TMEM: only the dV MMA reads it)
   uint8_t* sDQ = sDS + PB * Cfg::kPBytes;                 // fp32 dQ staging (D = 64 only)
-  float* sLse = reinterpret_cast<float*>(sDQ + Cfg::kDQStageBytes);   // [2][BM], already * log2e
+  float* sLse = reinterpret_cast<float*>(sDQ + Cfg::kDQStageBytes);   // [2][BM], already * log2e (not kFold)
   float* sDelta = sLse + 2 * BM;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * BM);
+  uint8_t* sAug = sDQ + Cfg::kDQStageBytes;                            // kFold: STAGES x [2][BM][16 B], then the ones tiles
+  uint8_t* sOnes = sAug + STAGES * Cfg::kAugBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDQ + Cfg::kDQStageBytes + Cfg::kStatBytes);
   uint64_t* kv_full = bars;                 // 1
   uint64_t* qdo_full = bars + 1;            // STAGES
   uint64_t* qdo_empty = qdo_full + STAGES;  // STAGES
@@ -247,6 +263,16 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     mbar_init(kv_tm, 256);
     mbar_fence_init();
   }
+  if (Cfg::kFold) {
+    // constant A operands of the two augmentation MMAs: three [128 rows][8 bf16] chunk tiles  zeros | ones | zeros
+    // (ones = 1, 1, 1, 0, 0, 0, 0, 0 in every row).  ones_S = chunks (ones, zeros) starts at tile 1, ones_dP = (zeros, ones)
+    // at tile 0; both with a K-chunk stride (LBO) of one tile.
+    for (int idx = threadIdx.x; idx < 3 * kBK; idx += kBwdThreads) {
+      const bool ones = idx >= kBK && idx < 2 * kBK;
+      st_shared_v4(smem_u32(sOnes) + idx * 16, ones ? 0x3F803F80u : 0u, ones ? 0x00003F80u : 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+  }
   if (warp == 1) {
     tmem_alloc<512>(tmem_slot);
     tmem_relinquish();
@@ -279,7 +305,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         const int st = i % STAGES, use = i / STAGES;
         if (use > 0) mbar_wait_relaxed(qdo_empty + st, (use - 1) & 1);
         MU_TRACE(0, i);                          // TMA: stage free, loads of tile i issued
-        mbar_expect_tx(qdo_full + st, 2 * Cfg::kQBytes);
+        mbar_expect_tx(qdo_full + st, 2 * Cfg::kQBytes + Cfg::kAugBytes);
+        if (Cfg::kFold) {          // the statistics slab of this query tile: K-chunk 0 (lse) and K-chunk 1 (delta)
+          tma_load_3d(sAug + st * Cfg::kAugBytes, &tmap_aug, qdo_full + st, 0, tile_of(i) * BM, b);
+          tma_load_3d(sAug + st * Cfg::kAugBytes + BM * 16, &tmap_aug, qdo_full + st, 8, tile_of(i) * BM, b);
+        }
         for (int blk = 0; blk < D / 64; ++blk) {
           tma_load_3d(sQ + st * Cfg::kQBytes + blk * (BM * 128), &tmap_q, qdo_full + st, blk * 64, tile_of(i) * BM, b);
           tma_load_3d(sDO + st * Cfg::kQBytes + blk * (BM * 128), &tmap_do, qdo_full + st, blk * 64, tile_of(i) * BM, b);
@@ -321,6 +351,19 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             if (elect_one()) umma_ts_lo(tmem_base + Cfg::kTmDP, tmem_base + Cfg::kTmV + kk * 8, da + offb, hi, idesc_s, kk > 0 ? 1u : 0u);
           } else {
             if (elect_one()) umma_ss_lo(tmem_base + Cfg::kTmDP, v_lo + offa, da + offb, hi, idesc_s, kk > 0 ? 1u : 0u);
+          }
+        }
+        if (Cfg::kFold) {
+          // canonical no-swizzle K-major operands: 8-row core matrices 128 B apart (SBO), K-chunks one tile apart (LBO)
+          const uint64_t nosw = ((uint64_t)((128u >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+          const uint64_t aug_d = nosw | (uint64_t)(((uint32_t)(BM * 16) >> 4) & 0x3FFFu) << 16 |
+                                 (uint64_t)desc_lo(smem_u32(sAug) + st * Cfg::kAugBytes);
+          const uint64_t ones_lbo = (uint64_t)(((uint32_t)(kBK * 16) >> 4) & 0x3FFFu) << 16;
+          const uint64_t ones_s = nosw | ones_lbo | (uint64_t)desc_lo(smem_u32(sOnes) + kBK * 16);
+          const uint64_t ones_dp = nosw | ones_lbo | (uint64_t)desc_lo(smem_u32(sOnes));
+          if (elect_one()) {
+            umma_ss(tmem_base + Cfg::kTmS, ones_s, aug_d, idesc_s, 1u);
+            umma_ss(tmem_base + Cfg::kTmDP, ones_dp, aug_d, idesc_s, 1u);
           }
         }
         if (elect_one()) umma_commit(s_full);
@@ -416,8 +459,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       l2 = ok ? lse_b[qi] : INFINITY;                    // +inf -> p = 0 for rows past N (scaled by log2e when staged)
       dl = ok ? delta_b[qi] : 0.f;
     };
-    float nl2, ndl;
-    fetch(0, nl2, ndl);
+    float nl2 = 0.f, ndl = 0.f;
+    if (!Cfg::kFold) fetch(0, nl2, ndl);
     if (Cfg::kKVT) {
       // thread <-> key row r: its 64 channels (128 bytes, 8 swizzled 16-byte chunks) become 32 packed TMEM columns;
       // the first warpgroup copies K_j, the second V_j
@@ -442,12 +485,14 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const bool tile_partial = k0 + kBK > nk;
     for (int i = 0; i < T; ++i) {
       const uint32_t my_lse = lse_addr + (i & 1) * BM * 4, my_delta = delta_addr + (i & 1) * BM * 4;
-      if (t < BM) {
-        st_shared_f32(my_lse + t * 4, nl2 * kLog2eB);
-        st_shared_f32(my_delta + t * 4, ndl);
+      if (!Cfg::kFold) {
+        if (t < BM) {
+          st_shared_f32(my_lse + t * 4, nl2 * kLog2eB);
+          st_shared_f32(my_delta + t * 4, ndl);
+        }
+        if (i + 1 < T) fetch(i + 1, nl2, ndl);
+        named_bar_sync(1, 256);
       }
-      if (i + 1 < T) fetch(i + 1, nl2, ndl);
-      named_bar_sync(1, 256);
       if (warp == 4) MU_TRACE(7, i);                     // softmax: waiting for S^T / dP^T
       mbar_wait(s_full, i & 1);
       if (warp == 4) MU_TRACE(8, i);                     // softmax: s_full(i)
@@ -490,20 +535,33 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         uint32_t pk[16], dk[16];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
+          float p0, p1, p2, p3, d0, d1, d2, d3;
+          if (Cfg::kFold) {
+            // S' = S - lse / scale and dP' = dP - delta came out of the tensor core
+            p0 = fast_exp2(__uint_as_float(s[cc][4 * e + 0]) * scale_log2);
+            p1 = fast_exp2(__uint_as_float(s[cc][4 * e + 1]) * scale_log2);
+            p2 = fast_exp2(__uint_as_float(s[cc][4 * e + 2]) * scale_log2);
+            p3 = fast_exp2(__uint_as_float(s[cc][4 * e + 3]) * scale_log2);
+            d0 = p0 * __uint_as_float(dp[cc][4 * e + 0]);
+            d1 = p1 * __uint_as_float(dp[cc][4 * e + 1]);
+            d2 = p2 * __uint_as_float(dp[cc][4 * e + 2]);
+            d3 = p3 * __uint_as_float(dp[cc][4 * e + 3]);
+          } else {
 #if MU_BWD_PROBE == 5    // no per-column statistics loads (wrong results): what do the broadcast LDS.128 cost?
-          const float4 l2 = make_float4(scale, scale, scale, scale), dl = l2;
+            const float4 l2 = make_float4(scale, scale, scale, scale), dl = l2;
 #else
-          const float4 l2 = ld_shared_v4f(my_lse + (c * 32 + 4 * e) * 4);
-          const float4 dl = ld_shared_v4f(my_delta + (c * 32 + 4 * e) * 4);
+            const float4 l2 = ld_shared_v4f(my_lse + (c * 32 + 4 * e) * 4);
+            const float4 dl = ld_shared_v4f(my_delta + (c * 32 + 4 * e) * 4);
 #endif
-          const float p0 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 0]), scale_log2, -l2.x));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 1]), scale_log2, -l2.y));
-          const float p2 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 2]), scale_log2, -l2.z));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 3]), scale_log2, -l2.w));
-          const float d0 = p0 * (__uint_as_float(dp[cc][4 * e + 0]) - dl.x);
-          const float d1 = p1 * (__uint_as_float(dp[cc][4 * e + 1]) - dl.y);
-          const float d2 = p2 * (__uint_as_float(dp[cc][4 * e + 2]) - dl.z);
-          const float d3 = p3 * (__uint_as_float(dp[cc][4 * e + 3]) - dl.w);
+            p0 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 0]), scale_log2, -l2.x));
+            p1 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 1]), scale_log2, -l2.y));
+            p2 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 2]), scale_log2, -l2.z));
+            p3 = fast_exp2(fmaf(__uint_as_float(s[cc][4 * e + 3]), scale_log2, -l2.w));
+            d0 = p0 * (__uint_as_float(dp[cc][4 * e + 0]) - dl.x);
+            d1 = p1 * (__uint_as_float(dp[cc][4 * e + 1]) - dl.y);
+            d2 = p2 * (__uint_as_float(dp[cc][4 * e + 2]) - dl.z);
+            d3 = p3 * (__uint_as_float(dp[cc][4 * e + 3]) - dl.w);
+          }
           pk[2 * e] = pack_bf16(p0, p1);
           pk[2 * e + 1] = pack_bf16(p2, p3);
           dk[2 * e] = pack_bf16(d0, d1);
@@ -789,6 +847,36 @@ __global__ void dq_convert_kernel(const float4* __restrict__ acc, uint2* __restr
   }
 }
 
+// aug bf16 [B][Npad][16] for MU_BWD_FOLD_STATS: columns 0-2 = -lse / scale, columns 8-10 = -delta, each split into three
+// bf16 terms (hi + mid + lo carries 24 bits); rows [N, Npad) get -3e4 in the lse slot, so that P = exp2(c S') = 0 for
+// query columns past N (a finite value: the slab also meets the zero rows of the other constant operand, and 0 * inf
+// would be NaN).
+__device__ __forceinline__ void split3_bf16(float a, uint32_t& w01, uint32_t& w2) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(a);
+  const float r1 = a - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+  w01 = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16);
+  w2 = (uint32_t)__bfloat16_as_ushort(lo);
+}
+__global__ void attn_bwd_aug_kernel(const float* __restrict__ lse, const float* __restrict__ delta, uint4* __restrict__ aug,
+                                    int N, int Npad, long total, float inv_scale) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / Npad;
+    const int n = (int)(i - b * Npad);
+    float a = -3.0e4f, d = 0.f;
+    if (n < N) {
+      a = fminf(fmaxf(-lse[b * N + n] * inv_scale, -3.0e4f), 3.0e4f);   // lse = -inf (a query without keys): finite, 0 * inf = NaN in dP'
+      d = -delta[b * N + n];
+    }
+    uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = make_uint4(0u, 0u, 0u, 0u);
+    split3_bf16(a, w0.x, w0.y);
+    split3_bf16(d, w1.x, w1.y);
+    aug[2 * i] = w0;
+    aug[2 * i + 1] = w1;
+  }
+}
+
 template <int D, int BM, int DH, int STAGES, int PB, bool QM = false>
 static int run(const void* q, const void* kc, const void* vc, const int32_t* n_keep, const int32_t* keep_idx,
                const void* d_o, const float* lse, const float* delta, void* dq, void* dkc, void* dvc, float* dq_acc,
@@ -796,8 +884,18 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
                int heads = 1, int nk_all = 0, int32_t* sem = nullptr) {
   if (NT == 0) NT = N;                     // self-attention: as many key tokens as queries
   using Cfg = BwdCfg<D, BM, DH, STAGES, PB>;
-  CUtensorMap tq, tdo, tk, tv, tdq;
+  CUtensorMap tq, tdo, tk, tv, tdq, taug;
   int rc;
+  std::memset(&taug, 0, sizeof(taug));
+  const float scale_run = scale_in > 0.f ? scale_in : 1.f / sqrtf((float)D);
+  if (Cfg::kFold) {           // the statistics slab lives at the start of the workspace (where the fp32 dQ tile used to)
+    const int Npad = round_up(N, BM);
+    const long total = (long)B * Npad;
+    attn_bwd_aug_kernel<<<(int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8), 256, 0, s>>>(
+        lse, delta, reinterpret_cast<uint4*>(dq_acc), N, Npad, total, 1.f / scale_run);
+    if ((rc = check_launch("attn_bwd_aug"))) return rc;
+    if ((rc = make_tmap_bf16_3d_w16(&taug, dq_acc, Npad, B, BM))) return rc;
+  }
   if (Cfg::kDQBf16) {
     if ((rc = make_tmap_bf16_3d(&tdq, dq, D, N, B, BM))) return rc;      // partial tiles are added straight into dq
   } else {
@@ -827,7 +925,7 @@ static int run(const void* q, const void* kc, const void* vc, const int32_t* n_k
   (void)nt;   // dk / dv need no clearing: the kernel writes every row (kept keys: gradients, masked keys: zeros)
   dim3 grid(NKP / kBK, B, D / DH);
   const float scale = scale_in > 0.f ? scale_in : 1.f / sqrtf((float)D);
-  kern<<<grid, kBwdThreads, Cfg::kSmemBytes, s>>>(tq, tdo, tk, tv, tdq, n_keep, keep_idx, lse, delta, dq_acc, (__nv_bfloat16*)dkc,
+  kern<<<grid, kBwdThreads, Cfg::kSmemBytes, s>>>(tq, tdo, tk, tv, tdq, taug, n_keep, keep_idx, lse, delta, dq_acc, (__nv_bfloat16*)dkc,
                                                   (__nv_bfloat16*)dvc, N, NKP, scale, NT, bits_t, heads,
                                                   round_up(N, 128) / 32, nk_all, sem);
   if ((rc = check_launch("attn_bwd_sm100"))) return rc;
@@ -846,7 +944,8 @@ extern "C" int mu_debug_bwd_trace(long long* host, int n) {   // tools/bwd_trace
 
 // fp32 dQ accumulator [B, N, C] + order semaphores int32 [B, C / DH, ceil(N / 64)] (sized for the smallest query tile)
 static size_t dq_acc_bytes(int B, int N, int C) {
-  if (MU_BWD_DQ_BF16 != 0 && MU_BWD_DQ_RED == 0 && C == 64) return 0;     // partial tiles are added into dq itself
+  if (MU_BWD_DQ_BF16 != 0 && MU_BWD_DQ_RED == 0 && C == 64)              // partial tiles are added into dq itself;
+    return MU_BWD_FOLD_STATS != 0 ? (size_t)B * round_up(N, 128) * 32 : 0;   // what is left is the statistics slab
   return (size_t)B * N * C * sizeof(float);
 }
 size_t attn_bwd_sm100_workspace(int B, int N, int C) {

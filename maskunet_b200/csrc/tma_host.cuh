@@ -107,6 +107,28 @@ inline int make_tmap_bf16_3d(CUtensorMap* map, const void* base, int cols, int r
   return 0;
 }
 
+// bf16 tensor [batch][rows][16 cols]; box = [1][box_rows][8 cols] (16-byte rows), NO swizzle: a box lands as consecutive
+// 8-row x 16-byte core matrices, the canonical no-swizzle K-major UMMA operand (SBO = 128 bytes).
+inline int make_tmap_bf16_3d_w16(CUtensorMap* map, const void* base, int rows, int batch, int box_rows) {
+  const TmapKey key = tmap_key(5, base, 16, rows, batch, 0, box_rows, 0);
+  if (tmap_cache_get(key, map)) return 0;
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return MU_ERR_DRIVER;
+  cuuint64_t dims[3] = {16, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {32, (cuuint64_t)32 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {8, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(w16) failed: CUresult %d (rows %d batch %d box_rows %d)", (int)r, rows, batch, box_rows);
+    return MU_ERR_DRIVER;
+  }
+  tmap_cache_put(key, map);
+  return 0;
+}
+
 // fp32 tensor [batch][rows][cols]; box = [1][box_rows][32 cols] (128-byte rows), 128-byte swizzle.
 // Used as the destination of TMA reduce-add stores (rows past `rows` are dropped).
 inline int make_tmap_f32_3d(CUtensorMap* map, const void* base, int cols, int rows, int batch, int box_rows) {

@@ -127,7 +127,8 @@ def test_c_abi_error_convention_without_a_device():
     assert rc != 0                                        # workspace too small (or no device): never a crash
     # the order semaphores of deterministic mode (int32 per sample, channel half, 64-query tile) and, for 128 / 256
     # channels, the fp32 dQ accumulator (64 channels add bf16 partial tiles straight into dq)
-    assert lib.mu_attn_bwd_workspace_bytes(2, 400, 64, _lib.MU_BF16) == 2 * 2 * 7 * 4 + 16
+    # (64 channels: instead of the accumulator, the 32-byte-per-query statistics slab of the folded lse / delta, rows padded to 128)
+    assert lib.mu_attn_bwd_workspace_bytes(2, 400, 64, _lib.MU_BF16) == 2 * 512 * 32 + 2 * 2 * 7 * 4 + 16
     assert lib.mu_attn_bwd_workspace_bytes(2, 400, 128, _lib.MU_BF16) == 2 * 400 * 128 * 4 + 2 * 2 * 7 * 4 + 16
     assert lib.mu_get_deterministic() == 0
     lib.mu_set_deterministic(1)
