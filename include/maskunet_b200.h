@@ -167,7 +167,8 @@ int mu_bn_act_bwd(const void* dy, const void* x, const void* r, const float* a, 
                   int32_t dtype, mu_stream_t stream);
 
 /* K9. MaxPool2d(2) on channels-last [B, H, W, C] (:216).  bwd = 0: out [B, H/2, W/2, C] = max over 2x2;
- * bwd = 1: dy [B, H/2, W/2, C] -> out = dx [B, H, W, C], gradient to the first maximum in scan order. */
+ * bwd = 1: dy [B, H/2, W/2, C] -> out = dx [B, H, W, C], gradient to the first maximum in scan order;
+ * bwd = 2: the same gradient ADDED to out, which already holds the skip connection's gradient of x (:304-312). */
 int mu_maxpool2(const void* x, const void* dy, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t bwd,
                 int32_t dtype, mu_stream_t stream);
 
@@ -210,6 +211,9 @@ int mu_cross_entropy_fused(const void* logits, const int64_t* labels, const floa
  *   training-mode BatchNorm2d that always follows (:200, :203), so the caller zeroes it first and passes it to
  *   mu_bn_act_fwd_stats.
  * mu_conv3x3_bwd_data: dx [B, H, W, Cin] = conv(dy [B, H, W, Cout], wd).
+ * mu_conv3x3_bwd_data_acc: dx += conv(dy, wd): dx already holds another gradient of the same activation (the
+ *   residual branch of a ConvBlock, ade_semantic.py:207: gelu(x + block(x))); the TMA unit adds every output tile into
+ *   it (bf16 reduce-add, each element added exactly once: bit-reproducible), which replaces autograd's accumulation pass.
  * mu_conv3x3_bwd_weight: dw f32 [Cout, Cin, 3, 3] = sum over pixels of dy (x) shifted x; workspace of
  *   mu_conv3x3_workspace_bytes(Cin, Cout) bytes (f32 [9, Cin, Cout] split-K accumulator, cleared inside). */
 int mu_conv_prep_weights(const float* w, void* wf, void* wd, int32_t Cout, int32_t Cin, int32_t taps,
@@ -218,6 +222,8 @@ int mu_conv3x3_fwd(const void* x, const void* wf, void* y, float* stats, int32_t
                    int32_t Cout, int32_t dtype, mu_stream_t stream);
 int mu_conv3x3_bwd_data(const void* dy, const void* wd, void* dx, int32_t B, int32_t H, int32_t W, int32_t Cin,
                         int32_t Cout, int32_t dtype, mu_stream_t stream);
+int mu_conv3x3_bwd_data_acc(const void* dy, const void* wd, void* dx, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                            int32_t Cout, int32_t dtype, mu_stream_t stream);
 size_t mu_conv3x3_workspace_bytes(int32_t Cin, int32_t Cout);
 int mu_conv3x3_bwd_weight(const void* x, const void* dy, void* workspace, size_t workspace_bytes, float* dw, int32_t B,
                           int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t dtype, mu_stream_t stream);

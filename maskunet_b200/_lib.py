@@ -47,6 +47,7 @@ SIGNATURES = {
     "mu_conv_prep_weights": [_P, _P, _P, _I, _I, _I, _P],
     "mu_conv3x3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "mu_conv3x3_bwd_data": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mu_conv3x3_bwd_data_acc": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "mu_conv3x3_bwd_weight": [_P, _P, _P, ctypes.c_size_t, _P, _I, _I, _I, _I, _I, _I, _P],
     "mu_bn_update_running": [_P, _P, _P, _P, _F, _F, ctypes.c_int64, _I, _P],
     "mu_instance_triplet_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _I, _F, _F, _P, _P, _P, _I, _P],

@@ -412,6 +412,14 @@ int mu_conv3x3_bwd_data(const void* dy, const void* wd, void* dx, int32_t B, int
   return launch_conv_fprop_sm100(dy, wd, dx, nullptr, B, H, W, Cout, Cin, 9, (cudaStream_t)stream);
 }
 
+int mu_conv3x3_bwd_data_acc(const void* dy, const void* wd, void* dx, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                            int32_t Cout, int32_t dtype, mu_stream_t stream) {
+  MU_BF16_ONLY("mu_conv3x3_bwd_data_acc");
+  MU_PTRS("mu_conv3x3_bwd_data_acc", dy, wd, dx);
+  MU_SM100_ONLY("mu_conv3x3_bwd_data_acc");
+  return launch_conv_fprop_sm100(dy, wd, dx, nullptr, B, H, W, Cout, Cin, 9, (cudaStream_t)stream, 1);
+}
+
 size_t mu_conv3x3_workspace_bytes(int32_t Cin, int32_t Cout) { return (size_t)9 * Cin * Cout * sizeof(float); }
 
 int mu_conv3x3_bwd_weight(const void* x, const void* dy, void* workspace, size_t workspace_bytes, float* dw, int32_t B,

@@ -118,7 +118,7 @@ int launch_bn_forward_stats(const void* x, const void* r, const float* gamma, co
                             int dtype, cudaStream_t s);
 // K7 (tcgen05, bf16 channels-last)
 int launch_conv_fprop_sm100(const void* x, const void* wt, void* y, float* stats, int B, int H, int W, int K, int N,
-                            int taps, cudaStream_t s);
+                            int taps, cudaStream_t s, int accum = 0);
 int launch_conv_wgrad_sm100(const void* x, const void* dy, float* ws, float* dw, int B, int H, int W, int Cin, int Cout,
                             cudaStream_t s);
 int launch_conv_prep_weights(const float* w, void* wf, void* wd, int Cout, int Cin, int taps, cudaStream_t s);

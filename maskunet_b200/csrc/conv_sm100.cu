@@ -40,6 +40,7 @@ struct ConvArgs {
   int TH, tiles_y, m_tiles, n_tiles;
   int mode, groups, taps;  // A loads per 64-channel chunk, taps served by each
   int a_bytes, a_stride, SA, SB, SO;  // ring geometry; SO = output staging buffers (1 or 2)
+  int accum;               // 1: the output tiles are ADDED into y by the TMA unit (y already holds an addend)
 };
 
 __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
@@ -353,7 +354,8 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (e == 0) {
-          tma_store_4d(&tmap_y, so, nt * NT + cb * 64, 0, y0 + m * p.TH, b);
+          if (p.accum) tma_reduce_add_4d(&tmap_y, so, nt * NT + cb * 64, 0, y0 + m * p.TH, b);
+          else tma_store_4d(&tmap_y, so, nt * NT + cb * 64, 0, y0 + m * p.TH, b);
           tma_store_commit();
         }
         if (stats != nullptr) {
@@ -658,9 +660,10 @@ static int conv_res_mode() {           // MU_CONV_RES=0 (environment): no reside
 
 template <int NT, int MT, int MODE, bool PAIR = false, bool RES = false>
 static int run_fprop(const void* x, const void* wt, void* y, float* stats, const float* bias, int B, int H, int W, int K,
-                     int N, int taps, cudaStream_t s) {
+                     int N, int taps, cudaStream_t s, int accum = 0) {
   ConvArgs p;
   p.B = B; p.H = H; p.W = W; p.K = K; p.N = N;
+  p.accum = accum;
   p.TH = 128 / W;
   p.tiles_y = H / (p.TH * MT);          // super tiles per image
   p.m_tiles = B * p.tiles_y;
@@ -743,8 +746,8 @@ static int run_fprop(const void* x, const void* wt, void* y, float* stats, const
 
 template <int NT, int MT>
 static int run_fprop_mode(const void* x, const void* wt, void* y, float* stats, int B, int H, int W, int K, int N,
-                          int taps, cudaStream_t s) {
-  if (taps == 1) return run_fprop<NT, MT, CONV_1X1>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
+                          int taps, cudaStream_t s, int accum) {
+  if (taps == 1) return run_fprop<NT, MT, CONV_1X1>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s, accum);
   // CTA pairs: an even number of super tiles (adjacent ones share a pair) and enough of them to fill the pairs
   const int m_tiles = B * (H / ((128 / W) * MT));
   // (measured per layer shape at 256 images, tools/bench_conv_ours.py: pairs gain 3-13 % at widths 64 and 128, lose
@@ -758,34 +761,34 @@ static int run_fprop_mode(const void* x, const void* wt, void* y, float* stats, 
     const int b_rows = pair ? 32 : 64;
     if (1024 + 4096 + 512 + 16384 + 2 * a_stride + 9 * ((K + 63) / 64) * b_rows * 128 <= kSmemLimit) {
       if (W == 128)
-        return pair ? run_fprop<64, MT, CONV_W128, true, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s)
-                    : run_fprop<64, MT, CONV_W128, false, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
-      return pair ? run_fprop<64, MT, CONV_ROWS, true, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s)
-                  : run_fprop<64, MT, CONV_ROWS, false, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
+        return pair ? run_fprop<64, MT, CONV_W128, true, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s, accum)
+                    : run_fprop<64, MT, CONV_W128, false, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s, accum);
+      return pair ? run_fprop<64, MT, CONV_ROWS, true, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s, accum)
+                  : run_fprop<64, MT, CONV_ROWS, false, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s, accum);
     }
   }
   if (W == 128)
-    return pair ? run_fprop<NT, MT, CONV_W128, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s)
-                : run_fprop<NT, MT, CONV_W128>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
-  return pair ? run_fprop<NT, MT, CONV_ROWS, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s)
-              : run_fprop<NT, MT, CONV_ROWS>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s);
+    return pair ? run_fprop<NT, MT, CONV_W128, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s, accum)
+                : run_fprop<NT, MT, CONV_W128>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s, accum);
+  return pair ? run_fprop<NT, MT, CONV_ROWS, true>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s, accum)
+              : run_fprop<NT, MT, CONV_ROWS>(x, wt, y, stats, nullptr, B, H, W, K, N, taps, s, accum);
 }
 
 // y [B,H,W,N] = conv(x [B,H,W,K], wt [taps][N][K]); stats (optional) f32 [2N] += (sum, sum of squares) per channel
 int launch_conv_fprop_sm100(const void* x, const void* wt, void* y, float* stats, int B, int H, int W, int K, int N,
-                            int taps, cudaStream_t s) {
+                            int taps, cudaStream_t s, int accum) {
   int rc;
   if ((rc = conv_geometry_ok("conv_fprop_sm100", B, H, W, K, N))) return rc;
   MU_REQUIRE(taps == 9 || taps == 1, MU_ERR_BAD_SHAPE, "conv_fprop_sm100: taps must be 9 or 1 (got %d)", taps);
   const bool pair = H % (2 * (128 / W)) == 0;       // two vertically adjacent tiles per CTA step
   if (N % 256 == 0)
-    return pair ? run_fprop_mode<256, 2>(x, wt, y, stats, B, H, W, K, N, taps, s)
-                : run_fprop_mode<256, 1>(x, wt, y, stats, B, H, W, K, N, taps, s);
+    return pair ? run_fprop_mode<256, 2>(x, wt, y, stats, B, H, W, K, N, taps, s, accum)
+                : run_fprop_mode<256, 1>(x, wt, y, stats, B, H, W, K, N, taps, s, accum);
   if (N % 128 == 0)
-    return pair ? run_fprop_mode<128, 2>(x, wt, y, stats, B, H, W, K, N, taps, s)
-                : run_fprop_mode<128, 1>(x, wt, y, stats, B, H, W, K, N, taps, s);
-  return pair ? run_fprop_mode<64, 2>(x, wt, y, stats, B, H, W, K, N, taps, s)
-              : run_fprop_mode<64, 1>(x, wt, y, stats, B, H, W, K, N, taps, s);
+    return pair ? run_fprop_mode<128, 2>(x, wt, y, stats, B, H, W, K, N, taps, s, accum)
+                : run_fprop_mode<128, 1>(x, wt, y, stats, B, H, W, K, N, taps, s, accum);
+  return pair ? run_fprop_mode<64, 2>(x, wt, y, stats, B, H, W, K, N, taps, s, accum)
+              : run_fprop_mode<64, 1>(x, wt, y, stats, B, H, W, K, N, taps, s, accum);
 }
 
 // ---- K12: 1x1 convolution heads (nn.Conv2d(64, c_out, kernel_size=1), ade_semantic.py:284; the embedding head

@@ -22,6 +22,9 @@
 // C = 256: the 64 KB token tile dominates shared memory; 64-column chunks in a 1-deep weight ring fit two CTAs per SM
 // instead of one: 0.362 -> 0.259 ms at B = 256, N = 1024 (128-column chunks, 2-deep ring: MU_P1_NC_256=128
 // MU_P1_WSTAGES_256=2).
+#ifndef MU_P1_STAGED_EPILOGUE
+#define MU_P1_STAGED_EPILOGUE 1
+#endif
 #ifndef MU_P1_NC_256
 #define MU_P1_NC_256 64
 #endif
@@ -49,11 +52,16 @@ struct P1Cfg {
   // columns per CTA (64 at C = 64), so that twice as many of these short, latency-bound CTAs are resident
   static constexpr int kAcc = (C == 64) ? MU_P1_ACC_BUFS_64 : 2;
   static constexpr int kTmemCols = kAcc * NC;           // 64, 128 or 256 (power of two)
-  static constexpr int kSmemBytes = 1024 + kXBytes + kWStages * kWBytes + 256;
+  // Epilogue staging: 2 KB per epilogue warp (32 token rows x 32 bf16 columns).  A thread owns a token ROW of the
+  // accumulator; storing its row straight to global memory makes every warp store touch 32 different 128-byte lines
+  // with 16 bytes each.  Through the staging tile the warp writes 8 rows x 64 contiguous bytes per instruction
+  // (MU_P1_STAGED_EPILOGUE=0: the direct stores).
+  static constexpr int kStageBytes = MU_P1_STAGED_EPILOGUE ? 4 * 2048 : 0;
+  static constexpr int kSmemBytes = 1024 + kXBytes + kWStages * kWBytes + kStageBytes + 256;
 };
 
 template <int C>
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kGemmThreads, C == 256 ? 2 : 5)   // (64 registers: five of these short CTAs per SM)
 qkv_project_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                          const float* __restrict__ bias, const int32_t* __restrict__ rank,
                          __nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ kc,
@@ -64,7 +72,8 @@ qkv_project_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sX = smem;
   uint8_t* sW = sX + Cfg::kXBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + Cfg::kWStages * Cfg::kWBytes);
+  uint8_t* sStage = sW + Cfg::kWStages * Cfg::kWBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::kStageBytes);
   uint64_t* x_full = bars;
   uint64_t* w_full = bars + 1;      // 2
   uint64_t* w_empty = bars + 3;     // 2
@@ -141,6 +150,54 @@ qkv_project_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       bidx = tok / N;
     }
     uint32_t v[32];
+#if MU_P1_STAGED_EPILOGUE
+    // destination rows of the four store rounds: round `it` writes rows it * 8 + lane / 4, 16-byte piece lane % 4
+    const int lane = (int)lane_id();
+    const uint32_t stage = smem_u32(sStage) + quad * 2048;
+    int kv_row[4];                                       // compacted K / V row of the token (-1: masked or past the end)
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 8 + (lane >> 2);
+      const int rkr = __shfl_sync(0xffffffffu, tok_ok ? rk : -1, row);
+      const int br = __shfl_sync(0xffffffffu, bidx, row);
+      kv_row[it] = rkr >= 0 ? br * NKP + rkr : -1;
+    }
+    for (int j = 0; j < Cfg::kChunks; ++j) {
+      const int st = Cfg::kAcc == 2 ? (j & 1) : 0, use = Cfg::kAcc == 2 ? (j >> 1) : j;
+      const int which = (j * NC) / C, col0 = j * NC - which * C;
+      __nv_bfloat16* const base = which == 0 ? q : (which == 1 ? kc : vc);
+      mbar_wait(acc_full + st, use & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < NC / 32; ++c) {
+        tmem_ld32(lane_base + st * NC + c * 32, v);
+        tmem_wait_ld();
+        if (c == NC / 32 - 1) {
+          tc_fence_before();
+          mbar_arrive(acc_free + st);
+        }
+        const float* bptr = bias + j * NC + c * 32;
+        __syncwarp();                                    // the previous round's reads of the staging tile are done
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          st_shared_v4(stage + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4),
+                       pack_bf16(__uint_as_float(v[8 * g + 0]) + __ldg(bptr + 8 * g + 0), __uint_as_float(v[8 * g + 1]) + __ldg(bptr + 8 * g + 1)),
+                       pack_bf16(__uint_as_float(v[8 * g + 2]) + __ldg(bptr + 8 * g + 2), __uint_as_float(v[8 * g + 3]) + __ldg(bptr + 8 * g + 3)),
+                       pack_bf16(__uint_as_float(v[8 * g + 4]) + __ldg(bptr + 8 * g + 4), __uint_as_float(v[8 * g + 5]) + __ldg(bptr + 8 * g + 5)),
+                       pack_bf16(__uint_as_float(v[8 * g + 6]) + __ldg(bptr + 8 * g + 6), __uint_as_float(v[8 * g + 7]) + __ldg(bptr + 8 * g + 7)));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = it * 8 + (lane >> 2), g = lane & 3;
+          const int qrow = t0 + quad * 32 + row;
+          const int drow = which == 0 ? (qrow < Mtot ? qrow : -1) : kv_row[it];
+          const float4 w = ld_shared_v4f(stage + row * 64 + ((g ^ ((row >> 1) & 3)) << 4));
+          if (drow >= 0) *reinterpret_cast<float4*>(base + (size_t)drow * C + col0 + c * 32 + g * 8) = w;
+        }
+      }
+    }
+#else
     for (int j = 0; j < Cfg::kChunks; ++j) {
       const int st = Cfg::kAcc == 2 ? (j & 1) : 0, use = Cfg::kAcc == 2 ? (j >> 1) : j;
       const int which = (j * NC) / C, col0 = j * NC - which * C;
@@ -173,6 +230,7 @@ qkv_project_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         }
       }
     }
+#endif
   }
   tc_fence_before();
   __syncthreads();

@@ -47,7 +47,9 @@ template <> struct V8<float> {
 };
 
 // ============================================================================ K9: MaxPool2d(2), NHWC
-template <typename T, bool BWD>
+// BWD = 2: `out` already holds another gradient of x (the skip connection's, ade_semantic.py:304/310/312) and the pooled
+// gradient is added to it in place (one fp32 add per element, rounded once: what autograd's accumulation pass computes).
+template <typename T, int BWD>
 __global__ void __launch_bounds__(256) maxpool2_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                        T* __restrict__ out, int B, int H, int W, int C) {
   const int G = C / 8, Ho = H / 2, Wo = W / 2;
@@ -81,6 +83,17 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const T* __restrict__ x, 
           if (v[k][e] > best) { best = v[k][e]; arg = k; }
 #pragma unroll
         for (int k = 0; k < 4; ++k) d[k][e] = (k == arg) ? g_[e] : 0.f;
+      }
+      if (BWD == 2) {
+        float o[4][8];
+        V8<T>::load(out + in0, o[0]);
+        V8<T>::load(out + in0 + C, o[1]);
+        V8<T>::load(out + in0 + (long)W * C, o[2]);
+        V8<T>::load(out + in0 + (long)W * C + C, o[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[k][e] += o[k][e];
       }
       V8<T>::store(out + in0, d[0]);
       V8<T>::store(out + in0 + C, d[1]);
@@ -737,13 +750,17 @@ int launch_maxpool2(const void* x, const void* dy, void* out, int B, int H, int 
   }
   const int grid = grid_for((long)B * (H / 2) * (W / 2) * (C / 8));
   if (!bwd) {
-    MU_T(dtype, (maxpool2_kernel<float, false><<<grid, 256, 0, s>>>((const float*)x, nullptr, (float*)out, B, H, W, C)),
-         (maxpool2_kernel<__nv_bfloat16, false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, nullptr,
-                                                                    (__nv_bfloat16*)out, B, H, W, C)));
+    MU_T(dtype, (maxpool2_kernel<float, 0><<<grid, 256, 0, s>>>((const float*)x, nullptr, (float*)out, B, H, W, C)),
+         (maxpool2_kernel<__nv_bfloat16, 0><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, nullptr,
+                                                                (__nv_bfloat16*)out, B, H, W, C)));
+  } else if (bwd == 1) {
+    MU_T(dtype, (maxpool2_kernel<float, 1><<<grid, 256, 0, s>>>((const float*)x, (const float*)dy, (float*)out, B, H, W, C)),
+         (maxpool2_kernel<__nv_bfloat16, 1><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
+                                                                (__nv_bfloat16*)out, B, H, W, C)));
   } else {
-    MU_T(dtype, (maxpool2_kernel<float, true><<<grid, 256, 0, s>>>((const float*)x, (const float*)dy, (float*)out, B, H, W, C)),
-         (maxpool2_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
-                                                                   (__nv_bfloat16*)out, B, H, W, C)));
+    MU_T(dtype, (maxpool2_kernel<float, 2><<<grid, 256, 0, s>>>((const float*)x, (const float*)dy, (float*)out, B, H, W, C)),
+         (maxpool2_kernel<__nv_bfloat16, 2><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
+                                                                (__nv_bfloat16*)out, B, H, W, C)));
   }
   return check_launch("maxpool2");
 }

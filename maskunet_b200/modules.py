@@ -14,6 +14,7 @@ to the reference's behaviour.
 """
 from __future__ import annotations
 
+import os
 import threading
 from typing import Optional
 
@@ -276,11 +277,22 @@ def invalidate_operand_caches(model: nn.Module) -> None:
             m.__dict__.pop(slot, None)
 
 
+def fold_skip_grads() -> bool:
+    """MASKUNET_FOLD_SKIP_GRADS=0 (environment, A/B runs): leave the accumulation of the two gradients of a residual /
+    skip activation to autograd (one extra pass over both) instead of adding inside the data-gradient kernels."""
+    return os.environ.get("MASKUNET_FOLD_SKIP_GRADS", "1") != "0"
+
+
 def conv_bn_act(conv: nn.Conv2d, bn: nn.BatchNorm2d, x: torch.Tensor, act: int,
-                residual: Optional[torch.Tensor] = None):
+                residual: Optional[torch.Tensor] = None, want_skip: bool = False):
     """act(BN(conv(x)) [+ residual]): one conv3x3 -> BatchNorm2d -> activation link of ade_semantic.py:198-210.
     On the production layout the convolution is our implicit-GEMM kernel and its epilogue hands the BatchNorm
-    batch statistics to the fused normalise + activate kernel."""
+    batch statistics to the fused normalise + activate kernel.
+
+    ``want_skip``: returns (result, x_skip) -- x_skip is x for a second consumer (the residual add of :207); when the
+    convolution is ours and x needs a gradient, it is the alias through which that consumer's gradient reaches the
+    data-gradient kernel (ops._Conv3x3Skip), otherwise x itself."""
+    x_in = x
     weight = conv.weight
     if (conv.in_channels < 8 and x.dim() == 4 and x.is_cuda and x.dtype == torch.bfloat16 and conv.bias is None
             and conv.kernel_size == (3, 3) and x.is_contiguous(memory_format=torch.channels_last)):
@@ -298,10 +310,15 @@ def conv_bn_act(conv: nn.Conv2d, bn: nn.BatchNorm2d, x: torch.Tensor, act: int,
             wf = _inference_cache(conv, "_mu_conv_operand", (conv.weight,),
                                   lambda: ops.conv_prep_weights(weight.detach().contiguous(), False)[0])
             y, sums = ops.conv3x3_fwd(x, wf, bn.training)
+        elif want_skip and x.requires_grad and x is x_in and fold_skip_grads():
+            y, sums, x_skip = ops.conv3x3_skip(x, weight, bn.training)
+            return fused_bn_act(y, bn, act, residual, sums=sums if bn.training else None), x_skip
         else:
             y, sums, _ = ops.conv3x3(x, weight, bn.training)
-        return fused_bn_act(y, bn, act, residual, sums=sums if bn.training else None)
-    return fused_bn_act(conv(x[:, :conv.in_channels]), bn, act, residual)
+        out = fused_bn_act(y, bn, act, residual, sums=sums if bn.training else None)
+        return (out, x_in) if want_skip else out
+    out = fused_bn_act(conv(x[:, :conv.in_channels]), bn, act, residual)
+    return (out, x_in) if want_skip else out
 
 
 class ConvBlock(nn.Module):
@@ -317,9 +334,10 @@ class ConvBlock(nn.Module):
 
     def forward(self, x):
         conv1, bn1, _, conv2, bn2 = self.conv_block
-        h = conv_bn_act(conv1, bn1, x, ops.ACT_GELU)
         if self.residual:
-            return conv_bn_act(conv2, bn2, h, ops.ACT_GELU, residual=x)
+            h, x_skip = conv_bn_act(conv1, bn1, x, ops.ACT_GELU, want_skip=True)
+            return conv_bn_act(conv2, bn2, h, ops.ACT_GELU, residual=x_skip)
+        h = conv_bn_act(conv1, bn1, x, ops.ACT_GELU)
         return conv_bn_act(conv2, bn2, h, ops.ACT_NONE)
 
 
@@ -338,13 +356,20 @@ class DownSample(nn.Module):
                                           ConvBlock(in_channels, out_channels), nn.BatchNorm2d(out_channels))
         self.emb_layer = _dead_embedding(emb_dim, out_channels)
 
-    def forward(self, x):
+    def forward(self, x, return_skip: bool = False):
+        """``return_skip`` (our extension; the U-Net trunk passes it): returns (result, x_skip), x_skip being x for the
+        skip connection -- the alias through which the UpSample's gradient of x reaches the pooling backward kernel."""
         pool, block1, block2, bn = self.maxpool_conv
+        x_skip = x
         if _fast_layout(x) and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
-            h = ops.maxpool2(x)                      # K9, channels-last kernel
+            if return_skip and x.requires_grad and torch.is_grad_enabled() and fold_skip_grads():
+                h, x_skip = ops.maxpool2_skip(x)
+            else:
+                h = ops.maxpool2(x)                  # K9, channels-last kernel
         else:
             h = pool(x)
-        return fused_bn_act(block2(block1(h)), bn, ops.ACT_NONE)
+        out = fused_bn_act(block2(block1(h)), bn, ops.ACT_NONE)
+        return (out, x_skip) if return_skip else out
 
 
 class UpSample(nn.Module):
@@ -418,9 +443,12 @@ class UNet(nn.Module):
 
     def _trunk(self, x):
         x1 = self.initial_conv(x)
-        x2 = self.self_attention1(self.downsample1(x1))
-        x3 = self.self_attention2(self.downsample2(x2))
-        x4 = self.self_attention3(self.downsample3(x3))
+        d, x1 = self.downsample1(x1, return_skip=True)      # (x1 .. x3 from here on: the skip-connection aliases)
+        x2 = self.self_attention1(d)
+        d, x2 = self.downsample2(x2, return_skip=True)
+        x3 = self.self_attention2(d)
+        d, x3 = self.downsample3(x3, return_skip=True)
+        x4 = self.self_attention3(d)
         x4 = self.bottom3(self.bottom2(self.bottom1(x4)))
         h = self.self_attention4(self.dropout(self.upsample1(x4, x3)))
         h = self.self_attention5(self.dropout(self.upsample2(h, x2)))

@@ -14,7 +14,7 @@ Layouts (B batch, C channels, N = H*W tokens, NKP = roundup(N, 128)):
 from __future__ import annotations
 
 import ctypes
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -597,6 +597,70 @@ def _conv_backward(ctx, dy, *unused):
 conv3x3.register_autograd(_conv_backward, setup_context=_conv_setup)
 
 
+@torch.library.custom_op("maskunet::conv3x3_bwd_data_acc", mutates_args=("dx",), device_types="cuda")
+def conv3x3_bwd_data_acc(dy: Tensor, wd: Tensor, dx: Tensor) -> None:
+    """dx += conv(dy, wd): the TMA unit adds the output tiles into dx (bf16 reduce-add, every element exactly once)."""
+    B, Cout, H, W = _nhwc(dy)
+    _cuda(wd)
+    Cin = wd.shape[1]
+    assert dy.dtype == torch.bfloat16 and dx.dtype == torch.bfloat16 and wd.shape == (9, Cin, Cout)
+    assert _nhwc(dx) == (B, Cin, H, W)
+    with torch.cuda.device(dy.device), _timed("mu_conv3x3_bwd_data_acc", (B, H, W, Cin, Cout)):
+        _count(1)
+        check(_L.mu_conv3x3_bwd_data_acc(_p(dy), _p(wd), _p(dx), B, H, W, Cin, Cout, MU_BF16, _stream(dy)),
+              "mu_conv3x3_bwd_data_acc")
+
+
+@conv3x3_bwd_data_acc.register_fake
+def _(dy, wd, dx):
+    return None
+
+
+def _addable(g: Optional[Tensor], like: Tensor) -> bool:
+    """True when the gradient ``g`` of a second consumer can take our gradient of ``like`` in place."""
+    return (g is not None and g.is_cuda and g.dtype == like.dtype and g.shape == like.shape and g.dim() == 4
+            and g.is_contiguous(memory_format=torch.channels_last) and g._base is None and not g.requires_grad)
+
+
+class _Conv3x3Skip(torch.autograd.Function):
+    """conv3x3 of an activation that has a SECOND consumer (the residual branch of gelu(x + block(x)),
+    ade_semantic.py:207).  Returns (y, sums, x_skip): ``x_skip`` is x itself, handed to the other consumer, so that
+    both gradients of x arrive here and the data-gradient kernel adds its tiles straight into the other one --
+    autograd's separate accumulation pass (one read of each gradient, one write) disappears."""
+
+    @staticmethod
+    def forward(ctx, x, weight, want_stats):
+        wf, wd = conv_prep_weights(weight.contiguous(), True)
+        y, sums = conv3x3_fwd(x, wf, want_stats)
+        ctx.save_for_backward(x, wd)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(sums)
+        return y, sums, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, _dsums, dskip):
+        x, wd = ctx.saved_tensors
+        dx = dw = None
+        if dy is None:
+            return (dskip if ctx.needs_input_grad[0] else None), None, None
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        if ctx.needs_input_grad[0]:
+            if _addable(dskip, x):
+                conv3x3_bwd_data_acc(dy, wd, dskip)
+                dx = dskip
+            else:
+                dx = conv3x3_bwd_data(dy, wd)
+                if dskip is not None:
+                    dx = dx + dskip
+        if ctx.needs_input_grad[1]:
+            dw = conv3x3_bwd_weight(x, dy)
+        return dx, dw, None
+
+
+def conv3x3_skip(x: Tensor, weight: Tensor, want_stats: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    return _Conv3x3Skip.apply(x, weight, want_stats)
+
+
 # ------------------------------------------------------------------ K12: 1x1 convolution heads (class-padded outputs)
 HEAD_PADS = (32, 64, 128, 160, 256)
 
@@ -752,6 +816,50 @@ def _(x, dy):
 maxpool2.register_autograd(
     lambda ctx, g: maxpool2_bwd(ctx.saved_tensors[0], g.contiguous(memory_format=torch.channels_last)),
     setup_context=lambda ctx, inputs, output: ctx.save_for_backward(inputs[0]))
+
+
+@torch.library.custom_op("maskunet::maxpool2_bwd_acc", mutates_args=("dx",), device_types="cuda")
+def maxpool2_bwd_acc(x: Tensor, dy: Tensor, dx: Tensor) -> None:
+    """dx += maxpool2 gradient (dx holds the skip connection's gradient of x)."""
+    B, C, H, W = _nhwc(x)
+    _nhwc(dy)
+    assert _nhwc(dx) == (B, C, H, W) and dx.dtype == x.dtype
+    with torch.cuda.device(x.device):
+        _count(1)
+        check(_L.mu_maxpool2(_p(x), _p(dy), _p(dx), B, H, W, C, 2, _code(x), _stream(x)), "mu_maxpool2")
+
+
+@maxpool2_bwd_acc.register_fake
+def _(x, dy, dx):
+    return None
+
+
+class _MaxPool2Skip(torch.autograd.Function):
+    """MaxPool2d(2) of an activation that is also a U-Net skip connection (ade_semantic.py:301-312: x1, x2, x3 feed a
+    DownSample and, later, an UpSample's concat).  Returns (pooled, x_skip); the pooling gradient is added into the
+    skip gradient in place (see _Conv3x3Skip)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        ctx.set_materialize_grads(False)
+        return maxpool2(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        (x,) = ctx.saved_tensors
+        if dy is None:
+            return dskip
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        if _addable(dskip, x):
+            maxpool2_bwd_acc(x, dy, dskip)
+            return dskip
+        dx = maxpool2_bwd(x, dy)
+        return dx if dskip is None else dx + dskip
+
+
+def maxpool2_skip(x: Tensor) -> Tuple[Tensor, Tensor]:
+    return _MaxPool2Skip.apply(x)
 
 
 # ------------------------------------------------------------------ K10: bilinear x2 (align_corners) + concat
