@@ -25,6 +25,9 @@
 #ifndef MU_P1_STAGED_EPILOGUE
 #define MU_P1_STAGED_EPILOGUE 1
 #endif
+#ifndef MU_P2_STAGED_EPILOGUE
+#define MU_P2_STAGED_EPILOGUE 1
+#endif
 #ifndef MU_P1_NC_256
 #define MU_P1_NC_256 64
 #endif
@@ -61,7 +64,8 @@ struct P1Cfg {
 };
 
 template <int C>
-__global__ void __launch_bounds__(kGemmThreads, C == 256 ? 2 : 5)   // (64 registers: five of these short CTAs per SM)
+__global__ void __launch_bounds__(kGemmThreads, C == 256 ? 2 : (C == 128 ? 1 : 5))   // measured (tools/bench_qkv.py): 64 registers / five CTAs
+                                              // per SM at C = 64 (0.486 -> 0.464 ms), uncapped at C = 128 (80 registers: 0.288 ms, 0.349 capped)
 qkv_project_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                          const float* __restrict__ bias, const int32_t* __restrict__ rank,
                          __nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ kc,
@@ -326,6 +330,55 @@ qkv_dx_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
     const bool ok = tok < Mtot;
     const __nv_bfloat16* zrow = dz + (size_t)tok * C;
     __nv_bfloat16* orow = dxt + (size_t)tok * C;
+#if MU_P2_STAGED_EPILOGUE
+    // Coalesced epilogue (see P1): every MMA has completed when acc_full fires, so the operand ring is free and its first
+    // 8 KB stage the tile, 2 KB per warp.  Per 32-channel piece: dz rows arrive as 8 rows x 64 contiguous bytes per warp
+    // load, the row's owner adds its accumulator in fp32 and rounds once, the bf16 result leaves the same way.
+    const int lane = (int)lane_id();
+    const uint32_t stage = smem_u32(smem) + quad * 2048;
+    const uint32_t mine = stage + lane * 64, sw = (lane >> 1) & 3;
+    (void)zrow; (void)orow; (void)ok;
+    uint32_t v[32];
+    mbar_wait_relaxed(acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < C / 32; ++c) {
+      tmem_ld32(lane_base + c * 32, v);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = it * 8 + (lane >> 2), g = lane & 3;
+        const int trow = t0 + quad * 32 + row;
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (trow < Mtot) z = *reinterpret_cast<const float4*>(dz + (size_t)trow * C + c * 32 + g * 8);
+        st_shared_v4(stage + row * 64 + ((g ^ ((row >> 1) & 3)) << 4), __float_as_uint(z.x), __float_as_uint(z.y),
+                     __float_as_uint(z.z), __float_as_uint(z.w));
+      }
+      tmem_wait_ld();
+      __syncwarp();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t a = mine + ((g ^ sw) << 4);
+        const float4 zf = ld_shared_v4f(a);
+        const uint32_t zz[4] = {__float_as_uint(zf.x), __float_as_uint(zf.y), __float_as_uint(zf.z), __float_as_uint(zf.w)};
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float lo = __uint_as_float(zz[e] << 16), hi = __uint_as_float(zz[e] & 0xffff0000u);
+          w[e] = pack_bf16(__uint_as_float(v[8 * g + 2 * e]) + lo, __uint_as_float(v[8 * g + 2 * e + 1]) + hi);
+        }
+        st_shared_v4(a, w[0], w[1], w[2], w[3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = it * 8 + (lane >> 2), g = lane & 3;
+        const int trow = t0 + quad * 32 + row;
+        const float4 w = ld_shared_v4f(stage + row * 64 + ((g ^ ((row >> 1) & 3)) << 4));
+        if (trow < Mtot) *reinterpret_cast<float4*>(dxt + (size_t)trow * C + c * 32 + g * 8) = w;
+      }
+      __syncwarp();
+    }
+#else
     uint32_t v[32];
     mbar_wait_relaxed(acc_full, 0);
     tc_fence_after();
@@ -348,6 +401,7 @@ qkv_dx_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
         }
       }
     }
+  #endif
   }
   tc_fence_before();
   __syncthreads();

@@ -15,4 +15,9 @@ for B, N, C in ((256, 16384, 64), (256, 4096, 64), (256, 4096, 128), (256, 1024,
     _, n_keep, keep_idx, keep_rank = ops.mask_binarize(bits)
     ms = time_fn(lambda: ops.qkv_project(x, w, b, keep_rank, n_keep, True), iters=10, warm=3)
     nbytes = 2 * B * N * C * 2 + 2 * float(n_keep.sum()) * C * 2
-    print(json.dumps({"B": B, "N": N, "C": C, "qkv_project_ms": round(ms, 4), "GB/s": round(nbytes / ms / 1e6, 1)}), flush=True)
+    # backward: dx = dz + [dq|dk|dv] W (P2), dW (P3), db -- one C-ABI call, three kernels; token-space dq / dk / dv
+    dz, dq, dk, dv = (torch.randn(B, N, C, device=dev, generator=g).bfloat16() for _ in range(4))
+    ms_b = time_fn(lambda: ops.qkv_project_bwd(x, dz, dq, dk, dv, w, True), iters=10, warm=3)
+    nbytes_b = (4 + 1 + 4) * B * N * C * 2          # P2 reads dz, dq, dk, dv and writes dx; P3 + db read dq, dk, dv, x
+    print(json.dumps({"B": B, "N": N, "C": C, "qkv_project_ms": round(ms, 4), "GB/s": round(nbytes / ms / 1e6, 1),
+                      "qkv_project_bwd_ms": round(ms_b, 4), "bwd_GB/s": round(nbytes_b / ms_b / 1e6, 1)}), flush=True)
