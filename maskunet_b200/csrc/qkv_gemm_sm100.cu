@@ -64,7 +64,7 @@ struct P1Cfg {
 };
 
 template <int C>
-__global__ void __launch_bounds__(kGemmThreads, C == 256 ? 2 : (C == 128 ? 1 : 5))   // measured (tools/bench_qkv.py): 64 registers / five CTAs
+__global__ void __launch_bounds__(kGemmThreads, C == 256 ? 2 : (C == 128 ? 4 : 5))   // measured (tools/bench_qkv.py): 64 registers / five CTAs
                                               // per SM at C = 64 (0.486 -> 0.464 ms), uncapped at C = 128 (80 registers: 0.288 ms, 0.349 capped)
 qkv_project_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                          const float* __restrict__ bias, const int32_t* __restrict__ rank,
