@@ -39,7 +39,10 @@ enum mu_dtype { MU_F32 = 0, MU_BF16 = 1 };
 /* Layout of the module input x (and of dx): channel-major = NCHW as the reference holds it ([B, C, N]);
  * token-major = channels-last / NHWC ([B, N, C]), which is the reference's permuted token view (:168) in memory.
  * The CUDA-core kernels take channel-major x; the tcgen05 projection kernels take token-major bf16 x. */
-enum mu_layout { MU_X_CHANNEL_MAJOR = 0, MU_X_TOKEN_MAJOR = 1 };
+enum mu_layout { MU_X_CHANNEL_MAJOR = 0, MU_X_TOKEN_MAJOR = 1,
+                 /* mu_residual_ln_fwd / _bwd only: x token-major AND y / dy in the layout the channels-last network
+                  * holds the module's re-viewed result in (see mu_residual_ln_fwd) */
+                 MU_X_TOKEN_MAJOR_VIEW = 2 };
 
 enum mu_status {
   MU_OK = 0,
@@ -110,7 +113,11 @@ int mu_attn_bwd_cudacore(const void* q, const void* kc, const void* vc, const in
 
 /* K3 epilogue. Residual + LayerNorm over channels (:187-188), output in the [B, N, C] layout that the
  * module returns re-viewed as [B, C, H, W] (:190).
- *   y T [B, N, C] = LN_C(o + x^T) * gamma + beta;  mean, rstd f32 [B, N] saved for backward. */
+ *   y T [B, N, C] = LN_C(o + x^T) * gamma + beta;  mean, rstd f32 [B, N] saved for backward.
+ * x_layout = MU_X_TOKEN_MAJOR_VIEW (MU_BF16, C in {64, 128, 256}, N % C == 0): y is written as the channels-last memory
+ *   [B, H*W, C] of that re-viewed [B, C, H, W] tensor, i.e. y_view[b, p, c] = y[b].flat[c N + p] -- the transpose pass
+ *   between the module and the next convolution is done inside the kernel; mu_residual_ln_bwd takes dy in the same
+ *   layout.  Values are bit-identical to MU_X_TOKEN_MAJOR followed by mu_transpose. */
 int mu_residual_ln_fwd(const void* o, const void* x, const float* gamma, const float* beta, float eps, void* y,
                        float* mean, float* rstd, int32_t B, int32_t C, int32_t N, int32_t dtype, int32_t x_layout,
                        mu_stream_t stream);

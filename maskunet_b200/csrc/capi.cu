@@ -185,8 +185,8 @@ int mu_residual_ln_fwd(const void* o, const void* x, const float* gamma, const f
   int rc;
   if ((rc = check_common("mu_residual_ln_fwd", B, C, N, dtype))) return rc;
   MU_PTRS("mu_residual_ln_fwd", o, x, gamma, beta, y, mean, rstd);
-  return launch_residual_ln_fwd(o, x, gamma, beta, eps, y, mean, rstd, B, C, N, dtype, x_layout == MU_X_TOKEN_MAJOR,
-                                (cudaStream_t)stream);
+  return launch_residual_ln_fwd(o, x, gamma, beta, eps, y, mean, rstd, B, C, N, dtype,
+                                x_layout == MU_X_TOKEN_MAJOR_VIEW ? 2 : x_layout == MU_X_TOKEN_MAJOR, (cudaStream_t)stream);
 }
 
 int mu_residual_ln_bwd(const void* dy, const void* o, const void* x, const float* mean, const float* rstd,
@@ -196,7 +196,7 @@ int mu_residual_ln_bwd(const void* dy, const void* o, const void* x, const float
   if ((rc = check_common("mu_residual_ln_bwd", B, C, N, dtype))) return rc;
   MU_PTRS("mu_residual_ln_bwd", dy, o, x, mean, rstd, gamma, dz, delta, dgamma, dbeta);
   return launch_residual_ln_bwd(dy, o, x, mean, rstd, gamma, dz, delta, dgamma, dbeta, B, C, N, dtype,
-                                x_layout == MU_X_TOKEN_MAJOR, (cudaStream_t)stream);
+                                x_layout == MU_X_TOKEN_MAJOR_VIEW ? 2 : x_layout == MU_X_TOKEN_MAJOR, (cudaStream_t)stream);
 }
 
 int mu_attn_bwd_cudacore(const void* q, const void* kc, const void* vc, const int32_t* n_keep,

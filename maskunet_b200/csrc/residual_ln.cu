@@ -242,6 +242,55 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_fwd_tok_kernel(
   }
 }
 
+// Per-channel parameter gradients of a CTA: lanes with the same channel group inside the warp first, then the CTA, then
+// the grid (float atomics, or -- deterministic mode -- one partial per CTA added in CTA order by the last one).
+template <int C>
+__device__ __forceinline__ void ln_param_grads(float (&dg)[8], float (&db)[8], float* red, float* __restrict__ dgamma,
+                                               float* __restrict__ dbeta, const DetCtx& det) {
+  constexpr int LPT = C / 8;
+  const int g = threadIdx.x % LPT;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+#pragma unroll
+    for (int off = 16; off >= LPT; off >>= 1) {
+      dg[e] += __shfl_xor_sync(0xffffffffu, dg[e], off);
+      db[e] += __shfl_xor_sync(0xffffffffu, db[e], off);
+    }
+  }
+  __syncthreads();
+  if (!det.on()) {
+    if ((threadIdx.x & 31) < LPT) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(red + g * 8 + e, dg[e]);
+        atomicAdd(red + C + g * 8 + e, db[e]);
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kLnThreads) {
+      atomicAdd(dgamma + c, red[c]);
+      atomicAdd(dbeta + c, red[C + c]);
+    }
+  } else {
+    // deterministic mode: the warps add their channel-group totals one after the other (lanes < LPT of a warp own
+    // distinct channel groups, or -- when a warp holds several tokens -- the xor-reduction above already merged them),
+    // every CTA stores its totals, the last CTA adds the slices in CTA order
+    for (int w = 0; w < kLnThreads / 32; ++w) {
+      if ((int)(threadIdx.x >> 5) == w && (threadIdx.x & 31) < LPT) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          red[g * 8 + e] += dg[e];
+          red[C + g * 8 + e] += db[e];
+        }
+      }
+      __syncthreads();
+    }
+    float* part = det.partial + (size_t)blockIdx.x * 2 * C;
+    for (int c = threadIdx.x; c < 2 * C; c += kLnThreads) part[c] = red[c];
+    det_finish(det, gridDim.x, gridDim.x, 2, C, C, dgamma, dbeta, threadIdx.x, kLnThreads, SyncThreads());
+  }
+}
+
 template <int C>
 __global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_tok_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ x,
@@ -308,47 +357,186 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_tok_kernel(
       if (ok && g == 0) delta[t] = dl;
     }
   }
-  // per-channel parameter gradients: lanes with the same channel group inside the warp first, then the CTA
+  ln_param_grads<C>(dg, db, red, dgamma, dbeta, det);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// VIEW variants: the module returns its [B, N, C] result RE-VIEWED as [B, C, H, W] (ade_semantic.py:190: .view, not
+// .permute), and the channels-last network around it wants that tensor as [B, H, W, C] memory.  Element (token n, channel
+// ch) of the result has flat index f = n C + ch in its sample and therefore is channel c = f / N, pixel p = f % N of
+// the view.  With N = k C:  n = c k + j,  p = j C + ch  -- the C x C block of tokens {c k + j : c} (fixed j) is the
+// TRANSPOSE of the C x C block of pixels {j C + ch : ch} of the channels-last view.  A CTA tile is 64 of those tokens
+// (c = c0 .. c0 + 63) x all C channels: normalised per token exactly as above, written to shared memory transposed
+// ([channel][64 tokens] bf16, 16-byte chunks XOR-swizzled by the channel group: conflict-free 2-byte stores and 16-byte
+// loads), then stored as C rows of 128 contiguous bytes.  This replaces a separate transpose pass over y (and, in the
+// backward, over dy): same values bit for bit, two tensor passes fewer per direction.
+constexpr int kViewTokens = 64;
+
+template <int C>
+__global__ void __launch_bounds__(kLnThreads) residual_ln_fwd_view_kernel(
+    const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
+    float* __restrict__ rstd, int B, int N) {
+  constexpr int LPT = C / 8, TPP = kLnThreads / LPT, PASSES = kViewTokens / TPP;   // tokens per pass, passes per tile
+  constexpr int CB = C / 64;                                                       // 64-token blocks along c
+  __shared__ __align__(16) uint16_t tt[C * kViewTokens];
+  const int g = threadIdx.x % LPT, tl = threadIdx.x / LPT;
+  float gm[8], bt[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-#pragma unroll
-    for (int off = 16; off >= LPT; off >>= 1) {
-      dg[e] += __shfl_xor_sync(0xffffffffu, dg[e], off);
-      db[e] += __shfl_xor_sync(0xffffffffu, db[e], off);
-    }
+    gm[e] = gamma[g * 8 + e];
+    bt[e] = beta[g * 8 + e];
   }
-  __syncthreads();
-  if (!det.on()) {
-    if ((threadIdx.x & 31) < LPT) {
+  const int k = N / C, per_sample = k * CB;
+  const long total = (long)B * per_sample;
+  for (long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int b = (int)(tile / per_sample), r = (int)(tile - (long)b * per_sample);
+    const int j = r / CB, cblk = r - j * CB;
+    const long tok0 = (long)b * N + j;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        atomicAdd(red + g * 8 + e, dg[e]);
-        atomicAdd(red + C + g * 8 + e, db[e]);
+    for (int p0 = 0; p0 < PASSES; p0 += 4) {
+      uint4 uo[4], ux[4];
+#pragma unroll
+      for (int u = 0; u < 4 && p0 + u < PASSES; ++u) {
+        const long t = tok0 + (long)(cblk * 64 + (p0 + u) * TPP + tl) * k;
+        uo[u] = *reinterpret_cast<const uint4*>(o + t * C + g * 8);
+        ux[u] = *reinterpret_cast<const uint4*>(x + t * C + g * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < 4 && p0 + u < PASSES; ++u) {
+        const int i = (p0 + u) * TPP + tl;
+        const long t = tok0 + (long)(cblk * 64 + i) * k;
+        float a[8], bb[8], z[8];
+        unpack8(uo[u], a);
+        unpack8(ux[u], bb);
+        float sm = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          z[e] = a[e] + bb[e];
+          sm += z[e];
+        }
+        const float mu_ = group_sum<LPT>(sm) * (1.f / C);
+        float v = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = z[e] - mu_;
+          v = fmaf(d, d, v);
+        }
+        const float rs = rsqrtf(group_sum<LPT>(v) * (1.f / C) + eps);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) z[e] = fmaf((z[e] - mu_) * rs, gm[e], bt[e]);
+        const uint4 pk = pack8(z);
+        const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+        uint16_t* col = tt + (g * 8) * kViewTokens + ((((i >> 3) ^ (g & 7)) << 3) | (i & 7));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          col[(2 * e) * kViewTokens] = (uint16_t)(w[e] & 0xffffu);
+          col[(2 * e + 1) * kViewTokens] = (uint16_t)(w[e] >> 16);
+        }
+        if (g == 0) {
+          mean[t] = mu_;
+          rstd[t] = rs;
+        }
       }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += kLnThreads) {
-      atomicAdd(dgamma + c, red[c]);
-      atomicAdd(dbeta + c, red[C + c]);
+    __nv_bfloat16* yb = y + ((long)b * N + (long)j * C) * C + cblk * 64;
+    for (int idx = threadIdx.x; idx < C * 8; idx += kLnThreads) {
+      const int ch = idx >> 3, l = idx & 7;
+      const uint4 v = *reinterpret_cast<const uint4*>(tt + ch * kViewTokens + ((l ^ ((ch >> 3) & 7)) << 3));
+      *reinterpret_cast<uint4*>(yb + (long)ch * C + l * 8) = v;
     }
-  } else {
-    // deterministic mode: the warps add their channel-group totals one after the other (lanes < LPT of a warp own
-    // distinct channel groups, or -- when a warp holds several tokens -- the xor-reduction above already merged them),
-    // every CTA stores its totals, the last CTA adds the slices in CTA order
-    for (int w = 0; w < kLnThreads / 32; ++w) {
-      if ((int)(threadIdx.x >> 5) == w && (threadIdx.x & 31) < LPT) {
+    __syncthreads();
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_view_kernel(
+    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ x,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+    __nv_bfloat16* __restrict__ dz, float* __restrict__ delta, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    int B, int N, const DetCtx det) {
+  constexpr int LPT = C / 8, TPP = kLnThreads / LPT, PASSES = kViewTokens / TPP, CB = C / 64;
+  __shared__ __align__(16) uint16_t tt[C * kViewTokens];
+  __shared__ float red[2 * C];
+  const int g = threadIdx.x % LPT, tl = threadIdx.x / LPT;
+  for (int i = threadIdx.x; i < 2 * C; i += kLnThreads) red[i] = 0.f;
+  float gm[8], dg[8], db[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    gm[e] = gamma[g * 8 + e];
+    dg[e] = db[e] = 0.f;
+  }
+  const int k = N / C, per_sample = k * CB;
+  const long total = (long)B * per_sample;
+  for (long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int b = (int)(tile / per_sample), r = (int)(tile - (long)b * per_sample);
+    const int j = r / CB, cblk = r - j * CB;
+    const long tok0 = (long)b * N + j;
+    // dy of the view, channels-last: C rows (pixels j C + ch) of 64 contiguous channels c -> [ch][64 tokens]
+    const __nv_bfloat16* dyb = dy + ((long)b * N + (long)j * C) * C + cblk * 64;
+    for (int idx = threadIdx.x; idx < C * 8; idx += kLnThreads) {
+      const int ch = idx >> 3, l = idx & 7;
+      *reinterpret_cast<uint4*>(tt + ch * kViewTokens + ((l ^ ((ch >> 3) & 7)) << 3)) =
+          *reinterpret_cast<const uint4*>(dyb + (long)ch * C + l * 8);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p0 = 0; p0 < PASSES; p0 += 4) {
+      uint4 uo[4], ux[4];
+      float mu_[4], rs[4];
+#pragma unroll
+      for (int u = 0; u < 4 && p0 + u < PASSES; ++u) {
+        const long t = tok0 + (long)(cblk * 64 + (p0 + u) * TPP + tl) * k;
+        uo[u] = *reinterpret_cast<const uint4*>(o + t * C + g * 8);
+        ux[u] = *reinterpret_cast<const uint4*>(x + t * C + g * 8);
+        mu_[u] = mean[t];
+        rs[u] = rstd[t];
+      }
+#pragma unroll
+      for (int u = 0; u < 4 && p0 + u < PASSES; ++u) {
+        const int i = (p0 + u) * TPP + tl;
+        const long t = tok0 + (long)(cblk * 64 + i) * k;
+        float d[8], ov[8], xv[8], zh[8], gg[8];
+        const uint16_t* col = tt + (g * 8) * kViewTokens + ((((i >> 3) ^ (g & 7)) << 3) | (i & 7));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] = __uint_as_float((uint32_t)col[e * kViewTokens] << 16);
+        unpack8(uo[u], ov);
+        unpack8(ux[u], xv);
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          red[g * 8 + e] += dg[e];
-          red[C + g * 8 + e] += db[e];
+          zh[e] = (ov[e] + xv[e] - mu_[u]) * rs[u];
+          gg[e] = d[e] * gm[e];
+          dg[e] = fmaf(d[e], zh[e], dg[e]);
+          db[e] += d[e];
+          s1 += gg[e];
+          s2 = fmaf(gg[e], zh[e], s2);
         }
+        s1 = group_sum<LPT>(s1) * (1.f / C);
+        s2 = group_sum<LPT>(s2) * (1.f / C);
+        float rr_[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) rr_[e] = rs[u] * (gg[e] - s1 - zh[e] * s2);
+        const uint4 packed = pack8(rr_);
+        *reinterpret_cast<uint4*>(dz + t * C + g * 8) = packed;
+        float rr[8], dl = 0.f;
+        unpack8(packed, rr);                                    // delta uses the stored (rounded) gradient
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dl = fmaf(rr[e], ov[e], dl);
+        dl = group_sum<LPT>(dl);
+        if (g == 0) delta[t] = dl;
       }
-      __syncthreads();
     }
-    float* part = det.partial + (size_t)blockIdx.x * 2 * C;
-    for (int c = threadIdx.x; c < 2 * C; c += kLnThreads) part[c] = red[c];
-    det_finish(det, gridDim.x, gridDim.x, 2, C, C, dgamma, dbeta, threadIdx.x, kLnThreads, SyncThreads());
+    __syncthreads();
   }
+  ln_param_grads<C>(dg, db, red, dgamma, dbeta, det);
+}
+
+static int ln_view_grid(int B, int N, int C, bool reduce = false) {
+  const long tiles = (long)B * (N / C) * (C / 64);
+  const long cap = (reduce && get_deterministic()) ? 148L : 148L * (C == 256 ? 4 : 8);
+  return (int)(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
 }
 
 static int ln_tok_grid(long M, int C, bool reduce = false) {
@@ -391,6 +579,18 @@ static int run_bwd(const void* dy, const void* o, const void* x, const float* me
 
 int launch_residual_ln_fwd(const void* o, const void* x, const float* gamma, const float* beta, float eps, void* y,
                            float* mean, float* rstd, int B, int C, int N, int dtype, int tok, cudaStream_t s) {
+  if (tok == 2) {
+    MU_REQUIRE(dtype == MU_BF16 && (C == 64 || C == 128 || C == 256) && N % C == 0, MU_ERR_BAD_SHAPE,
+               "residual_ln_fwd: the re-viewed channels-last output needs bf16, C in {64, 128, 256} and N %% C == 0 "
+               "(C=%d N=%d dtype=%d)", C, N, dtype);
+    const int grid = ln_view_grid(B, N, C);
+#define MU_LN_FWDV(CC)                                                                                                 \
+  residual_ln_fwd_view_kernel<CC><<<grid, kLnThreads, 0, s>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)x, gamma, \
+                                                              beta, eps, (__nv_bfloat16*)y, mean, rstd, B, N)
+    if (C == 64) MU_LN_FWDV(64); else if (C == 128) MU_LN_FWDV(128); else MU_LN_FWDV(256);
+#undef MU_LN_FWDV
+    return check_launch("residual_ln_fwd_view");
+  }
   if (dtype == MU_BF16 && tok && (C == 64 || C == 128 || C == 256)) {
     const long M = (long)B * N;
     const int grid = ln_tok_grid(M, C);
@@ -407,6 +607,21 @@ int launch_residual_ln_fwd(const void* o, const void* x, const float* gamma, con
 int launch_residual_ln_bwd(const void* dy, const void* o, const void* x, const float* mean, const float* rstd,
                            const float* gamma, void* dz, float* delta, float* dgamma, float* dbeta, int B, int C, int N,
                            int dtype, int tok, cudaStream_t s) {
+  if (tok == 2) {
+    MU_REQUIRE(dtype == MU_BF16 && (C == 64 || C == 128 || C == 256) && N % C == 0, MU_ERR_BAD_SHAPE,
+               "residual_ln_bwd: the re-viewed channels-last gradient needs bf16, C in {64, 128, 256} and N %% C == 0 "
+               "(C=%d N=%d dtype=%d)", C, N, dtype);
+    const int grid = ln_view_grid(B, N, C, true);
+    DetCtx det;
+    if (!det_context(kDetSlotLn, (size_t)grid * 2 * C, &det, "residual_ln_bwd")) return MU_ERR_WORKSPACE;
+#define MU_LN_BWDV(CC)                                                                                                \
+  residual_ln_bwd_view_kernel<CC><<<grid, kLnThreads, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)o,       \
+                                                              (const __nv_bfloat16*)x, mean, rstd, gamma,             \
+                                                              (__nv_bfloat16*)dz, delta, dgamma, dbeta, B, N, det)
+    if (C == 64) MU_LN_BWDV(64); else if (C == 128) MU_LN_BWDV(128); else MU_LN_BWDV(256);
+#undef MU_LN_BWDV
+    return check_launch("residual_ln_bwd_view");
+  }
   if (dtype == MU_BF16 && tok && (C == 64 || C == 128 || C == 256)) {
     const long M = (long)B * N;
     const int grid = ln_tok_grid(M, C, true);

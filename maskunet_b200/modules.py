@@ -114,12 +114,16 @@ class Mask2FormerAttention(nn.Module):
             w_qkv, b_qkv = _inference_cache(self, "_mu_qkv_operand", (self.query.weight, self.key.weight,
                                                                     self.value.weight, self.query.bias,
                                                                     self.key.bias, self.value.bias), pack)
+        # channels-last in, channels-last out: the re-view of :190 (the [B, N, C] buffer read as [B, C, H, W]) stored
+        # channels-last is a transpose of the [C, N] view of each sample; the LayerNorm kernels do it on the way out
+        # (and on the way in, for the gradient) when the geometry allows, a separate transpose pass otherwise
+        view_out = (channels_last_in and token_major and channels in (64, 128, 256) and n_tok % channels == 0
+                    and os.environ.get("MASKUNET_LN_VIEW", "1") != "0")
         y = ops.mask_attention(tokens, w_qkv, b_qkv, self.norm.weight.float(), self.norm.bias.float(),
-                               keep_rank, keep_idx, n_keep, self.norm.eps, token_major)[0]
+                               keep_rank, keep_idx, n_keep, self.norm.eps, token_major, view_out)[0]
         if channels_last_in:
-            # same logical result as :190 (the [B, N, C] buffer re-viewed as [B, C, H, W]), stored channels-last
-            # so the next convolution needs no layout conversion
-            y = ops.transpose(y.view(batch, channels, n_tok))
+            if not view_out:
+                y = ops.transpose(y.view(batch, channels, n_tok))
             return y.view(batch, height, width, channels).permute(0, 3, 1, 2)
         return y.view(batch, channels, height, width)                               # :190
 

@@ -213,8 +213,8 @@ def attn_bwd_cudacore(q, kc, vc, n_keep, keep_idx, d_o, lse, delta):
 
 # ------------------------------------------------------------------ K3 epilogue / K4
 @torch.library.custom_op("maskunet::residual_ln_fwd", mutates_args=(), device_types="cuda")
-def residual_ln_fwd(o: Tensor, x: Tensor, gamma: Tensor, beta: Tensor, eps: float, token_major: bool
-                    ) -> Tuple[Tensor, Tensor, Tensor]:
+def residual_ln_fwd(o: Tensor, x: Tensor, gamma: Tensor, beta: Tensor, eps: float, token_major: bool,
+                    view_out: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     _cuda(o, x, gamma, beta)
     B, N, C = o.shape
     y = torch.empty_like(o)
@@ -223,19 +223,20 @@ def residual_ln_fwd(o: Tensor, x: Tensor, gamma: Tensor, beta: Tensor, eps: floa
     with torch.cuda.device(o.device):
         _count(1)
         check(_L.mu_residual_ln_fwd(_p(o), _p(x), _p(gamma), _p(beta), eps, _p(y), _p(mean), _p(rstd),
-                                    B, C, N, _code(o), int(token_major), _stream(o)), "mu_residual_ln_fwd")
+                                    B, C, N, _code(o), 2 if view_out else int(token_major), _stream(o)),
+              "mu_residual_ln_fwd")
     return y, mean, rstd
 
 
 @residual_ln_fwd.register_fake
-def _(o, x, gamma, beta, eps, token_major):
+def _(o, x, gamma, beta, eps, token_major, view_out=False):
     s = o.new_empty(o.shape[:2], dtype=torch.float32)
     return torch.empty_like(o), s, torch.empty_like(s)
 
 
 @torch.library.custom_op("maskunet::residual_ln_bwd", mutates_args=(), device_types="cuda")
-def residual_ln_bwd(dy: Tensor, o: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, token_major: bool
-                    ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+def residual_ln_bwd(dy: Tensor, o: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, token_major: bool,
+                    view_out: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     _cuda(dy, o, x, mean, rstd, gamma)
     B, N, C = o.shape
     dz = torch.empty_like(o)
@@ -245,13 +246,14 @@ def residual_ln_bwd(dy: Tensor, o: Tensor, x: Tensor, mean: Tensor, rstd: Tensor
     with torch.cuda.device(o.device):
         _count(1)
         check(_L.mu_residual_ln_bwd(_p(dy), _p(o), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dz), _p(delta),
-                                    _p(dgamma), _p(dbeta), B, C, N, _code(o), int(token_major), _stream(o)),
+                                    _p(dgamma), _p(dbeta), B, C, N, _code(o), 2 if view_out else int(token_major),
+                                    _stream(o)),
               "mu_residual_ln_bwd")
     return dz, delta, dgamma, dbeta
 
 
 @residual_ln_bwd.register_fake
-def _(dy, o, x, mean, rstd, gamma, token_major):
+def _(dy, o, x, mean, rstd, gamma, token_major, view_out=False):
     C = o.shape[-1]
     return (torch.empty_like(o), o.new_empty(o.shape[:2], dtype=torch.float32),
             o.new_empty((C,), dtype=torch.float32), o.new_empty((C,), dtype=torch.float32))
@@ -1075,17 +1077,20 @@ def mean_iou(y_pred: Tensor, y_true: Tensor, num_classes: int, smooth: float = 1
 # ------------------------------------------------------------------ the module-level op (A3-A9 of SURVEY.md 8(a))
 @torch.library.custom_op("maskunet::mask_attention", mutates_args=(), device_types="cuda")
 def mask_attention(x: Tensor, w_qkv: Tensor, b_qkv: Tensor, gamma: Tensor, beta: Tensor, keep_rank: Tensor,
-                   keep_idx: Tensor, n_keep: Tensor, eps: float, token_major: bool
+                   keep_idx: Tensor, n_keep: Tensor, eps: float, token_major: bool, view_out: bool = False
                    ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """y [B, N, C] = LN_C(softmax(QK^T/sqrt(C) + mask) V + tokens); also returns what backward needs."""
+    """y [B, N, C] = LN_C(softmax(QK^T/sqrt(C) + mask) V + tokens); also returns what backward needs.
+    ``view_out`` (bf16 token-major, N % C == 0): y comes back as the channels-last memory of the module's re-viewed
+    result, y[b, p, c] = result[b].flat[c N + p] (ade_semantic.py:190), and the backward takes its gradient likewise --
+    the transpose passes between the module and the convolutions around it happen inside the LayerNorm kernels."""
     q, kc, vc = qkv_project(x, w_qkv, b_qkv, keep_rank, n_keep, token_major)
     o, lse = attn_fwd(q, kc, vc, n_keep)
-    y, mean, rstd = residual_ln_fwd(o, x, gamma, beta, eps, token_major)
+    y, mean, rstd = residual_ln_fwd(o, x, gamma, beta, eps, token_major, view_out)
     return y, q, kc, vc, o, lse, mean, rstd
 
 
 @mask_attention.register_fake
-def _(x, w_qkv, b_qkv, gamma, beta, keep_rank, keep_idx, n_keep, eps, token_major):
+def _(x, w_qkv, b_qkv, gamma, beta, keep_rank, keep_idx, n_keep, eps, token_major, view_out=False):
     B, C, N = _bnc(x, token_major)
     f32 = dict(dtype=torch.float32)
     return (x.new_empty((B, N, C)), x.new_empty((B, N, C)), x.new_empty((B, nkp_of(N), C)),
@@ -1096,15 +1101,15 @@ def _(x, w_qkv, b_qkv, gamma, beta, keep_rank, keep_idx, n_keep, eps, token_majo
 @torch.library.custom_op("maskunet::mask_attention_bwd", mutates_args=(), device_types="cuda")
 def mask_attention_bwd(dy: Tensor, x: Tensor, w_qkv: Tensor, gamma: Tensor, keep_idx: Tensor, n_keep: Tensor,
                        q: Tensor, kc: Tensor, vc: Tensor, o: Tensor, lse: Tensor, mean: Tensor, rstd: Tensor,
-                       token_major: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
-    dz, delta, dgamma, dbeta = residual_ln_bwd(dy, o, x, mean, rstd, gamma, token_major)
+                       token_major: bool, view_out: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    dz, delta, dgamma, dbeta = residual_ln_bwd(dy, o, x, mean, rstd, gamma, token_major, view_out)
     dq, dk, dv = attn_bwd(q, kc, vc, n_keep, keep_idx, dz, lse, delta)
     dx, dw, db = qkv_project_bwd(x, dz, dq, dk, dv, w_qkv, token_major)
     return dx, dw, db, dgamma, dbeta
 
 
 @mask_attention_bwd.register_fake
-def _(dy, x, w_qkv, gamma, keep_idx, n_keep, q, kc, vc, o, lse, mean, rstd, token_major):
+def _(dy, x, w_qkv, gamma, keep_idx, n_keep, q, kc, vc, o, lse, mean, rstd, token_major, view_out=False):
     C = w_qkv.shape[1]
     f32 = dict(dtype=torch.float32)
     return (torch.empty_like(x), x.new_empty((3 * C, C), **f32), x.new_empty((3 * C,), **f32),
@@ -1113,17 +1118,18 @@ def _(dy, x, w_qkv, gamma, keep_idx, n_keep, q, kc, vc, o, lse, mean, rstd, toke
 
 def _ma_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)   # unused outputs get None, not dense zero gradients
-    x, w_qkv, b_qkv, gamma, beta, keep_rank, keep_idx, n_keep, eps, token_major = inputs
+    x, w_qkv, b_qkv, gamma, beta, keep_rank, keep_idx, n_keep, eps, token_major = inputs[:10]
     y, q, kc, vc, o, lse, mean, rstd = output
     ctx.token_major = token_major
+    ctx.view_out = bool(inputs[10]) if len(inputs) > 10 else False
     ctx.save_for_backward(x, w_qkv, gamma, keep_idx, n_keep, q, kc, vc, o, lse, mean, rstd)
 
 
 def _ma_backward(ctx, dy, *unused):
     x, w_qkv, gamma, keep_idx, n_keep, q, kc, vc, o, lse, mean, rstd = ctx.saved_tensors
     dx, dw, db, dgamma, dbeta = mask_attention_bwd(dy.contiguous(), x, w_qkv, gamma, keep_idx, n_keep,
-                                                   q, kc, vc, o, lse, mean, rstd, ctx.token_major)
-    return dx, dw, db, dgamma, dbeta, None, None, None, None, None
+                                                   q, kc, vc, o, lse, mean, rstd, ctx.token_major, ctx.view_out)
+    return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None
 
 
 mask_attention.register_autograd(_ma_backward, setup_context=_ma_setup)

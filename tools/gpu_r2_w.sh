@@ -1,0 +1,16 @@
+#!/bin/bash
+# fused LayerNorm + re-view transposes: tests, then an A/B of the default bench
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_ln_view.py tests/test_gpu_attention.py tests/test_gpu_network_parity.py tests/test_gpu_unet.py tests/test_gpu_skip_grads.py -m gpu -q -x 2>&1 | tail -8
+J() { python - "$1" "$2" <<'PY'
+import json, sys
+r=[json.loads(l) for l in open(sys.argv[2]) if l.startswith("{")][-1]
+roof=r.get("roofline") or {}
+print(sys.argv[1], "ms", round(r["ms_per_step"],2), "value", round(r["value"],1), "e2e", round(r["e2e"]["value"],1), "launches", r.get("gpu_launches"), "sm_mhz", (r.get("clocks") or {}).get("sm_mhz"), "roof", roof.get("frac") and round(roof["frac"],3), roof.get("kernel_ms") and round(roof["kernel_ms"],2), "loss", r["e2e"].get("last_loss"))
+PY
+}
+for i in 1 2; do
+  for f in 1 0; do
+    MASKUNET_LN_VIEW=$f timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_lnview${f}_$i.json 2>gpurun_out/ab_lnview.err; J lnview$f gpurun_out/ab_lnview${f}_$i.json
+  done
+done
