@@ -233,6 +233,169 @@ __global__ void __launch_bounds__(256) upcat_bwd_kernel(const T* __restrict__ do
   }
 }
 
+// ---- power-of-two shapes (every U-Net call): the two halves of the concat as separate, warp-uniform index ranges with
+// several independent 16-byte loads in flight per thread.  The single-range kernels above mix copy lanes and
+// interpolation lanes in every warp and keep one load -> store chain per thread: 3.1-3.3 TB/s at [256, 64 + 64, 128, 128]
+// (tools/step_breakdown.py); same arithmetic in the same order here, so results are bit-identical.
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 a;
+  __device__ __forceinline__ void ld(const __nv_bfloat16* p) { a = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void st(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = a; }
+  __device__ __forceinline__ void f32(float (&v)[8]) const {
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] = __uint_as_float(w[e] << 16);
+      v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+    }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void ld(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void st(float* p) const {
+    *reinterpret_cast<float4*>(p) = a;
+    *reinterpret_cast<float4*>(p + 4) = b;
+  }
+  __device__ __forceinline__ void f32(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+// dst[pix, dst_off + g*8 ..] = src[pix, src_off + g*8 ..] for G = 2^lg channel groups per pixel, four vectors in flight
+template <typename T>
+__device__ __forceinline__ void copy_channel_slab(const T* __restrict__ src, int src_pitch, int src_off, T* __restrict__ dst,
+                                                  int dst_pitch, int dst_off, unsigned n, int lg) {
+  const unsigned stride = gridDim.x * blockDim.x, mask = (1u << lg) - 1u;
+  for (unsigned base = blockIdx.x * blockDim.x + threadIdx.x; base < n; base += 4u * stride) {
+    Raw8<T> v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned i = base + u * stride;
+      if (i < n) v[u].ld(src + (size_t)(i >> lg) * src_pitch + src_off + (i & mask) * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned i = base + u * stride;
+      if (i < n) v[u].st(dst + (size_t)(i >> lg) * dst_pitch + dst_off + (i & mask) * 8);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upcat_fwd_split_kernel(const T* __restrict__ skip, const T* __restrict__ x,
+                                                              T* __restrict__ out, int B, int H, int W, int Cs, int Cx) {
+  const int H2 = 2 * H, W2 = 2 * W, Ct = Cs + Cx, Gx = Cx / 8;
+  const unsigned n_pix = (unsigned)B * H2 * W2;
+  copy_channel_slab<T>(skip, Cs, 0, out, Ct, 0, n_pix * (Cs / 8), ilog2_u(Cs / 8));
+  const float rh = H2 > 1 ? (float)(H - 1) / (H2 - 1) : 0.f, rw = W2 > 1 ? (float)(W - 1) / (W2 - 1) : 0.f;
+  const int lg = ilog2_u(Gx), lw = ilog2_u(W2), lh = ilog2_u(H2);
+  const unsigned n_up = n_pix * Gx, stride = gridDim.x * blockDim.x;
+  for (unsigned base = blockIdx.x * blockDim.x + threadIdx.x; base < n_up; base += 2u * stride) {
+    Raw8<T> a[2], bq[2], c[2], d[2];
+    float h0l[2], h1l[2], w0l[2], w1l[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned i = base + u * stride;
+      if (i < n_up) {
+        const int g = i & (Gx - 1), w2 = (i >> lg) & (W2 - 1), h2 = (i >> (lg + lw)) & (H2 - 1), b = i >> (lg + lw + lh);
+        int h1, hp, w1, wp;
+        src_index(h2, rh, H, h1, hp, h0l[u], h1l[u]);
+        src_index(w2, rw, W, w1, wp, w0l[u], w1l[u]);
+        const long p0 = (((long)b * H + h1) * W + w1) * Cx + g * 8;
+        a[u].ld(x + p0);
+        bq[u].ld(x + p0 + (long)wp * Cx);
+        c[u].ld(x + p0 + (long)hp * W * Cx);
+        d[u].ld(x + p0 + (long)hp * W * Cx + (long)wp * Cx);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned i = base + u * stride;
+      if (i < n_up) {
+        float o[8], fa[8], fb[8], fc[8], fd[8];
+        a[u].f32(fa);
+        bq[u].f32(fb);
+        c[u].f32(fc);
+        d[u].f32(fd);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          o[e] = h0l[u] * (w0l[u] * fa[e] + w1l[u] * fb[e]) + h1l[u] * (w0l[u] * fc[e] + w1l[u] * fd[e]);
+        V8<T>::store(out + (size_t)(i >> lg) * Ct + Cs + (i & (Gx - 1)) * 8, o);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upcat_bwd_split_kernel(const T* __restrict__ dout, T* __restrict__ dskip,
+                                                              T* __restrict__ dx, int B, int H, int W, int Cs, int Cx) {
+  const int H2 = 2 * H, W2 = 2 * W, Ct = Cs + Cx, Gx = Cx / 8;
+  copy_channel_slab<T>(dout, Ct, 0, dskip, Cs, 0, (unsigned)B * H2 * W2 * (Cs / 8), ilog2_u(Cs / 8));
+  const float rh = H2 > 1 ? (float)(H - 1) / (H2 - 1) : 0.f, rw = W2 > 1 ? (float)(W - 1) / (W2 - 1) : 0.f;
+  const int lg = ilog2_u(Gx), lw = ilog2_u(W), lh = ilog2_u(H);
+  const unsigned n_x = (unsigned)B * H * W * Gx, stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_x; i += stride) {
+    const int g = i & (Gx - 1), w = (i >> lg) & (W - 1), h = (i >> (lg + lw)) & (H - 1), b = i >> (lg + lw + lh);
+    // weights of the five candidate output rows / columns 2h - 2 .. 2h + 2 (zero: no tap of that row lands on h)
+    float wh[5], ww[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int h2 = 2 * h - 2 + k, w2 = 2 * w - 2 + k;
+      wh[k] = ww[k] = 0.f;
+      if (h2 >= 0 && h2 < H2) {
+        int h1, hp;
+        float l0, l1;
+        src_index(h2, rh, H, h1, hp, l0, l1);
+        if (h1 == h) wh[k] += l0;
+        if (h1 + hp == h) wh[k] += l1;
+      }
+      if (w2 >= 0 && w2 < W2) {
+        int w1, wp;
+        float l0, l1;
+        src_index(w2, rw, W, w1, wp, l0, l1);
+        if (w1 == w) ww[k] += l0;
+        if (w1 + wp == w) ww[k] += l1;
+      }
+    }
+    float acc[8] = {};
+    const T* base = dout + (((long)b * H2 + (2 * h - 2)) * W2 + (2 * w - 2)) * Ct + Cs + g * 8;
+    // two candidate rows per round: up to ten independent loads in flight, accumulated in row / column order
+#pragma unroll
+    for (int k0 = 0; k0 < 5; k0 += 2) {
+      Raw8<T> v[2][5];
+#pragma unroll
+      for (int dk = 0; dk < 2; ++dk) {
+        const int k = k0 + dk;
+        if (k < 5 && wh[k < 5 ? k : 4] != 0.f) {
+#pragma unroll
+          for (int l = 0; l < 5; ++l)
+            if (ww[l] != 0.f) v[dk][l].ld(base + ((long)k * W2 + l) * Ct);
+        }
+      }
+#pragma unroll
+      for (int dk = 0; dk < 2; ++dk) {
+        const int k = k0 + dk;
+        if (k >= 5 || wh[k < 5 ? k : 4] == 0.f) continue;
+#pragma unroll
+        for (int l = 0; l < 5; ++l) {
+          if (ww[l] == 0.f) continue;
+          const float wgt = wh[k] * ww[l];
+          float f[8];
+          v[dk][l].f32(f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, f[e], acc[e]);
+        }
+      }
+    }
+    V8<T>::store(dx + (size_t)i * 8, acc);
+  }
+}
+
 // ============================================================================ K11: LayerNorm over (C, H, W) per sample
 // x, y: [B][L] with L = H*W*C in NHWC order; gamma / beta: f32 [L] in the same order.
 template <typename T>
@@ -765,6 +928,11 @@ int launch_maxpool2(const void* x, const void* dy, void* out, int B, int H, int 
   return check_launch("maxpool2");
 }
 
+static int spatial_split_mode() {        // MU_UPCAT_SPLIT=0 (environment, A/B runs and tests): the single-range kernels
+  const char* e = getenv("MU_UPCAT_SPLIT");
+  return e != nullptr ? atoi(e) : 1;
+}
+
 int launch_upcat_fwd(const void* skip, const void* x, void* out, int B, int H, int W, int Cs, int Cx, int dtype,
                      cudaStream_t s) {
   if (Cs % 8 || Cx % 8) {
@@ -775,7 +943,11 @@ int launch_upcat_fwd(const void* skip, const void* x, void* out, int B, int H, i
   const int grid = grid_for(total);
   auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
   const bool p2 = pow2((Cs + Cx) / 8) && pow2(Cs / 8) && pow2(Cx / 8) && pow2(H) && pow2(W) && total < (1L << 32);
-  if (p2) {
+  if (p2 && spatial_split_mode()) {
+    MU_T(dtype, (upcat_fwd_split_kernel<float><<<grid, 256, 0, s>>>((const float*)skip, (const float*)x, (float*)out, B, H, W, Cs, Cx)),
+         (upcat_fwd_split_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)skip, (const __nv_bfloat16*)x,
+                                                                     (__nv_bfloat16*)out, B, H, W, Cs, Cx)));
+  } else if (p2) {
     MU_T(dtype, (upcat_fwd_kernel<float, true><<<grid, 256, 0, s>>>((const float*)skip, (const float*)x, (float*)out, B, H, W, Cs, Cx)),
          (upcat_fwd_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)skip, (const __nv_bfloat16*)x,
                                                                      (__nv_bfloat16*)out, B, H, W, Cs, Cx)));
@@ -797,7 +969,11 @@ int launch_upcat_bwd(const void* dout, void* dskip, void* dx, int B, int H, int 
   const int grid = grid_for(total);
   auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
   const bool p2 = pow2(Cs / 8) && pow2(Cx / 8) && pow2(H) && pow2(W) && total < (1L << 32);
-  if (p2) {
+  if (p2 && spatial_split_mode()) {
+    MU_T(dtype, (upcat_bwd_split_kernel<float><<<grid, 256, 0, s>>>((const float*)dout, (float*)dskip, (float*)dx, B, H, W, Cs, Cx)),
+         (upcat_bwd_split_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dskip,
+                                                                     (__nv_bfloat16*)dx, B, H, W, Cs, Cx)));
+  } else if (p2) {
     MU_T(dtype, (upcat_bwd_kernel<float, true><<<grid, 256, 0, s>>>((const float*)dout, (float*)dskip, (float*)dx, B, H, W, Cs, Cx)),
          (upcat_bwd_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dskip,
                                                                      (__nv_bfloat16*)dx, B, H, W, Cs, Cx)));

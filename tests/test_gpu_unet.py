@@ -214,6 +214,39 @@ def test_upsample_concat_matches_torch(dtype, tol, H, W):
     assert float((sk.grad.float() - skr.grad).norm() / skr.grad.norm()) < tol
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 64, 64), (3, 128, 128, 32, 32), (2, 256, 256, 16, 16), (1, 16, 32, 1, 2),
+                                   (2, 8, 8, 2, 1)],
+                         ids=lambda s: "b%d_cs%d_cx%d_%dx%d" % s)
+def test_upsample_concat_split_kernels_bit_identical_and_match_torch(dtype, tol, shape, monkeypatch):
+    """Power-of-two shapes (every U-Net call) take the split-range kernels (skip copy and interpolation as separate
+    warp-uniform ranges): bit-identical to the single-range kernels (MU_UPCAT_SPLIT=0), both within tolerance of torch."""
+    from maskunet_b200 import ops
+    B, Cs, Cx, H, W = shape
+    torch.manual_seed(7)
+    x = _cl(torch.randn(B, Cx, H, W, device=DEV).to(dtype))
+    sk = _cl(torch.randn(B, Cs, 2 * H, 2 * W, device=DEV).to(dtype))
+    dy = _cl(torch.randn(B, Cs + Cx, 2 * H, 2 * W, device=DEV).to(dtype))
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MU_UPCAT_SPLIT", flag)
+        xq, sq = x.clone(memory_format=torch.preserve_format).requires_grad_(True), \
+            sk.clone(memory_format=torch.preserve_format).requires_grad_(True)
+        y = ops.upsample_concat(sq, xq)
+        y.backward(dy)
+        res[flag] = (y.detach(), xq.grad, sq.grad)
+    for a, b in zip(res["1"], res["0"]):
+        assert torch.equal(a, b)
+    xr, skr = x.float().requires_grad_(True), sk.float().requires_grad_(True)
+    up = torch.nn.functional.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=True)
+    yr = torch.cat([skr, up], 1)
+    yr.backward(dy.float())
+    y, gx, gs = res["1"]
+    assert float((y.float() - yr).norm() / yr.norm()) < tol
+    assert float((gx.float() - xr.grad).norm() / xr.grad.norm()) < tol
+    assert torch.equal(gs.float(), skr.grad)
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
 def test_sample_layernorm_matches_torch(dtype, tol):
     from maskunet_b200 import ops
