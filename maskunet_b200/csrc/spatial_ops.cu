@@ -364,32 +364,22 @@ __global__ void __launch_bounds__(256) upcat_bwd_split_kernel(const T* __restric
     }
     float acc[8] = {};
     const T* base = dout + (((long)b * H2 + (2 * h - 2)) * W2 + (2 * w - 2)) * Ct + Cs + g * 8;
-    // two candidate rows per round: up to ten independent loads in flight, accumulated in row / column order
+    // (two candidate rows per round, ten loads in flight, was measured slower: 80 registers, 0.98 against 0.90 ms per step)
 #pragma unroll
-    for (int k0 = 0; k0 < 5; k0 += 2) {
-      Raw8<T> v[2][5];
+    for (int k = 0; k < 5; ++k) {
+      if (wh[k] == 0.f) continue;
+      Raw8<T> v[5];
 #pragma unroll
-      for (int dk = 0; dk < 2; ++dk) {
-        const int k = k0 + dk;
-        if (k < 5 && wh[k < 5 ? k : 4] != 0.f) {
+      for (int l = 0; l < 5; ++l)
+        if (ww[l] != 0.f) v[l].ld(base + ((long)k * W2 + l) * Ct);
 #pragma unroll
-          for (int l = 0; l < 5; ++l)
-            if (ww[l] != 0.f) v[dk][l].ld(base + ((long)k * W2 + l) * Ct);
-        }
-      }
+      for (int l = 0; l < 5; ++l) {
+        if (ww[l] == 0.f) continue;
+        const float wgt = wh[k] * ww[l];
+        float f[8];
+        v[l].f32(f);
 #pragma unroll
-      for (int dk = 0; dk < 2; ++dk) {
-        const int k = k0 + dk;
-        if (k >= 5 || wh[k < 5 ? k : 4] == 0.f) continue;
-#pragma unroll
-        for (int l = 0; l < 5; ++l) {
-          if (ww[l] == 0.f) continue;
-          const float wgt = wh[k] * ww[l];
-          float f[8];
-          v[dk][l].f32(f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, f[e], acc[e]);
-        }
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(wgt, f[e], acc[e]);
       }
     }
     V8<T>::store(dx + (size_t)i * 8, acc);
