@@ -5,11 +5,14 @@
 // One CTA owns one 128-key tile j of one sample (compacted kept keys) and walks over all query tiles i:
 //   MMA1  S^T  = K_j  Q_i^T            [128 keys x BM queries]   TMEM
 //   MMA2  dP^T = V_j  dO_i^T           [128 x BM]                TMEM
-//   threads (row = key): P^T = exp2(S^T c - lse), dS^T = P^T (dP^T - delta)  -> bf16 tiles in shared memory
-//   MMA3  dV_j += P^T  dO_i            [128 x DH]  TMEM, accumulates over i
+//         (D = 64: one more K = 16 step each adds  ones . aug^T, so that the accumulators hold S - lse / scale and
+//          dP - delta: the per-query statistics enter through the tensor core, see MU_BWD_FOLD_STATS)
+//   threads (row = key): P^T = exp2(S^T c - lse) -> TMEM (bf16), dS^T = P^T (dP^T - delta) -> bf16 tile in shared memory
+//   MMA3  dV_j += P^T  dO_i            [128 x DH]  TMEM, accumulates over i (A operand from TMEM)
 //   MMA4  dK_j += dS^T Q_i             [128 x DH]  TMEM, accumulates over i
 //   MMA5  dQ_i  = dS K_j  (D = 64: [BM queries x 64];  D >= 128: transposed, [128 channels x BM queries])
-//         read back by a second warpgroup and added into an fp32 dQ accumulator with red.global.add
+//         read back by a second warpgroup, staged in shared memory and added by the TMA unit (cp.reduce.async.bulk.tensor)
+//         into the bf16 dq itself (D = 64) or an fp32 accumulator (D >= 128)
 // D = 256 splits the accumulator width over blockIdx.z (DH = 128 channels each) because dK + dV alone
 // would need 512 TMEM columns.  The 1/sqrt(C) factor of dS is applied when dK / dQ leave the chip.
 #include <atomic>

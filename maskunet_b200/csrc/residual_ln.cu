@@ -379,7 +379,9 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_fwd_view_kernel(
     float* __restrict__ rstd, int B, int N) {
   constexpr int LPT = C / 8, TPP = kLnThreads / LPT, PASSES = kViewTokens / TPP;   // tokens per pass, passes per tile
   constexpr int CB = C / 64;                                                       // 64-token blocks along c
-  __shared__ __align__(16) uint16_t tt[C * kViewTokens];
+  // two tiles (C <= 128): tile t + 1 is written while stragglers still store tile t -- one barrier per tile instead of two
+  constexpr int NBUF = C <= 128 ? 2 : 1;
+  __shared__ __align__(16) uint16_t tt_all[NBUF * C * kViewTokens];
   const int g = threadIdx.x % LPT, tl = threadIdx.x / LPT;
   float gm[8], bt[8];
 #pragma unroll
@@ -389,7 +391,9 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_fwd_view_kernel(
   }
   const int k = N / C, per_sample = k * CB;
   const long total = (long)B * per_sample;
-  for (long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+  int parity = 0;
+  for (long tile = blockIdx.x; tile < total; tile += gridDim.x, parity ^= (NBUF - 1)) {
+    uint16_t* tt = tt_all + parity * (C * kViewTokens);
     const int b = (int)(tile / per_sample), r = (int)(tile - (long)b * per_sample);
     const int j = r / CB, cblk = r - j * CB;
     const long tok0 = (long)b * N + j;
@@ -446,18 +450,20 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_fwd_view_kernel(
       const uint4 v = *reinterpret_cast<const uint4*>(tt + ch * kViewTokens + ((l ^ ((ch >> 3) & 7)) << 3));
       *reinterpret_cast<uint4*>(yb + (long)ch * C + l * 8) = v;
     }
-    __syncthreads();
+    if (NBUF == 1) __syncthreads();
   }
 }
 
 template <int C>
-__global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_view_kernel(
+__global__ void __launch_bounds__(kLnThreads, C == 64 ? 3 : 2) residual_ln_bwd_view_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ x,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
     __nv_bfloat16* __restrict__ dz, float* __restrict__ delta, float* __restrict__ dgamma, float* __restrict__ dbeta,
     int B, int N, const DetCtx det) {
   constexpr int LPT = C / 8, TPP = kLnThreads / LPT, PASSES = kViewTokens / TPP, CB = C / 64;
-  __shared__ __align__(16) uint16_t tt[C * kViewTokens];
+  constexpr int NBUF = C <= 128 ? 2 : 1;                  // (see the forward kernel)
+  constexpr int G0 = PASSES < 4 ? PASSES : 4;             // passes whose o / x / statistics loads are issued with the dy loads
+  __shared__ __align__(16) uint16_t tt_all[NBUF * C * kViewTokens];
   __shared__ float red[2 * C];
   const int g = threadIdx.x % LPT, tl = threadIdx.x / LPT;
   for (int i = threadIdx.x; i < 2 * C; i += kLnThreads) red[i] = 0.f;
@@ -469,29 +475,49 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_view_kernel(
   }
   const int k = N / C, per_sample = k * CB;
   const long total = (long)B * per_sample;
-  for (long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+  int parity = 0;
+  for (long tile = blockIdx.x; tile < total; tile += gridDim.x, parity ^= (NBUF - 1)) {
+    uint16_t* tt = tt_all + parity * (C * kViewTokens);
     const int b = (int)(tile / per_sample), r = (int)(tile - (long)b * per_sample);
     const int j = r / CB, cblk = r - j * CB;
     const long tok0 = (long)b * N + j;
-    // dy of the view, channels-last: C rows (pixels j C + ch) of 64 contiguous channels c -> [ch][64 tokens]
+    // dy of the view, channels-last: C rows (pixels j C + ch) of 64 contiguous channels c -> [ch][64 tokens].
+    // All global loads of the tile are issued before the barrier: the dy rows AND the first passes' o / x / statistics,
+    // which do not depend on the shared-memory tile (one memory round trip per tile instead of two).
     const __nv_bfloat16* dyb = dy + ((long)b * N + (long)j * C) * C + cblk * 64;
-    for (int idx = threadIdx.x; idx < C * 8; idx += kLnThreads) {
-      const int ch = idx >> 3, l = idx & 7;
-      *reinterpret_cast<uint4*>(tt + ch * kViewTokens + ((l ^ ((ch >> 3) & 7)) << 3)) =
-          *reinterpret_cast<const uint4*>(dyb + (long)ch * C + l * 8);
+    uint4 dyv[C * 8 / kLnThreads];
+#pragma unroll
+    for (int it = 0; it < C * 8 / kLnThreads; ++it) {
+      const int idx = it * kLnThreads + threadIdx.x, ch = idx >> 3, l = idx & 7;
+      dyv[it] = *reinterpret_cast<const uint4*>(dyb + (long)ch * C + l * 8);
+    }
+    uint4 uo[4], ux[4];
+    float mu_[4], rs[4];
+#pragma unroll
+    for (int u = 0; u < G0; ++u) {
+      const long t = tok0 + (long)(cblk * 64 + u * TPP + tl) * k;
+      uo[u] = *reinterpret_cast<const uint4*>(o + t * C + g * 8);
+      ux[u] = *reinterpret_cast<const uint4*>(x + t * C + g * 8);
+      mu_[u] = mean[t];
+      rs[u] = rstd[t];
+    }
+#pragma unroll
+    for (int it = 0; it < C * 8 / kLnThreads; ++it) {
+      const int idx = it * kLnThreads + threadIdx.x, ch = idx >> 3, l = idx & 7;
+      *reinterpret_cast<uint4*>(tt + ch * kViewTokens + ((l ^ ((ch >> 3) & 7)) << 3)) = dyv[it];
     }
     __syncthreads();
 #pragma unroll
     for (int p0 = 0; p0 < PASSES; p0 += 4) {
-      uint4 uo[4], ux[4];
-      float mu_[4], rs[4];
+      if (p0 > 0) {
 #pragma unroll
-      for (int u = 0; u < 4 && p0 + u < PASSES; ++u) {
-        const long t = tok0 + (long)(cblk * 64 + (p0 + u) * TPP + tl) * k;
-        uo[u] = *reinterpret_cast<const uint4*>(o + t * C + g * 8);
-        ux[u] = *reinterpret_cast<const uint4*>(x + t * C + g * 8);
-        mu_[u] = mean[t];
-        rs[u] = rstd[t];
+        for (int u = 0; u < 4 && p0 + u < PASSES; ++u) {
+          const long t = tok0 + (long)(cblk * 64 + (p0 + u) * TPP + tl) * k;
+          uo[u] = *reinterpret_cast<const uint4*>(o + t * C + g * 8);
+          ux[u] = *reinterpret_cast<const uint4*>(x + t * C + g * 8);
+          mu_[u] = mean[t];
+          rs[u] = rstd[t];
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4 && p0 + u < PASSES; ++u) {
@@ -528,7 +554,7 @@ __global__ void __launch_bounds__(kLnThreads) residual_ln_bwd_view_kernel(
         if (g == 0) delta[t] = dl;
       }
     }
-    __syncthreads();
+    if (NBUF == 1) __syncthreads();
   }
   ln_param_grads<C>(dg, db, red, dgamma, dbeta, det);
 }
