@@ -28,6 +28,9 @@
 #ifndef MU_P2_STAGED_EPILOGUE
 #define MU_P2_STAGED_EPILOGUE 1
 #endif
+#ifndef MU_P3_FOLD_DB
+#define MU_P3_FOLD_DB 1
+#endif
 #ifndef MU_P1_NC_256
 #define MU_P1_NC_256 64
 #endif
@@ -419,20 +422,28 @@ struct P3Cfg {
   static constexpr int kABytes = 2 * 16384;               // two [128 tokens x 64 out-channels] blocks
   static constexpr int kXBytes = (C / 64) * 16384;        // [128 tokens x C]
   static constexpr int kStageBytes = kABytes + kXBytes;
-  static constexpr int kTmemCols = C;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+  // MU_P3_FOLD_DB: the bias gradient db = column sums of dq | dk | dv is one more output COLUMN of this GEMM:
+  // [dq|dk|dv]^T . 1.  A constant all-ones B tile (16 token rows x 128 bytes: all ones is its own swizzle image) and one
+  // N = 16 MMA per K step put it into TMEM columns [C, C + 16); the separate pass over dq, dk, dv (qkv_db_kernel, 1.6 GB
+  // at the 16384-token site) disappears.  Free-running mode only: deterministic mode keeps the ordered db kernel.
+  static constexpr int kOnesBytes = MU_P3_FOLD_DB ? 2048 : 0;
+  static constexpr int kTmemCols = MU_P3_FOLD_DB ? 2 * C : C;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kOnesBytes + 256;
 };
 
 template <int C>
 __global__ void __launch_bounds__(kGemmThreads)
 qkv_dw_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_dk,
                     const __grid_constant__ CUtensorMap tmap_dv, const __grid_constant__ CUtensorMap tmap_x,
-                    float* __restrict__ dw, int Mtot, int chunks_per_cta, float* __restrict__ det_slices) {
+                    float* __restrict__ dw, int Mtot, int chunks_per_cta, float* __restrict__ det_slices,
+                    float* __restrict__ db) {
   using Cfg = P3Cfg<C>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint8_t* sOnes = smem + S * Cfg::kStageBytes;             // (1024-byte aligned: the stages are multiples of 16 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + Cfg::kOnesBytes);
+  const bool fold_db = MU_P3_FOLD_DB != 0 && db != nullptr;
   uint64_t* full = bars;
   uint64_t* empty = bars + S;
   uint64_t* acc_full = bars + 2 * S;
@@ -465,6 +476,11 @@ qkv_dw_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
   if (warp == 1) {
     tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     tmem_relinquish();
+  }
+  if (fold_db) {
+    for (int i = threadIdx.x; i < Cfg::kOnesBytes / 16; i += kGemmThreads)
+      st_shared_v4(smem_u32(sOnes) + i * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);   // bf16 1.0 pairs
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -502,6 +518,13 @@ qkv_dw_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           if (elect_one()) umma_ss_lo(tmem_base, a_lo + kk * 128, x_lo + kk * 128, hi, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+        if (fold_db) {        // db column: the same A tiles against the all-ones B tile (every K step reads the same 16 rows)
+          constexpr uint32_t idesc1 = make_idesc_bf16(128, 16, 1, 1);
+          const uint32_t ones_lo = desc_lo(smem_u32(sOnes));
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            if (elect_one()) umma_ss_lo(tmem_base + C, a_lo + kk * 128, ones_lo, hi, idesc1, (j > 0 || kk > 0) ? 1u : 0u);
+        }
         if (elect_one()) umma_commit(empty + st);
       }
       if (elect_one()) umma_commit(acc_full);
@@ -535,6 +558,11 @@ qkv_dw_sm100_kernel(const __grid_constant__ CUtensorMap tmap_dq, const __grid_co
           for (int e = 0; e < 32; ++e) atomicAdd(wrow + c * 32 + e, __uint_as_float(v[e]));
         }
       }
+    }
+    if (fold_db) {            // column C of the accumulator: this CTA's share of db for the row's output channel
+      tmem_ld32(lane_base + C, v);
+      tmem_wait_ld();
+      if (valid) atomicAdd(db + src[h] * C + col[h] + (r & 63), __uint_as_float(v[0]));
     }
   }
   tc_fence_before();
@@ -615,6 +643,7 @@ static int run_bwd(const void* xt, const void* dz, const void* dq, const void* d
   const int Mtot = B * N;
   CUtensorMap tdq, tdk, tdv, tw, tx;
   int rc;
+  bool db_folded = false;
   if ((rc = make_tmap_bf16_3d(&tdq, dq, C, Mtot, 1, 128))) return rc;
   if ((rc = make_tmap_bf16_3d(&tdk, dk, C, Mtot, 1, 128))) return rc;
   if ((rc = make_tmap_bf16_3d(&tdv, dv, C, Mtot, 1, 128))) return rc;
@@ -638,7 +667,9 @@ static int run_bwd(const void* xt, const void* dz, const void* dq, const void* d
     dim3 grid((total_chunks + per - 1) / per, Cfg::kMTiles);
     DetCtx det;
     if (!det_context(kDetSlotMisc, (size_t)grid.x * 3 * C * C, &det, "qkv_project_bwd (dW)")) return MU_ERR_WORKSPACE;
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(tdq, tdk, tdv, tx, dw, Mtot, per, det.partial);
+    db_folded = MU_P3_FOLD_DB != 0 && !det.on();       // free-running: db comes out of the same GEMM (its ones column)
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(tdq, tdk, tdv, tx, dw, Mtot, per, det.partial,
+                                                    db_folded ? db : nullptr);
     if ((rc = check_launch("qkv_dw_sm100"))) return rc;
     if (det.on()) {
       const int n = 3 * C * C;
@@ -646,7 +677,7 @@ static int run_bwd(const void* xt, const void* dz, const void* dq, const void* d
       if ((rc = check_launch("qkv_dw_sum_slices"))) return rc;
     }
   }
-  {
+  if (!db_folded) {
     int rows = (Mtot + 295) / 296;
     if (rows < 256) rows = 256;
     dim3 grid((Mtot + rows - 1) / rows, 3);

@@ -270,7 +270,8 @@ def qkv_project_bwd(x: Tensor, dz: Tensor, dq: Tensor, dk: Tensor, dv: Tensor, w
     db = torch.zeros((3 * C,), dtype=torch.float32, device=x.device)
     w_lp = w_qkv.to(torch.bfloat16) if token_major else w_qkv
     with torch.cuda.device(x.device):
-        _count(3 if token_major else 2)
+        # P2, P3 (+ the bias-gradient kernel in deterministic mode: otherwise db is a column of the P3 GEMM)
+        _count((3 if _L.mu_get_deterministic() else 2) if token_major else 2)
         check(_L.mu_qkv_project_bwd(_p(x), _p(dz), _p(dq), _p(dk), _p(dv), _p(w_qkv), _p(w_lp), _p(dx), _p(dw),
                                     _p(db), B, C, N, _code(x), int(token_major), _stream(x)), "mu_qkv_project_bwd")
     return dx, dw, db
