@@ -259,11 +259,22 @@ int mu_conv1x1_prep(const float* w, const float* bias, void* wf, void* wd, float
                     int32_t Np, mu_stream_t stream);
 int mu_conv1x1_fwd(const void* x, const void* wf, const float* bias_p, void* y, int32_t B, int32_t H, int32_t W,
                    int32_t Cin, int32_t Np, int32_t dtype, mu_stream_t stream);
+/* mu_conv1x1_fwd that also ADDS the per-channel (sum, sum of squares) of its rounded outputs to stats f32 [2 * Np] (the
+ * caller zeroes it): the statistics pass of the BatchNorm2d that follows the head convolution (:284-286). */
+int mu_conv1x1_fwd_stats(const void* x, const void* wf, const float* bias_p, void* y, float* stats, int32_t B, int32_t H,
+                         int32_t W, int32_t Cin, int32_t Np, int32_t dtype, mu_stream_t stream);
 int mu_conv1x1_bwd_data(const void* dy, const void* wd, void* dx, int32_t B, int32_t H, int32_t W, int32_t Cin,
                         int32_t Np, int32_t dtype, mu_stream_t stream);
 size_t mu_conv1x1_workspace_bytes(int32_t Cin, int32_t Np);
 int mu_conv1x1_bwd_weight(const void* x, const void* dy, void* workspace, size_t workspace_bytes, float* dw, int32_t B,
                           int32_t H, int32_t W, int32_t Cin, int32_t Np, int32_t dtype, mu_stream_t stream);
+/* mu_conv1x1_bwd_weight that also returns the bias gradient db f32 [Np] = sum over pixels of dy.  With 64 input channels
+ * (every head of the U-Net) in free-running mode it is carried by the weight-gradient GEMM itself (the unused half of the
+ * 128-row accumulator tile, through an all-ones operand tile); otherwise it is reduced from dy by the column-sums kernel.
+ * workspace: max(mu_conv1x1_workspace_bytes(Cin, Np), 2 * Np floats). */
+int mu_conv1x1_bwd_weight_bias(const void* x, const void* dy, void* workspace, size_t workspace_bytes, float* dw,
+                               float* db, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Np, int32_t dtype,
+                               mu_stream_t stream);
 int mu_column_sums(const void* x, float* sums, int64_t M, int32_t C, int32_t dtype, mu_stream_t stream);
 
 /* Logit post-processing on the device: the class map `argmax(softmax(y_pred / 0.5, dim=1), dim=1)`

@@ -39,8 +39,10 @@ SIGNATURES = {
     "mu_column_sums": [_P, _P, ctypes.c_int64, _I, _I, _P],
     "mu_conv1x1_prep": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mu_conv1x1_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mu_conv1x1_fwd_stats": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "mu_conv1x1_bwd_data": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "mu_conv1x1_bwd_weight": [_P, _P, _P, ctypes.c_size_t, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mu_conv1x1_bwd_weight_bias": [_P, _P, _P, ctypes.c_size_t, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "mu_bn_act_fwd": [_P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
     "mu_bn_act_apply": [_P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
     "mu_bn_act_fwd_stats": [_P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],

@@ -367,6 +367,14 @@ int mu_conv1x1_fwd(const void* x, const void* wf, const float* bias_p, void* y, 
   return launch_conv1x1_fprop_sm100(x, wf, bias_p, y, B, H, W, Cin, Np, (cudaStream_t)stream);
 }
 
+int mu_conv1x1_fwd_stats(const void* x, const void* wf, const float* bias_p, void* y, float* stats, int32_t B, int32_t H,
+                         int32_t W, int32_t Cin, int32_t Np, int32_t dtype, mu_stream_t stream) {
+  MU_BF16_ONLY("mu_conv1x1_fwd_stats");
+  MU_PTRS("mu_conv1x1_fwd_stats", x, wf, y, stats);
+  MU_SM100_ONLY("mu_conv1x1_fwd_stats");
+  return launch_conv1x1_fprop_sm100(x, wf, bias_p, y, B, H, W, Cin, Np, (cudaStream_t)stream, stats);
+}
+
 int mu_conv1x1_bwd_data(const void* dy, const void* wd, void* dx, int32_t B, int32_t H, int32_t W, int32_t Cin,
                         int32_t Np, int32_t dtype, mu_stream_t stream) {
   MU_BF16_ONLY("mu_conv1x1_bwd_data");
@@ -386,6 +394,30 @@ int mu_conv1x1_bwd_weight(const void* x, const void* dy, void* workspace, size_t
              mu_conv1x1_workspace_bytes(Cin, Np));
   MU_SM100_ONLY("mu_conv1x1_bwd_weight");
   return launch_conv1x1_wgrad_sm100(x, dy, (float*)workspace, dw, B, H, W, Cin, Np, (cudaStream_t)stream);
+}
+
+int mu_conv1x1_bwd_weight_bias(const void* x, const void* dy, void* workspace, size_t workspace_bytes, float* dw,
+                               float* db, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Np, int32_t dtype,
+                               mu_stream_t stream) {
+  MU_BF16_ONLY("mu_conv1x1_bwd_weight_bias");
+  MU_PTRS("mu_conv1x1_bwd_weight_bias", x, dy, workspace, dw, db);
+  MU_REQUIRE(workspace_bytes >= mu_conv1x1_workspace_bytes(Cin, Np) && workspace_bytes >= 2 * (size_t)Np * sizeof(float),
+             MU_ERR_WORKSPACE, "mu_conv1x1_bwd_weight_bias: workspace too small (%zu < %zu)", workspace_bytes,
+             mu_conv1x1_workspace_bytes(Cin, Np));
+  MU_SM100_ONLY("mu_conv1x1_bwd_weight_bias");
+  int db_done = 0;
+  int rc = launch_conv1x1_wgrad_sm100(x, dy, (float*)workspace, dw, B, H, W, Cin, Np, (cudaStream_t)stream, db, &db_done);
+  if (rc || db_done) return rc;
+  // not carried by the GEMM (deterministic mode, or more than 64 input channels): the ordered column sums of dy, through
+  // the workspace (free again: the finish kernel of the weight gradient precedes this in the stream)
+  rc = launch_column_sums(dy, (float*)workspace, (long)B * H * W, Np, MU_BF16, (cudaStream_t)stream);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(db, workspace, (size_t)Np * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_error("mu_conv1x1_bwd_weight_bias: cudaMemcpyAsync: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
 }
 
 int mu_conv_prep_weights(const float* w, void* wf, void* wd, int32_t Cout, int32_t Cin, int32_t taps,

@@ -135,9 +135,9 @@ int launch_sample_ln_bwd(const void* dy, const void* x, const float* gamma, cons
 int launch_ce_fused(const void* logits, const int64_t* labels, const float* valid_count, long ignore_index,
                     void* dlogits, float* loss_sum, long M, int C, int pitch, int dtype, cudaStream_t s);
 int launch_conv1x1_fprop_sm100(const void* x, const void* wt, const float* bias, void* y, int B, int H, int W, int K,
-                               int Np, cudaStream_t s);
+                               int Np, cudaStream_t s, float* stats = nullptr);
 int launch_conv1x1_wgrad_sm100(const void* x, const void* dy, float* ws, float* dw, int B, int H, int W, int Cin, int Np,
-                               cudaStream_t s);
+                               cudaStream_t s, float* db = nullptr, int* db_done = nullptr);
 int launch_conv1x1_prep(const float* w, const float* bias, void* wf, void* wd, float* bias_p, int Cout, int Cin, int Np,
                         cudaStream_t s);
 int launch_column_sums(const void* x, float* sums, long M, int C, int dtype, cudaStream_t s);

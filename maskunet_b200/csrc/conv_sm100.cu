@@ -267,7 +267,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     const int r = quad * 32 + (int)lane_id();              // pixel row of the tile == TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t so_base = smem_u32(sO);
-    // (the BatchNorm partial sums below assume full 64-channel blocks: NT = 32 / 160 launches pass stats = NULL)
+    // (NT = 32 / 160, the 1x1 heads: the last 64-channel block is half wide -- the channel pairs past NT are skipped)
     const int sq = e >> 5, cp = e & 31;                    // statistics: rows sq*32.., channel pair cp
     const int SO = p.SO;
     uint32_t buf = 0, pacc = 0, so_idx = 0;
@@ -285,6 +285,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           if (sq == round) {
 #pragma unroll
             for (int i = 0; i < kBlocks; ++i) {
+              if (i * 64 + 2 * cp >= NT) continue;
               const int chn = nt_done * NT + i * 64 + 2 * cp;
               s_stats[chn] += acc[i][0];
               s_stats[chn + 1] += acc[i][1];
@@ -299,6 +300,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       }
 #pragma unroll
       for (int i = 0; i < kBlocks; ++i) {
+        if (i * 64 + 2 * cp >= NT) continue;
         const int chn = nt_done * NT + i * 64 + 2 * cp;
         atomicAdd(s_stats + chn, acc[i][0]);
         atomicAdd(s_stats + chn + 1, acc[i][1]);
@@ -358,7 +360,7 @@ conv_fprop_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           else tma_store_4d(&tmap_y, so, nt * NT + cb * 64, 0, y0 + m * p.TH, b);
           tma_store_commit();
         }
-        if (stats != nullptr) {
+        if (stats != nullptr && cb * 64 + 2 * cp < NT) {
           // BatchNorm partial sums of the ROUNDED outputs (what the normalisation will read back)
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
@@ -424,12 +426,18 @@ struct WgradArgs {
   int n_cb, n_nb;           // ci / co blocks over the grid
   int S, chunks_per_cta;
   long slice_floats;        // deterministic mode: every pixel split (blockIdx.y) STORES into its own [taps][Cin][Cout] slice
+  int ones_off;             // 1x1 convolution with 64 input channels: byte offset of an all-ones [128 px][128 B] tile (0: none)
 };
 
 template <int NB>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
-                        float* __restrict__ ws, const WgradArgs p) {
+                        float* __restrict__ ws, const WgradArgs p, float* __restrict__ db) {
+  // db != NULL (1x1 heads with 64 input channels, free-running mode): the bias gradient, the column sums of dy, comes out
+  // of the same GEMM.  The M = 128 tile of such a convolution has only 64 real rows (input channels); the second 64-row
+  // block of the MN-major A operand is addressed through the descriptor's LBO, which here points at a constant all-ones
+  // tile: rows 64..127 of the accumulator are then  sum over pixels of 1 * dy[p, co] = db[co]  -- no extra MMA, and
+  // the separate pass over dy (1.3 GB for the 160-channel logits gradient of 256 images) disappears.
   constexpr int kDyBlocks = (NB + 63) / 64;
   constexpr int kDyBytes = kDyBlocks * 16384;
   constexpr int kTmemCols = NB == 128 ? 512 : 256;       // 3 taps x 128 | 3 x 64 | 1 x 160 (1x1 mode) | 1 x 32
@@ -470,6 +478,13 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   if (warp == 1) {
     tmem_alloc<kTmemCols>(tmem_slot);
     tmem_relinquish();
+  }
+  const bool fold_db = db != nullptr && p.ones_off != 0;
+  if (fold_db) {
+    const uint32_t ones = smem_u32(smem) + p.ones_off;
+    for (int i = threadIdx.x; i < 16384 / 16; i += kConvThreads)
+      st_shared_v4(ones + i * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);      // bf16 1.0 pairs
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -526,7 +541,9 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
           if (m < m_tiles_cta) {
-            const uint32_t a_lo = (x_lo + a_off[m]) | a_lbo[m];
+            uint32_t a_lo = (x_lo + a_off[m]) | a_lbo[m];
+            if (fold_db)          // second 64-row block of the A operand = the ones tile (distance from THIS stage's x tile)
+              a_lo = x_lo | (((((uint32_t)p.ones_off - st * (uint32_t)stage_bytes) >> 4) & 0x3FFFu) << 16);
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
               if (elect_one())
@@ -576,6 +593,11 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
               red_add_v4f(dst + c * 32 + q * 4, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                           __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
           }
+        } else if (fold_db && r == 64) {           // rows 64..127 all hold this CTA's share of db: row 64 adds it
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            red_add_v4f(db + nb * NB + c * 32 + q * 4, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                        __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
         }
       }
     }
@@ -807,24 +829,25 @@ static int conv1x1_geometry_ok(const char* fn, int B, int H, int W, int K, int N
 }
 
 template <int NT>
-static int run_conv1x1(const void* x, const void* wt, const float* bias, void* y, int B, int H, int W, int K,
+static int run_conv1x1(const void* x, const void* wt, const float* bias, void* y, float* stats, int B, int H, int W, int K,
                        cudaStream_t s) {
   const bool pair = H % (2 * (128 / W)) == 0;
-  return pair ? run_fprop<NT, 2, CONV_1X1>(x, wt, y, nullptr, bias, B, H, W, K, NT, 1, s)
-              : run_fprop<NT, 1, CONV_1X1>(x, wt, y, nullptr, bias, B, H, W, K, NT, 1, s);
+  return pair ? run_fprop<NT, 2, CONV_1X1>(x, wt, y, stats, bias, B, H, W, K, NT, 1, s)
+              : run_fprop<NT, 1, CONV_1X1>(x, wt, y, stats, bias, B, H, W, K, NT, 1, s);
 }
 
 // y [B,H,W,Np] = x [B,H,W,K] . wt[Np][Kpad]^T + bias[Np]
+// stats (optional): f32 [2 Np] += per-channel (sum, sum of squares) of the rounded outputs, as in launch_conv_fprop_sm100
 int launch_conv1x1_fprop_sm100(const void* x, const void* wt, const float* bias, void* y, int B, int H, int W, int K,
-                               int Np, cudaStream_t s) {
+                               int Np, cudaStream_t s, float* stats) {
   int rc;
   if ((rc = conv1x1_geometry_ok("conv1x1_fprop_sm100", B, H, W, K, Np))) return rc;
   switch (Np) {
-    case 32: return run_conv1x1<32>(x, wt, bias, y, B, H, W, K, s);
-    case 64: return run_conv1x1<64>(x, wt, bias, y, B, H, W, K, s);
-    case 128: return run_conv1x1<128>(x, wt, bias, y, B, H, W, K, s);
-    case 160: return run_conv1x1<160>(x, wt, bias, y, B, H, W, K, s);
-    default: return run_conv1x1<256>(x, wt, bias, y, B, H, W, K, s);
+    case 32: return run_conv1x1<32>(x, wt, bias, y, stats, B, H, W, K, s);
+    case 64: return run_conv1x1<64>(x, wt, bias, y, stats, B, H, W, K, s);
+    case 128: return run_conv1x1<128>(x, wt, bias, y, stats, B, H, W, K, s);
+    case 160: return run_conv1x1<160>(x, wt, bias, y, stats, B, H, W, K, s);
+    default: return run_conv1x1<256>(x, wt, bias, y, stats, B, H, W, K, s);
   }
 }
 
@@ -832,7 +855,7 @@ int launch_conv1x1_fprop_sm100(const void* x, const void* wt, const float* bias,
 // registered scratch, *n_slices of them; free-running: the caller's workspace, cleared here, one slice)
 template <int NB>
 static int run_wgrad(const void* x, const void* dy, float** ws_io, int* n_slices, int B, int H, int W, int Cin, int Cout,
-                     int taps, cudaStream_t s) {
+                     int taps, cudaStream_t s, float* db = nullptr, int* db_done = nullptr) {
   WgradArgs p;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.TH = 128 / W;
@@ -852,13 +875,16 @@ static int run_wgrad(const void* x, const void* dy, float** ws_io, int* n_slices
   p.n_cb = (Cin + 64 * p.ci_blocks - 1) / (64 * p.ci_blocks);
   p.n_nb = Cout / NB;
   const int stage = p.ci_blocks * p.x_stride + ((NB + 63) / 64) * 16384;
-  p.S = (kSmemLimit - 1024 - 512) / stage;
+  // bias gradient as rows 64..127 of the accumulator (see the kernel): 1x1, 64 input channels, caller wants db
+  const bool db_room = db != nullptr && taps == 1 && Cin == 64 && p.ci_blocks == 1;
+  const int ones_bytes = db_room ? 1024 + 16384 : 0;     // (the ones tile starts 1024 bytes past the barriers' 512)
+  p.S = (kSmemLimit - 1024 - 512 - ones_bytes) / stage;
   if (p.S > kMaxRing) p.S = kMaxRing;
   if (p.S < 2) {
     set_error("conv_wgrad: shared memory budget exceeded (stage %d)", stage);
     return MU_ERR_BAD_SHAPE;
   }
-  const int smem = 1024 + 512 + p.S * stage;
+  const int smem = 1024 + 512 + p.S * stage + ones_bytes;
   const int combos = (taps == 1 ? 1 : 3) * p.n_cb * p.n_nb;
   // split-K: whole waves only.  One CTA per SM is resident (shared memory), so combos * splits must not exceed a
   // multiple of the SM count by a few CTAs (297 CTAs on 148 SMs ran as three waves, the last with one CTA).
@@ -883,13 +909,17 @@ static int run_wgrad(const void* x, const void* dy, float** ws_io, int* n_slices
     *n_slices = 1;
   }
   *ws_io = ws;
+  const bool fold_db = db_room && !det.on();            // deterministic mode keeps the ordered column sums
+  p.ones_off = fold_db ? p.S * stage + 1024 : 0;
+  if (db_done != nullptr) *db_done = fold_db ? 1 : 0;
+  if (fold_db) cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), s);
   CUtensorMap tx, td;
   int rc;
   if ((rc = make_tmap_bf16_nhwc(&tx, x, Cin, W, H, B, box_w, box_h))) return rc;
   if ((rc = make_tmap_bf16_nhwc(&td, dy, Cout, W, H, B, W, p.TH))) return rc;
   auto kern = conv_wgrad_sm100_kernel<NB>;
   set_max_dynamic_smem_once(kern, smem);
-  kern<<<dim3(combos, splits), kConvThreads, smem, s>>>(tx, td, ws, p);
+  kern<<<dim3(combos, splits), kConvThreads, smem, s>>>(tx, td, ws, p, fold_db ? db : nullptr);
   return check_launch("conv_wgrad_sm100");
 }
 
@@ -908,17 +938,20 @@ int launch_conv_wgrad_sm100(const void* x, const void* dy, float* ws, float* dw,
 }
 
 // dw f32 [Np][Cin] of a 1x1 convolution whose output gradient dy carries Np (padded) channels; ws f32 [Cin][Np]
+// db (optional) f32 [Np]: the bias gradient (column sums of dy); *db_done = 1 when this call produced it (the weight-
+// gradient GEMM carries it for 64 input channels in free-running mode), 0 when the caller still has to reduce dy itself
 int launch_conv1x1_wgrad_sm100(const void* x, const void* dy, float* ws, float* dw, int B, int H, int W, int Cin, int Np,
-                               cudaStream_t s) {
+                               cudaStream_t s, float* db, int* db_done) {
   int rc;
   if ((rc = conv1x1_geometry_ok("conv1x1_wgrad_sm100", B, H, W, Cin, Np))) return rc;
   MU_REQUIRE(Cin % 64 == 0, MU_ERR_BAD_SHAPE, "conv1x1_wgrad_sm100: input channels must be a multiple of 64 (got %d)", Cin);
   int n_slices = 1;
+  if (db_done != nullptr) *db_done = 0;
   switch (Np) {
-    case 32: rc = run_wgrad<32>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s); break;
-    case 64: rc = run_wgrad<64>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s); break;
-    case 128: rc = run_wgrad<128>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s); break;
-    case 160: rc = run_wgrad<160>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s); break;
+    case 32: rc = run_wgrad<32>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s, db, db_done); break;
+    case 64: rc = run_wgrad<64>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s, db, db_done); break;
+    case 128: rc = run_wgrad<128>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s, db, db_done); break;
+    case 160: rc = run_wgrad<160>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s, db, db_done); break;
     default: rc = run_wgrad<128>(x, dy, &ws, &n_slices, B, H, W, Cin, Np, 1, s); break;   // 256 = two 128-channel blocks
   }
   if (rc) return rc;

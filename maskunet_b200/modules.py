@@ -481,8 +481,11 @@ class UNet(nn.Module):
         if self._own_conv1x1(conv, h):
             n_pad = ops.pad_channels(max(conv.out_channels, min_pad))
             bias = conv.bias.float() if conv.bias is not None else None
-            y_pad = ops.conv1x1(h, conv.weight, bias, n_pad)[0]
-            out_pad = fused_bn_act(y_pad, bn, ops.ACT_RELU)
+            # (training: the epilogue of the head convolution hands the BatchNorm its batch statistics, MASKUNET_HEAD_STATS=0:
+            # a separate statistics pass over the class-padded logits)
+            want = bn.training and os.environ.get("MASKUNET_HEAD_STATS", "1") != "0"
+            y_pad, _, sums = ops.conv1x1(h, conv.weight, bias, n_pad, want)
+            out_pad = fused_bn_act(y_pad, bn, ops.ACT_RELU, sums=sums if want else None)
             if keep_padded:
                 self._padded_logits = out_pad       # train.Trainer starts backward from the padded tensor
             return out_pad[:, :conv.out_channels] if n_pad > conv.out_channels else out_pad

@@ -697,9 +697,12 @@ def _(x):
 
 
 @torch.library.custom_op("maskunet::conv1x1", mutates_args=(), device_types="cuda")
-def conv1x1(x: Tensor, weight: Tensor, bias: Tensor | None, n_pad: int) -> Tuple[Tensor, Tensor]:
+def conv1x1(x: Tensor, weight: Tensor, bias: Tensor | None, n_pad: int, want_stats: bool = False
+            ) -> Tuple[Tensor, Tensor, Tensor]:
     """nn.Conv2d(Cin, Cout, 1) on tcgen05: x bf16 channels-last [B, Cin, H, W], weight f32 [Cout, Cin, 1, 1],
-    bias f32 [Cout].  Returns (y [B, n_pad, H, W] with channels >= Cout zero, wd = data-gradient operand)."""
+    bias f32 [Cout].  Returns (y [B, n_pad, H, W] with channels >= Cout zero, wd = data-gradient operand, sums f32
+    [2 n_pad] = per-channel (sum, sum of squares) of y from the epilogue -- the statistics pass of the BatchNorm2d that
+    follows the head -- or an empty tensor when not wanted)."""
     B, Cin, H, W = _nhwc(x)
     _cuda(weight)
     Cout = weight.shape[0]
@@ -709,19 +712,26 @@ def conv1x1(x: Tensor, weight: Tensor, bias: Tensor | None, n_pad: int) -> Tuple
     wd = torch.empty((Cin, (n_pad + 63) // 64 * 64), dtype=torch.bfloat16, device=dev)
     bias_p = torch.empty((n_pad,), dtype=torch.float32, device=dev)
     y = _empty_cl(x, B, n_pad, H, W)
+    sums = torch.zeros((2 * n_pad,), dtype=torch.float32, device=dev) if want_stats else \
+        torch.empty((0,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev), _timed("mu_conv1x1_fwd", (B, H, W, Cin, n_pad)):
         _count(2)
         check(_L.mu_conv1x1_prep(_p(weight.contiguous()), _optp(bias), _p(wf), _p(wd), _p(bias_p), Cout, Cin, n_pad,
                                  _stream(x)), "mu_conv1x1_prep")
-        check(_L.mu_conv1x1_fwd(_p(x), _p(wf), _p(bias_p), _p(y), B, H, W, Cin, n_pad, MU_BF16, _stream(x)),
-              "mu_conv1x1_fwd")
-    return y, wd
+        if want_stats:
+            check(_L.mu_conv1x1_fwd_stats(_p(x), _p(wf), _p(bias_p), _p(y), _p(sums), B, H, W, Cin, n_pad, MU_BF16,
+                                          _stream(x)), "mu_conv1x1_fwd_stats")
+        else:
+            check(_L.mu_conv1x1_fwd(_p(x), _p(wf), _p(bias_p), _p(y), B, H, W, Cin, n_pad, MU_BF16, _stream(x)),
+                  "mu_conv1x1_fwd")
+    return y, wd, sums
 
 
 @conv1x1.register_fake
-def _(x, weight, bias, n_pad):
+def _(x, weight, bias, n_pad, want_stats=False):
     B, Cin, H, W = x.shape
-    return _empty_cl(x, B, n_pad, H, W), x.new_empty((Cin, (n_pad + 63) // 64 * 64), dtype=torch.bfloat16)
+    return (_empty_cl(x, B, n_pad, H, W), x.new_empty((Cin, (n_pad + 63) // 64 * 64), dtype=torch.bfloat16),
+            x.new_empty((2 * n_pad if want_stats else 0,), dtype=torch.float32))
 
 
 @torch.library.custom_op("maskunet::conv1x1_bwd", mutates_args=(), device_types="cuda")
@@ -732,18 +742,20 @@ def conv1x1_bwd(x: Tensor, dy: Tensor, wd: Tensor, want_dx: bool) -> Tuple[Tenso
     dev = x.device
     dx = _empty_cl(x, B, Cin, H, W) if want_dx else x.new_empty((0,))
     dw = torch.empty((n_pad, Cin), dtype=torch.float32, device=dev)
-    ws_bytes = int(_L.mu_conv1x1_workspace_bytes(Cin, n_pad))
+    ws_bytes = max(int(_L.mu_conv1x1_workspace_bytes(Cin, n_pad)), 2 * n_pad * 4)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    sums = torch.empty((2 * n_pad,), dtype=torch.float32, device=dev)
+    db = torch.empty((n_pad,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev), _timed("mu_conv1x1_bwd", (B, H, W, Cin, n_pad)):
-        _count(4 if want_dx else 3)
+        # data gradient, weight gradient + its finish kernel; the bias gradient rides in the weight-gradient GEMM (64 input
+        # channels, free-running mode) or costs one more kernel
+        folded = Cin == 64 and not _L.mu_get_deterministic()
+        _count((3 if want_dx else 2) + (0 if folded else 1))
         if want_dx:
             check(_L.mu_conv1x1_bwd_data(_p(dy), _p(wd), _p(dx), B, H, W, Cin, n_pad, MU_BF16, _stream(x)),
                   "mu_conv1x1_bwd_data")
-        check(_L.mu_conv1x1_bwd_weight(_p(x), _p(dy), _p(ws), ws_bytes, _p(dw), B, H, W, Cin, n_pad, MU_BF16,
-                                       _stream(x)), "mu_conv1x1_bwd_weight")
-        check(_L.mu_column_sums(_p(dy), _p(sums), B * H * W, n_pad, MU_BF16, _stream(x)), "mu_column_sums")
-    return dx, dw, sums[:n_pad].clone()
+        check(_L.mu_conv1x1_bwd_weight_bias(_p(x), _p(dy), _p(ws), ws_bytes, _p(dw), _p(db), B, H, W, Cin, n_pad, MU_BF16,
+                                            _stream(x)), "mu_conv1x1_bwd_weight_bias")
+    return dx, dw, db
 
 
 @conv1x1_bwd.register_fake
@@ -755,7 +767,7 @@ def _(x, dy, wd, want_dx):
 
 def _c1_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)
-    x, weight, bias, n_pad = inputs
+    x, weight, bias, n_pad = inputs[:4]
     ctx.save_for_backward(x, output[1])
     ctx.cout = weight.shape[0]
     ctx.has_bias = bias is not None
@@ -767,7 +779,7 @@ def _c1_backward(ctx, dy, *unused):
     dx, dw, db = conv1x1_bwd(x, dy, wd, bool(ctx.needs_input_grad[0]))
     cout = ctx.cout
     return (dx if ctx.needs_input_grad[0] else None, dw[:cout].reshape(cout, x.shape[1], 1, 1).contiguous(),
-            db[:cout].contiguous() if ctx.has_bias else None, None)
+            db[:cout].contiguous() if ctx.has_bias else None, None, None)
 
 
 conv1x1.register_autograd(_c1_backward, setup_context=_c1_setup)

@@ -156,6 +156,15 @@ def test_conv1x1_head_forward_and_gradients(case):
     assert rel_err(xq.grad.float(), xr.grad) < 6e-3
     assert rel_err(wq.grad, wr.grad) < 2e-3
     assert rel_err(bq.grad, br.grad) < 2e-3
+    # the epilogue statistics of the head (every padded width, incl. the half-wide last block of 32 / 160): same outputs
+    # bit for bit, sums = those of the stored (rounded) outputs, zero for the pad channels
+    y_s, _, sums = ops.conv1x1(x, w, bias, n_pad, True)
+    assert torch.equal(y_s, y_pad.detach())
+    yf = y_s.float()
+    s_ref = torch.cat([yf.sum((0, 2, 3)), (yf * yf).sum((0, 2, 3))])
+    assert sums.shape == (2 * n_pad,) and rel_err(sums, s_ref) < 1e-4
+    if n_pad > Cout:
+        assert float(sums[Cout:n_pad].abs().max()) == 0.0 and float(sums[n_pad + Cout:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("C,P", [(19, 32), (40, 64), (100, 128), (133, 160), (200, 256), (17, 24)])
